@@ -1,0 +1,152 @@
+// ============================================================================
+// TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+//
+// CPU oracle: a sequential, index-ordered FP64 restatement of the kinematic-icp
+// registration hot path.  Only tests/, __graft_entry__.smoke() and the
+// cpu_baseline / --impl reference legs of bench.py may build, link or call
+// anything in oracle/.  The product library (kinematic-icp_b200/csrc) never
+// includes this header and has no CPU fallback.
+//
+// PARITY STATUS: "parity unpinned" by the reference's own tests — the reference
+// ships no tests, fixtures or golden vectors.  The first-party
+// half (Registration.cpp) IS pinned against the reference's own source compiled
+// here (oracle/_ref, see oracle/Makefile + oracle/ref_wrapper.cpp).  The
+// third-party half (kiss_icp::VoxelHashMap, KISS-ICP v1.2.0, fetched by
+// cpp/kinematic_icp/kiss_icp/kiss-icp.cmake:29-31 and absent offline) is
+// restated from its published algorithm and stays unpinned.
+//
+// Every function cites the reference file:line (relative to /root/reference)
+// or the KISS-ICP v1.2.0 source file it restates.
+// ============================================================================
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <unordered_map>
+#include <vector>
+
+namespace kicp_oracle {
+
+struct Vec3 {
+    double x, y, z;
+};
+inline Vec3 operator+(const Vec3 &a, const Vec3 &b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline Vec3 operator-(const Vec3 &a, const Vec3 &b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline Vec3 operator*(double s, const Vec3 &a) { return {s * a.x, s * a.y, s * a.z}; }
+inline double dot(const Vec3 &a, const Vec3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline Vec3 cross(const Vec3 &a, const Vec3 &b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+double norm(const Vec3 &a);
+
+// Unit quaternion, Eigen coefficient order (x, y, z, w).
+struct Quat {
+    double x, y, z, w;
+};
+
+// Sophus::SE3d as the reference uses it: unit quaternion + translation.
+struct SE3 {
+    Quat q{0, 0, 0, 1};
+    Vec3 t{0, 0, 0};
+    static SE3 from_pose7(const double *p);  // {qx,qy,qz,qw,tx,ty,tz}
+    void to_pose7(double *p) const;
+};
+
+Vec3 rotate(const Quat &q, const Vec3 &p);  // Sophus SO3Base::operator*(Point)
+Vec3 transform(const SE3 &T, const Vec3 &p);  // Sophus SE3Base::operator*(Point)
+SE3 compose(const SE3 &a, const SE3 &b);      // Sophus SE3Base::operator*(SE3)
+SE3 inverse(const SE3 &a);
+SE3 se3_exp(const double tangent[6]);          // Sophus SE3::exp
+void se3_log(const SE3 &T, double tangent[6]);  // Sophus SE3::log
+double so3_log_theta(const Quat &q);            // Sophus SO3::logAndTheta().theta
+
+// ---------------------------------------------------------------------------
+// kiss_icp::VoxelHashMap (KISS-ICP v1.2.0 cpp/kiss_icp/core/VoxelHashMap.{hpp,cpp},
+// VoxelUtils.hpp) — restated, see SURVEY.md §8(c).
+// ---------------------------------------------------------------------------
+struct Voxel {
+    int32_t x, y, z;
+    bool operator==(const Voxel &o) const { return x == o.x && y == o.y && z == o.z; }
+};
+struct VoxelHash {
+    size_t operator()(const Voxel &v) const {
+        // KISS-ICP v1.2.0 VoxelUtils.hpp std::hash<Voxel>: 3-prime XOR on the
+        // coordinates reinterpreted as uint32.  Only iteration order depends on it.
+        return (static_cast<uint32_t>(v.x) * 73856093u) ^ (static_cast<uint32_t>(v.y) * 19349669u) ^
+               (static_cast<uint32_t>(v.z) * 83492791u);
+    }
+};
+Voxel PointToVoxel(const Vec3 &p, double voxel_size);
+extern const Voxel kVoxelShifts[27];  // KISS-ICP v1.2.0 VoxelHashMap.cpp voxel_shifts
+
+struct VoxelHashMap {
+    VoxelHashMap(double voxel_size, double max_distance, unsigned max_points_per_voxel)
+        : voxel_size_(voxel_size), max_distance_(max_distance), max_points_per_voxel_(max_points_per_voxel) {}
+    void Clear() { map_.clear(); }
+    bool Empty() const { return map_.empty(); }
+    void Update(const std::vector<Vec3> &points, const Vec3 &origin);
+    void Update(const std::vector<Vec3> &points, const SE3 &pose);
+    void AddPoints(const std::vector<Vec3> &points);
+    void RemovePointsFarFromLocation(const Vec3 &origin);
+    std::vector<Vec3> Pointcloud() const;
+    // returns (closest, distance); (0,0,0), DBL_MAX when the 27-neighbourhood is empty
+    std::pair<Vec3, double> GetClosestNeighbor(const Vec3 &query) const;
+    size_t NumPoints() const;
+
+    double voxel_size_;
+    double max_distance_;
+    unsigned max_points_per_voxel_;
+    std::unordered_map<Voxel, std::vector<Vec3>, VoxelHash> map_;
+};
+
+std::vector<Vec3> VoxelDownsample(const std::vector<Vec3> &frame, double voxel_size);
+std::vector<Vec3> Preprocess(const std::vector<Vec3> &frame, const std::vector<double> &timestamps,
+                             const SE3 &relative_motion, double max_range, double min_range, bool deskew);
+
+// ---------------------------------------------------------------------------
+// kinematic_icp::KinematicRegistration (cpp/kinematic_icp/registration/Registration.cpp)
+// ---------------------------------------------------------------------------
+struct RegParams {
+    int max_num_iterations = 10;
+    double convergence_criterion = 1e-3;
+    bool use_adaptive_odometry_regularization = true;
+    double fixed_regularization = 0.0;
+};
+
+struct IterSums {  // per-solve sums BEFORE the /N normalisation (Registration.cpp:110-118)
+    double JTJ00, JTJ01, JTJ11, JTr0, JTr1, N, sumsq;
+};
+
+struct RegStats {
+    int iterations = 0;   // number of ComputePerturbation solves performed
+    int associations = 0; // number of DataAssociation passes
+    double beta = 0.0;
+    double last_dx_norm = 0.0;
+    std::vector<IterSums> sums;
+    std::vector<double> dx;  // (d, theta) per solve, interleaved
+};
+
+SE3 ComputeRobotMotion(const std::vector<Vec3> &frame, const VoxelHashMap &voxel_map, const SE3 &last_robot_pose,
+                       const SE3 &relative_wheel_odometry, double max_correspondence_distance, const RegParams &params,
+                       RegStats *stats, int num_threads = 1);
+
+// CorrespondenceThreshold (cpp/kinematic_icp/correspondence_threshold/CorrespondenceThreshold.cpp)
+struct CorrespondenceThreshold {
+    CorrespondenceThreshold(double map_discretization_error, double max_range, bool use_adaptive, double fixed)
+        : map_discretization_error_(map_discretization_error),
+          max_range_(max_range),
+          use_adaptive_threshold_(use_adaptive),
+          fixed_threshold_(fixed),
+          odom_sse_(0.0),
+          num_samples_(1e-8) {}
+    void UpdateOdometryError(const SE3 &odometry_error);
+    double ComputeThreshold() const;
+    void Reset() {
+        odom_sse_ = 0.0;
+        num_samples_ = 1e-8;
+    }
+    double map_discretization_error_, max_range_;
+    bool use_adaptive_threshold_;
+    double fixed_threshold_, odom_sse_, num_samples_;
+};
+
+}  // namespace kicp_oracle
