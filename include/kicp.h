@@ -1,0 +1,158 @@
+/*
+ * kicp.h — C ABI of the B200-native kinematic-icp registration hot path (libkicp_b200.so).
+ *
+ * The reference (PRBonn/kinematic-icp @ 07c2851, v0.1.1) has no FFI: its hot path is a C++ value API
+ * (SURVEY.md §8(b)).  This header is the boundary a binding for that path would bind; every entry point cites
+ * the reference interface it replaces (paths relative to the reference root).  The C++ facade in
+ * kinematic-icp_b200/cpp/ (same class names, namespaces and signatures as the reference headers) sits on top
+ * of exactly these functions, so the ROS 2 nodes keep including "kinematic_icp/pipeline/KinematicICP.hpp" unchanged.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns an int status (KICP_OK == 0);
+ *   - points are row-major xyz doubles (std::vector<Eigen::Vector3d> is layout-compatible: 3 contiguous doubles);
+ *   - a pose is double[7] = {qx, qy, qz, qw, tx, ty, tz} — Eigen::Quaterniond coefficient order followed by the
+ *     translation, i.e. the two members of Sophus::SE3d;
+ *   - host pointers unless the name says "device"; calls are synchronous unless the name says "async";
+ *   - there is NO CPU fallback: without a CUDA device every call fails with KICP_ERR_CUDA.
+ */
+#ifndef KICP_H_
+#define KICP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KICP_VERSION 100
+#define KICP_MAX_ITERATIONS 64 /* upper bound accepted for max_num_iterations (reference default: 10) */
+
+enum kicp_status {
+    KICP_OK = 0,
+    KICP_ERR_CUDA = 1,        /* CUDA runtime error (no device, launch failure, out of memory); see kicp_last_error */
+    KICP_ERR_INVALID = 2,     /* bad argument */
+    KICP_ERR_UNSUPPORTED = 3, /* e.g. max_points_per_voxel > 255 */
+    KICP_ERR_NCCL = 4,
+    KICP_ERR_CAPACITY = 5,
+    /* The reference divides by the correspondence count with no guard (Registration.cpp:119-125): with zero
+     * correspondences its pose becomes NaN.  We stay drop-in (the returned pose IS NaN) and also say so. */
+    KICP_WARN_NO_CORRESPONDENCES = 16
+};
+
+typedef struct kicp_ctx kicp_ctx;   /* one GPU: device id, stream, scratch, optional NCCL communicator */
+typedef struct kicp_map kicp_map;   /* kiss_icp::VoxelHashMap resident in HBM */
+typedef struct kicp_scan kicp_scan; /* a scan (the `frame` argument of ComputeRobotMotion) resident in HBM */
+
+/* kinematic_icp::KinematicRegistration's public fields (registration/Registration.hpp:45-49).  max_num_threads_
+ * has no GPU meaning and is not carried. */
+typedef struct kicp_reg_params {
+    int32_t max_num_iterations;                   /* Registration.hpp:45, default 10 (pipeline/KinematicICP.hpp:52) */
+    int32_t use_adaptive_odometry_regularization; /* Registration.hpp:48, default true (KinematicICP.hpp:55) */
+    double convergence_criterion;                 /* Registration.hpp:46, default 1e-3 (KinematicICP.hpp:53) */
+    double fixed_regularization;                  /* Registration.hpp:49, default 0.0 (KinematicICP.hpp:56) */
+} kicp_reg_params;
+
+/* Result of one registration.  sums[j] are the normal-equation sums of solve j BEFORE the /N normalisation
+ * (Registration.cpp:110-118): {JTJ00, JTJ01, JTJ11, JTr0, JTr1, N, sum |r|^2, 0}; dx[j] = (d, theta). */
+typedef struct kicp_reg_result {
+    double pose[7];          /* the SE3d ComputeRobotMotion returns */
+    double beta;             /* odometry regularisation actually used (Registration.cpp:171-177) */
+    double last_dx_norm;
+    int32_t iterations;      /* number of ComputePerturbation solves == DataAssociation passes executed */
+    int32_t status;          /* KICP_OK or KICP_WARN_NO_CORRESPONDENCES */
+    double sums[KICP_MAX_ITERATIONS][8];
+    double dx[KICP_MAX_ITERATIONS][2];
+} kicp_reg_result;
+
+const char *kicp_status_string(int status);
+/* Thread-local text of the last failure (CUDA / NCCL error string and the call site). */
+const char *kicp_last_error(void);
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+int kicp_ctx_create(int device, kicp_ctx **out);
+int kicp_ctx_destroy(kicp_ctx *ctx);
+int kicp_ctx_synchronize(kicp_ctx *ctx);
+/* The CUDA stream (cudaStream_t) all work of this context is enqueued on — so a caller can time it with events. */
+void *kicp_ctx_stream(kicp_ctx *ctx);
+/* Number of this library's kernels launched on the context since creation (bench.py reports gpu_launches). */
+int64_t kicp_ctx_launch_count(kicp_ctx *ctx);
+/* Per-kernel device timing with CUDA events recorded on the context stream around (a) the binning of each
+ * registration (init + Morton keys + radix sort + gather) and (b) every launch of the association kernel.  Only
+ * launches that did work are counted in assoc_* (a launch issued after convergence exits at its first instruction
+ * and is reported under idle_*).  kicp_ctx_profile_end synchronises the stream. */
+typedef struct kicp_profile {
+    double assoc_ms;          /* summed duration of the association launches that did work */
+    int64_t assoc_launches;
+    double idle_ms;           /* launches issued after convergence (early exit) */
+    int64_t idle_launches;
+    double prep_ms;           /* init + keys + sort + gather, summed over registrations */
+    int64_t registrations;
+} kicp_profile;
+int kicp_ctx_profile_begin(kicp_ctx *ctx);
+int kicp_ctx_profile_end(kicp_ctx *ctx, kicp_profile *out);
+/* Pinned host memory for truly asynchronous copies (std::vector storage works too, just slower). */
+int kicp_host_alloc(uint64_t bytes, void **out);
+int kicp_host_free(void *p);
+
+/* ---- kiss_icp::VoxelHashMap (KISS-ICP v1.2.0 core/VoxelHashMap.hpp; used by the reference at
+ *      pipeline/KinematicICP.hpp:79,88,92, pipeline/KinematicICP.cpp:79, registration/Registration.cpp:74,157) --- */
+/* VoxelHashMap(voxel_size, max_distance, max_points_per_voxel) */
+int kicp_map_create(kicp_ctx *ctx, double voxel_size, double max_distance, uint32_t max_points_per_voxel, kicp_map **out);
+int kicp_map_destroy(kicp_map *map);
+int kicp_map_clear(kicp_map *map);                         /* Clear(), KinematicICP.hpp:88 */
+int kicp_map_empty(kicp_map *map, int32_t *empty);         /* Empty(), Registration.cpp:157 */
+int kicp_map_num_points(kicp_map *map, int64_t *n);
+int kicp_map_num_voxels(kicp_map *map, int64_t *n);
+int kicp_map_add_points(kicp_map *map, const double *xyz, int64_t n);                /* AddPoints(points) */
+int kicp_map_remove_far(kicp_map *map, const double origin[3]);                      /* RemovePointsFarFromLocation */
+int kicp_map_update(kicp_map *map, const double *xyz, int64_t n, const double origin[3]); /* Update(points, origin) */
+/* Update(points, pose): transform by pose, AddPoints, evict around pose.translation()  (KinematicICP.cpp:79) */
+int kicp_map_update_pose(kicp_map *map, const double *xyz, int64_t n, const double pose[7]);
+/* Pointcloud(), KinematicICP.hpp:92.  *n receives the count; fails with KICP_ERR_CAPACITY if cap is too small. */
+int kicp_map_pointcloud(kicp_map *map, double *out_xyz, int64_t cap, int64_t *n);
+/* Voxel-grouped dump: keys[V][3], counts[V], points[total][3] in per-voxel insertion order (tests, checkpoints). */
+int kicp_map_export_voxels(kicp_map *map, int32_t *keys, int32_t *counts, double *points, int64_t cap_voxels,
+                           int64_t cap_points, int64_t *num_voxels, int64_t *num_points);
+/* Bulk load of a voxel-grouped map (replaces the content): the inverse of kicp_map_export_voxels. */
+int kicp_map_load_voxels(kicp_map *map, const int32_t *keys, const int32_t *counts, const double *points,
+                         int64_t num_voxels);
+/* GetClosestNeighbor(query) for n queries: (closest point, distance); (0,0,0), DBL_MAX when nothing is found. */
+int kicp_map_nearest(kicp_map *map, const double *queries, int64_t n, double *out_points, double *out_dist);
+
+/* ---- kinematic_icp::KinematicRegistration::ComputeRobotMotion (registration/Registration.hpp:39-43,
+ *      registration/Registration.cpp:151-190; single call site pipeline/KinematicICP.cpp:68-72) -------------- */
+/* frame: n host points in the robot base frame.  Returns last_robot_pose * relative_wheel_odometry when the map is
+ * empty (Registration.cpp:157).  `result` may be NULL. */
+int kicp_register(kicp_map *map, const double *frame_xyz, int64_t n, const double last_robot_pose[7],
+                  const double relative_wheel_odometry[7], double max_correspondence_distance,
+                  const kicp_reg_params *params, double out_pose[7], kicp_reg_result *result);
+
+/* Same computation with the scan already resident in HBM, enqueued without a host synchronisation: `result` is
+ * written by an asynchronous device-to-host copy and is valid after kicp_ctx_synchronize (pinned memory from
+ * kicp_host_alloc keeps the copy asynchronous). */
+int kicp_scan_create(kicp_ctx *ctx, int64_t capacity, kicp_scan **out);
+int kicp_scan_destroy(kicp_scan *scan);
+int kicp_scan_upload(kicp_scan *scan, const double *xyz, int64_t n);       /* synchronous host -> HBM copy */
+int kicp_scan_upload_async(kicp_scan *scan, const double *xyz, int64_t n); /* enqueued on the context stream */
+int kicp_register_scan_async(kicp_map *map, kicp_scan *scan, const double last_robot_pose[7],
+                             const double relative_wheel_odometry[7], double max_correspondence_distance,
+                             const kicp_reg_params *params, kicp_reg_result *result);
+
+/* ---- multi-GPU: the scan's points shard by contiguous index range, the map is replicated, and each IRLS
+ *      iteration ends with one sum-allreduce of the 8 accumulated doubles. ------------------- */
+#define KICP_UNIQUE_ID_BYTES 128
+int kicp_comm_unique_id(uint8_t id[KICP_UNIQUE_ID_BYTES]); /* ncclGetUniqueId on rank 0; broadcast it out of band */
+int kicp_comm_init(kicp_ctx *ctx, const uint8_t id[KICP_UNIQUE_ID_BYTES], int32_t nranks, int32_t rank);
+int kicp_comm_destroy(kicp_ctx *ctx);
+/* Every rank calls this with ITS shard (frame_xyz / n are the local range).  All ranks return the same pose. */
+int kicp_register_sharded(kicp_map *map, const double *frame_xyz, int64_t n_local, const double last_robot_pose[7],
+                          const double relative_wheel_odometry[7], double max_correspondence_distance,
+                          const kicp_reg_params *params, double out_pose[7], kicp_reg_result *result);
+int kicp_register_scan_sharded_async(kicp_map *map, kicp_scan *scan_shard, const double last_robot_pose[7],
+                                     const double relative_wheel_odometry[7], double max_correspondence_distance,
+                                     const kicp_reg_params *params, kicp_reg_result *result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KICP_H_ */

@@ -1,0 +1,107 @@
+// Multi-GPU plumbing: one process per GPU, one NCCL communicator per context, one sum-allreduce of the 8
+// accumulated doubles per IRLS iteration.  NCCL is resolved lazily with dlopen so that a
+// single-GPU user of libkicp_b200.so does not need libnccl at all; under PyTorch the already-loaded
+// libnccl.so.2 is the one that gets picked up.
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "kicp_internal.h"
+
+namespace {
+typedef struct ncclComm *ncclComm_t;
+typedef struct {
+    char internal[128];
+} ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclSum = 0 };
+enum { ncclFloat64 = 8 };
+
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+    const char *(*GetErrorString)(ncclResult_t);
+    bool ok = false;
+};
+
+NcclApi &nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+            api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+        }
+    }
+    return api;
+}
+
+int nccl_fail(ncclResult_t r, const char *what) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "NCCL error %d (%s) in %s", (int)r, nccl().ok ? nccl().GetErrorString(r) : "?", what);
+    kicp_set_error(buf);
+    return KICP_ERR_NCCL;
+}
+}  // namespace
+
+extern "C" int kicp_comm_unique_id(uint8_t id[KICP_UNIQUE_ID_BYTES]) {
+    if (!id) return KICP_ERR_INVALID;
+    if (!nccl().ok) {
+        kicp_set_error("libnccl.so.2 could not be loaded");
+        return KICP_ERR_NCCL;
+    }
+    ncclUniqueId uid;
+    ncclResult_t r = nccl().GetUniqueId(&uid);
+    if (r != 0) return nccl_fail(r, "ncclGetUniqueId");
+    static_assert(sizeof(uid) == KICP_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    memcpy(id, &uid, sizeof(uid));
+    return KICP_OK;
+}
+
+extern "C" int kicp_comm_init(kicp_ctx *ctx, const uint8_t id[KICP_UNIQUE_ID_BYTES], int32_t nranks, int32_t rank) {
+    if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return KICP_ERR_INVALID;
+    if (!nccl().ok) {
+        kicp_set_error("libnccl.so.2 could not be loaded");
+        return KICP_ERR_NCCL;
+    }
+    KICP_CUDA(cudaSetDevice(ctx->device));
+    kicp_comm_destroy(ctx);
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    ncclComm_t comm = nullptr;
+    ncclResult_t r = nccl().CommInitRank(&comm, nranks, uid, rank);
+    if (r != 0) return nccl_fail(r, "ncclCommInitRank");
+    ctx->nccl_comm = comm;
+    ctx->nranks = nranks, ctx->rank = rank;
+    return KICP_OK;
+}
+
+extern "C" int kicp_comm_destroy(kicp_ctx *ctx) {
+    if (!ctx) return KICP_ERR_INVALID;
+    if (ctx->nccl_comm) {
+        cudaStreamSynchronize(ctx->stream);
+        nccl().CommDestroy((ncclComm_t)ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    ctx->nranks = 1, ctx->rank = 0;
+    return KICP_OK;
+}
+
+// in-place sum of 8 doubles across the communicator, enqueued on the context stream
+int kicp_comm_allreduce8(kicp_ctx *ctx, double *d_buf) {
+    if (!ctx->nccl_comm) return KICP_ERR_INVALID;
+    ncclResult_t r = nccl().AllReduce(d_buf, d_buf, 8, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+    if (r != 0) return nccl_fail(r, "ncclAllReduce");
+    ctx->launches++;
+    return KICP_OK;
+}

@@ -1,0 +1,73 @@
+// Device-side helpers shared by the map and registration kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "kicp_internal.h"
+
+// KISS-ICP v1.2.0 VoxelHashMap.cpp `voxel_shifts`: centre, 6 faces, 12 edges, 8 corners.  The visiting order
+// matters only for exact distance ties (strict <, first minimum wins) — we keep it so ties resolve identically.
+// Packed 2 bits per entry per axis (value + 1) so a lane can decode its shift without a divergent table read.
+namespace kicp_dev {
+constexpr int kShifts[27][3] = {
+    {0, 0, 0},   {1, 0, 0},   {-1, 0, 0},  {0, 1, 0},   {0, -1, 0},  {0, 0, 1},   {0, 0, -1},  {1, 1, 0},   {1, -1, 0},
+    {-1, 1, 0},  {-1, -1, 0}, {1, 0, 1},   {1, 0, -1},  {-1, 0, 1},  {-1, 0, -1}, {0, 1, 1},   {0, 1, -1},  {0, -1, 1},
+    {0, -1, -1}, {1, 1, 1},   {1, 1, -1},  {1, -1, 1},  {1, -1, -1}, {-1, 1, 1},  {-1, 1, -1}, {-1, -1, 1}, {-1, -1, -1}};
+constexpr unsigned long long pack_axis(int a) {
+    unsigned long long r = 0;
+    for (int k = 0; k < 27; ++k) r |= (unsigned long long)(kShifts[k][a] + 1) << (2 * k);
+    return r;
+}
+constexpr unsigned long long kShiftX = pack_axis(0), kShiftY = pack_axis(1), kShiftZ = pack_axis(2);
+
+__device__ __forceinline__ int shift_x(int k) { return (int)((kShiftX >> (2 * k)) & 3ull) - 1; }
+__device__ __forceinline__ int shift_y(int k) { return (int)((kShiftY >> (2 * k)) & 3ull) - 1; }
+__device__ __forceinline__ int shift_z(int k) { return (int)((kShiftZ >> (2 * k)) & 3ull) - 1; }
+
+// Voxel hash: the reference's 3-prime XOR (KISS VoxelUtils.hpp) followed by a murmur3 finaliser so that linear
+// probing sees well-mixed low bits.  The hash only decides WHERE a voxel lives, never which neighbour wins.
+__host__ __device__ __forceinline__ uint32_t voxel_hash(int x, int y, int z) {
+    uint32_t h = ((uint32_t)x * 73856093u) ^ ((uint32_t)y * 19349669u) ^ ((uint32_t)z * 83492791u);
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return h;
+}
+
+// PointToVoxel (KISS VoxelUtils.hpp): static_cast<int>(floor(x / voxel_size)).  A true FP64 division, not a
+// multiplication by the reciprocal, so voxel boundaries fall exactly where the reference puts them.
+__device__ __forceinline__ int voxel_coord(double x, double vs) { return (int)floor(x / vs); }
+
+// Read-only probe (no concurrent writers): returns the slot's meta word, or KICP_SLOT_EMPTY when absent.
+__device__ __forceinline__ uint32_t map_probe(const MapView &m, int kx, int ky, int kz) {
+    uint32_t h = voxel_hash(kx, ky, kz) & m.mask;
+    while (true) {
+        const int4 s = __ldg(&m.slots[h]);
+        if ((uint32_t)s.w == KICP_SLOT_EMPTY) return KICP_SLOT_EMPTY;
+        if (s.x == kx && s.y == ky && s.z == kz) return (uint32_t)s.w;
+        h = (h + 1) & m.mask;
+    }
+}
+
+struct Pose {  // Sophus::SE3d: unit quaternion (x,y,z,w) + translation
+    double qx, qy, qz, qw, tx, ty, tz;
+};
+
+// Sophus SO3Base::operator*(Point): uv = 2 (q.vec x p); p + w uv + q.vec x uv
+__device__ __forceinline__ void quat_rotate(double qx, double qy, double qz, double qw, double px, double py, double pz,
+                                            double &ox, double &oy, double &oz) {
+    double ux = qy * pz - qz * py, uy = qz * px - qx * pz, uz = qx * py - qy * px;
+    ux = ux + ux, uy = uy + uy, uz = uz + uz;
+    ox = px + qw * ux + (qy * uz - qz * uy);
+    oy = py + qw * uy + (qz * ux - qx * uz);
+    oz = pz + qw * uz + (qx * uy - qy * ux);
+}
+__device__ __forceinline__ void pose_apply(const Pose &T, double px, double py, double pz, double &ox, double &oy, double &oz) {
+    quat_rotate(T.qx, T.qy, T.qz, T.qw, px, py, pz, ox, oy, oz);
+    ox += T.tx, oy += T.ty, oz += T.tz;
+}
+
+}  // namespace kicp_dev

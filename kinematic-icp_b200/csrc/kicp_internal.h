@@ -1,0 +1,116 @@
+// Internal definitions shared by the translation units of libkicp_b200.so.  Not installed.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "kicp.h"
+
+#define KICP_SLOT_EMPTY 0xFFFFFFFFu
+#define KICP_SLOT_LOCKED 0xFFFFFFFEu
+#define KICP_MAX_CAP 255  // max_points_per_voxel: the count shares the slot's meta word (low 8 bits)
+
+// ---------------------------------------------------------------------------------------------------------
+// HBM layout of the voxel map (kiss_icp::VoxelHashMap on the device)
+//
+//   slots[nslots]      int4 {kx, ky, kz, meta}   open-addressed, linear probing, nslots = 2^k, load <= 0.25
+//                                                meta = (block << 8) | count, 0xFFFFFFFF = empty
+//   blk[blocks_cap]    int4 {kx, ky, kz, count}  one header per occupied voxel ("block"), dense [0, num_blocks)
+//   pts[blocks_cap * cap * 3] double             block b owns points [b*cap, b*cap + count), insertion order
+//
+// One 16-byte load resolves a probe to (block, count); a voxel's points are one contiguous <= cap*24 B run.
+// ---------------------------------------------------------------------------------------------------------
+struct MapView {
+    const int4 *slots;
+    uint32_t mask;  // nslots - 1
+    const double *pts;
+    int cap;
+    double voxel_size;
+};
+
+struct kicp_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    // registration scratch (grown on demand)
+    struct RegState *d_state = nullptr;
+    double *d_sorted = nullptr;   // scan reordered by Morton key of the voxel at the initial guess
+    uint32_t *d_keys = nullptr, *d_keys_alt = nullptr;
+    int32_t *d_idx = nullptr, *d_idx_alt = nullptr;
+    void *d_sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
+    int64_t scratch_cap = 0;
+    int assoc_ctas_per_sm = 1;  // resident CTAs of the association kernel per SM (occupancy query)
+    kicp_scan *upload_scan = nullptr;  // staging scan used by the host-pointer entry points
+    kicp_reg_result *h_result = nullptr;  // pinned bounce buffer for synchronous calls
+    // profiling (kicp_ctx_profile_begin/end): event pairs per registration
+    bool profiling = false;
+    struct ProfReg {
+        cudaEvent_t prep0, prep1;
+        std::vector<cudaEvent_t> it;  // 2 per association launch
+        int32_t *d_iters;             // device word receiving the registration's iteration count
+    };
+    std::vector<ProfReg> prof;
+    int32_t *d_prof_iters = nullptr;
+    int64_t prof_cap = 0;
+    // multi-GPU
+    void *nccl_comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+struct kicp_map {
+    kicp_ctx *ctx = nullptr;
+    double voxel_size = 1.0, max_distance = 100.0;
+    uint32_t cap = 20;
+    int4 *slots = nullptr;
+    uint32_t nslots = 0;
+    int4 *blk = nullptr;
+    double *pts = nullptr;
+    int32_t *pend_head = nullptr;  // per block, -1 when idle
+    uint32_t blocks_cap = 0;
+    uint32_t num_blocks = 0;  // host mirror
+    int64_t num_points = 0;   // host mirror
+    uint32_t *d_counters = nullptr;  // [0] num_blocks [1] touched [2] overflow [3] points added [4] dead
+    // staging for AddPoints
+    double *d_in = nullptr, *d_xyz_t = nullptr;
+    int32_t *d_next = nullptr, *d_touched = nullptr;
+    int64_t in_cap = 0;
+    MapView view() const { return MapView{slots, nslots - 1, pts, (int)cap, voxel_size}; }
+};
+
+struct kicp_scan {
+    kicp_ctx *ctx = nullptr;
+    double *d_xyz = nullptr;
+    int64_t cap = 0, n = 0;
+};
+
+// error plumbing ------------------------------------------------------------------------------------------
+void kicp_set_error(const std::string &msg);
+int kicp_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define KICP_CUDA(call)                                                       \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) return kicp_cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define KICP_CHECK_LAUNCH(ctx)                                                \
+    do {                                                                      \
+        (ctx)->launches++;                                                    \
+        cudaError_t e__ = cudaGetLastError();                                 \
+        if (e__ != cudaSuccess) return kicp_cuda_fail(e__, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+#define KICP_TRY(call)                 \
+    do {                               \
+        int s__ = (call);              \
+        if (s__ != KICP_OK) return s__; \
+    } while (0)
+
+// defined in kicp_map.cu, used by the registration entry points
+int kicp_scan_reserve(kicp_scan *scan, int64_t n);
+// defined in kicp_comm.cu
+int kicp_comm_allreduce8(kicp_ctx *ctx, double *d_buf);

@@ -1,0 +1,720 @@
+// kiss_icp::VoxelHashMap resident in HBM: context, storage management, AddPoints / RemovePointsFarFromLocation /
+// Update / Pointcloud / GetClosestNeighbor.  (KISS-ICP v1.2.0 core/VoxelHashMap.{hpp,cpp}; reference call sites
+// pipeline/KinematicICP.hpp:79,88,92, pipeline/KinematicICP.cpp:79, registration/Registration.cpp:74,157.)
+//
+// This translation unit is compiled with -fmad=false: every decision (voxel floor, the < map_resolution spacing
+// test, the >= max_distance^2 eviction test, the nearest-neighbour argmin) is evaluated in plain IEEE double
+// arithmetic in the same operation order as the reference, so the device map is bit-identical to the CPU one.
+#include <algorithm>
+#include <cfloat>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "kicp_device.cuh"
+
+using namespace kicp_dev;
+
+// ---------------------------------------------------------------------------------------------- error plumbing
+static thread_local std::string g_last_error;
+void kicp_set_error(const std::string &msg) { g_last_error = msg; }
+int kicp_cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    g_last_error = buf;
+    cudaGetLastError();  // clear the sticky-free error state
+    return KICP_ERR_CUDA;
+}
+extern "C" const char *kicp_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char *kicp_status_string(int s) {
+    switch (s) {
+        case KICP_OK: return "ok";
+        case KICP_ERR_CUDA: return "CUDA error";
+        case KICP_ERR_INVALID: return "invalid argument";
+        case KICP_ERR_UNSUPPORTED: return "unsupported configuration";
+        case KICP_ERR_NCCL: return "NCCL error";
+        case KICP_ERR_CAPACITY: return "capacity exceeded";
+        case KICP_WARN_NO_CORRESPONDENCES: return "no correspondences (pose is NaN, as in the reference)";
+        default: return "unknown status";
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- context
+extern "C" int kicp_ctx_create(int device, kicp_ctx **out) {
+    if (!out) return KICP_ERR_INVALID;
+    int count = 0;
+    KICP_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) {
+        kicp_set_error("kicp_ctx_create: no such CUDA device (this library has no CPU fallback)");
+        return KICP_ERR_CUDA;
+    }
+    KICP_CUDA(cudaSetDevice(device));
+    kicp_ctx *c = new kicp_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    KICP_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    KICP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    KICP_CUDA(cudaMallocHost(&c->h_result, sizeof(kicp_reg_result)));
+    *out = c;
+    return KICP_OK;
+}
+
+extern "C" int kicp_ctx_synchronize(kicp_ctx *ctx) {
+    if (!ctx) return KICP_ERR_INVALID;
+    KICP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return KICP_OK;
+}
+extern "C" void *kicp_ctx_stream(kicp_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" int64_t kicp_ctx_launch_count(kicp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int kicp_host_alloc(uint64_t bytes, void **out) {
+    if (!out) return KICP_ERR_INVALID;
+    KICP_CUDA(cudaMallocHost(out, bytes));
+    return KICP_OK;
+}
+extern "C" int kicp_host_free(void *p) {
+    KICP_CUDA(cudaFreeHost(p));
+    return KICP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------ scans
+int kicp_scan_reserve(kicp_scan *s, int64_t n) {
+    if (n <= s->cap) return KICP_OK;
+    KICP_CUDA(cudaSetDevice(s->ctx->device));
+    KICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    if (s->d_xyz) KICP_CUDA(cudaFree(s->d_xyz));
+    s->d_xyz = nullptr;
+    const int64_t cap = std::max<int64_t>(n + n / 4, 1024);
+    KICP_CUDA(cudaMalloc(&s->d_xyz, (size_t)cap * 3 * sizeof(double)));
+    s->cap = cap;
+    return KICP_OK;
+}
+extern "C" int kicp_scan_create(kicp_ctx *ctx, int64_t capacity, kicp_scan **out) {
+    if (!ctx || !out || capacity < 0) return KICP_ERR_INVALID;
+    kicp_scan *s = new kicp_scan();
+    s->ctx = ctx;
+    int st = kicp_scan_reserve(s, capacity);
+    if (st != KICP_OK) {
+        delete s;
+        return st;
+    }
+    *out = s;
+    return KICP_OK;
+}
+extern "C" int kicp_scan_destroy(kicp_scan *s) {
+    if (!s) return KICP_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    cudaFree(s->d_xyz);
+    delete s;
+    return KICP_OK;
+}
+extern "C" int kicp_scan_upload_async(kicp_scan *s, const double *xyz, int64_t n) {
+    if (!s || n < 0 || (n > 0 && !xyz)) return KICP_ERR_INVALID;
+    KICP_CUDA(cudaSetDevice(s->ctx->device));
+    KICP_TRY(kicp_scan_reserve(s, n));
+    if (n > 0)
+        KICP_CUDA(cudaMemcpyAsync(s->d_xyz, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, s->ctx->stream));
+    s->n = n;
+    return KICP_OK;
+}
+extern "C" int kicp_scan_upload(kicp_scan *s, const double *xyz, int64_t n) {
+    KICP_TRY(kicp_scan_upload_async(s, xyz, n));
+    KICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    return KICP_OK;
+}
+
+extern "C" int kicp_ctx_destroy(kicp_ctx *ctx) {
+    if (!ctx) return KICP_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    kicp_comm_destroy(ctx);
+    if (ctx->upload_scan) kicp_scan_destroy(ctx->upload_scan);
+    cudaFree(ctx->d_state);
+    cudaFree(ctx->d_sorted);
+    cudaFree(ctx->d_keys);
+    cudaFree(ctx->d_keys_alt);
+    cudaFree(ctx->d_idx);
+    cudaFree(ctx->d_idx_alt);
+    cudaFree(ctx->d_sort_tmp);
+    cudaFree(ctx->d_prof_iters);
+    cudaFreeHost(ctx->h_result);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return KICP_OK;
+}
+
+// -------------------------------------------------------------------------------------------------- map kernels
+struct MapRW {
+    int4 *slots;
+    uint32_t mask;
+    int4 *blk;
+    double *pts;
+    int32_t *pend_head;
+    uint32_t blocks_cap;
+    int cap;
+    double voxel_size;
+};
+
+// Insert a key known to be absent (rebuild / bulk load): claim the first empty slot of the probe chain.
+__device__ __forceinline__ void table_insert_unique(int4 *slots, uint32_t mask, int kx, int ky, int kz, uint32_t meta) {
+    uint32_t h = voxel_hash(kx, ky, kz) & mask;
+    while (true) {
+        const uint32_t old = atomicCAS((unsigned int *)&slots[h].w, KICP_SLOT_EMPTY, meta);
+        if (old == KICP_SLOT_EMPTY) {
+            slots[h].x = kx, slots[h].y = ky, slots[h].z = kz;
+            return;
+        }
+        h = (h + 1) & mask;
+    }
+}
+
+__global__ void k_table_rebuild(int4 *slots, uint32_t mask, const int4 *blk, uint32_t num_blocks) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= num_blocks) return;
+    const int4 h = blk[b];
+    table_insert_unique(slots, mask, h.x, h.y, h.z, (b << 8) | (uint32_t)h.w);
+}
+
+// AddPoints, phase 1: per input point, (optionally) transform by the pose, find or create its voxel, and push the
+// point's index on that voxel's pending list.
+__global__ void k_add_find_or_create(MapRW m, const double *__restrict__ xyz, int64_t n, int has_pose, Pose pose,
+                                     double *__restrict__ xyz_t, int32_t *__restrict__ pend_next, uint32_t *counters,
+                                     int32_t *__restrict__ touched) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+    if (has_pose) {
+        double ox, oy, oz;
+        pose_apply(pose, px, py, pz, ox, oy, oz);
+        px = ox, py = oy, pz = oz;
+    }
+    xyz_t[3 * i] = px, xyz_t[3 * i + 1] = py, xyz_t[3 * i + 2] = pz;
+    const int kx = voxel_coord(px, m.voxel_size), ky = voxel_coord(py, m.voxel_size), kz = voxel_coord(pz, m.voxel_size);
+    uint32_t h = voxel_hash(kx, ky, kz) & m.mask;
+    uint32_t block = 0xFFFFFFFFu;
+    volatile int4 *vs = m.slots;
+    while (true) {
+        uint32_t meta = (uint32_t)vs[h].w;
+        if (meta == KICP_SLOT_EMPTY) {
+            const uint32_t old = atomicCAS((unsigned int *)&m.slots[h].w, KICP_SLOT_EMPTY, KICP_SLOT_LOCKED);
+            if (old == KICP_SLOT_EMPTY) {  // we create the voxel
+                const uint32_t b = atomicAdd(&counters[0], 1u);
+                if (b >= m.blocks_cap) {   // cannot happen: the host reserves num_blocks + n before the launch
+                    atomicExch(&counters[2], 1u);
+                    return;
+                }
+                vs[h].x = kx, vs[h].y = ky, vs[h].z = kz;
+                m.blk[b] = make_int4(kx, ky, kz, 0);
+                __threadfence();
+                atomicExch((unsigned int *)&m.slots[h].w, b << 8);
+                block = b;
+                break;
+            }
+            meta = old;
+        }
+        if (meta == KICP_SLOT_LOCKED) continue;  // another thread is publishing this slot: re-read it
+        __threadfence();
+        if (vs[h].x == kx && vs[h].y == ky && vs[h].z == kz) {
+            block = meta >> 8;
+            break;
+        }
+        h = (h + 1) & m.mask;
+    }
+    const int32_t prev = atomicExch(&m.pend_head[block], (int32_t)i);
+    pend_next[i] = prev;
+    if (prev == -1) touched[atomicAdd(&counters[1], 1u)] = (int32_t)block;
+}
+
+// AddPoints, phase 2: one thread per touched voxel replays ITS pending points in input order against the voxel's
+// current content — exactly the reference's greedy rule, which never looks outside the point's own voxel:
+//   skip if the voxel is full, or if any stored point is closer than map_resolution; else append.
+__global__ void k_add_commit(MapRW m, const double *__restrict__ xyz_t, const int32_t *__restrict__ pend_next,
+                             uint32_t *counters, const int32_t *__restrict__ touched, double map_resolution) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= counters[1]) return;
+    const uint32_t b = (uint32_t)touched[t];
+    const int4 hdr = m.blk[b];
+    int cnt = hdr.w;
+    const int cnt0 = cnt;
+    double *vp = m.pts + (size_t)b * m.cap * 3;
+    const int32_t head = m.pend_head[b];
+    int32_t last = -1;
+    while (cnt < m.cap) {
+        int32_t best = 0x7FFFFFFF;
+        for (int32_t i = head; i != -1; i = pend_next[i])
+            if (i > last && i < best) best = i;
+        if (best == 0x7FFFFFFF) break;
+        last = best;
+        const double px = xyz_t[3 * (size_t)best], py = xyz_t[3 * (size_t)best + 1], pz = xyz_t[3 * (size_t)best + 2];
+        bool too_close = false;
+        for (int j = 0; j < cnt; ++j) {
+            const double dx = vp[3 * j] - px, dy = vp[3 * j + 1] - py, dz = vp[3 * j + 2] - pz;
+            if (sqrt(dx * dx + dy * dy + dz * dz) < map_resolution) {
+                too_close = true;
+                break;
+            }
+        }
+        if (too_close) continue;
+        vp[3 * cnt] = px, vp[3 * cnt + 1] = py, vp[3 * cnt + 2] = pz;
+        ++cnt;
+    }
+    m.pend_head[b] = -1;
+    if (cnt != cnt0) {
+        m.blk[b].w = cnt;
+        atomicAdd(&counters[3], (uint32_t)(cnt - cnt0));
+        uint32_t h = voxel_hash(hdr.x, hdr.y, hdr.z) & m.mask;
+        while (true) {
+            const int4 s = m.slots[h];
+            if (s.x == hdr.x && s.y == hdr.y && s.z == hdr.z && (uint32_t)s.w != KICP_SLOT_EMPTY) {
+                m.slots[h].w = (int)((b << 8) | (uint32_t)cnt);
+                break;
+            }
+            h = (h + 1) & m.mask;
+        }
+    }
+}
+
+// RemovePointsFarFromLocation: a voxel dies when its FIRST point is >= max_distance from the origin.
+__global__ void k_mark_far(const int4 *blk, const double *pts, int cap, uint32_t num_blocks, double ox, double oy, double oz,
+                           double max_distance2, uint32_t *keep, uint32_t *counters) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= num_blocks) return;
+    const double *p = pts + (size_t)b * cap * 3;
+    const double dx = p[0] - ox, dy = p[1] - oy, dz = p[2] - oz;
+    const bool dead = (dx * dx + dy * dy + dz * dz) >= max_distance2;
+    keep[b] = dead ? 0u : 1u;
+    if (dead) {
+        atomicAdd(&counters[4], 1u);
+        atomicAdd(&counters[3], (uint32_t)blk[b].w);  // points removed
+    }
+}
+
+// single-CTA exclusive scan (maintenance path, a few hundred thousand elements at most)
+__global__ void k_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n ? in[i] : 0u;
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sums[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0u;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+                if (lane >= o) w += y;
+            }
+            warp_sums[lane] = w;  // inclusive
+        }
+        __syncthreads();
+        const uint32_t prefix = carry + (wid ? warp_sums[wid - 1] : 0u);
+        if (i < n) out[i] = prefix + x - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = prefix + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void k_compact_blocks(const int4 *blk, const double *pts, int cap, uint32_t num_blocks, const uint32_t *keep,
+                                 const uint32_t *new_id, int4 *blk_out, double *pts_out) {
+    // one warp per block: header by lane 0, points copied cooperatively
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= num_blocks || !keep[b]) return;
+    const uint32_t nb = new_id[b];
+    const int4 h = blk[b];
+    if (lane == 0) blk_out[nb] = h;
+    const double *src = pts + (size_t)b * cap * 3;
+    double *dst = pts_out + (size_t)nb * cap * 3;
+    for (int i = lane; i < h.w * 3; i += 32) dst[i] = src[i];
+}
+
+__global__ void k_fill_i32(int32_t *p, int32_t v, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// bulk load: voxel v becomes block v
+__global__ void k_load_voxels(int4 *blk, double *pts, int cap, const int32_t *keys, const int32_t *counts,
+                              const int64_t *offsets, const double *points, uint32_t num_voxels) {
+    const uint32_t v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (v >= num_voxels) return;
+    const int c = counts[v];
+    if (lane == 0) blk[v] = make_int4(keys[3 * v], keys[3 * v + 1], keys[3 * v + 2], c);
+    const double *src = points + offsets[v] * 3;
+    double *dst = pts + (size_t)v * cap * 3;
+    for (int i = lane; i < c * 3; i += 32) dst[i] = src[i];
+}
+
+// GetClosestNeighbor for a batch of queries, one thread each, evaluated exactly like the reference:
+// shifts in KISS order, per voxel first-minimum of (x - q).norm() under strict <, global strict <.
+__global__ void k_nearest(MapView m, const double *__restrict__ q, int64_t n, double *__restrict__ out_pts,
+                          double *__restrict__ out_dist) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
+    const int vx = voxel_coord(qx, m.voxel_size), vy = voxel_coord(qy, m.voxel_size), vz = voxel_coord(qz, m.voxel_size);
+    double bx = 0.0, by = 0.0, bz = 0.0, bd = DBL_MAX;
+    for (int k = 0; k < 27; ++k) {
+        const uint32_t meta = map_probe(m, vx + shift_x(k), vy + shift_y(k), vz + shift_z(k));
+        if (meta == KICP_SLOT_EMPTY) continue;
+        const double *vp = m.pts + (size_t)(meta >> 8) * m.cap * 3;
+        const int cnt = (int)(meta & 0xFFu);
+        for (int j = 0; j < cnt; ++j) {
+            const double dx = vp[3 * j] - qx, dy = vp[3 * j + 1] - qy, dz = vp[3 * j + 2] - qz;
+            const double d = sqrt(dx * dx + dy * dy + dz * dz);
+            if (d < bd) bd = d, bx = vp[3 * j], by = vp[3 * j + 1], bz = vp[3 * j + 2];
+        }
+    }
+    out_pts[3 * i] = bx, out_pts[3 * i + 1] = by, out_pts[3 * i + 2] = bz;
+    out_dist[i] = bd;
+}
+
+// -------------------------------------------------------------------------------------------- host-side storage
+static uint32_t next_pow2(uint64_t v) {
+    uint64_t p = 1;
+    while (p < v) p <<= 1;
+    return (uint32_t)p;
+}
+
+static int map_rebuild_table(kicp_map *m, uint32_t nslots) {
+    kicp_ctx *c = m->ctx;
+    if (nslots != m->nslots) {
+        if (m->slots) KICP_CUDA(cudaFree(m->slots));
+        m->slots = nullptr;
+        KICP_CUDA(cudaMalloc(&m->slots, (size_t)nslots * sizeof(int4)));
+        m->nslots = nslots;
+    }
+    KICP_CUDA(cudaMemsetAsync(m->slots, 0xFF, (size_t)m->nslots * sizeof(int4), c->stream));
+    if (m->num_blocks) {
+        k_table_rebuild<<<(m->num_blocks + 255) / 256, 256, 0, c->stream>>>(m->slots, m->nslots - 1, m->blk, m->num_blocks);
+        KICP_CHECK_LAUNCH(c);
+    }
+    return KICP_OK;
+}
+
+// make room for `extra` more voxels (blocks) and keep the table load factor <= 0.25
+static int map_reserve(kicp_map *m, uint64_t extra) {
+    kicp_ctx *c = m->ctx;
+    const uint64_t need = (uint64_t)m->num_blocks + extra;
+    if (need >= (1ull << 24)) {
+        kicp_set_error("voxel map: more than 2^24 voxels");
+        return KICP_ERR_CAPACITY;
+    }
+    if (need > m->blocks_cap) {
+        const uint32_t ncap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(need + need / 2, 4096), (1ull << 24));
+        int4 *nblk = nullptr;
+        double *npts = nullptr;
+        int32_t *nhead = nullptr;
+        KICP_CUDA(cudaMalloc(&nblk, (size_t)ncap * sizeof(int4)));
+        KICP_CUDA(cudaMalloc(&npts, (size_t)ncap * m->cap * 3 * sizeof(double)));
+        KICP_CUDA(cudaMalloc(&nhead, (size_t)ncap * sizeof(int32_t)));
+        if (m->num_blocks) {
+            KICP_CUDA(cudaMemcpyAsync(nblk, m->blk, (size_t)m->num_blocks * sizeof(int4), cudaMemcpyDeviceToDevice, c->stream));
+            KICP_CUDA(cudaMemcpyAsync(npts, m->pts, (size_t)m->num_blocks * m->cap * 3 * sizeof(double),
+                                      cudaMemcpyDeviceToDevice, c->stream));
+        }
+        k_fill_i32<<<(ncap + 255) / 256, 256, 0, c->stream>>>(nhead, -1, ncap);
+        KICP_CHECK_LAUNCH(c);
+        KICP_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(m->blk), cudaFree(m->pts), cudaFree(m->pend_head);
+        m->blk = nblk, m->pts = npts, m->pend_head = nhead, m->blocks_cap = ncap;
+    }
+    const uint32_t want_slots = std::max<uint32_t>(next_pow2(need * 4), 1024u);
+    if (want_slots > m->nslots) KICP_TRY(map_rebuild_table(m, want_slots));
+    return KICP_OK;
+}
+
+static int map_reserve_input(kicp_map *m, int64_t n) {
+    if (n <= m->in_cap) return KICP_OK;
+    kicp_ctx *c = m->ctx;
+    KICP_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(m->d_in), cudaFree(m->d_xyz_t), cudaFree(m->d_next), cudaFree(m->d_touched);
+    m->d_in = m->d_xyz_t = nullptr, m->d_next = m->d_touched = nullptr;
+    const int64_t cap = std::max<int64_t>(n + n / 4, 4096);
+    KICP_CUDA(cudaMalloc(&m->d_in, (size_t)cap * 3 * sizeof(double)));
+    KICP_CUDA(cudaMalloc(&m->d_xyz_t, (size_t)cap * 3 * sizeof(double)));
+    KICP_CUDA(cudaMalloc(&m->d_next, (size_t)cap * sizeof(int32_t)));
+    KICP_CUDA(cudaMalloc(&m->d_touched, (size_t)cap * sizeof(int32_t)));
+    m->in_cap = cap;
+    return KICP_OK;
+}
+
+extern "C" int kicp_map_create(kicp_ctx *ctx, double voxel_size, double max_distance, uint32_t max_points_per_voxel,
+                               kicp_map **out) {
+    if (!ctx || !out || !(voxel_size > 0.0) || max_points_per_voxel == 0) return KICP_ERR_INVALID;
+    if (max_points_per_voxel > KICP_MAX_CAP) {
+        kicp_set_error("max_points_per_voxel > 255 is not supported (the count shares the slot's meta word)");
+        return KICP_ERR_UNSUPPORTED;
+    }
+    KICP_CUDA(cudaSetDevice(ctx->device));
+    kicp_map *m = new kicp_map();
+    m->ctx = ctx;
+    m->voxel_size = voxel_size, m->max_distance = max_distance, m->cap = max_points_per_voxel;
+    cudaError_t e = cudaMalloc(&m->d_counters, 8 * sizeof(uint32_t));
+    if (e != cudaSuccess) {
+        delete m;
+        return kicp_cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+    }
+    int st = map_reserve(m, 1024);
+    if (st != KICP_OK) {
+        kicp_map_destroy(m);
+        return st;
+    }
+    *out = m;
+    return KICP_OK;
+}
+
+extern "C" int kicp_map_destroy(kicp_map *m) {
+    if (!m) return KICP_OK;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    cudaFree(m->slots), cudaFree(m->blk), cudaFree(m->pts), cudaFree(m->pend_head), cudaFree(m->d_counters);
+    cudaFree(m->d_in), cudaFree(m->d_xyz_t), cudaFree(m->d_next), cudaFree(m->d_touched);
+    delete m;
+    return KICP_OK;
+}
+
+extern "C" int kicp_map_clear(kicp_map *m) {
+    if (!m) return KICP_ERR_INVALID;
+    KICP_CUDA(cudaSetDevice(m->ctx->device));
+    m->num_blocks = 0, m->num_points = 0;
+    KICP_CUDA(cudaMemsetAsync(m->slots, 0xFF, (size_t)m->nslots * sizeof(int4), m->ctx->stream));
+    KICP_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    return KICP_OK;
+}
+extern "C" int kicp_map_empty(kicp_map *m, int32_t *empty) {
+    if (!m || !empty) return KICP_ERR_INVALID;
+    *empty = m->num_blocks == 0;
+    return KICP_OK;
+}
+extern "C" int kicp_map_num_points(kicp_map *m, int64_t *n) {
+    if (!m || !n) return KICP_ERR_INVALID;
+    *n = m->num_points;
+    return KICP_OK;
+}
+extern "C" int kicp_map_num_voxels(kicp_map *m, int64_t *n) {
+    if (!m || !n) return KICP_ERR_INVALID;
+    *n = m->num_blocks;
+    return KICP_OK;
+}
+
+static int map_add_points_impl(kicp_map *m, const double *xyz, int64_t n, const double *pose7) {
+    if (!m || n < 0 || (n > 0 && !xyz)) return KICP_ERR_INVALID;
+    if (n == 0) return KICP_OK;
+    kicp_ctx *c = m->ctx;
+    KICP_CUDA(cudaSetDevice(c->device));
+    KICP_TRY(map_reserve_input(m, n));
+    KICP_TRY(map_reserve(m, (uint64_t)n));  // worst case: every point opens a new voxel
+    KICP_CUDA(cudaMemcpyAsync(m->d_in, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    uint32_t init[8] = {m->num_blocks, 0, 0, 0, 0, 0, 0, 0};
+    KICP_CUDA(cudaMemcpyAsync(m->d_counters, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    MapRW rw{m->slots, m->nslots - 1, m->blk, m->pts, m->pend_head, m->blocks_cap, (int)m->cap, m->voxel_size};
+    Pose pose{0, 0, 0, 1, 0, 0, 0};
+    if (pose7) pose = Pose{pose7[0], pose7[1], pose7[2], pose7[3], pose7[4], pose7[5], pose7[6]};
+    const int threads = 256;
+    k_add_find_or_create<<<(unsigned)((n + threads - 1) / threads), threads, 0, c->stream>>>(
+        rw, m->d_in, n, pose7 ? 1 : 0, pose, m->d_xyz_t, m->d_next, m->d_counters, m->d_touched);
+    KICP_CHECK_LAUNCH(c);
+    // KISS AddPoints: map_resolution = sqrt(voxel_size^2 / max_points_per_voxel)
+    const double map_resolution = std::sqrt(m->voxel_size * m->voxel_size / (double)m->cap);
+    k_add_commit<<<(unsigned)((n + threads - 1) / threads), threads, 0, c->stream>>>(rw, m->d_xyz_t, m->d_next, m->d_counters,
+                                                                                 m->d_touched, map_resolution);
+    KICP_CHECK_LAUNCH(c);
+    uint32_t res[8];
+    KICP_CUDA(cudaMemcpyAsync(res, m->d_counters, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
+    KICP_CUDA(cudaStreamSynchronize(c->stream));
+    if (res[2]) {
+        kicp_set_error("voxel map: block storage overflow during AddPoints");
+        return KICP_ERR_CAPACITY;
+    }
+    m->num_blocks = res[0];
+    m->num_points += res[3];
+    return KICP_OK;
+}
+
+extern "C" int kicp_map_add_points(kicp_map *m, const double *xyz, int64_t n) { return map_add_points_impl(m, xyz, n, nullptr); }
+
+extern "C" int kicp_map_remove_far(kicp_map *m, const double origin[3]) {
+    if (!m || !origin) return KICP_ERR_INVALID;
+    if (m->num_blocks == 0) return KICP_OK;
+    kicp_ctx *c = m->ctx;
+    KICP_CUDA(cudaSetDevice(c->device));
+    uint32_t *keep = nullptr, *new_id = nullptr;
+    KICP_CUDA(cudaMalloc(&keep, (size_t)m->num_blocks * sizeof(uint32_t)));
+    KICP_CUDA(cudaMalloc(&new_id, (size_t)m->num_blocks * sizeof(uint32_t)));
+    uint32_t init[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    KICP_CUDA(cudaMemcpyAsync(m->d_counters, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    k_mark_far<<<(m->num_blocks + 255) / 256, 256, 0, c->stream>>>(m->blk, m->pts, (int)m->cap, m->num_blocks, origin[0], origin[1],
+                                                                  origin[2], m->max_distance * m->max_distance, keep,
+                                                                  m->d_counters);
+    KICP_CHECK_LAUNCH(c);
+    uint32_t res[8];
+    KICP_CUDA(cudaMemcpyAsync(res, m->d_counters, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
+    KICP_CUDA(cudaStreamSynchronize(c->stream));
+    int st = KICP_OK;
+    if (res[4] > 0) {
+        // compact surviving blocks (order preserved) into fresh storage and rebuild the table
+        const uint32_t survivors = m->num_blocks - res[4];
+        int4 *nblk = nullptr;
+        double *npts = nullptr;
+        cudaError_t e1 = cudaMalloc(&nblk, (size_t)m->blocks_cap * sizeof(int4));
+        cudaError_t e2 = cudaMalloc(&npts, (size_t)m->blocks_cap * m->cap * 3 * sizeof(double));
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            cudaFree(nblk), cudaFree(npts), cudaFree(keep), cudaFree(new_id);
+            return kicp_cuda_fail(e1 != cudaSuccess ? e1 : e2, "cudaMalloc", __FILE__, __LINE__);
+        }
+        k_exclusive_scan<<<1, 1024, 0, c->stream>>>(keep, new_id, m->num_blocks, &m->d_counters[5]);
+        c->launches++;
+        k_compact_blocks<<<(unsigned)(((uint64_t)m->num_blocks * 32 + 255) / 256), 256, 0, c->stream>>>(
+            m->blk, m->pts, (int)m->cap, m->num_blocks, keep, new_id, nblk, npts);
+        c->launches++;
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            cudaFree(nblk), cudaFree(npts), cudaFree(keep), cudaFree(new_id);
+            return kicp_cuda_fail(e, "compact", __FILE__, __LINE__);
+        }
+        cudaFree(m->blk), cudaFree(m->pts);
+        m->blk = nblk, m->pts = npts;
+        m->num_blocks = survivors;
+        m->num_points -= res[3];
+        st = map_rebuild_table(m, m->nslots);
+        if (st == KICP_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) st = KICP_ERR_CUDA;
+    }
+    cudaFree(keep), cudaFree(new_id);
+    return st;
+}
+
+extern "C" int kicp_map_update(kicp_map *m, const double *xyz, int64_t n, const double origin[3]) {
+    KICP_TRY(map_add_points_impl(m, xyz, n, nullptr));
+    return kicp_map_remove_far(m, origin);
+}
+extern "C" int kicp_map_update_pose(kicp_map *m, const double *xyz, int64_t n, const double pose[7]) {
+    if (!pose) return KICP_ERR_INVALID;
+    KICP_TRY(map_add_points_impl(m, xyz, n, pose));
+    return kicp_map_remove_far(m, pose + 4);
+}
+
+static int map_download(kicp_map *m, std::vector<int4> &hdr, std::vector<double> &pts) {
+    kicp_ctx *c = m->ctx;
+    KICP_CUDA(cudaSetDevice(c->device));
+    hdr.resize(m->num_blocks);
+    pts.resize((size_t)m->num_blocks * m->cap * 3);
+    if (m->num_blocks) {
+        KICP_CUDA(cudaMemcpyAsync(hdr.data(), m->blk, hdr.size() * sizeof(int4), cudaMemcpyDeviceToHost, c->stream));
+        KICP_CUDA(cudaMemcpyAsync(pts.data(), m->pts, pts.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    KICP_CUDA(cudaStreamSynchronize(c->stream));
+    return KICP_OK;
+}
+
+extern "C" int kicp_map_pointcloud(kicp_map *m, double *out_xyz, int64_t cap, int64_t *n) {
+    if (!m || !n) return KICP_ERR_INVALID;
+    *n = m->num_points;
+    if (m->num_points > cap) return KICP_ERR_CAPACITY;
+    if (m->num_points == 0) return KICP_OK;
+    if (!out_xyz) return KICP_ERR_INVALID;
+    std::vector<int4> hdr;
+    std::vector<double> pts;
+    KICP_TRY(map_download(m, hdr, pts));
+    int64_t w = 0;
+    for (uint32_t b = 0; b < m->num_blocks; ++b) {
+        std::memcpy(out_xyz + 3 * w, pts.data() + (size_t)b * m->cap * 3, (size_t)hdr[b].w * 3 * sizeof(double));
+        w += hdr[b].w;
+    }
+    return KICP_OK;
+}
+
+extern "C" int kicp_map_export_voxels(kicp_map *m, int32_t *keys, int32_t *counts, double *points, int64_t cap_voxels,
+                                      int64_t cap_points, int64_t *num_voxels, int64_t *num_points) {
+    if (!m || !num_voxels || !num_points) return KICP_ERR_INVALID;
+    *num_voxels = m->num_blocks, *num_points = m->num_points;
+    if ((int64_t)m->num_blocks > cap_voxels || m->num_points > cap_points) return KICP_ERR_CAPACITY;
+    if (m->num_blocks == 0) return KICP_OK;
+    if (!keys || !counts || !points) return KICP_ERR_INVALID;
+    std::vector<int4> hdr;
+    std::vector<double> pts;
+    KICP_TRY(map_download(m, hdr, pts));
+    int64_t w = 0;
+    for (uint32_t b = 0; b < m->num_blocks; ++b) {
+        keys[3 * b] = hdr[b].x, keys[3 * b + 1] = hdr[b].y, keys[3 * b + 2] = hdr[b].z;
+        counts[b] = hdr[b].w;
+        std::memcpy(points + 3 * w, pts.data() + (size_t)b * m->cap * 3, (size_t)hdr[b].w * 3 * sizeof(double));
+        w += hdr[b].w;
+    }
+    return KICP_OK;
+}
+
+extern "C" int kicp_map_load_voxels(kicp_map *m, const int32_t *keys, const int32_t *counts, const double *points,
+                                    int64_t num_voxels) {
+    if (!m || num_voxels < 0 || (num_voxels > 0 && (!keys || !counts || !points))) return KICP_ERR_INVALID;
+    kicp_ctx *c = m->ctx;
+    KICP_CUDA(cudaSetDevice(c->device));
+    KICP_TRY(kicp_map_clear(m));
+    if (num_voxels == 0) return KICP_OK;
+    std::vector<int64_t> offsets((size_t)num_voxels);
+    int64_t total = 0;
+    for (int64_t v = 0; v < num_voxels; ++v) {
+        if (counts[v] <= 0 || counts[v] > (int32_t)m->cap) {
+            kicp_set_error("kicp_map_load_voxels: voxel count outside [1, max_points_per_voxel]");
+            return KICP_ERR_INVALID;
+        }
+        offsets[v] = total;
+        total += counts[v];
+    }
+    KICP_TRY(map_reserve(m, (uint64_t)num_voxels));
+    int32_t *d_keys = nullptr, *d_counts = nullptr;
+    int64_t *d_off = nullptr;
+    double *d_pts = nullptr;
+    KICP_CUDA(cudaMalloc(&d_keys, (size_t)num_voxels * 3 * sizeof(int32_t)));
+    KICP_CUDA(cudaMalloc(&d_counts, (size_t)num_voxels * sizeof(int32_t)));
+    KICP_CUDA(cudaMalloc(&d_off, (size_t)num_voxels * sizeof(int64_t)));
+    KICP_CUDA(cudaMalloc(&d_pts, (size_t)total * 3 * sizeof(double)));
+    KICP_CUDA(cudaMemcpyAsync(d_keys, keys, (size_t)num_voxels * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    KICP_CUDA(cudaMemcpyAsync(d_counts, counts, (size_t)num_voxels * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    KICP_CUDA(cudaMemcpyAsync(d_off, offsets.data(), (size_t)num_voxels * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    KICP_CUDA(cudaMemcpyAsync(d_pts, points, (size_t)total * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_load_voxels<<<(unsigned)(((uint64_t)num_voxels * 32 + 255) / 256), 256, 0, c->stream>>>(
+        m->blk, m->pts, (int)m->cap, d_keys, d_counts, d_off, d_pts, (uint32_t)num_voxels);
+    KICP_CHECK_LAUNCH(c);
+    m->num_blocks = (uint32_t)num_voxels;
+    m->num_points = total;
+    int st = map_rebuild_table(m, m->nslots);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_keys), cudaFree(d_counts), cudaFree(d_off), cudaFree(d_pts);
+    if (st != KICP_OK) return st;
+    if (e != cudaSuccess) return kicp_cuda_fail(e, "load_voxels", __FILE__, __LINE__);
+    return KICP_OK;
+}
+
+extern "C" int kicp_map_nearest(kicp_map *m, const double *queries, int64_t n, double *out_points, double *out_dist) {
+    if (!m || n < 0 || (n > 0 && (!queries || !out_points || !out_dist))) return KICP_ERR_INVALID;
+    if (n == 0) return KICP_OK;
+    kicp_ctx *c = m->ctx;
+    KICP_CUDA(cudaSetDevice(c->device));
+    double *d_q = nullptr, *d_p = nullptr, *d_d = nullptr;
+    KICP_CUDA(cudaMalloc(&d_q, (size_t)n * 3 * sizeof(double)));
+    KICP_CUDA(cudaMalloc(&d_p, (size_t)n * 3 * sizeof(double)));
+    KICP_CUDA(cudaMalloc(&d_d, (size_t)n * sizeof(double)));
+    KICP_CUDA(cudaMemcpyAsync(d_q, queries, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_nearest<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(m->view(), d_q, n, d_p, d_d);
+    KICP_CHECK_LAUNCH(c);
+    KICP_CUDA(cudaMemcpyAsync(out_points, d_p, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    KICP_CUDA(cudaMemcpyAsync(out_dist, d_d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_q), cudaFree(d_p), cudaFree(d_d);
+    if (e != cudaSuccess) return kicp_cuda_fail(e, "nearest", __FILE__, __LINE__);
+    return KICP_OK;
+}

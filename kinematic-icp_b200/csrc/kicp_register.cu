@@ -1,0 +1,579 @@
+// kinematic_icp::KinematicRegistration::ComputeRobotMotion on the device
+// (reference: cpp/kinematic_icp/registration/Registration.cpp:48-190 + kiss_icp::VoxelHashMap::GetClosestNeighbor).
+//
+// One registration = k_reg_init, a Morton binning of the scan (keys -> radix sort -> gather, once, at the initial
+// guess), then up to max_num_iterations launches of k_assoc.  k_assoc fuses, for every scan point,
+//   q = T p                                          Registration.cpp:74
+//   27-voxel probe + nearest neighbour               GetClosestNeighbor (KISS-ICP v1.2.0)
+//   gate d < tau                                     Registration.cpp:75
+//   r = T p - n,  J = [R e_x | R (-p_y, p_x, 0)]     Registration.cpp:86-93
+//   sum of J^T J, J^T r, N, |r|^2                    Registration.cpp:95-118, 48-60
+// and its last CTA solves the 2x2 system, applies the unicycle motion model and decides convergence
+// (Registration.cpp:119-125, 159-167, 181-184) — so the iteration loop never returns to the host.
+// The correspondence list of the reference is never materialised: association and linearisation use the same T.
+#include <cfloat>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "kicp_device.cuh"
+
+using namespace kicp_dev;
+
+#define KICP_WARPS 8     // warps per CTA in k_assoc
+#define KICP_CH 192      // candidates staged in shared memory per pass (27 voxels x 20 points = 540 worst case)
+
+struct RegState {
+    double q[4];  // current estimate: unit quaternion (x, y, z, w) ...
+    double t[3];  // ... translation ...
+    double R[9];  // ... and the rotation matrix of q, row-major
+    double tau, conv, fixed_reg, beta;
+    int adaptive, max_iter;
+    int iter, done, status;
+    unsigned int ticket, window_counter;
+    int fused_tail;
+    int *iters_out;  // optional: where to publish the iteration count when the registration finishes (profiling)
+    double acc[8];  // JTJ00 JTJ01 JTJ11 JTr0 JTr1 N sum|r|^2 (unused)
+    kicp_reg_result result;
+};
+
+// ------------------------------------------------------------------------------------------ SE3 helpers (Sophus)
+__device__ void quat_to_matrix(const double q[4], double R[9]) {  // Eigen::Quaternion::toRotationMatrix
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w;
+    const double txx = tx * x, txy = ty * x, txz = tz * x;
+    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = 1 - (tyy + tzz), R[1] = txy - twz, R[2] = txz + twy;
+    R[3] = txy + twz, R[4] = 1 - (txx + tzz), R[5] = tyz - twx;
+    R[6] = txz - twy, R[7] = tyz + twx, R[8] = 1 - (txx + tyy);
+}
+
+// Sophus SE3 product: q = normalize(a.q * b.q) (the SO3(quaternion) ctor normalises), t = a.t + a.q * b.t
+__device__ void se3_compose(const double aq[4], const double at[3], const double bq[4], const double bt[3], double oq[4],
+                            double ot[3]) {
+    const double ax = aq[0], ay = aq[1], az = aq[2], aw = aq[3];
+    const double bx = bq[0], by = bq[1], bz = bq[2], bw = bq[3];
+    double w = aw * bw - ax * bx - ay * by - az * bz;
+    double x = aw * bx + ax * bw + ay * bz - az * by;
+    double y = aw * by + ay * bw + az * bx - ax * bz;
+    double z = aw * bz + az * bw + ax * by - ay * bx;
+    const double len = sqrt(x * x + y * y + z * z + w * w);
+    x /= len, y /= len, z /= len, w /= len;
+    double rx, ry, rz;
+    quat_rotate(ax, ay, az, aw, bt[0], bt[1], bt[2], rx, ry, rz);
+    oq[0] = x, oq[1] = y, oq[2] = z, oq[3] = w;
+    ot[0] = at[0] + rx, ot[1] = at[1] + ry, ot[2] = at[2] + rz;
+}
+
+// Sophus SE3::exp for the tangent the motion model produces: (ux, uy, 0, 0, 0, theta)
+__device__ void se3_exp_planar(double ux, double uy, double theta_in, double oq[4], double ot[3]) {
+    const double eps = 1e-10;  // Sophus::Constants<double>::epsilon()
+    const double wx = 0.0, wy = 0.0, wz = theta_in;
+    const double theta_sq = wx * wx + wy * wy + wz * wz;
+    double theta, imag, real;
+    if (theta_sq < eps * eps) {
+        theta = 0.0;
+        const double theta_po4 = theta_sq * theta_sq;
+        imag = 0.5 - (1.0 / 48.0) * theta_sq + (1.0 / 3840.0) * theta_po4;
+        real = 1.0 - (1.0 / 8.0) * theta_sq + (1.0 / 384.0) * theta_po4;
+    } else {
+        theta = sqrt(theta_sq);
+        const double half_theta = 0.5 * theta;
+        imag = sin(half_theta) / theta;
+        real = cos(half_theta);
+    }
+    oq[0] = imag * wx, oq[1] = imag * wy, oq[2] = imag * wz, oq[3] = real;
+    // V = I + (1-cos)/th^2 W + (th - sin)/th^3 W^2, or V = R when theta < eps;  W = hat(0, 0, wz)
+    double V[9];
+    if (theta < eps) {
+        quat_to_matrix(oq, V);
+    } else {
+        const double c1 = (1.0 - cos(theta)) / (theta * theta);
+        const double c2 = (theta - sin(theta)) / (theta * theta * theta);
+        const double w2 = wz * wz;
+        V[0] = 1.0 + c2 * (-w2), V[1] = c1 * (-wz), V[2] = 0.0;
+        V[3] = c1 * wz, V[4] = 1.0 + c2 * (-w2), V[5] = 0.0;
+        V[6] = 0.0, V[7] = 0.0, V[8] = 1.0;
+    }
+    ot[0] = V[0] * ux + V[1] * uy;
+    ot[1] = V[3] * ux + V[4] * uy;
+    ot[2] = V[6] * ux + V[7] * uy;
+}
+
+// ---------------------------------------------------------------------------------------------------- kernels
+struct RegArgs {
+    Pose last, odom;
+    double tau, conv, fixed_reg;
+    int adaptive, max_iter, fused_tail;
+    int *iters_out;
+};
+
+// current_estimate = last_robot_pose * relative_wheel_odometry   (Registration.cpp:156)
+__global__ void k_reg_init(RegState *st, RegArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double lq[4] = {a.last.qx, a.last.qy, a.last.qz, a.last.qw}, lt[3] = {a.last.tx, a.last.ty, a.last.tz};
+    const double oq[4] = {a.odom.qx, a.odom.qy, a.odom.qz, a.odom.qw}, ot[3] = {a.odom.tx, a.odom.ty, a.odom.tz};
+    se3_compose(lq, lt, oq, ot, st->q, st->t);
+    quat_to_matrix(st->q, st->R);
+    st->tau = a.tau, st->conv = a.conv, st->fixed_reg = a.fixed_reg, st->beta = 0.0;
+    st->adaptive = a.adaptive, st->max_iter = a.max_iter, st->fused_tail = a.fused_tail;
+    st->iter = 0, st->done = a.max_iter <= 0 ? 1 : 0, st->status = KICP_OK;
+    st->ticket = 0, st->window_counter = 0;
+    st->iters_out = a.iters_out;
+    if (a.iters_out) *a.iters_out = 0;
+    for (int k = 0; k < 8; ++k) st->acc[k] = 0.0;
+    kicp_reg_result *r = &st->result;
+    for (int k = 0; k < 4; ++k) r->pose[k] = st->q[k];
+    for (int k = 0; k < 3; ++k) r->pose[4 + k] = st->t[k];
+    r->beta = 0.0, r->last_dx_norm = 0.0, r->iterations = 0, r->status = KICP_OK;
+}
+
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {  // 10 bits -> every third bit
+    v &= 1023u;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+// Morton key of the voxel each point falls in at the initial guess.  The key only orders the scan so that
+// consecutive points share voxel neighbourhoods; k_assoc re-derives every voxel from the current estimate, so a
+// stale or aliased key costs locality, never correctness.
+__global__ void k_morton_keys(const RegState *st, const double *__restrict__ xyz, int n, double voxel_size,
+                              uint32_t *__restrict__ keys, int32_t *__restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+    const double *R = st->R, *t = st->t;
+    const double qx = R[0] * px + R[1] * py + R[2] * pz + t[0];
+    const double qy = R[3] * px + R[4] * py + R[5] * pz + t[1];
+    const double qz = R[6] * px + R[7] * py + R[8] * pz + t[2];
+    const int ox = voxel_coord(t[0], voxel_size) - 512, oy = voxel_coord(t[1], voxel_size) - 512,
+              oz = voxel_coord(t[2], voxel_size) - 512;
+    const uint32_t ux = (uint32_t)(voxel_coord(qx, voxel_size) - ox), uy = (uint32_t)(voxel_coord(qy, voxel_size) - oy),
+                   uz = (uint32_t)(voxel_coord(qz, voxel_size) - oz);
+    keys[i] = spread10(ux) | (spread10(uy) << 1) | (spread10(uz) << 2);
+    idx[i] = i;
+}
+
+__global__ void k_gather(const double *__restrict__ xyz, const int32_t *__restrict__ idx, int n, double *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = idx[i];
+    out[3 * i] = xyz[3 * s], out[3 * i + 1] = xyz[3 * s + 1], out[3 * i + 2] = xyz[3 * s + 2];
+}
+
+// ComputePerturbation's tail + motion model + pose update + convergence test (one thread).
+// `acc` holds the (all-reduced) sums of this iteration.
+__device__ void solve_and_update(RegState *st) {
+    double s[8];
+    for (int k = 0; k < 8; ++k) s[k] = __ldcg(&st->acc[k]);  // written by other CTAs' atomics: read through L2
+    const int j = st->iter;
+    kicp_reg_result *res = &st->result;
+    if (j < KICP_MAX_ITERATIONS)
+        for (int k = 0; k < 8; ++k) res->sums[j][k] = s[k];
+    const double N = s[5];
+    if (j == 0) {
+        // ComputeOdometryRegularization (Registration.cpp:48-60): beta = 1 / (mean |T0 p - n|^2 + DBL_MIN), computed
+        // once from the first association; the fixed value otherwise (:171-177)
+        st->beta = st->adaptive ? 1.0 / (s[6] / N + DBL_MIN) : st->fixed_reg;
+        res->beta = st->beta;
+    }
+    // JTJ /= N; JTr /= N; JTJ += diag(beta, 0); dx = -(JTJ^-1 JTr)     (Registration.cpp:119-125)
+    const double a = s[0] / N + st->beta, b = s[1] / N, d = s[2] / N + 0.0;
+    const double r0 = s[3] / N, r1 = s[4] / N;
+    const double invdet = 1.0 / (a * d - b * b);
+    const double i00 = d * invdet, i01 = -b * invdet, i10 = -b * invdet, i11 = a * invdet;
+    const double dx0 = -(i00 * r0 + i01 * r1), dx1 = -(i10 * r0 + i11 * r1);
+    // motion_model (Registration.cpp:159-167), epsilon = DBL_MIN
+    const double ux = dx0 * sin(dx1) / (dx1 + DBL_MIN);
+    const double uy = dx0 * (1.0 - cos(dx1)) / (dx1 + DBL_MIN);
+    double dq[4], dt[3], nq[4], nt[3];
+    se3_exp_planar(ux, uy, dx1, dq, dt);
+    se3_compose(st->q, st->t, dq, dt, nq, nt);  // current_estimate = current_estimate * delta_motion  (:182)
+    for (int k = 0; k < 4; ++k) st->q[k] = nq[k];
+    for (int k = 0; k < 3; ++k) st->t[k] = nt[k];
+    quat_to_matrix(st->q, st->R);
+    const double dxn = sqrt(dx0 * dx0 + dx1 * dx1);
+    if (j < KICP_MAX_ITERATIONS) res->dx[j][0] = dx0, res->dx[j][1] = dx1;
+    res->last_dx_norm = dxn;
+    res->iterations = j + 1;
+    for (int k = 0; k < 4; ++k) res->pose[k] = st->q[k];
+    for (int k = 0; k < 3; ++k) res->pose[4 + k] = st->t[k];
+    st->iter = j + 1;
+    int done = (dxn < st->conv) || (j + 1 >= st->max_iter);  // break BEFORE re-association (:184)
+    if (!(N > 0.0)) {  // the reference has no guard: the pose is NaN from here on; stop early and say so
+        st->status = KICP_WARN_NO_CORRESPONDENCES;
+        done = 1;
+    }
+    res->status = st->status;
+    st->done = done;
+    if (st->iters_out) *st->iters_out = j + 1;
+    for (int k = 0; k < 8; ++k) st->acc[k] = 0.0;
+}
+
+__global__ void k_solve(RegState *st) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && !st->done) solve_and_update(st);
+}
+
+// The fused association + linearisation + reduction kernel.  One warp owns a window of 32 consecutive (Morton-
+// sorted) scan points.  Lanes that fall in the same voxel form a group; for each group the warp probes the 27
+// neighbour voxels (lanes 0..26, one hash probe each), stages their points in shared memory, and scans them with
+// 32 / 2^ceil(log2 P) lanes per query point so small groups still use every lane.
+__global__ void __launch_bounds__(KICP_WARPS * 32) k_assoc(RegState *st, const double *__restrict__ scan, int n, MapView map) {
+    if (st->done) return;
+    extern __shared__ double smem_d[];
+    __shared__ double s_T[12];
+    __shared__ double s_part[KICP_WARPS][8];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned FULL = 0xFFFFFFFFu;
+    // per-warp shared memory: candidate coordinates (SoA), their global point indices, query broadcast, results
+    double *sx = smem_d + (size_t)wid * (3 * KICP_CH + 3 * 32 + 32);
+    double *sy = sx + KICP_CH, *sz = sy + KICP_CH;
+    double *sq = sz + KICP_CH;      // [32][3] query points of the current group
+    double *sres_d = sq + 96;       // [32]    winning squared distance per query slot
+    int *sg = (int *)(smem_d + (size_t)KICP_WARPS * (3 * KICP_CH + 3 * 32 + 32)) + wid * (KICP_CH + 32);
+    int *sres_g = sg + KICP_CH;     // [32]    winning global point index per query slot
+
+    if (threadIdx.x < 9) s_T[threadIdx.x] = st->R[threadIdx.x];
+    if (threadIdx.x >= 9 && threadIdx.x < 12) s_T[threadIdx.x] = st->t[threadIdx.x - 9];
+    __syncthreads();
+    const double tau = st->tau, vs = map.voxel_size;
+    const int num_windows = (n + 31) >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0, cntN = 0, ssq = 0;
+
+    while (true) {
+        int w = 0;
+        if (lane == 0) w = (int)atomicAdd(&st->window_counter, 1u);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= num_windows) break;
+        const int i = w * 32 + lane;
+        const bool valid = i < n;
+        double px = 0, py = 0, pz = 0;
+        if (valid) px = scan[3 * (size_t)i], py = scan[3 * (size_t)i + 1], pz = scan[3 * (size_t)i + 2];
+        const double qx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[9];
+        const double qy = s_T[3] * px + s_T[4] * py + s_T[5] * pz + s_T[10];
+        const double qz = s_T[6] * px + s_T[7] * py + s_T[8] * pz + s_T[11];
+        const int vx = voxel_coord(qx, vs), vy = voxel_coord(qy, vs), vz = voxel_coord(qz, vs);
+        const unsigned vmask = __ballot_sync(FULL, valid);
+        unsigned gmask = 0;
+        if (valid) gmask = __match_any_sync(vmask, vx) & __match_any_sync(vmask, vy) & __match_any_sync(vmask, vz);
+        double best = DBL_MAX;
+        int bestg = -1;
+        unsigned remaining = vmask;
+        while (remaining) {
+            const int leader = __ffs(remaining) - 1;
+            const unsigned gm = __shfl_sync(FULL, gmask, leader);
+            const int cvx = __shfl_sync(FULL, vx, leader), cvy = __shfl_sync(FULL, vy, leader), cvz = __shfl_sync(FULL, vz, leader);
+            const int P = __popc(gm);
+            const bool member = (gm >> lane) & 1u;
+            const int myslot = __popc(gm & lt_mask);
+            if (member) sq[3 * myslot] = qx, sq[3 * myslot + 1] = qy, sq[3 * myslot + 2] = qz;
+            // 27-neighbour probe, KISS shift order (lane k <-> voxel_shifts[k])
+            int cnt = 0;
+            unsigned blk = 0;
+            if (lane < 27) {
+                const uint32_t meta = map_probe(map, cvx + shift_x(lane), cvy + shift_y(lane), cvz + shift_z(lane));
+                if (meta != KICP_SLOT_EMPTY) cnt = (int)(meta & 0xFFu), blk = meta >> 8;
+            }
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const int off = incl - cnt;
+            const int C = __shfl_sync(FULL, incl, 31);
+            // lanes per query point: 32 / 2^ceil(log2 P)
+            const int lg = P <= 1 ? 0 : 32 - __clz(P - 1);
+            const int L = 32 >> lg;
+            const int slot = lane >> (5 - lg), sub = lane & (L - 1);
+            const bool worker = slot < P;
+            __syncwarp();
+            double wqx = 0, wqy = 0, wqz = 0;
+            if (worker) wqx = sq[3 * slot], wqy = sq[3 * slot + 1], wqz = sq[3 * slot + 2];
+            double wbest = DBL_MAX;
+            int wc = 0x7FFFFFFF, wg = -1;
+            for (int base = 0; base < C; base += KICP_CH) {
+                for (int j = 0; j < cnt; ++j) {
+                    const int c = off + j - base;
+                    if (c >= 0 && c < KICP_CH) sg[c] = (int)(blk * (unsigned)map.cap) + j;
+                }
+                __syncwarp();
+                const int m = min(KICP_CH, C - base);
+                for (int c = lane; c < m; c += 32) {
+                    const double *gp = map.pts + (size_t)sg[c] * 3;
+                    sx[c] = __ldg(gp), sy[c] = __ldg(gp + 1), sz[c] = __ldg(gp + 2);
+                }
+                __syncwarp();
+                if (worker) {
+                    for (int c = sub; c < m; c += L) {
+                        const double dx = sx[c] - wqx, dy = sy[c] - wqy, dz = sz[c] - wqz;
+                        const double d2 = dx * dx + dy * dy + dz * dz;
+                        if (d2 < wbest) wbest = d2, wc = base + c, wg = sg[c];  // strict <: first minimum wins
+                    }
+                }
+                __syncwarp();
+            }
+            for (int o = L >> 1; o > 0; o >>= 1) {
+                const double od = __shfl_xor_sync(FULL, wbest, o);
+                const int oc = __shfl_xor_sync(FULL, wc, o), og = __shfl_xor_sync(FULL, wg, o);
+                if (od < wbest || (od == wbest && oc < wc)) wbest = od, wc = oc, wg = og;
+            }
+            if (worker && sub == 0) sres_d[slot] = wbest, sres_g[slot] = wg;
+            __syncwarp();
+            if (member) best = sres_d[myslot], bestg = sres_g[myslot];
+            __syncwarp();
+            remaining &= ~gm;
+        }
+        if (valid && bestg >= 0) {
+            const double *gp = map.pts + (size_t)bestg * 3;
+            const double rx = qx - __ldg(gp), ry = qy - __ldg(gp + 1), rz = qz - __ldg(gp + 2);  // r = T p - n
+            const double rr = rx * rx + ry * ry + rz * rz;
+            if (sqrt(rr) < tau) {  // distance < max_correspondance_distance   (Registration.cpp:75)
+                // J = [R e_x | R (-p_y, p_x, 0)]      (Registration.cpp:89-91)
+                const double c0x = s_T[0], c0y = s_T[3], c0z = s_T[6];
+                const double c1x = s_T[1] * px - s_T[0] * py, c1y = s_T[4] * px - s_T[3] * py, c1z = s_T[7] * px - s_T[6] * py;
+                a00 += c0x * c0x + c0y * c0y + c0z * c0z;
+                a01 += c0x * c1x + c0y * c1y + c0z * c1z;
+                a11 += c1x * c1x + c1y * c1y + c1z * c1z;
+                b0 += c0x * rx + c0y * ry + c0z * rz;
+                b1 += c1x * rx + c1y * ry + c1z * rz;
+                cntN += 1.0;
+                ssq += rr;
+            }
+        }
+        (void)best;
+    }
+
+    // warp shuffle reduction -> one partial per warp -> one set of atomics per CTA
+    double v[7] = {a00, a01, a11, b0, b1, cntN, ssq};
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) s_part[wid][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double s = 0.0;
+        for (int k = 0; k < KICP_WARPS; ++k) s += s_part[k][threadIdx.x];
+        atomicAdd(&st->acc[threadIdx.x], s);
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicAdd(&st->ticket, 1u);
+        s_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        st->ticket = 0;
+        st->window_counter = 0;
+        if (st->fused_tail) solve_and_update(st);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------- host
+static size_t assoc_smem_bytes() {
+    return (size_t)KICP_WARPS * ((3 * KICP_CH + 3 * 32 + 32) * sizeof(double) + (KICP_CH + 32) * sizeof(int));
+}
+
+static int reg_reserve(kicp_ctx *c, int64_t n) {
+    if (!c->d_state) {
+        KICP_CUDA(cudaMalloc(&c->d_state, sizeof(RegState)));
+        KICP_CUDA(cudaFuncSetAttribute(k_assoc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)assoc_smem_bytes()));
+        int per_sm = 0;
+        KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc, KICP_WARPS * 32, assoc_smem_bytes()));
+        c->assoc_ctas_per_sm = std::max(per_sm, 1);
+    }
+    if (n <= c->scratch_cap) return KICP_OK;
+    KICP_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_sorted), cudaFree(c->d_keys), cudaFree(c->d_keys_alt), cudaFree(c->d_idx), cudaFree(c->d_idx_alt);
+    cudaFree(c->d_sort_tmp);
+    c->d_sorted = nullptr, c->d_keys = c->d_keys_alt = nullptr, c->d_idx = c->d_idx_alt = nullptr, c->d_sort_tmp = nullptr;
+    const int64_t cap = std::max<int64_t>(n + n / 4, 4096);
+    KICP_CUDA(cudaMalloc(&c->d_sorted, (size_t)cap * 3 * sizeof(double)));
+    KICP_CUDA(cudaMalloc(&c->d_keys, (size_t)cap * sizeof(uint32_t)));
+    KICP_CUDA(cudaMalloc(&c->d_keys_alt, (size_t)cap * sizeof(uint32_t)));
+    KICP_CUDA(cudaMalloc(&c->d_idx, (size_t)cap * sizeof(int32_t)));
+    KICP_CUDA(cudaMalloc(&c->d_idx_alt, (size_t)cap * sizeof(int32_t)));
+    size_t bytes = 0;
+    KICP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->d_keys, c->d_keys_alt, c->d_idx, c->d_idx_alt, (int)cap, 0, 30,
+                                              c->stream));
+    KICP_CUDA(cudaMalloc(&c->d_sort_tmp, bytes));
+    c->sort_tmp_bytes = bytes;
+    c->scratch_cap = cap;
+    return KICP_OK;
+}
+
+static int check_params(const kicp_reg_params *p) {
+    if (!p) return KICP_ERR_INVALID;
+    if (p->max_num_iterations > KICP_MAX_ITERATIONS) {
+        kicp_set_error("max_num_iterations exceeds KICP_MAX_ITERATIONS");
+        return KICP_ERR_INVALID;
+    }
+    return KICP_OK;
+}
+
+// Enqueue one full registration on the context stream.  `sharded` inserts the 8-double allreduce between the
+// association and the solve of every iteration.
+static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[7], const double odom[7], double tau,
+                                const kicp_reg_params *p, kicp_reg_result *result, bool sharded) {
+    if (!m || !scan || !last || !odom) return KICP_ERR_INVALID;
+    KICP_TRY(check_params(p));
+    kicp_ctx *c = m->ctx;
+    if (scan->ctx != c) return KICP_ERR_INVALID;
+    if (scan->n > 0x7FFFFFE0ll) return KICP_ERR_CAPACITY;
+    if (sharded && !c->nccl_comm) {
+        kicp_set_error("kicp_register_sharded: kicp_comm_init has not been called on this context");
+        return KICP_ERR_INVALID;
+    }
+    KICP_CUDA(cudaSetDevice(c->device));
+    const int n = (int)scan->n;
+    KICP_TRY(reg_reserve(c, n));
+    RegArgs a;
+    a.last = Pose{last[0], last[1], last[2], last[3], last[4], last[5], last[6]};
+    a.odom = Pose{odom[0], odom[1], odom[2], odom[3], odom[4], odom[5], odom[6]};
+    a.tau = tau, a.conv = p->convergence_criterion, a.fixed_reg = p->fixed_regularization;
+    a.adaptive = p->use_adaptive_odometry_regularization ? 1 : 0;
+    // an empty map returns the prediction (Registration.cpp:157): no association, no solve
+    a.max_iter = m->num_blocks == 0 ? 0 : p->max_num_iterations;
+    a.fused_tail = sharded ? 0 : 1;
+    a.iters_out = nullptr;
+    kicp_ctx::ProfReg *pr = nullptr;
+    if (c->profiling && (int64_t)c->prof.size() < c->prof_cap) {
+        c->prof.emplace_back();
+        pr = &c->prof.back();
+        pr->d_iters = c->d_prof_iters + (c->prof.size() - 1);
+        a.iters_out = pr->d_iters;
+        KICP_CUDA(cudaEventCreate(&pr->prep0));
+        KICP_CUDA(cudaEventCreate(&pr->prep1));
+        KICP_CUDA(cudaEventRecord(pr->prep0, c->stream));
+    }
+    k_reg_init<<<1, 32, 0, c->stream>>>(c->d_state, a);
+    KICP_CHECK_LAUNCH(c);
+    if (a.max_iter > 0) {
+        const double *d_pts = scan->d_xyz;
+        if (n > 0) {
+            const int threads = 256, blocks = (n + threads - 1) / threads;
+            k_morton_keys<<<blocks, threads, 0, c->stream>>>(c->d_state, scan->d_xyz, n, m->voxel_size, c->d_keys, c->d_idx);
+            KICP_CHECK_LAUNCH(c);
+            size_t bytes = c->sort_tmp_bytes;
+            KICP_CUDA(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, bytes, c->d_keys, c->d_keys_alt, c->d_idx, c->d_idx_alt, n, 0,
+                                                      30, c->stream));
+            c->launches += 3;  // CUB's histogram + onesweep passes (library kernels, not counted individually)
+            k_gather<<<blocks, threads, 0, c->stream>>>(scan->d_xyz, c->d_idx_alt, n, c->d_sorted);
+            KICP_CHECK_LAUNCH(c);
+            d_pts = c->d_sorted;
+        }
+        if (pr) KICP_CUDA(cudaEventRecord(pr->prep1, c->stream));
+        const int num_windows = (n + 31) / 32;
+        // persistent-style grid: every CTA is resident and pulls windows from a device-side counter
+        int grid = std::max(1, std::min((num_windows + KICP_WARPS - 1) / KICP_WARPS, c->sm_count * c->assoc_ctas_per_sm));
+        for (int j = 0; j < a.max_iter; ++j) {
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (pr) {
+                KICP_CUDA(cudaEventCreate(&e0));
+                KICP_CUDA(cudaEventCreate(&e1));
+                pr->it.push_back(e0), pr->it.push_back(e1);
+                KICP_CUDA(cudaEventRecord(e0, c->stream));
+            }
+            k_assoc<<<grid, KICP_WARPS * 32, assoc_smem_bytes(), c->stream>>>(c->d_state, d_pts, n, m->view());
+            KICP_CHECK_LAUNCH(c);
+            if (pr) KICP_CUDA(cudaEventRecord(e1, c->stream));
+            if (sharded) {
+                KICP_TRY(kicp_comm_allreduce8(c, c->d_state->acc));
+                k_solve<<<1, 32, 0, c->stream>>>(c->d_state);
+                KICP_CHECK_LAUNCH(c);
+            }
+        }
+    }
+    if (result)
+        KICP_CUDA(cudaMemcpyAsync(result, &c->d_state->result, sizeof(kicp_reg_result), cudaMemcpyDeviceToHost, c->stream));
+    return KICP_OK;
+}
+
+extern "C" int kicp_ctx_profile_begin(kicp_ctx *c) {
+    if (!c) return KICP_ERR_INVALID;
+    KICP_CUDA(cudaSetDevice(c->device));
+    if (!c->d_prof_iters) {
+        c->prof_cap = 1 << 16;
+        KICP_CUDA(cudaMalloc(&c->d_prof_iters, (size_t)c->prof_cap * sizeof(int32_t)));
+    }
+    c->prof.clear();
+    c->prof.reserve(4096);
+    c->profiling = true;
+    return KICP_OK;
+}
+
+extern "C" int kicp_ctx_profile_end(kicp_ctx *c, kicp_profile *out) {
+    if (!c || !out) return KICP_ERR_INVALID;
+    KICP_CUDA(cudaSetDevice(c->device));
+    c->profiling = false;
+    KICP_CUDA(cudaStreamSynchronize(c->stream));
+    kicp_profile p{};
+    std::vector<int32_t> iters(c->prof.size());
+    if (!iters.empty())
+        KICP_CUDA(cudaMemcpy(iters.data(), c->d_prof_iters, iters.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (size_t r = 0; r < c->prof.size(); ++r) {
+        kicp_ctx::ProfReg &pr = c->prof[r];
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pr.prep0, pr.prep1) == cudaSuccess) p.prep_ms += ms;
+        for (size_t k = 0; k + 1 < pr.it.size(); k += 2) {
+            ms = 0.f;
+            cudaEventElapsedTime(&ms, pr.it[k], pr.it[k + 1]);
+            if ((int)(k / 2) < iters[r]) {
+                p.assoc_ms += ms, p.assoc_launches++;
+            } else {
+                p.idle_ms += ms, p.idle_launches++;
+            }
+            cudaEventDestroy(pr.it[k]), cudaEventDestroy(pr.it[k + 1]);
+        }
+        cudaEventDestroy(pr.prep0), cudaEventDestroy(pr.prep1);
+        p.registrations++;
+    }
+    cudaGetLastError();
+    c->prof.clear();
+    *out = p;
+    return KICP_OK;
+}
+
+extern "C" int kicp_register_scan_async(kicp_map *map, kicp_scan *scan, const double last[7], const double odom[7], double tau,
+                                        const kicp_reg_params *params, kicp_reg_result *result) {
+    return enqueue_registration(map, scan, last, odom, tau, params, result, false);
+}
+extern "C" int kicp_register_scan_sharded_async(kicp_map *map, kicp_scan *scan, const double last[7], const double odom[7],
+                                                double tau, const kicp_reg_params *params, kicp_reg_result *result) {
+    return enqueue_registration(map, scan, last, odom, tau, params, result, true);
+}
+
+static int register_host(kicp_map *map, const double *frame_xyz, int64_t n, const double last[7], const double odom[7],
+                         double tau, const kicp_reg_params *params, double out_pose[7], kicp_reg_result *result, bool sharded) {
+    if (!map || n < 0 || (n > 0 && !frame_xyz) || !out_pose) return KICP_ERR_INVALID;
+    kicp_ctx *c = map->ctx;
+    if (!c->upload_scan) KICP_TRY(kicp_scan_create(c, n, &c->upload_scan));
+    KICP_TRY(kicp_scan_upload_async(c->upload_scan, frame_xyz, n));
+    KICP_TRY(enqueue_registration(map, c->upload_scan, last, odom, tau, params, c->h_result, sharded));
+    KICP_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 7; ++k) out_pose[k] = c->h_result->pose[k];
+    if (result) *result = *c->h_result;
+    return c->h_result->status;
+}
+
+extern "C" int kicp_register(kicp_map *map, const double *frame_xyz, int64_t n, const double last[7], const double odom[7],
+                             double tau, const kicp_reg_params *params, double out_pose[7], kicp_reg_result *result) {
+    return register_host(map, frame_xyz, n, last, odom, tau, params, out_pose, result, false);
+}
+extern "C" int kicp_register_sharded(kicp_map *map, const double *frame_xyz, int64_t n_local, const double last[7],
+                                     const double odom[7], double tau, const kicp_reg_params *params, double out_pose[7],
+                                     kicp_reg_result *result) {
+    return register_host(map, frame_xyz, n_local, last, odom, tau, params, out_pose, result, true);
+}

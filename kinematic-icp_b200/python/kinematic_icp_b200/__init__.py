@@ -1,0 +1,249 @@
+"""B200-native kinematic-icp registration hot path — host-side mirror of the reference's C++ interface.
+
+The classes keep the reference's names and argument meaning:
+
+    kiss_icp::VoxelHashMap                      -> VoxelHashMap       (KISS-ICP v1.2.0 core/VoxelHashMap.hpp)
+    kinematic_icp::KinematicRegistration        -> KinematicRegistration  (registration/Registration.hpp:32-50)
+
+Poses are pose7 = [qx, qy, qz, qw, tx, ty, tz] (Sophus::SE3d's two members); point clouds are (N, 3) float64 arrays.
+Everything runs on the GPU through libkicp_b200.so (include/kicp.h); there is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import (KICP_OK, KICP_WARN_NO_CORRESPONDENCES, KicpError, RegParams, RegResult, as_points, as_pose, check, dp,
+                    lib)
+
+__all__ = ["Context", "VoxelHashMap", "Scan", "KinematicRegistration", "KicpError", "RegParams", "RegResult",
+           "pinned_empty"]
+
+
+class Context:
+    """One GPU: device id, stream, scratch, optional NCCL communicator (kicp_ctx)."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        check(lib().kicp_ctx_create(int(device), C.byref(self.h)), "kicp_ctx_create")
+        self.device = device
+
+    def synchronize(self):
+        check(lib().kicp_ctx_synchronize(self.h), "kicp_ctx_synchronize")
+
+    @property
+    def stream(self):
+        return lib().kicp_ctx_stream(self.h)
+
+    @property
+    def launch_count(self):
+        return int(lib().kicp_ctx_launch_count(self.h))
+
+    def profile_begin(self):
+        check(lib().kicp_ctx_profile_begin(self.h), "kicp_ctx_profile_begin")
+
+    def profile_end(self):
+        p = _capi.Profile()
+        check(lib().kicp_ctx_profile_end(self.h, C.byref(p)), "kicp_ctx_profile_end")
+        return p
+
+    def comm_init(self, unique_id, nranks, rank):
+        buf = (C.c_uint8 * _capi.KICP_UNIQUE_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        check(lib().kicp_comm_init(self.h, buf, int(nranks), int(rank)), "kicp_comm_init")
+
+    def close(self):
+        if self.h:
+            lib().kicp_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def comm_unique_id():
+    buf = (C.c_uint8 * _capi.KICP_UNIQUE_ID_BYTES)()
+    check(lib().kicp_comm_unique_id(buf), "kicp_comm_unique_id")
+    return bytes(buf)
+
+
+_PINNED = {}
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array backed by pinned host memory (kicp_host_alloc) so host<->device copies are truly asynchronous."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    check(lib().kicp_host_alloc(max(nbytes, 1), C.byref(p)), "kicp_host_alloc")
+    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[arr.ctypes.data] = p
+    return arr
+
+
+def pinned_result():
+    """A RegResult in pinned host memory, for kicp_register_scan_async."""
+    p = C.c_void_p()
+    check(lib().kicp_host_alloc(C.sizeof(RegResult), C.byref(p)), "kicp_host_alloc")
+    return RegResult.from_address(p.value)
+
+
+class VoxelHashMap:
+    """kiss_icp::VoxelHashMap(voxel_size, max_distance, max_points_per_voxel), resident in HBM."""
+
+    def __init__(self, ctx, voxel_size, max_distance, max_points_per_voxel):
+        self.ctx = ctx
+        self.voxel_size_, self.max_distance_, self.max_points_per_voxel_ = voxel_size, max_distance, max_points_per_voxel
+        self.h = C.c_void_p()
+        check(lib().kicp_map_create(ctx.h, float(voxel_size), float(max_distance), int(max_points_per_voxel), C.byref(self.h)),
+              "kicp_map_create")
+
+    def close(self):
+        if self.h:
+            lib().kicp_map_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def Clear(self):
+        check(lib().kicp_map_clear(self.h), "kicp_map_clear")
+
+    def Empty(self):
+        e = C.c_int32()
+        check(lib().kicp_map_empty(self.h, C.byref(e)), "kicp_map_empty")
+        return bool(e.value)
+
+    def num_points(self):
+        n = C.c_int64()
+        check(lib().kicp_map_num_points(self.h, C.byref(n)), "kicp_map_num_points")
+        return n.value
+
+    def num_voxels(self):
+        n = C.c_int64()
+        check(lib().kicp_map_num_voxels(self.h, C.byref(n)), "kicp_map_num_voxels")
+        return n.value
+
+    def AddPoints(self, points):
+        points = as_points(points)
+        check(lib().kicp_map_add_points(self.h, dp(points), len(points)), "kicp_map_add_points")
+
+    def RemovePointsFarFromLocation(self, origin):
+        o = np.ascontiguousarray(origin, dtype=np.float64).reshape(3)
+        check(lib().kicp_map_remove_far(self.h, dp(o)), "kicp_map_remove_far")
+
+    def Update(self, points, origin_or_pose):
+        """Update(points, origin) for a 3-vector, Update(points, pose) for a pose7 (KinematicICP.cpp:79)."""
+        points = as_points(points)
+        a = np.ascontiguousarray(origin_or_pose, dtype=np.float64).ravel()
+        if a.size == 3:
+            check(lib().kicp_map_update(self.h, dp(points), len(points), dp(a)), "kicp_map_update")
+        elif a.size == 7:
+            check(lib().kicp_map_update_pose(self.h, dp(points), len(points), dp(a)), "kicp_map_update_pose")
+        else:
+            raise ValueError("origin (3,) or pose7 (7,) expected")
+
+    def Pointcloud(self):
+        n = self.num_points()
+        out = np.empty((max(n, 1), 3))
+        m = C.c_int64()
+        check(lib().kicp_map_pointcloud(self.h, dp(out), n, C.byref(m)), "kicp_map_pointcloud")
+        return out[: m.value].copy()
+
+    def export_voxels(self):
+        V, n = self.num_voxels(), self.num_points()
+        keys = np.empty((max(V, 1), 3), dtype=np.int32)
+        counts = np.empty(max(V, 1), dtype=np.int32)
+        pts = np.empty((max(n, 1), 3))
+        nv, npts = C.c_int64(), C.c_int64()
+        check(lib().kicp_map_export_voxels(self.h, keys.ctypes.data_as(_capi.c_ip), counts.ctypes.data_as(_capi.c_ip), dp(pts),
+                                           V, n, C.byref(nv), C.byref(npts)), "kicp_map_export_voxels")
+        return keys[:V].copy(), counts[:V].copy(), pts[:n].copy()
+
+    def load_voxels(self, keys, counts, points):
+        keys = np.ascontiguousarray(keys, dtype=np.int32).reshape(-1, 3)
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        points = as_points(points) if len(points) else np.zeros((0, 3))
+        check(lib().kicp_map_load_voxels(self.h, keys.ctypes.data_as(_capi.c_ip), counts.ctypes.data_as(_capi.c_ip), dp(points),
+                                         len(counts)), "kicp_map_load_voxels")
+
+    def GetClosestNeighbor(self, queries):
+        """Batched GetClosestNeighbor: returns (points (N,3), distances (N,)); (0,0,0), DBL_MAX where nothing is found."""
+        q = as_points(queries)
+        out = np.empty_like(q)
+        d = np.empty(len(q))
+        check(lib().kicp_map_nearest(self.h, dp(q), len(q), dp(out), dp(d)), "kicp_map_nearest")
+        return out, d
+
+
+class Scan:
+    """A scan resident in HBM (kicp_scan): the `frame` argument of ComputeRobotMotion, uploaded once."""
+
+    def __init__(self, ctx, capacity=0):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        check(lib().kicp_scan_create(ctx.h, int(capacity), C.byref(self.h)), "kicp_scan_create")
+
+    def upload(self, points, asynchronous=False):
+        points = as_points(points)
+        self._keepalive = points
+        f = lib().kicp_scan_upload_async if asynchronous else lib().kicp_scan_upload
+        check(f(self.h, dp(points), len(points)), "kicp_scan_upload")
+
+    def close(self):
+        if self.h:
+            lib().kicp_scan_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class KinematicRegistration:
+    """kinematic_icp::KinematicRegistration (registration/Registration.hpp:32-50).
+
+    max_num_threads is accepted for signature parity and ignored: the GPU path has no thread cap."""
+
+    def __init__(self, max_num_iteration=10, convergence_criterion=1e-3, max_num_threads=1,
+                 use_adaptive_odometry_regularization=True, fixed_regularization=0.0):
+        self.max_num_iterations_ = max_num_iteration
+        self.convergence_criterion_ = convergence_criterion
+        self.max_num_threads_ = max_num_threads
+        self.use_adaptive_odometry_regularization_ = use_adaptive_odometry_regularization
+        self.fixed_regularization_ = fixed_regularization
+        self.last_result = None
+
+    def _params(self):
+        return RegParams(int(self.max_num_iterations_), int(bool(self.use_adaptive_odometry_regularization_)),
+                         float(self.convergence_criterion_), float(self.fixed_regularization_))
+
+    def ComputeRobotMotion(self, frame, voxel_map, last_robot_pose, relative_wheel_odometry, max_correspondence_distance):
+        """Host points in, pose7 out (synchronous) — the reference's call at pipeline/KinematicICP.cpp:68-72."""
+        frame = as_points(frame)
+        out = np.empty(7)
+        res = RegResult()
+        p = self._params()
+        st = lib().kicp_register(voxel_map.h, dp(frame), len(frame), dp(as_pose(last_robot_pose)),
+                                 dp(as_pose(relative_wheel_odometry)), float(max_correspondence_distance), C.byref(p), dp(out),
+                                 C.byref(res))
+        check(st, "kicp_register", allow=(KICP_OK, KICP_WARN_NO_CORRESPONDENCES))
+        self.last_result = res
+        return out
+
+    def ComputeRobotMotionSharded(self, frame_shard, voxel_map, last_robot_pose, relative_wheel_odometry,
+                                  max_correspondence_distance):
+        """Every rank passes its contiguous index range of the scan; all ranks return the same pose."""
+        frame = as_points(frame_shard)
+        out = np.empty(7)
+        res = RegResult()
+        p = self._params()
+        st = lib().kicp_register_sharded(voxel_map.h, dp(frame), len(frame), dp(as_pose(last_robot_pose)),
+                                         dp(as_pose(relative_wheel_odometry)), float(max_correspondence_distance), C.byref(p),
+                                         dp(out), C.byref(res))
+        check(st, "kicp_register_sharded", allow=(KICP_OK, KICP_WARN_NO_CORRESPONDENCES))
+        self.last_result = res
+        return out
+
+    def enqueue(self, scan, voxel_map, last_robot_pose, relative_wheel_odometry, max_correspondence_distance, result,
+                sharded=False):
+        """Device-resident scan, no host synchronisation; `result` (pinned_result()) is valid after ctx.synchronize()."""
+        p = self._params()
+        f = lib().kicp_register_scan_sharded_async if sharded else lib().kicp_register_scan_async
+        check(f(voxel_map.h, scan.h, dp(as_pose(last_robot_pose)), dp(as_pose(relative_wheel_odometry)),
+                float(max_correspondence_distance), C.byref(p), C.byref(result)), "kicp_register_scan_async")
+
+
+def shard_range(n, nranks, rank):
+    """Contiguous index range [lo, hi) of rank `rank` out of `nranks`."""
+    return n * rank // nranks, n * (rank + 1) // nranks

@@ -352,12 +352,31 @@ Correspondences DataAssociation(const std::vector<Vec3> &points, const VoxelHash
     return correspondences;
 }
 
+// std::transform_reduce as libstdc++ (GCC 13) evaluates it for random-access iterators — the reference calls it at
+// Registration.cpp:50-55 and :104-113.  It is NOT a left fold: elements are combined in groups of four,
+// init = op(init, op(op(f(x0), f(x1)), op(f(x2), f(x3)))), then the remainder one by one.  Mirrored here so that the
+// single-threaded reference and the oracle agree bit for bit.
+template <typename T, typename It, typename BinaryOp, typename UnaryOp>
+T transform_reduce_like_libstdcxx(It first, It last, T init, BinaryOp binary_op, UnaryOp unary_op) {
+    while ((last - first) >= 4) {
+        T v1 = binary_op(unary_op(first[0]), unary_op(first[1]));
+        T v2 = binary_op(unary_op(first[2]), unary_op(first[3]));
+        T v3 = binary_op(v1, v2);
+        init = binary_op(init, v3);
+        first += 4;
+    }
+    for (; first != last; ++first) init = binary_op(init, unary_op(*first));
+    return init;
+}
+
 // Registration.cpp:48-60
 double ComputeOdometryRegularization(const Correspondences &associations, const SE3 &odometry_initial_guess,
                                      double *sumsq_out) {
-    double sum_of_squared_residuals = 0.0;
-    for (const auto &[source, target] : associations)
-        sum_of_squared_residuals += squaredNorm(transform(odometry_initial_guess, source) - target);
+    const double sum_of_squared_residuals = transform_reduce_like_libstdcxx(
+        associations.cbegin(), associations.cend(), 0.0, [](double a, double b) { return a + b; },
+        [&](const std::pair<Vec3, Vec3> &association) {
+            return squaredNorm(transform(odometry_initial_guess, association.first) - association.second);
+        });
     const double N = static_cast<double>(associations.size());
     const double mean_squared_residual = sum_of_squared_residuals / N;
     if (sumsq_out) *sumsq_out = sum_of_squared_residuals;
@@ -367,17 +386,22 @@ double ComputeOdometryRegularization(const Correspondences &associations, const 
 // Registration.cpp:83-126.  J = [R e_x | R (-p_y, p_x, 0)], r = T p - n, w == 1.
 void ComputePerturbation(const Correspondences &correspondences, const SE3 &current_estimate, double beta, double dx[2],
                          IterSums *sums_out) {
-    double JTJ00 = 0, JTJ01 = 0, JTJ11 = 0, JTr0 = 0, JTr1 = 0;
+    struct LS {
+        double JTJ00, JTJ01, JTJ11, JTr0, JTr1;
+    };
     const Vec3 c0 = rotate(current_estimate.q, Vec3{1.0, 0.0, 0.0});
-    for (const auto &[source, target] : correspondences) {
-        const Vec3 residual = transform(current_estimate, source) - target;
-        const Vec3 c1 = rotate(current_estimate.q, Vec3{-source.y, source.x, 0.0});
-        JTJ00 += dot(c0, c0);
-        JTJ01 += dot(c0, c1);
-        JTJ11 += dot(c1, c1);
-        JTr0 += dot(c0, residual);
-        JTr1 += dot(c1, residual);
-    }
+    const LS total = transform_reduce_like_libstdcxx(
+        correspondences.cbegin(), correspondences.cend(), LS{0, 0, 0, 0, 0},
+        [](LS a, const LS &b) {
+            return LS{a.JTJ00 + b.JTJ00, a.JTJ01 + b.JTJ01, a.JTJ11 + b.JTJ11, a.JTr0 + b.JTr0, a.JTr1 + b.JTr1};
+        },
+        [&](const std::pair<Vec3, Vec3> &c) {
+            const Vec3 &source = c.first, &target = c.second;
+            const Vec3 residual = transform(current_estimate, source) - target;
+            const Vec3 c1 = rotate(current_estimate.q, Vec3{-source.y, source.x, 0.0});
+            return LS{dot(c0, c0), dot(c0, c1), dot(c1, c1), dot(c0, residual), dot(c1, residual)};
+        });
+    const double JTJ00 = total.JTJ00, JTJ01 = total.JTJ01, JTJ11 = total.JTJ11, JTr0 = total.JTr0, JTr1 = total.JTr1;
     const double num_correspondences = static_cast<double>(correspondences.size());
     if (sums_out) *sums_out = {JTJ00, JTJ01, JTJ11, JTr0, JTr1, num_correspondences, 0.0};
     // JTJ /= N; JTr /= N; JTJ += diag(beta, 0); dx = -(JTJ^-1 JTr)      (:119-125)

@@ -1,0 +1,68 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/kicp.h declares; host-side helpers."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build():
+    import __graft_entry__ as g
+    g.build()
+
+
+def test_library_exports_every_declared_symbol():
+    _build()
+    from kinematic_icp_b200 import _capi
+    hdr = open(os.path.join(ROOT, "include", "kicp.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(kicp_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    L = C.CDLL(_capi.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), "libkicp_b200.so does not export %s" % name
+    assert declared == {s[0] for s in _capi.SYMBOLS}, "python binding and header disagree"
+
+
+def test_struct_layout_matches_header():
+    from kinematic_icp_b200 import _capi
+    assert C.sizeof(_capi.RegParams) == 24
+    assert C.sizeof(_capi.RegResult) == 7 * 8 + 8 + 8 + 4 + 4 + 64 * 8 * 8 + 64 * 2 * 8
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device the product fails loudly instead of computing on the host."""
+    import kinematic_icp_b200 as kb
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    with pytest.raises(kb.KicpError) as e:
+        kb.Context(0)
+    assert e.value.status == kb._capi.KICP_ERR_CUDA
+
+
+def test_product_never_imports_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/."""
+    pkg = os.path.join(ROOT, "kinematic-icp_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", "Makefile")):
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                assert "kicp_oracle" not in txt and "oracle/" not in txt.replace("the oracle", ""), os.path.join(base, f)
+
+
+def test_shard_range_partitions_the_scan():
+    import kinematic_icp_b200 as kb
+    for n in (0, 1, 7, 261675):
+        for g in (1, 2, 4, 8):
+            r = [kb.shard_range(n, g, k) for k in range(g)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[k][1] == r[k + 1][0] for k in range(g - 1))
+            assert max(hi - lo for lo, hi in r) - min(hi - lo for lo, hi in r) <= 1

@@ -1,0 +1,200 @@
+"""GPU parity: the CUDA path through the C-ABI against the CPU oracle and the reference-derived golden vectors.
+
+Tolerance (BASELINE.json north_star): final pose within 1e-6 m / 1e-7 rad of the CPU reference.  The map and the
+nearest-neighbour lookup are integer/index work and must be bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL_T, TOL_R = 1e-6, 1e-7
+DBL_MAX = np.finfo(np.float64).max
+
+
+def gpu_map_from_oracle(kb, ctx, om):
+    keys, counts, pts = om.export_voxels()
+    gm = kb.VoxelHashMap(ctx, om.voxel_size, om.max_distance, om.max_points_per_voxel)
+    gm.load_voxels(keys, counts, pts)
+    return gm
+
+
+def sorted_voxels(keys, counts, pts):
+    off = np.concatenate([[0], np.cumsum(counts)])
+    order = np.lexsort((keys[:, 2], keys[:, 1], keys[:, 0]))
+    return keys[order], counts[order], np.concatenate([pts[off[i]:off[i + 1]] for i in order]) if len(order) else pts
+
+
+def test_map_addpoints_bit_exact(oracle, gpu_ctx):
+    """AddPoints on the device reproduces the greedy, input-order dependent CPU result exactly."""
+    import kinematic_icp_b200 as kb
+    ko = oracle
+    rng = np.random.default_rng(11)
+    om = ko.OracleMap(1.0, 100.0, 20)
+    gm = kb.VoxelHashMap(gpu_ctx, 1.0, 100.0, 20)
+    assert gm.Empty()
+    for it in range(6):
+        # clustered points: many per voxel, negative coordinates, repeated inserts
+        pts = rng.normal(size=(6000, 3)) * [6.0, 6.0, 1.5] + [-2.0, 1.0, 0.0]
+        om.add_points(pts)
+        gm.AddPoints(pts)
+        assert gm.num_points() == om.num_points() and gm.num_voxels() == om.num_voxels()
+    k1, c1, p1 = sorted_voxels(*gm.export_voxels())
+    k0, c0, p0 = om.export_voxels()
+    assert np.array_equal(k1, k0) and np.array_equal(c1, c0) and np.array_equal(p1, p0)
+    assert not gm.Empty() and len(gm.Pointcloud()) == om.num_points()
+    gm.Clear()
+    assert gm.Empty() and gm.num_points() == 0
+
+
+def test_map_update_and_eviction_bit_exact(oracle, gpu_ctx):
+    """Update(points, origin) / RemovePointsFarFromLocation: first-point rule, >= max_distance."""
+    import kinematic_icp_b200 as kb
+    ko = oracle
+    rng = np.random.default_rng(12)
+    om = ko.OracleMap(0.5, 12.0, 8)
+    gm = kb.VoxelHashMap(gpu_ctx, 0.5, 12.0, 8)
+    for it in range(8):
+        origin = np.array([3.0 * it, 0.5 * it, 0.0])
+        pts = rng.uniform(-10, 10, size=(5000, 3)) * [1, 1, 0.2] + origin
+        om.update_origin(pts, origin)
+        gm.Update(pts, origin)
+        assert gm.num_points() == om.num_points() and gm.num_voxels() == om.num_voxels()
+    k1, c1, p1 = sorted_voxels(*gm.export_voxels())
+    k0, c0, p0 = om.export_voxels()
+    assert np.array_equal(k1, k0) and np.array_equal(c1, c0) and np.array_equal(p1, p0)
+
+
+def test_map_update_pose_bit_exact(oracle, gpu_ctx, workload):
+    """Update(points, pose) with the pose applied on the device (Sophus quaternion formula, no FMA contraction)."""
+    import kinematic_icp_b200 as kb
+    ko = oracle
+    w = workload(1)
+    om = ko.OracleMap(1.0, 100.0, 20)
+    gm = kb.VoxelHashMap(gpu_ctx, 1.0, 100.0, 20)
+    pose = ko.planar_pose(50.0, 0.0, 1.2)
+    for k in range(3):
+        om.update_pose(w.scan, pose)
+        gm.Update(w.scan, pose)
+        pose = ko.se3_compose(pose, ko.se3_exp([0.8, 0.05, 0, 0, 0, 0.03]))
+    k1, c1, p1 = sorted_voxels(*gm.export_voxels())
+    k0, c0, p0 = om.export_voxels()
+    assert np.array_equal(k1, k0) and np.array_equal(c1, c0) and np.array_equal(p1, p0)
+
+
+def test_nearest_neighbour_bit_exact(oracle, gpu_ctx, workload):
+    """GetClosestNeighbor: same point and same distance, bit for bit, including the empty-neighbourhood case."""
+    import kinematic_icp_b200 as kb
+    ko = oracle
+    w = workload(2)
+    gm = gpu_map_from_oracle(kb, gpu_ctx, w.map)
+    q = ko.se3_transform(w.prior, w.scan)
+    rng = np.random.default_rng(3)
+    q = np.concatenate([q, rng.uniform(-120, 120, size=(4000, 3)), np.floor(q[:2000]) + 0.0, -np.abs(q[:500])])
+    pg, dg = gm.GetClosestNeighbor(q)
+    po, do = w.map.nearest(q)
+    assert np.array_equal(dg, do) and np.array_equal(pg, po)
+    assert (do == DBL_MAX).sum() > 0  # the case is covered
+
+
+def check_registration(ko, kb, ctx, om, gm, scan, last, odom, tau, ref_pose=None, **kw):
+    reg = kb.KinematicRegistration(kw.get("max_iter", 10), kw.get("conv", 1e-3), 1, kw.get("adaptive", True),
+                                   kw.get("fixed_reg", 0.0))
+    pose = reg.ComputeRobotMotion(scan, gm, last, odom, tau)
+    po, st = om.register(scan, last, odom, tau, max_iter=kw.get("max_iter", 10), conv=kw.get("conv", 1e-3),
+                         adaptive=kw.get("adaptive", True), fixed_reg=kw.get("fixed_reg", 0.0))
+    res = reg.last_result
+    dt, ang = ko.pose_delta(pose, po)
+    assert dt <= TOL_T and ang <= TOL_R, (dt, ang)
+    assert res.iterations == st.iterations
+    # N per iteration is an integer count of accepted correspondences: any NN or gate flip would show here
+    assert np.array_equal(res.sums_np()[:, 5], st.sums_np()[:, 5])
+    assert np.allclose(res.sums_np()[:, :5], st.sums_np()[:, :5], rtol=1e-9, atol=1e-9)
+    assert res.beta == pytest.approx(st.beta, rel=1e-10)
+    if ref_pose is not None:
+        dt, ang = ko.pose_delta(pose, ref_pose)
+        assert dt <= TOL_T and ang <= TOL_R, (dt, ang)
+    return pose, dt, ang
+
+
+@pytest.mark.parametrize("name", ["reg_cfg1", "reg_cfg2_small"])
+def test_registration_vs_reference_golden(oracle, gpu_ctx, name):
+    """Final pose against the pose the reference's own Registration.cpp produced (tests/golden)."""
+    import kinematic_icp_b200 as kb
+    ko = oracle
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    om = ko.OracleMap(float(z["voxel_size"]), float(z["max_range"]), int(z["max_points_per_voxel"]))
+    om.add_points(z["map_points"])
+    gm = kb.VoxelHashMap(gpu_ctx, float(z["voxel_size"]), float(z["max_range"]), int(z["max_points_per_voxel"]))
+    gm.load_voxels(z["map_keys"], z["map_counts"], z["map_points"])
+    for case in z["cases"]:
+        check_registration(ko, kb, gpu_ctx, om, gm, z["scan"], z["last_pose"], z["rel_odom"], case[4], ref_pose=case[5:],
+                           max_iter=int(case[0]), conv=case[1], adaptive=bool(case[2]), fixed_reg=case[3])
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4])
+def test_registration_configs_vs_oracle(oracle, gpu_ctx, workload, cfg):
+    """BASELINE.json configs 1-4 at full size: pose, iteration count, per-iteration N and sums."""
+    import kinematic_icp_b200 as kb
+    ko = oracle
+    w = workload(cfg)
+    gm = gpu_map_from_oracle(kb, gpu_ctx, w.map)
+    pose, dt, ang = check_registration(ko, kb, gpu_ctx, w.map, gm, w.scan, w.last_pose, w.rel_odom, w.tau)
+    print("cfg%d N=%d M=%d pose delta %.3e m %.3e rad" % (cfg, w.N, w.map.num_points(), dt, ang))
+    gm.close()
+
+
+def test_registration_edge_cases(oracle, gpu_ctx, workload):
+    import kinematic_icp_b200 as kb
+    ko = oracle
+    w = workload(1)
+    # empty map: the prediction, no iterations (Registration.cpp:157)
+    gm = kb.VoxelHashMap(gpu_ctx, 1.0, 100.0, 20)
+    reg = kb.KinematicRegistration()
+    pose = reg.ComputeRobotMotion(w.scan, gm, w.last_pose, w.rel_odom, w.tau)
+    dt, ang = ko.pose_delta(pose, ko.se3_compose(w.last_pose, w.rel_odom))
+    assert dt < 1e-15 and ang < 1e-15 and reg.last_result.iterations == 0
+    gm.close()
+    gm = gpu_map_from_oracle(kb, gpu_ctx, w.map)
+    # ragged sizes around the 32-point window and the empty scan
+    for n in (1, 31, 32, 33, 1000):
+        check_registration(ko, kb, gpu_ctx, w.map, gm, w.scan[:n], w.last_pose, w.rel_odom, w.tau)
+    # no correspondences: NaN pose as in the reference, plus a status
+    reg = kb.KinematicRegistration()
+    pose = reg.ComputeRobotMotion(w.scan + 500.0, gm, w.last_pose, w.rel_odom, w.tau)
+    assert np.all(np.isnan(pose)) and reg.last_result.status == kb.KICP_WARN_NO_CORRESPONDENCES
+    pose = reg.ComputeRobotMotion(np.zeros((0, 3)), gm, w.last_pose, w.rel_odom, w.tau)
+    assert np.all(np.isnan(pose))
+    # strict gate and max_iter = 1, tiny tau, fixed regularisation
+    check_registration(ko, kb, gpu_ctx, w.map, gm, w.scan, w.last_pose, w.rel_odom, 0.3, max_iter=1)
+    check_registration(ko, kb, gpu_ctx, w.map, gm, w.scan, w.last_pose, w.rel_odom, w.tau, adaptive=False, fixed_reg=2.0)
+    check_registration(ko, kb, gpu_ctx, w.map, gm, w.scan, w.last_pose, w.rel_odom, w.tau, conv=1e-6, max_iter=40)
+    # points not representable in float32, general 3-D poses
+    rng = np.random.default_rng(2)
+    scan = w.scan + rng.normal(size=w.scan.shape) * 1e-3
+    last = ko.se3_compose(w.last_pose, ko.se3_exp([0, 0, 0, 0.01, -0.02, 0.0]))
+    check_registration(ko, kb, gpu_ctx, w.map, gm, scan, last, w.rel_odom, w.tau)
+    gm.close()
+
+
+def test_device_resident_async_path(oracle, gpu_ctx, workload):
+    """kicp_register_scan_async: scan already in HBM, several registrations enqueued, one synchronisation."""
+    import kinematic_icp_b200 as kb
+    ko = oracle
+    w = workload(2)
+    gm = gpu_map_from_oracle(kb, gpu_ctx, w.map)
+    scan = kb.Scan(gpu_ctx, w.N)
+    scan.upload(w.scan)
+    reg = kb.KinematicRegistration()
+    results = [kb.pinned_result() for _ in range(3)]
+    for r in results:
+        reg.enqueue(scan, gm, w.last_pose, w.rel_odom, w.tau, r)
+    gpu_ctx.synchronize()
+    po, st = w.map.register(w.scan, w.last_pose, w.rel_odom, w.tau)
+    for r in results:
+        dt, ang = ko.pose_delta(r.pose_np(), po)
+        assert dt <= TOL_T and ang <= TOL_R and r.iterations == st.iterations
+    assert gpu_ctx.launch_count > 0
+    scan.close()
+    gm.close()
