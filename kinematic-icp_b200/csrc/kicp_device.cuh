@@ -21,6 +21,17 @@ constexpr unsigned long long pack_axis(int a) {
 }
 constexpr unsigned long long kShiftX = pack_axis(0), kShiftY = pack_axis(1), kShiftZ = pack_axis(2);
 
+// 27-bit masks of the shifts whose x / y / z component is 0, +1, -1 (bit k <-> voxel_shifts[k])
+constexpr uint32_t axis_mask(int a, int val) {
+    uint32_t r = 0;
+    for (int k = 0; k < 27; ++k)
+        if (kShifts[k][a] == val) r |= 1u << k;
+    return r;
+}
+constexpr uint32_t kX0 = axis_mask(0, 0), kXP = axis_mask(0, 1), kXM = axis_mask(0, -1);
+constexpr uint32_t kY0 = axis_mask(1, 0), kYP = axis_mask(1, 1), kYM = axis_mask(1, -1);
+constexpr uint32_t kZ0 = axis_mask(2, 0), kZP = axis_mask(2, 1), kZM = axis_mask(2, -1);
+
 __device__ __forceinline__ int shift_x(int k) { return (int)((kShiftX >> (2 * k)) & 3ull) - 1; }
 __device__ __forceinline__ int shift_y(int k) { return (int)((kShiftY >> (2 * k)) & 3ull) - 1; }
 __device__ __forceinline__ int shift_z(int k) { return (int)((kShiftZ >> (2 * k)) & 3ull) - 1; }

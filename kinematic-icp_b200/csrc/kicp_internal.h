@@ -10,6 +10,7 @@
 
 #define KICP_SLOT_EMPTY 0xFFFFFFFFu
 #define KICP_SLOT_LOCKED 0xFFFFFFFEu
+#define KICP_PSTRIDE 4    // doubles per stored map point: {x, y, z, pad} = one 32-byte sector, two 16-byte loads
 #define KICP_MAX_CAP 255  // max_points_per_voxel: the count shares the slot's meta word (low 8 bits)
 
 // ---------------------------------------------------------------------------------------------------------
@@ -18,9 +19,10 @@
 //   slots[nslots]      int4 {kx, ky, kz, meta}   open-addressed, linear probing, nslots = 2^k, load <= 0.25
 //                                                meta = (block << 8) | count, 0xFFFFFFFF = empty
 //   blk[blocks_cap]    int4 {kx, ky, kz, count}  one header per occupied voxel ("block"), dense [0, num_blocks)
-//   pts[blocks_cap * cap * 3] double             block b owns points [b*cap, b*cap + count), insertion order
+//   pts[blocks_cap * cap * 4] double             block b owns points [b*cap, b*cap + count), insertion order;
+//                                                each point is {x, y, z, pad}: exactly one 32-byte sector
 //
-// One 16-byte load resolves a probe to (block, count); a voxel's points are one contiguous <= cap*24 B run.
+// One 16-byte load resolves a probe to (block, count); a voxel's points are one contiguous <= cap*32 B run.
 // ---------------------------------------------------------------------------------------------------------
 struct MapView {
     const int4 *slots;
@@ -44,6 +46,9 @@ struct kicp_ctx {
     size_t sort_tmp_bytes = 0;
     int64_t scratch_cap = 0;
     int assoc_ctas_per_sm = 1;  // resident CTAs of the association kernel per SM (occupancy query)
+    int pruned_ctas_per_sm = 1;
+    int assoc_variant = 1;  // 0 = staged (27-voxel neighbourhood through shared memory), 1 = pruned (thread per point)
+    int sort_bits = 30;     // Morton key bits used by the binning sort; 0 disables the binning
     kicp_scan *upload_scan = nullptr;  // staging scan used by the host-pointer entry points
     kicp_reg_result *h_result = nullptr;  // pinned bounce buffer for synchronous calls
     // profiling (kicp_ctx_profile_begin/end): event pairs per registration

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -56,6 +57,8 @@ extern "C" int kicp_ctx_create(int device, kicp_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     KICP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     KICP_CUDA(cudaMallocHost(&c->h_result, sizeof(kicp_reg_result)));
+    if (const char *e = getenv("KICP_ASSOC")) c->assoc_variant = strcmp(e, "staged") ? 1 : 0;
+    if (const char *e = getenv("KICP_SORT_BITS")) c->sort_bits = std::min(30, std::max(0, atoi(e)));
     *out = c;
     return KICP_OK;
 }
@@ -238,7 +241,7 @@ __global__ void k_add_commit(MapRW m, const double *__restrict__ xyz_t, const in
     const int4 hdr = m.blk[b];
     int cnt = hdr.w;
     const int cnt0 = cnt;
-    double *vp = m.pts + (size_t)b * m.cap * 3;
+    double *vp = m.pts + (size_t)b * m.cap * KICP_PSTRIDE;
     const int32_t head = m.pend_head[b];
     int32_t last = -1;
     while (cnt < m.cap) {
@@ -250,14 +253,14 @@ __global__ void k_add_commit(MapRW m, const double *__restrict__ xyz_t, const in
         const double px = xyz_t[3 * (size_t)best], py = xyz_t[3 * (size_t)best + 1], pz = xyz_t[3 * (size_t)best + 2];
         bool too_close = false;
         for (int j = 0; j < cnt; ++j) {
-            const double dx = vp[3 * j] - px, dy = vp[3 * j + 1] - py, dz = vp[3 * j + 2] - pz;
+            const double dx = vp[KICP_PSTRIDE * j] - px, dy = vp[KICP_PSTRIDE * j + 1] - py, dz = vp[KICP_PSTRIDE * j + 2] - pz;
             if (sqrt(dx * dx + dy * dy + dz * dz) < map_resolution) {
                 too_close = true;
                 break;
             }
         }
         if (too_close) continue;
-        vp[3 * cnt] = px, vp[3 * cnt + 1] = py, vp[3 * cnt + 2] = pz;
+        vp[KICP_PSTRIDE * cnt] = px, vp[KICP_PSTRIDE * cnt + 1] = py, vp[KICP_PSTRIDE * cnt + 2] = pz, vp[KICP_PSTRIDE * cnt + 3] = 0.0;
         ++cnt;
     }
     m.pend_head[b] = -1;
@@ -281,7 +284,7 @@ __global__ void k_mark_far(const int4 *blk, const double *pts, int cap, uint32_t
                            double max_distance2, uint32_t *keep, uint32_t *counters) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= num_blocks) return;
-    const double *p = pts + (size_t)b * cap * 3;
+    const double *p = pts + (size_t)b * cap * KICP_PSTRIDE;
     const double dx = p[0] - ox, dy = p[1] - oy, dz = p[2] - oz;
     const bool dead = (dx * dx + dy * dy + dz * dz) >= max_distance2;
     keep[b] = dead ? 0u : 1u;
@@ -335,9 +338,9 @@ __global__ void k_compact_blocks(const int4 *blk, const double *pts, int cap, ui
     const uint32_t nb = new_id[b];
     const int4 h = blk[b];
     if (lane == 0) blk_out[nb] = h;
-    const double *src = pts + (size_t)b * cap * 3;
-    double *dst = pts_out + (size_t)nb * cap * 3;
-    for (int i = lane; i < h.w * 3; i += 32) dst[i] = src[i];
+    const double *src = pts + (size_t)b * cap * KICP_PSTRIDE;
+    double *dst = pts_out + (size_t)nb * cap * KICP_PSTRIDE;
+    for (int i = lane; i < h.w * KICP_PSTRIDE; i += 32) dst[i] = src[i];
 }
 
 __global__ void k_fill_i32(int32_t *p, int32_t v, uint32_t n) {
@@ -354,8 +357,8 @@ __global__ void k_load_voxels(int4 *blk, double *pts, int cap, const int32_t *ke
     const int c = counts[v];
     if (lane == 0) blk[v] = make_int4(keys[3 * v], keys[3 * v + 1], keys[3 * v + 2], c);
     const double *src = points + offsets[v] * 3;
-    double *dst = pts + (size_t)v * cap * 3;
-    for (int i = lane; i < c * 3; i += 32) dst[i] = src[i];
+    double *dst = pts + (size_t)v * cap * KICP_PSTRIDE;
+    for (int i = lane; i < c * KICP_PSTRIDE; i += 32) dst[i] = (i & 3) == 3 ? 0.0 : src[(i >> 2) * 3 + (i & 3)];
 }
 
 // GetClosestNeighbor for a batch of queries, one thread each, evaluated exactly like the reference:
@@ -370,12 +373,12 @@ __global__ void k_nearest(MapView m, const double *__restrict__ q, int64_t n, do
     for (int k = 0; k < 27; ++k) {
         const uint32_t meta = map_probe(m, vx + shift_x(k), vy + shift_y(k), vz + shift_z(k));
         if (meta == KICP_SLOT_EMPTY) continue;
-        const double *vp = m.pts + (size_t)(meta >> 8) * m.cap * 3;
+        const double *vp = m.pts + (size_t)(meta >> 8) * m.cap * KICP_PSTRIDE;
         const int cnt = (int)(meta & 0xFFu);
         for (int j = 0; j < cnt; ++j) {
-            const double dx = vp[3 * j] - qx, dy = vp[3 * j + 1] - qy, dz = vp[3 * j + 2] - qz;
+            const double dx = vp[KICP_PSTRIDE * j] - qx, dy = vp[KICP_PSTRIDE * j + 1] - qy, dz = vp[KICP_PSTRIDE * j + 2] - qz;
             const double d = sqrt(dx * dx + dy * dy + dz * dz);
-            if (d < bd) bd = d, bx = vp[3 * j], by = vp[3 * j + 1], bz = vp[3 * j + 2];
+            if (d < bd) bd = d, bx = vp[KICP_PSTRIDE * j], by = vp[KICP_PSTRIDE * j + 1], bz = vp[KICP_PSTRIDE * j + 2];
         }
     }
     out_pts[3 * i] = bx, out_pts[3 * i + 1] = by, out_pts[3 * i + 2] = bz;
@@ -419,11 +422,11 @@ static int map_reserve(kicp_map *m, uint64_t extra) {
         double *npts = nullptr;
         int32_t *nhead = nullptr;
         KICP_CUDA(cudaMalloc(&nblk, (size_t)ncap * sizeof(int4)));
-        KICP_CUDA(cudaMalloc(&npts, (size_t)ncap * m->cap * 3 * sizeof(double)));
+        KICP_CUDA(cudaMalloc(&npts, (size_t)ncap * m->cap * KICP_PSTRIDE * sizeof(double)));
         KICP_CUDA(cudaMalloc(&nhead, (size_t)ncap * sizeof(int32_t)));
         if (m->num_blocks) {
             KICP_CUDA(cudaMemcpyAsync(nblk, m->blk, (size_t)m->num_blocks * sizeof(int4), cudaMemcpyDeviceToDevice, c->stream));
-            KICP_CUDA(cudaMemcpyAsync(npts, m->pts, (size_t)m->num_blocks * m->cap * 3 * sizeof(double),
+            KICP_CUDA(cudaMemcpyAsync(npts, m->pts, (size_t)m->num_blocks * m->cap * KICP_PSTRIDE * sizeof(double),
                                       cudaMemcpyDeviceToDevice, c->stream));
         }
         k_fill_i32<<<(ncap + 255) / 256, 256, 0, c->stream>>>(nhead, -1, ncap);
@@ -571,7 +574,7 @@ extern "C" int kicp_map_remove_far(kicp_map *m, const double origin[3]) {
         int4 *nblk = nullptr;
         double *npts = nullptr;
         cudaError_t e1 = cudaMalloc(&nblk, (size_t)m->blocks_cap * sizeof(int4));
-        cudaError_t e2 = cudaMalloc(&npts, (size_t)m->blocks_cap * m->cap * 3 * sizeof(double));
+        cudaError_t e2 = cudaMalloc(&npts, (size_t)m->blocks_cap * m->cap * KICP_PSTRIDE * sizeof(double));
         if (e1 != cudaSuccess || e2 != cudaSuccess) {
             cudaFree(nblk), cudaFree(npts), cudaFree(keep), cudaFree(new_id);
             return kicp_cuda_fail(e1 != cudaSuccess ? e1 : e2, "cudaMalloc", __FILE__, __LINE__);
@@ -611,7 +614,7 @@ static int map_download(kicp_map *m, std::vector<int4> &hdr, std::vector<double>
     kicp_ctx *c = m->ctx;
     KICP_CUDA(cudaSetDevice(c->device));
     hdr.resize(m->num_blocks);
-    pts.resize((size_t)m->num_blocks * m->cap * 3);
+    pts.resize((size_t)m->num_blocks * m->cap * KICP_PSTRIDE);
     if (m->num_blocks) {
         KICP_CUDA(cudaMemcpyAsync(hdr.data(), m->blk, hdr.size() * sizeof(int4), cudaMemcpyDeviceToHost, c->stream));
         KICP_CUDA(cudaMemcpyAsync(pts.data(), m->pts, pts.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -631,8 +634,9 @@ extern "C" int kicp_map_pointcloud(kicp_map *m, double *out_xyz, int64_t cap, in
     KICP_TRY(map_download(m, hdr, pts));
     int64_t w = 0;
     for (uint32_t b = 0; b < m->num_blocks; ++b) {
-        std::memcpy(out_xyz + 3 * w, pts.data() + (size_t)b * m->cap * 3, (size_t)hdr[b].w * 3 * sizeof(double));
-        w += hdr[b].w;
+        const double *src = pts.data() + (size_t)b * m->cap * KICP_PSTRIDE;
+        for (int j = 0; j < hdr[b].w; ++j, ++w)
+            out_xyz[3 * w] = src[KICP_PSTRIDE * j], out_xyz[3 * w + 1] = src[KICP_PSTRIDE * j + 1], out_xyz[3 * w + 2] = src[KICP_PSTRIDE * j + 2];
     }
     return KICP_OK;
 }
@@ -651,8 +655,9 @@ extern "C" int kicp_map_export_voxels(kicp_map *m, int32_t *keys, int32_t *count
     for (uint32_t b = 0; b < m->num_blocks; ++b) {
         keys[3 * b] = hdr[b].x, keys[3 * b + 1] = hdr[b].y, keys[3 * b + 2] = hdr[b].z;
         counts[b] = hdr[b].w;
-        std::memcpy(points + 3 * w, pts.data() + (size_t)b * m->cap * 3, (size_t)hdr[b].w * 3 * sizeof(double));
-        w += hdr[b].w;
+        const double *src = pts.data() + (size_t)b * m->cap * KICP_PSTRIDE;
+        for (int j = 0; j < hdr[b].w; ++j, ++w)
+            points[3 * w] = src[KICP_PSTRIDE * j], points[3 * w + 1] = src[KICP_PSTRIDE * j + 1], points[3 * w + 2] = src[KICP_PSTRIDE * j + 2];
     }
     return KICP_OK;
 }

@@ -12,6 +12,8 @@
 // (Registration.cpp:119-125, 159-167, 181-184) — so the iteration loop never returns to the host.
 // The correspondence list of the reference is never materialised: association and linearisation use the same T.
 #include <cfloat>
+#include <cstdlib>
+#include <cstring>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "kicp_device.cuh"
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(KICP_WARPS * 32) k_assoc(RegState *st, const d
                 __syncwarp();
                 const int m = min(KICP_CH, C - base);
                 for (int c = lane; c < m; c += 32) {
-                    const double *gp = map.pts + (size_t)sg[c] * 3;
+                    const double *gp = map.pts + (size_t)sg[c] * KICP_PSTRIDE;
                     sx[c] = __ldg(gp), sy[c] = __ldg(gp + 1), sz[c] = __ldg(gp + 2);
                 }
                 __syncwarp();
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(KICP_WARPS * 32) k_assoc(RegState *st, const d
             remaining &= ~gm;
         }
         if (valid && bestg >= 0) {
-            const double *gp = map.pts + (size_t)bestg * 3;
+            const double *gp = map.pts + (size_t)bestg * KICP_PSTRIDE;
             const double rx = qx - __ldg(gp), ry = qy - __ldg(gp + 1), rz = qz - __ldg(gp + 2);  // r = T p - n
             const double rr = rx * rx + ry * ry + rz * rz;
             if (sqrt(rr) < tau) {  // distance < max_correspondance_distance   (Registration.cpp:75)
@@ -381,7 +383,219 @@ __global__ void __launch_bounds__(KICP_WARPS * 32) k_assoc(RegState *st, const d
     }
 }
 
+
+
+// Scan the `cnt` points of one voxel (32-byte records), four at a time: eight independent 16-byte loads are issued
+// before the first distance is formed.  Strict `<` in storage order keeps the first minimum, as the reference does.
+__device__ __forceinline__ void scan_voxel(const double *__restrict__ vp, int cnt, double qx, double qy, double qz, double &best,
+                                           double &bx, double &by, double &bz, bool &have) {
+    for (int j = 0; __any_sync(0xFFFFFFFFu, j < cnt); j += 4) {
+        double2 xy[4], zw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (j + u < cnt) {
+                const double2 *p2 = reinterpret_cast<const double2 *>(vp + (size_t)(j + u) * KICP_PSTRIDE);
+                xy[u] = __ldg(p2), zw[u] = __ldg(p2 + 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (j + u < cnt) {
+                const double dx = xy[u].x - qx, dy = xy[u].y - qy, dz = zw[u].x - qz;
+                const double d2 = dx * dx + dy * dy + dz * dz;
+                if (d2 < best) best = d2, bx = xy[u].x, by = xy[u].y, bz = zw[u].x, have = true;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_assoc_pruned: one thread per scan point, exact pruning of the 27-voxel neighbourhood.
+//
+// GetClosestNeighbor returns the nearest of all points stored in the 27 voxels around the query.  A voxel whose
+// CUBE is farther from the query than the best distance found so far cannot contain that point, so it can be
+// skipped without changing the result: with q in voxel v, the gap to the cube of v + s is
+//     lb^2 = sum over axes of { (upper face - q)^2 if s = +1, (q - lower face)^2 if s = -1, 0 if s = 0 }.
+// The voxels are visited in the reference's own order (centre, faces, edges, corners), so the strict `<` keeps the
+// same point on exact ties; a voxel is skipped only when lb^2 exceeds the current best by a safety margin that
+// covers the rounding of the face coordinates (1e-6 relative + 1e-10 absolute, orders of magnitude above 1 ulp).
+// Typical result on the 0.5 m / 1.0 m maps: ~3 voxels and ~15-25 candidate distances per point instead of 27 / 145+.
+//
+// The loop is organised around memory-level parallelism, because the path is latency-bound once pruned: the
+// centre voxel first, then rounds of up to four neighbour voxels whose home hash slots are loaded together, and
+// every voxel's points are read four at a time (eight independent 16-byte loads per lane).  Map data is read
+// straight from L1/L2 (the map fits the 126 MB L2).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(KICP_WARPS * 32, 2) k_assoc_pruned(RegState *st, const double *__restrict__ scan, int n, MapView map) {
+    if (st->done) return;
+    __shared__ double s_T[12];
+    __shared__ double s_part[KICP_WARPS][8];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned FULL = 0xFFFFFFFFu;
+    if (threadIdx.x < 9) s_T[threadIdx.x] = st->R[threadIdx.x];
+    if (threadIdx.x >= 9 && threadIdx.x < 12) s_T[threadIdx.x] = st->t[threadIdx.x - 9];
+    __syncthreads();
+    const double tau = st->tau, vs = map.voxel_size;
+    const int num_windows = (n + 31) >> 5;
+    double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0, cntN = 0, ssq = 0;
+
+    while (true) {
+        int w = 0;
+        if (lane == 0) w = (int)atomicAdd(&st->window_counter, 1u);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= num_windows) break;
+        const int i = w * 32 + lane;
+        const bool valid = i < n;
+        double px = 0, py = 0, pz = 0;
+        if (valid) px = scan[3 * (size_t)i], py = scan[3 * (size_t)i + 1], pz = scan[3 * (size_t)i + 2];
+        const double qx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[9];
+        const double qy = s_T[3] * px + s_T[4] * py + s_T[5] * pz + s_T[10];
+        const double qz = s_T[6] * px + s_T[7] * py + s_T[8] * pz + s_T[11];
+        const int vx = voxel_coord(qx, vs), vy = voxel_coord(qy, vs), vz = voxel_coord(qz, vs);
+        // squared gaps to the six faces of the query voxel
+        double t;
+        t = (double)(vx + 1) * vs - qx; const double gxp = t * t;
+        t = qx - (double)vx * vs;       const double gxm = t * t;
+        t = (double)(vy + 1) * vs - qy; const double gyp = t * t;
+        t = qy - (double)vy * vs;       const double gym = t * t;
+        t = (double)(vz + 1) * vs - qz; const double gzp = t * t;
+        t = qz - (double)vz * vs;       const double gzm = t * t;
+
+        double best = DBL_MAX, bx = 0, by = 0, bz = 0;
+        bool have = false;
+        // round 0: the query's own voxel — it usually yields a best distance that prunes most of the other 26
+        {
+            const uint32_t meta = valid ? map_probe(map, vx, vy, vz) : KICP_SLOT_EMPTY;
+            const int cnt = meta == KICP_SLOT_EMPTY ? 0 : (int)(meta & 0xFFu);
+            scan_voxel(map.pts + (size_t)(meta >> 8) * map.cap * KICP_PSTRIDE, cnt, qx, qy, qz, best, bx, by, bz, have);
+        }
+        unsigned mask = valid ? 0x07FFFFFEu : 0u;  // shifts still to consider, bit k <-> voxel_shifts[k]
+        while (__any_sync(FULL, mask != 0u)) {
+            // drop every shift whose cube is provably too far, then take the next (up to) 4 in KISS order
+            const double bound = best * (1.0 + 1e-6) + 1e-10;
+            mask &= (kX0 | (gxp <= bound ? kXP : 0u) | (gxm <= bound ? kXM : 0u)) &
+                    (kY0 | (gyp <= bound ? kYP : 0u) | (gym <= bound ? kYM : 0u)) &
+                    (kZ0 | (gzp <= bound ? kZP : 0u) | (gzm <= bound ? kZM : 0u));
+            int kx[4], ky[4], kz[4];
+            uint32_t hh[4];
+            double lb[4];
+            bool use[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                use[u] = false;
+                kx[u] = ky[u] = kz[u] = 0, hh[u] = 0, lb[u] = 0.0;
+                while (mask) {
+                    const int k = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int sx = shift_x(k), sy = shift_y(k), sz = shift_z(k);
+                    const double lb2 = (sx > 0 ? gxp : (sx < 0 ? gxm : 0.0)) + (sy > 0 ? gyp : (sy < 0 ? gym : 0.0)) +
+                                       (sz > 0 ? gzp : (sz < 0 ? gzm : 0.0));
+                    if (lb2 > bound) continue;
+                    use[u] = true, lb[u] = lb2;
+                    kx[u] = vx + sx, ky[u] = vy + sy, kz[u] = vz + sz;
+                    hh[u] = voxel_hash(kx[u], ky[u], kz[u]) & map.mask;
+                    break;
+                }
+            }
+            // four independent home-slot loads in flight, then resolve the (rare) longer probe chains
+            int4 s0[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s0[u] = __ldg(&map.slots[hh[u]]);
+            uint32_t metas[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint32_t meta = KICP_SLOT_EMPTY;
+                if (use[u]) {
+                    int4 sl = s0[u];
+                    uint32_t h = hh[u];
+                    while (true) {
+                        if ((uint32_t)sl.w == KICP_SLOT_EMPTY) break;
+                        if (sl.x == kx[u] && sl.y == ky[u] && sl.z == kz[u]) {
+                            meta = (uint32_t)sl.w;
+                            break;
+                        }
+                        h = (h + 1) & map.mask;
+                        sl = __ldg(&map.slots[h]);
+                    }
+                }
+                metas[u] = meta;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                // re-check against the best found meanwhile; KISS order is kept, so strict < resolves ties identically
+                int cnt = metas[u] == KICP_SLOT_EMPTY ? 0 : (int)(metas[u] & 0xFFu);
+                if (lb[u] > best * (1.0 + 1e-6) + 1e-10) cnt = 0;
+                if (__any_sync(FULL, cnt > 0))
+                    scan_voxel(map.pts + (size_t)(metas[u] >> 8) * map.cap * KICP_PSTRIDE, cnt, qx, qy, qz, best, bx, by, bz, have);
+            }
+        }
+        if (have) {
+            const double rx = qx - bx, ry = qy - by, rz = qz - bz;  // r = T p - n
+            const double rr = rx * rx + ry * ry + rz * rz;
+            if (sqrt(rr) < tau) {  // distance < max_correspondance_distance   (Registration.cpp:75)
+                const double c0x = s_T[0], c0y = s_T[3], c0z = s_T[6];
+                const double c1x = s_T[1] * px - s_T[0] * py, c1y = s_T[4] * px - s_T[3] * py, c1z = s_T[7] * px - s_T[6] * py;
+                a00 += c0x * c0x + c0y * c0y + c0z * c0z;
+                a01 += c0x * c1x + c0y * c1y + c0z * c1z;
+                a11 += c1x * c1x + c1y * c1y + c1z * c1z;
+                b0 += c0x * rx + c0y * ry + c0z * rz;
+                b1 += c1x * rx + c1y * ry + c1z * rz;
+                cntN += 1.0;
+                ssq += rr;
+            }
+        }
+    }
+
+    double v[7] = {a00, a01, a11, b0, b1, cntN, ssq};
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) s_part[wid][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double s = 0.0;
+        for (int k = 0; k < KICP_WARPS; ++k) s += s_part[k][threadIdx.x];
+        atomicAdd(&st->acc[threadIdx.x], s);
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicAdd(&st->ticket, 1u);
+        s_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        st->ticket = 0;
+        st->window_counter = 0;
+        if (st->fused_tail) solve_and_update(st);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------- host
+// Kernel variant and binning granularity are per-context options (kicp_ctx_set_option); the defaults are the
+// measured best (profiles/) and can be overridden with KICP_ASSOC=staged|pruned and KICP_SORT_BITS=0..30 so that
+// bench.py / ncu can compare variants on the same inputs.
+extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value) {
+    if (!c || !name) return KICP_ERR_INVALID;
+    if (!strcmp(name, "assoc_variant")) {
+        if (value != 0 && value != 1) return KICP_ERR_INVALID;
+        c->assoc_variant = value;
+    } else if (!strcmp(name, "sort_bits")) {
+        if (value < 0 || value > 30) return KICP_ERR_INVALID;
+        c->sort_bits = value;
+    } else {
+        return KICP_ERR_INVALID;
+    }
+    return KICP_OK;
+}
+
 static size_t assoc_smem_bytes() {
     return (size_t)KICP_WARPS * ((3 * KICP_CH + 3 * 32 + 32) * sizeof(double) + (KICP_CH + 32) * sizeof(int));
 }
@@ -393,6 +607,8 @@ static int reg_reserve(kicp_ctx *c, int64_t n) {
         int per_sm = 0;
         KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc, KICP_WARPS * 32, assoc_smem_bytes()));
         c->assoc_ctas_per_sm = std::max(per_sm, 1);
+        KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc_pruned, KICP_WARPS * 32, 0));
+        c->pruned_ctas_per_sm = std::max(per_sm, 1);
     }
     if (n <= c->scratch_cap) return KICP_OK;
     KICP_CUDA(cudaStreamSynchronize(c->stream));
@@ -462,13 +678,14 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
     KICP_CHECK_LAUNCH(c);
     if (a.max_iter > 0) {
         const double *d_pts = scan->d_xyz;
-        if (n > 0) {
+        const int sbits = c->sort_bits;
+        if (n > 0 && sbits > 0) {
             const int threads = 256, blocks = (n + threads - 1) / threads;
             k_morton_keys<<<blocks, threads, 0, c->stream>>>(c->d_state, scan->d_xyz, n, m->voxel_size, c->d_keys, c->d_idx);
             KICP_CHECK_LAUNCH(c);
             size_t bytes = c->sort_tmp_bytes;
-            KICP_CUDA(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, bytes, c->d_keys, c->d_keys_alt, c->d_idx, c->d_idx_alt, n, 0,
-                                                      30, c->stream));
+            KICP_CUDA(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, bytes, c->d_keys, c->d_keys_alt, c->d_idx, c->d_idx_alt, n,
+                                                      30 - sbits, 30, c->stream));
             c->launches += 3;  // CUB's histogram + onesweep passes (library kernels, not counted individually)
             k_gather<<<blocks, threads, 0, c->stream>>>(scan->d_xyz, c->d_idx_alt, n, c->d_sorted);
             KICP_CHECK_LAUNCH(c);
@@ -477,7 +694,9 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
         if (pr) KICP_CUDA(cudaEventRecord(pr->prep1, c->stream));
         const int num_windows = (n + 31) / 32;
         // persistent-style grid: every CTA is resident and pulls windows from a device-side counter
-        int grid = std::max(1, std::min((num_windows + KICP_WARPS - 1) / KICP_WARPS, c->sm_count * c->assoc_ctas_per_sm));
+        const bool pruned = c->assoc_variant == 1;
+        const int per_sm = pruned ? c->pruned_ctas_per_sm : c->assoc_ctas_per_sm;
+        int grid = std::max(1, std::min((num_windows + KICP_WARPS - 1) / KICP_WARPS, c->sm_count * per_sm));
         for (int j = 0; j < a.max_iter; ++j) {
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (pr) {
@@ -486,7 +705,10 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
                 pr->it.push_back(e0), pr->it.push_back(e1);
                 KICP_CUDA(cudaEventRecord(e0, c->stream));
             }
-            k_assoc<<<grid, KICP_WARPS * 32, assoc_smem_bytes(), c->stream>>>(c->d_state, d_pts, n, m->view());
+            if (pruned)
+                k_assoc_pruned<<<grid, KICP_WARPS * 32, 0, c->stream>>>(c->d_state, d_pts, n, m->view());
+            else
+                k_assoc<<<grid, KICP_WARPS * 32, assoc_smem_bytes(), c->stream>>>(c->d_state, d_pts, n, m->view());
             KICP_CHECK_LAUNCH(c);
             if (pr) KICP_CUDA(cudaEventRecord(e1, c->stream));
             if (sharded) {

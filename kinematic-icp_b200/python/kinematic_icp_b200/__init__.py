@@ -39,6 +39,9 @@ class Context:
     def launch_count(self):
         return int(lib().kicp_ctx_launch_count(self.h))
 
+    def set_option(self, name, value):
+        check(lib().kicp_ctx_set_option(self.h, name.encode(), int(value)), "kicp_ctx_set_option")
+
     def profile_begin(self):
         check(lib().kicp_ctx_profile_begin(self.h), "kicp_ctx_profile_begin")
 

@@ -67,6 +67,7 @@ SYMBOLS = [
     ("kicp_ctx_synchronize", C.c_int, [_P]),
     ("kicp_ctx_stream", _P, [_P]),
     ("kicp_ctx_launch_count", C.c_int64, [_P]),
+    ("kicp_ctx_set_option", C.c_int, [_P, C.c_char_p, C.c_int32]),
     ("kicp_ctx_profile_begin", C.c_int, [_P]),
     ("kicp_ctx_profile_end", C.c_int, [_P, C.POINTER(Profile)]),
     ("kicp_host_alloc", C.c_int, [C.c_uint64, C.POINTER(_P)]),

@@ -170,3 +170,43 @@ double kor_threshold_compute(void *h) { return static_cast<CorrespondenceThresho
 void kor_threshold_reset(void *h) { static_cast<CorrespondenceThreshold *>(h)->Reset(); }
 
 }  // extern "C"
+
+// Diagnostic (tests / design analysis): work the exact-pruning traversal does per point — hash probes issued and
+// candidate distances evaluated — with the same pruning rule as the CUDA kernel k_assoc_pruned.
+extern "C" void kor_pruned_work(void *h, const double *xyz, int64_t n, const double *pose7, int32_t *probes, int32_t *cands,
+                                int32_t *empty_centre) {
+    auto *m = static_cast<VoxelHashMap *>(h);
+    const SE3 T = SE3::from_pose7(pose7);
+    const double vs = m->voxel_size_;
+    for (int64_t i = 0; i < n; ++i) {
+        const Vec3 q = transform(T, {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]});
+        const Voxel v = PointToVoxel(q, vs);
+        const double g[3][2] = {{(v.x + 1) * vs - q.x, q.x - v.x * vs}, {(v.y + 1) * vs - q.y, q.y - v.y * vs}, {(v.z + 1) * vs - q.z, q.z - v.z * vs}};
+        double best = 1.7976931348623157e308;
+        int np = 0, nc = 0;
+        for (int k = 0; k < 27; ++k) {
+            const Voxel &s = kVoxelShifts[k];
+            const int sh[3] = {s.x, s.y, s.z};
+            double lb2 = 0;
+            for (int a = 0; a < 3; ++a) {
+                const double d = sh[a] > 0 ? g[a][0] : (sh[a] < 0 ? g[a][1] : 0.0);
+                lb2 += d * d;
+            }
+            if (lb2 > best * (1 + 1e-6) + 1e-10) continue;
+            ++np;
+            auto it = m->map_.find({v.x + s.x, v.y + s.y, v.z + s.z});
+            if (it == m->map_.end()) {
+                if (k == 0 && empty_centre) empty_centre[i] = 1;
+                continue;
+            }
+            if (k == 0 && empty_centre) empty_centre[i] = 0;
+            for (const Vec3 &p : it->second) {
+                ++nc;
+                const Vec3 d = p - q;
+                const double d2 = d.x * d.x + d.y * d.y + d.z * d.z;
+                if (d2 < best) best = d2;
+            }
+        }
+        probes[i] = np, cands[i] = nc;
+    }
+}

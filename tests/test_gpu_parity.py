@@ -135,13 +135,22 @@ def test_registration_vs_reference_golden(oracle, gpu_ctx, name):
 
 @pytest.mark.parametrize("cfg", [1, 2, 3, 4])
 def test_registration_configs_vs_oracle(oracle, gpu_ctx, workload, cfg):
-    """BASELINE.json configs 1-4 at full size: pose, iteration count, per-iteration N and sums."""
+    """BASELINE.json configs 1-4 at full size: pose, iteration count, per-iteration N and sums — for both kernel
+    variants (pruned thread-per-point, staged-through-shared-memory) and with the binning sort on and off."""
     import kinematic_icp_b200 as kb
     ko = oracle
     w = workload(cfg)
     gm = gpu_map_from_oracle(kb, gpu_ctx, w.map)
-    pose, dt, ang = check_registration(ko, kb, gpu_ctx, w.map, gm, w.scan, w.last_pose, w.rel_odom, w.tau)
-    print("cfg%d N=%d M=%d pose delta %.3e m %.3e rad" % (cfg, w.N, w.map.num_points(), dt, ang))
+    try:
+        for variant, sort_bits in ((1, 30), (0, 30), (1, 0), (1, 12)):
+            gpu_ctx.set_option("assoc_variant", variant)
+            gpu_ctx.set_option("sort_bits", sort_bits)
+            pose, dt, ang = check_registration(ko, kb, gpu_ctx, w.map, gm, w.scan, w.last_pose, w.rel_odom, w.tau)
+            print("cfg%d variant=%d sort_bits=%d N=%d M=%d pose delta %.3e m %.3e rad" %
+                  (cfg, variant, sort_bits, w.N, w.map.num_points(), dt, ang))
+    finally:
+        gpu_ctx.set_option("assoc_variant", 1)
+        gpu_ctx.set_option("sort_bits", 30)
     gm.close()
 
 
