@@ -52,8 +52,42 @@ __host__ __device__ __forceinline__ uint32_t voxel_hash(int x, int y, int z) {
 // multiplication by the reciprocal, so voxel boundaries fall exactly where the reference puts them.
 __device__ __forceinline__ int voxel_coord(double x, double vs) { return (int)floor(x / vs); }
 
+// DIVERGENCE SAFETY.  nvcc keeps loop-invariant kernel parameters (table mask, base pointers) in UNIFORM registers,
+// which are shared by the 32 lanes of a warp.  Inside a per-lane loop (a hash-probe chain, a voxel scan) that is only
+// sound while the sibling lanes wait at the reconvergence point; observed on sm_100a (cuda-gdb): siblings
+// ran past a BSYNC.RECONVERGENT, re-used the uniform register, and the lanes still probing read mask == 0 and spun on
+// slot 0 forever.  Two rules keep every kernel in this library safe (scripts/check_ur_loops.py verifies rule 1 on the
+// SASS):
+//   1. the map view used inside per-lane loops is read back from a PER-LANE copy in shared memory (MapRegs): a value
+//      loaded from a lane-dependent address cannot be proven warp-uniform, so ptxas keeps it in per-thread registers
+//      (a copy at a uniform address is not enough — ptxas moves it back into a uniform register with R2UR);
+//   2. every divergent phase ends with a hard __syncwarp().
+struct MapRegs {
+    const int4 *slots;
+    const double *pts;
+    uint32_t mask;
+    int cap;
+};
+
+// All threads of the CTA call this once at kernel start (it contains a __syncthreads()); shared_copies[32].
+__device__ __forceinline__ MapRegs map_regs(const MapView &m, MapView *shared_copies) {
+    if (threadIdx.x < 32) shared_copies[threadIdx.x] = m;
+    __syncthreads();
+    const volatile MapView *v = shared_copies + (threadIdx.x & 31);
+    MapRegs r;
+    r.slots = v->slots, r.pts = v->pts, r.mask = v->mask, r.cap = v->cap;
+    return r;
+}
+
+// Same trick for a single 32-bit value (the table mask of the map-maintenance kernels): shared_words[32].
+__device__ __forceinline__ uint32_t lane_private(uint32_t v, uint32_t *shared_words) {
+    if (threadIdx.x < 32) shared_words[threadIdx.x] = v;
+    __syncthreads();
+    return ((const volatile uint32_t *)shared_words)[threadIdx.x & 31];
+}
+
 // Read-only probe (no concurrent writers): returns the slot's meta word, or KICP_SLOT_EMPTY when absent.
-__device__ __forceinline__ uint32_t map_probe(const MapView &m, int kx, int ky, int kz) {
+__device__ __forceinline__ uint32_t map_probe(const MapRegs &m, int kx, int ky, int kz) {
     uint32_t h = voxel_hash(kx, ky, kz) & m.mask;
     while (true) {
         const int4 s = __ldg(&m.slots[h]);

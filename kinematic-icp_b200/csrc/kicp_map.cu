@@ -173,7 +173,9 @@ __device__ __forceinline__ void table_insert_unique(int4 *slots, uint32_t mask, 
     }
 }
 
-__global__ void k_table_rebuild(int4 *slots, uint32_t mask, const int4 *blk, uint32_t num_blocks) {
+__global__ void k_table_rebuild(int4 *slots, uint32_t mask_in, const int4 *blk, uint32_t num_blocks) {
+    __shared__ uint32_t s_mask[32];
+    const uint32_t mask = lane_private(mask_in, s_mask);  // divergence safety, see kicp_device.cuh
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= num_blocks) return;
     const int4 h = blk[b];
@@ -185,6 +187,8 @@ __global__ void k_table_rebuild(int4 *slots, uint32_t mask, const int4 *blk, uin
 __global__ void k_add_find_or_create(MapRW m, const double *__restrict__ xyz, int64_t n, int has_pose, Pose pose,
                                      double *__restrict__ xyz_t, int32_t *__restrict__ pend_next, uint32_t *counters,
                                      int32_t *__restrict__ touched) {
+    __shared__ uint32_t s_mask[32];
+    const uint32_t tmask = lane_private(m.mask, s_mask);  // divergence safety, see kicp_device.cuh
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
@@ -195,7 +199,7 @@ __global__ void k_add_find_or_create(MapRW m, const double *__restrict__ xyz, in
     }
     xyz_t[3 * i] = px, xyz_t[3 * i + 1] = py, xyz_t[3 * i + 2] = pz;
     const int kx = voxel_coord(px, m.voxel_size), ky = voxel_coord(py, m.voxel_size), kz = voxel_coord(pz, m.voxel_size);
-    uint32_t h = voxel_hash(kx, ky, kz) & m.mask;
+    uint32_t h = voxel_hash(kx, ky, kz) & tmask;
     uint32_t block = 0xFFFFFFFFu;
     volatile int4 *vs = m.slots;
     while (true) {
@@ -223,7 +227,7 @@ __global__ void k_add_find_or_create(MapRW m, const double *__restrict__ xyz, in
             block = meta >> 8;
             break;
         }
-        h = (h + 1) & m.mask;
+        h = (h + 1) & tmask;
     }
     const int32_t prev = atomicExch(&m.pend_head[block], (int32_t)i);
     pend_next[i] = prev;
@@ -235,6 +239,8 @@ __global__ void k_add_find_or_create(MapRW m, const double *__restrict__ xyz, in
 //   skip if the voxel is full, or if any stored point is closer than map_resolution; else append.
 __global__ void k_add_commit(MapRW m, const double *__restrict__ xyz_t, const int32_t *__restrict__ pend_next,
                              uint32_t *counters, const int32_t *__restrict__ touched, double map_resolution) {
+    __shared__ uint32_t s_mask[32];
+    const uint32_t tmask = lane_private(m.mask, s_mask);  // divergence safety, see kicp_device.cuh
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= counters[1]) return;
     const uint32_t b = (uint32_t)touched[t];
@@ -267,14 +273,14 @@ __global__ void k_add_commit(MapRW m, const double *__restrict__ xyz_t, const in
     if (cnt != cnt0) {
         m.blk[b].w = cnt;
         atomicAdd(&counters[3], (uint32_t)(cnt - cnt0));
-        uint32_t h = voxel_hash(hdr.x, hdr.y, hdr.z) & m.mask;
+        uint32_t h = voxel_hash(hdr.x, hdr.y, hdr.z) & tmask;
         while (true) {
             const int4 s = m.slots[h];
             if (s.x == hdr.x && s.y == hdr.y && s.z == hdr.z && (uint32_t)s.w != KICP_SLOT_EMPTY) {
                 m.slots[h].w = (int)((b << 8) | (uint32_t)cnt);
                 break;
             }
-            h = (h + 1) & m.mask;
+            h = (h + 1) & tmask;
         }
     }
 }
@@ -365,15 +371,17 @@ __global__ void k_load_voxels(int4 *blk, double *pts, int cap, const int32_t *ke
 // shifts in KISS order, per voxel first-minimum of (x - q).norm() under strict <, global strict <.
 __global__ void k_nearest(MapView m, const double *__restrict__ q, int64_t n, double *__restrict__ out_pts,
                           double *__restrict__ out_dist) {
+    __shared__ MapView s_map[32];
+    const MapRegs mr = map_regs(m, s_map);  // per-thread copy of the map view (divergence safety, kicp_device.cuh)
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
     const int vx = voxel_coord(qx, m.voxel_size), vy = voxel_coord(qy, m.voxel_size), vz = voxel_coord(qz, m.voxel_size);
     double bx = 0.0, by = 0.0, bz = 0.0, bd = DBL_MAX;
     for (int k = 0; k < 27; ++k) {
-        const uint32_t meta = map_probe(m, vx + shift_x(k), vy + shift_y(k), vz + shift_z(k));
+        const uint32_t meta = map_probe(mr, vx + shift_x(k), vy + shift_y(k), vz + shift_z(k));
         if (meta == KICP_SLOT_EMPTY) continue;
-        const double *vp = m.pts + (size_t)(meta >> 8) * m.cap * KICP_PSTRIDE;
+        const double *vp = mr.pts + (size_t)(meta >> 8) * mr.cap * KICP_PSTRIDE;
         const int cnt = (int)(meta & 0xFFu);
         for (int j = 0; j < cnt; ++j) {
             const double dx = vp[KICP_PSTRIDE * j] - qx, dy = vp[KICP_PSTRIDE * j + 1] - qy, dz = vp[KICP_PSTRIDE * j + 2] - qz;

@@ -12,6 +12,9 @@
 // (Registration.cpp:119-125, 159-167, 181-184) — so the iteration loop never returns to the host.
 // The correspondence list of the reference is never materialised: association and linearisation use the same T.
 #include <cfloat>
+#include <chrono>
+#include <cstddef>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
@@ -241,6 +244,8 @@ __global__ void __launch_bounds__(KICP_WARPS * 32) k_assoc(RegState *st, const d
     if (threadIdx.x < 9) s_T[threadIdx.x] = st->R[threadIdx.x];
     if (threadIdx.x >= 9 && threadIdx.x < 12) s_T[threadIdx.x] = st->t[threadIdx.x - 9];
     __syncthreads();
+    __shared__ MapView s_map[32];
+    const MapRegs mr = map_regs(map, s_map);  // per-thread copy of the map view (divergence safety, kicp_device.cuh)
     const double tau = st->tau, vs = map.voxel_size;
     const int num_windows = (n + 31) >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -278,9 +283,10 @@ __global__ void __launch_bounds__(KICP_WARPS * 32) k_assoc(RegState *st, const d
             int cnt = 0;
             unsigned blk = 0;
             if (lane < 27) {
-                const uint32_t meta = map_probe(map, cvx + shift_x(lane), cvy + shift_y(lane), cvz + shift_z(lane));
+                const uint32_t meta = map_probe(mr, cvx + shift_x(lane), cvy + shift_y(lane), cvz + shift_z(lane));
                 if (meta != KICP_SLOT_EMPTY) cnt = (int)(meta & 0xFFu), blk = meta >> 8;
             }
+            __syncwarp();
             int incl = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -302,12 +308,12 @@ __global__ void __launch_bounds__(KICP_WARPS * 32) k_assoc(RegState *st, const d
             for (int base = 0; base < C; base += KICP_CH) {
                 for (int j = 0; j < cnt; ++j) {
                     const int c = off + j - base;
-                    if (c >= 0 && c < KICP_CH) sg[c] = (int)(blk * (unsigned)map.cap) + j;
+                    if (c >= 0 && c < KICP_CH) sg[c] = (int)(blk * (unsigned)mr.cap) + j;
                 }
                 __syncwarp();
                 const int m = min(KICP_CH, C - base);
                 for (int c = lane; c < m; c += 32) {
-                    const double *gp = map.pts + (size_t)sg[c] * KICP_PSTRIDE;
+                    const double *gp = mr.pts + (size_t)sg[c] * KICP_PSTRIDE;
                     sx[c] = __ldg(gp), sy[c] = __ldg(gp + 1), sz[c] = __ldg(gp + 2);
                 }
                 __syncwarp();
@@ -332,7 +338,7 @@ __global__ void __launch_bounds__(KICP_WARPS * 32) k_assoc(RegState *st, const d
             remaining &= ~gm;
         }
         if (valid && bestg >= 0) {
-            const double *gp = map.pts + (size_t)bestg * KICP_PSTRIDE;
+            const double *gp = mr.pts + (size_t)bestg * KICP_PSTRIDE;
             const double rx = qx - __ldg(gp), ry = qy - __ldg(gp + 1), rz = qz - __ldg(gp + 2);  // r = T p - n
             const double rr = rx * rx + ry * ry + rz * rz;
             if (sqrt(rr) < tau) {  // distance < max_correspondance_distance   (Registration.cpp:75)
@@ -385,27 +391,31 @@ __global__ void __launch_bounds__(KICP_WARPS * 32) k_assoc(RegState *st, const d
 
 
 
-// Scan the `cnt` points of one voxel (32-byte records), four at a time: eight independent 16-byte loads are issued
-// before the first distance is formed.  Strict `<` in storage order keeps the first minimum, as the reference does.
-__device__ __forceinline__ void scan_voxel(const double *__restrict__ vp, int cnt, double qx, double qy, double qz, double &best,
-                                           double &bx, double &by, double &bz, bool &have) {
-    for (int j = 0; __any_sync(0xFFFFFFFFu, j < cnt); j += 4) {
-        double2 xy[4], zw[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (j + u < cnt) {
-                const double2 *p2 = reinterpret_cast<const double2 *>(vp + (size_t)(j + u) * KICP_PSTRIDE);
-                xy[u] = __ldg(p2), zw[u] = __ldg(p2 + 1);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (j + u < cnt) {
-                const double dx = xy[u].x - qx, dy = xy[u].y - qy, dz = zw[u].x - qz;
-                const double d2 = dx * dx + dy * dy + dz * dz;
-                if (d2 < best) best = d2, bx = xy[u].x, by = xy[u].y, bz = zw[u].x, have = true;
-            }
-        }
+// One candidate step: squared distance of the 32-byte record at `p` to the query; strict `<` keeps the first minimum
+// (candidates are visited in the reference's order).  Only (d2, pointer) are tracked; the winner is re-read once.
+__device__ __forceinline__ void candidate_step(const double2 xy, const double2 zw, const double *p, double qx, double qy, double qz,
+                                               double &best, const double *&bestp) {
+    const double dx = xy.x - qx, dy = xy.y - qy, dz = zw.x - qz;
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    if (d2 < best) best = d2, bestp = p;
+}
+
+// Scan the `cnt` points of one voxel, two per step (four independent 16-byte loads in flight per lane).  The loop is
+// per-lane (no warp vote): lanes with fewer points simply leave earlier and reconverge behind it.
+__device__ __forceinline__ void scan_voxel(const double *vp, int cnt, double qx, double qy, double qz, double &best,
+                                           const double *&bestp) {
+    int j = 0;
+    for (; j + 1 < cnt; j += 2) {
+        const double *p0 = vp + (size_t)j * KICP_PSTRIDE, *p1 = p0 + KICP_PSTRIDE;
+        const double2 a0 = __ldg(reinterpret_cast<const double2 *>(p0)), b0 = __ldg(reinterpret_cast<const double2 *>(p0) + 1);
+        const double2 a1 = __ldg(reinterpret_cast<const double2 *>(p1)), b1 = __ldg(reinterpret_cast<const double2 *>(p1) + 1);
+        candidate_step(a0, b0, p0, qx, qy, qz, best, bestp);
+        candidate_step(a1, b1, p1, qx, qy, qz, best, bestp);
+    }
+    if (j < cnt) {
+        const double *p0 = vp + (size_t)j * KICP_PSTRIDE;
+        const double2 a0 = __ldg(reinterpret_cast<const double2 *>(p0)), b0 = __ldg(reinterpret_cast<const double2 *>(p0) + 1);
+        candidate_step(a0, b0, p0, qx, qy, qz, best, bestp);
     }
 }
 
@@ -426,7 +436,7 @@ __device__ __forceinline__ void scan_voxel(const double *__restrict__ vp, int cn
 // every voxel's points are read four at a time (eight independent 16-byte loads per lane).  Map data is read
 // straight from L1/L2 (the map fits the 126 MB L2).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(KICP_WARPS * 32, 2) k_assoc_pruned(RegState *st, const double *__restrict__ scan, int n, MapView map) {
+__global__ void __launch_bounds__(KICP_WARPS * 32, 3) k_assoc_pruned(RegState *st, const double *__restrict__ scan, int n, MapView map) {
     if (st->done) return;
     __shared__ double s_T[12];
     __shared__ double s_part[KICP_WARPS][8];
@@ -436,6 +446,8 @@ __global__ void __launch_bounds__(KICP_WARPS * 32, 2) k_assoc_pruned(RegState *s
     if (threadIdx.x < 9) s_T[threadIdx.x] = st->R[threadIdx.x];
     if (threadIdx.x >= 9 && threadIdx.x < 12) s_T[threadIdx.x] = st->t[threadIdx.x - 9];
     __syncthreads();
+    __shared__ MapView s_map[32];
+    const MapRegs mr = map_regs(map, s_map);  // per-thread copy of the map view (divergence safety, kicp_device.cuh)
     const double tau = st->tau, vs = map.voxel_size;
     const int num_windows = (n + 31) >> 5;
     double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0, cntN = 0, ssq = 0;
@@ -462,73 +474,85 @@ __global__ void __launch_bounds__(KICP_WARPS * 32, 2) k_assoc_pruned(RegState *s
         t = (double)(vz + 1) * vs - qz; const double gzp = t * t;
         t = qz - (double)vz * vs;       const double gzm = t * t;
 
-        double best = DBL_MAX, bx = 0, by = 0, bz = 0;
-        bool have = false;
+        double best = DBL_MAX;
+        const double *bestp = nullptr;
+        const uint32_t tmask = mr.mask;
+        const int4 *tslots = mr.slots;
+        const double *tpts = mr.pts;
+        const size_t tstride = (size_t)mr.cap * KICP_PSTRIDE;
         // round 0: the query's own voxel — it usually yields a best distance that prunes most of the other 26
-        {
-            const uint32_t meta = valid ? map_probe(map, vx, vy, vz) : KICP_SLOT_EMPTY;
-            const int cnt = meta == KICP_SLOT_EMPTY ? 0 : (int)(meta & 0xFFu);
-            scan_voxel(map.pts + (size_t)(meta >> 8) * map.cap * KICP_PSTRIDE, cnt, qx, qy, qz, best, bx, by, bz, have);
+        if (valid) {
+            const uint32_t meta = map_probe(mr, vx, vy, vz);
+            if (meta != KICP_SLOT_EMPTY) scan_voxel(tpts + (size_t)(meta >> 8) * tstride, (int)(meta & 0xFFu), qx, qy, qz, best, bestp);
         }
+        __syncwarp();
         unsigned mask = valid ? 0x07FFFFFEu : 0u;  // shifts still to consider, bit k <-> voxel_shifts[k]
-        while (__any_sync(FULL, mask != 0u)) {
-            // drop every shift whose cube is provably too far, then take the next (up to) 4 in KISS order
-            const double bound = best * (1.0 + 1e-6) + 1e-10;
-            mask &= (kX0 | (gxp <= bound ? kXP : 0u) | (gxm <= bound ? kXM : 0u)) &
-                    (kY0 | (gyp <= bound ? kYP : 0u) | (gym <= bound ? kYM : 0u)) &
-                    (kZ0 | (gzp <= bound ? kZP : 0u) | (gzm <= bound ? kZM : 0u));
-            int kx[4], ky[4], kz[4];
-            uint32_t hh[4];
-            double lb[4];
-            bool use[4];
+        while (__any_sync(FULL, mask != 0u)) {  // warp-uniform loop; inside a round every lane walks its own voxels
+            if (mask) {
+                // drop every shift whose cube is provably too far, then take the next (up to) 4 in KISS order
+                const double bound = best * (1.0 + 1e-6) + 1e-10;
+                mask &= (kX0 | (gxp <= bound ? kXP : 0u) | (gxm <= bound ? kXM : 0u)) &
+                        (kY0 | (gyp <= bound ? kYP : 0u) | (gym <= bound ? kYM : 0u)) &
+                        (kZ0 | (gzp <= bound ? kZP : 0u) | (gzm <= bound ? kZM : 0u));
+                int kx[4], ky[4], kz[4];
+                uint32_t hh[4];
+                double lb[4];
+                bool use[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                use[u] = false;
-                kx[u] = ky[u] = kz[u] = 0, hh[u] = 0, lb[u] = 0.0;
-                while (mask) {
-                    const int k = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const int sx = shift_x(k), sy = shift_y(k), sz = shift_z(k);
-                    const double lb2 = (sx > 0 ? gxp : (sx < 0 ? gxm : 0.0)) + (sy > 0 ? gyp : (sy < 0 ? gym : 0.0)) +
-                                       (sz > 0 ? gzp : (sz < 0 ? gzm : 0.0));
-                    if (lb2 > bound) continue;
-                    use[u] = true, lb[u] = lb2;
-                    kx[u] = vx + sx, ky[u] = vy + sy, kz[u] = vz + sz;
-                    hh[u] = voxel_hash(kx[u], ky[u], kz[u]) & map.mask;
-                    break;
-                }
-            }
-            // four independent home-slot loads in flight, then resolve the (rare) longer probe chains
-            int4 s0[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) s0[u] = __ldg(&map.slots[hh[u]]);
-            uint32_t metas[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                uint32_t meta = KICP_SLOT_EMPTY;
-                if (use[u]) {
-                    int4 sl = s0[u];
-                    uint32_t h = hh[u];
-                    while (true) {
-                        if ((uint32_t)sl.w == KICP_SLOT_EMPTY) break;
-                        if (sl.x == kx[u] && sl.y == ky[u] && sl.z == kz[u]) {
-                            meta = (uint32_t)sl.w;
-                            break;
-                        }
-                        h = (h + 1) & map.mask;
-                        sl = __ldg(&map.slots[h]);
+                for (int u = 0; u < 4; ++u) {
+                    use[u] = false;
+                    kx[u] = ky[u] = kz[u] = 0, hh[u] = 0, lb[u] = 0.0;
+                    while (mask) {
+                        const int k = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const int sx = shift_x(k), sy = shift_y(k), sz = shift_z(k);
+                        const double lb2 = (sx > 0 ? gxp : (sx < 0 ? gxm : 0.0)) + (sy > 0 ? gyp : (sy < 0 ? gym : 0.0)) +
+                                           (sz > 0 ? gzp : (sz < 0 ? gzm : 0.0));
+                        if (lb2 > bound) continue;
+                        use[u] = true, lb[u] = lb2;
+                        kx[u] = vx + sx, ky[u] = vy + sy, kz[u] = vz + sz;
+                        hh[u] = voxel_hash(kx[u], ky[u], kz[u]) & tmask;
+                        break;
                     }
                 }
-                metas[u] = meta;
-            }
+                // four independent home-slot loads in flight, then resolve the (rare) longer probe chains
+                int4 s0[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                // re-check against the best found meanwhile; KISS order is kept, so strict < resolves ties identically
-                int cnt = metas[u] == KICP_SLOT_EMPTY ? 0 : (int)(metas[u] & 0xFFu);
-                if (lb[u] > best * (1.0 + 1e-6) + 1e-10) cnt = 0;
-                if (__any_sync(FULL, cnt > 0))
-                    scan_voxel(map.pts + (size_t)(metas[u] >> 8) * map.cap * KICP_PSTRIDE, cnt, qx, qy, qz, best, bx, by, bz, have);
+                for (int u = 0; u < 4; ++u)
+                    if (use[u]) s0[u] = __ldg(&tslots[hh[u]]);
+                uint32_t metas[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint32_t meta = KICP_SLOT_EMPTY;
+                    if (use[u]) {
+                        int4 sl = s0[u];
+                        uint32_t h = hh[u];
+                        while (true) {
+                            if ((uint32_t)sl.w == KICP_SLOT_EMPTY) break;
+                            if (sl.x == kx[u] && sl.y == ky[u] && sl.z == kz[u]) {
+                                meta = (uint32_t)sl.w;
+                                break;
+                            }
+                            h = (h + 1) & tmask;
+                            sl = __ldg(&tslots[h]);
+                        }
+                    }
+                    metas[u] = meta;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    // re-check against the best found meanwhile; KISS order is kept, so strict < resolves ties identically
+                    if (metas[u] != KICP_SLOT_EMPTY && !(lb[u] > best * (1.0 + 1e-6) + 1e-10))
+                        scan_voxel(tpts + (size_t)(metas[u] >> 8) * tstride, (int)(metas[u] & 0xFFu), qx, qy, qz, best, bestp);
+                }
             }
+            __syncwarp();
+        }
+        const bool have = bestp != nullptr;
+        double bx = 0, by = 0, bz = 0;
+        if (have) {
+            const double2 a = __ldg(reinterpret_cast<const double2 *>(bestp)), b = __ldg(reinterpret_cast<const double2 *>(bestp) + 1);
+            bx = a.x, by = a.y, bz = b.x;
         }
         if (have) {
             const double rx = qx - bx, ry = qy - by, rz = qz - bz;  // r = T p - n
@@ -711,6 +735,20 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
                 k_assoc<<<grid, KICP_WARPS * 32, assoc_smem_bytes(), c->stream>>>(c->d_state, d_pts, n, m->view());
             KICP_CHECK_LAUNCH(c);
             if (pr) KICP_CUDA(cudaEventRecord(e1, c->stream));
+            if (getenv("KICP_DEBUG_SYNC")) {  // debugging aid: locate a misbehaving launch
+                fprintf(stderr, "[kicp] assoc launch %d (variant %d, grid %d, n %d, d_pts %p) ...", j, pruned ? 1 : 0, grid, n,
+                        (const void *)d_pts);
+                cudaEvent_t t0 = pr ? nullptr : nullptr;
+                (void)t0;
+                const auto wall0 = std::chrono::steady_clock::now();
+                cudaError_t e = cudaStreamSynchronize(c->stream);
+                const double wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+                fprintf(stderr, " [%.3f ms]", wall_ms);
+                RegState hs;
+                cudaMemcpy(&hs, c->d_state, offsetof(RegState, result), cudaMemcpyDeviceToHost);
+                fprintf(stderr, " %s iter=%d done=%d ticket=%u wc=%u N=%.0f\n", cudaGetErrorString(e), hs.iter, hs.done, hs.ticket,
+                        hs.window_counter, hs.acc[5]);
+            }
             if (sharded) {
                 KICP_TRY(kicp_comm_allreduce8(c, c->d_state->acc));
                 k_solve<<<1, 32, 0, c->stream>>>(c->d_state);
