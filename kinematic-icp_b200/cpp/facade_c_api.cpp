@@ -1,0 +1,45 @@
+// extern "C" test hooks over the C++ facade (so tests can drive kinematic_icp::pipeline::KinematicICP from Python).
+#include <cstdint>
+#include <vector>
+
+#include "kinematic_icp/pipeline/KinematicICP.hpp"
+
+namespace {
+std::vector<Eigen::Vector3d> to_eigen(const double *xyz, int64_t n) {
+    std::vector<Eigen::Vector3d> v(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i) v[i] = Eigen::Vector3d(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    return v;
+}
+}  // namespace
+
+extern "C" {
+void *kfac_pipeline_create(double max_range, double min_range, double voxel_size, unsigned max_points_per_voxel,
+                           int use_adaptive_threshold, double fixed_threshold, int max_num_iterations, double convergence_criterion,
+                           int max_num_threads, int use_adaptive_reg, double fixed_reg, int deskew) {
+    kinematic_icp::pipeline::Config c;
+    c.max_range = max_range, c.min_range = min_range, c.voxel_size = voxel_size, c.max_points_per_voxel = max_points_per_voxel;
+    c.use_adaptive_threshold = use_adaptive_threshold != 0, c.fixed_threshold = fixed_threshold;
+    c.max_num_iterations = max_num_iterations, c.convergence_criterion = convergence_criterion, c.max_num_threads = max_num_threads;
+    c.use_adaptive_odometry_regularization = use_adaptive_reg != 0, c.fixed_regularization = fixed_reg, c.deskew = deskew != 0;
+    try {
+        return new kinematic_icp::pipeline::KinematicICP(c);
+    } catch (const std::exception &) {
+        return nullptr;
+    }
+}
+void kfac_pipeline_destroy(void *h) { delete static_cast<kinematic_icp::pipeline::KinematicICP *>(h); }
+void kfac_pipeline_set_pose(void *h, const double *pose7) {
+    static_cast<kinematic_icp::pipeline::KinematicICP *>(h)->SetPose(kicp::from_pose7(pose7));
+}
+int64_t kfac_pipeline_register_frame(void *h, const double *xyz, int64_t n, const double *stamps, int64_t n_stamps,
+                                     const double *lidar_to_base7, const double *rel_odom7, double *out_pose7) {
+    auto *p = static_cast<kinematic_icp::pipeline::KinematicICP *>(h);
+    std::vector<double> ts(stamps, stamps + n_stamps);
+    const auto [frame, source] = p->RegisterFrame(to_eigen(xyz, n), ts, kicp::from_pose7(lidar_to_base7), kicp::from_pose7(rel_odom7));
+    kicp::to_pose7(p->pose(), out_pose7);
+    return static_cast<int64_t>(source.size());
+}
+int64_t kfac_pipeline_num_map_points(void *h) {
+    return static_cast<int64_t>(static_cast<kinematic_icp::pipeline::KinematicICP *>(h)->LocalMap().size());
+}
+}

@@ -353,3 +353,67 @@ class RefMap:
         ref_lib().kref_register(self.h, _dp(frame), len(frame), _dp(pose7(last_pose)), _dp(pose7(rel_odom)), float(tau),
                                 int(max_iter), float(conv), int(bool(adaptive)), float(fixed_reg), int(threads), _dp(out))
         return out
+
+
+class _Pipeline:
+    """kinematic_icp::pipeline::KinematicICP behind one of three builds with the same C entry points:
+       prefix kref_  oracle/_ref/libkicp_ref.so      the reference's pipeline + the reference's Registration.cpp + CPU map
+       prefix kgpu_  oracle/_ref/libkicp_ref_gpu.so  the reference's pipeline source over the product's GPU facade
+       prefix kfac_  kinematic-icp_b200/lib/libkinematic_icp_b200.so   the product's own facade pipeline (GPU)."""
+
+    def __init__(self, L, prefix, max_range=100.0, min_range=0.0, voxel_size=1.0, max_points_per_voxel=20, use_adaptive_threshold=True,
+                 fixed_threshold=1.0, max_num_iterations=10, convergence_criterion=1e-3, max_num_threads=1, use_adaptive_reg=True,
+                 fixed_reg=0.0, deskew=False):
+        self.L, self.p = L, prefix
+        f = getattr(L, prefix + "pipeline_create")
+        f.restype = C.c_void_p
+        f.argtypes = [C.c_double, C.c_double, C.c_double, C.c_uint, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int,
+                      C.c_double, C.c_int]
+        getattr(L, prefix + "pipeline_destroy").argtypes = [C.c_void_p]
+        getattr(L, prefix + "pipeline_set_pose").argtypes = [C.c_void_p, c_dp]
+        g = getattr(L, prefix + "pipeline_register_frame")
+        g.argtypes = [C.c_void_p, c_dp, C.c_int64, c_dp, C.c_int64, c_dp, c_dp, c_dp]
+        g.restype = C.c_int64
+        h = getattr(L, prefix + "pipeline_num_map_points")
+        h.argtypes = [C.c_void_p]
+        h.restype = C.c_int64
+        self.h = C.c_void_p(f(max_range, min_range, voxel_size, max_points_per_voxel, int(use_adaptive_threshold), fixed_threshold,
+                              max_num_iterations, convergence_criterion, max_num_threads, int(use_adaptive_reg), fixed_reg, int(deskew)))
+        if not self.h:
+            raise RuntimeError("pipeline_create failed (no CUDA device?)")
+
+    def set_pose(self, p7):
+        getattr(self.L, self.p + "pipeline_set_pose")(self.h, _dp(pose7(p7)))
+
+    def register_frame(self, pts, stamps, lidar_to_base, rel_odom):
+        pts = _pts(pts)
+        stamps = np.ascontiguousarray(stamps, dtype=np.float64)
+        out = np.empty(7)
+        n_src = getattr(self.L, self.p + "pipeline_register_frame")(self.h, _dp(pts), len(pts), _dp(stamps), len(stamps),
+                                                                     _dp(pose7(lidar_to_base)), _dp(pose7(rel_odom)), _dp(out))
+        return out, int(n_src)
+
+    def num_map_points(self):
+        return int(getattr(self.L, self.p + "pipeline_num_map_points")(self.h))
+
+    def close(self):
+        if self.h:
+            getattr(self.L, self.p + "pipeline_destroy")(self.h)
+            self.h = None
+
+
+def ref_pipeline(**kw):
+    return _Pipeline(ref_lib(), "kref_", **kw)
+
+
+def ref_gpu_pipeline(**kw):
+    return _Pipeline(C.CDLL(os.path.join(_HERE, "_ref", "libkicp_ref_gpu.so")), "kgpu_", **kw)
+
+
+def ref_gpu_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libkicp_ref_gpu.so"))
+
+
+def facade_pipeline(**kw):
+    root = os.path.normpath(os.path.join(_HERE, "..", "kinematic-icp_b200", "lib"))
+    return _Pipeline(C.CDLL(os.path.join(root, "libkinematic_icp_b200.so")), "kfac_", **kw)

@@ -49,8 +49,25 @@ def threshold_fixture():
     print("threshold", taus[:3])
 
 
+def pipeline_fixture():
+    """kinematic_icp::pipeline::KinematicICP::RegisterFrame over a short drive — the reference's own KinematicICP.cpp +
+    Registration.cpp + CorrespondenceThreshold.cpp (oracle/_ref), single-threaded."""
+    from oracle import sequences as S
+    out = {}
+    for tag, deskew in (("plain", False), ("deskew", True)):
+        seq = S.make_sequence(deskew=deskew)
+        pipe = ko.ref_pipeline(max_num_threads=1, deskew=deskew)
+        poses, n_src, n_map = S.run_pipeline(pipe, seq)
+        pipe.close()
+        out[tag + "_poses"], out[tag + "_n_src"], out[tag + "_n_map"] = poses, n_src, n_map
+        print("pipeline", tag, n_src.tolist(), n_map.tolist())
+    out.update(S.pack_sequence(S.make_sequence(deskew=False)))  # the frames / odometry both runs consumed
+    np.savez_compressed(os.path.join(HERE, "pipeline_seq.npz"), **out)
+
+
 if __name__ == "__main__":
     assert ko.ref_available(), "build oracle/_ref first: make -C oracle ref"
     registration_fixture("reg_cfg1", 1)
     registration_fixture("reg_cfg2_small", 2, M=30_000, n_az=450)
     threshold_fixture()
+    pipeline_fixture()

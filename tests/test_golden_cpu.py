@@ -52,3 +52,16 @@ def test_oracle_matches_reference_build_live(oracle, workload):
         po, _ = w.map.register(w.scan, w.last_pose, w.rel_odom, w.tau)
         dt, ang = ko.pose_delta(pr, po)
         assert dt < 1e-12 and ang < 1e-12
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cpp/kinematic_icp"), reason="reference tree not present (GPU box)")
+def test_pipeline_golden_is_reproducible(oracle):
+    """The committed pipeline fixture equals a fresh run of the reference's own pipeline sources (threads = 1)."""
+    from oracle import sequences as S
+    ko = oracle
+    z = np.load(os.path.join(GOLDEN, "pipeline_seq.npz"))
+    seq = S.unpack_sequence(z, True)
+    pipe = ko.ref_pipeline(max_num_threads=1, deskew=True)
+    poses, n_src, n_map = S.run_pipeline(pipe, seq)
+    pipe.close()
+    assert np.array_equal(poses, z["deskew_poses"]) and np.array_equal(n_map, z["deskew_n_map"])
