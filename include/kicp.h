@@ -77,8 +77,8 @@ void *kicp_ctx_stream(kicp_ctx *ctx);
 /* Number of this library's kernels launched on the context since creation (bench.py reports gpu_launches). */
 int64_t kicp_ctx_launch_count(kicp_ctx *ctx);
 /* Tuning knobs (defaults are the measured best): "assoc_variant" 0 = 27-voxel neighbourhood staged through shared
- * memory, 1 = exact-pruning thread-per-point kernel; "sort_bits" 0..30 = Morton key bits of the per-registration
- * binning sort (0 disables it).  Every setting computes the same result. */
+ * memory, 1 = exact-pruning thread-per-point kernel; "sort_bits" 0..30 = Morton key bits of the optional per-registration
+ * binning sort (default 0 = off).  Every setting computes the same result. */
 int kicp_ctx_set_option(kicp_ctx *ctx, const char *name, int32_t value);
 /* Per-kernel device timing with CUDA events recorded on the context stream around (a) the binning of each
  * registration (init + Morton keys + radix sort + gather) and (b) every launch of the association kernel.  Only

@@ -48,7 +48,7 @@ struct kicp_ctx {
     int assoc_ctas_per_sm = 1;  // resident CTAs of the association kernel per SM (occupancy query)
     int pruned_ctas_per_sm = 1;
     int assoc_variant = 1;  // 0 = staged (27-voxel neighbourhood through shared memory), 1 = pruned (thread per point)
-    int sort_bits = 30;     // Morton key bits used by the binning sort; 0 disables the binning
+    int sort_bits = 0;      // Morton key bits of the optional binning sort (0 = off, the measured best: DESIGN.md §5)
     kicp_scan *upload_scan = nullptr;  // staging scan used by the host-pointer entry points
     kicp_reg_result *h_result = nullptr;  // pinned bounce buffer for synchronous calls
     // profiling (kicp_ctx_profile_begin/end): event pairs per registration

@@ -150,7 +150,7 @@ def test_registration_configs_vs_oracle(oracle, gpu_ctx, workload, cfg):
                   (cfg, variant, sort_bits, w.N, w.map.num_points(), dt, ang))
     finally:
         gpu_ctx.set_option("assoc_variant", 1)
-        gpu_ctx.set_option("sort_bits", 30)
+        gpu_ctx.set_option("sort_bits", 0)
     gm.close()
 
 
