@@ -38,6 +38,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", type=int, default=4, help="BASELINE.json config id 1..4 (default 4 = the quoted one)")
     ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"])
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1 sharded mode: fused peer-memory exchange inside the persistent kernel (default) or NCCL allreduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between steps")
     return ap.parse_args()
@@ -206,7 +208,13 @@ def main():
         else:
             uid = torch.empty(_capi.KICP_UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
         dist.broadcast(uid, 0)
-        ctx.comm_init(bytes(uid.cpu().tolist()), world, rank)
+        if args.comm == "nccl":
+            ctx.comm_init(bytes(uid.cpu().tolist()), world, rank)
+        else:  # fused exchange over NVLink peer memory: all-gather the CUDA-IPC handles of the mailboxes
+            mine = torch.tensor(list(ctx.p2p_handle()), dtype=torch.uint8, device=dev)
+            allh = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            ctx.p2p_init([bytes(h.cpu().tolist()) for h in allh], world, rank)
     lo, hi = kb.shard_range(w.N, world, rank) if sharded else (0, w.N)
     shard = np.ascontiguousarray(w.scan[lo:hi])
     scan = kb.Scan(ctx, len(shard))
@@ -315,7 +323,8 @@ def main():
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         roofline = None
         if prof is not None and prof.assoc_launches > 0:
-            t_k = prof.assoc_ms / prof.assoc_launches * 1e-3
+            # average duration of ONE association pass: launches that run several iterations count each of them
+            t_k = prof.assoc_ms / max(prof.assoc_iterations, 1) * 1e-3
             achieved = n_local * a_pt / t_k / 1e9
             traffic = None
             ncu_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -323,7 +332,7 @@ def main():
                 traffic = json.load(open(ncu_path)).get("dram_bytes_per_launch")
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "kernel": "k_assoc", "kernel_us": t_k * 1e6,
-                        "launches_timed": int(prof.assoc_launches),
+                        "launches_timed": int(prof.assoc_launches), "iterations_timed": int(prof.assoc_iterations),
                         "algorithmic_bytes_per_point": a_pt, "mean_candidates_per_point": cbar,
                         "mean_occupied_voxels_of_27": kbar, "peak_source": peak_src,
                         "note": "logical gather bytes N*A_pt per launch; the map (%.0f MB) fits the 126 MB L2 and each "
@@ -338,7 +347,8 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(w, {
                 "parallelism": ("1 GPU" if world == 1 else ("scan sharded by index range over %d GPUs, map replicated, "
-                                "1 NCCL allreduce of 8 doubles per iteration" % world if sharded else
+                                "per-iteration exchange of 8 doubles: %s" % (world, "fused into the persistent kernel over NVLink peer memory"
+                                if args.comm == "p2p" else "NCCL allreduce") if sharded else
                                 "%d independent replicas" % world)),
                 "l2": "flushed before every timed step (%d MiB write, untimed)" % (L2_FLUSH_BYTES >> 20)
                       if not args.no_flush else "NOT flushed (diagnostic run)",

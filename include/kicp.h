@@ -77,7 +77,8 @@ void *kicp_ctx_stream(kicp_ctx *ctx);
 /* Number of this library's kernels launched on the context since creation (bench.py reports gpu_launches). */
 int64_t kicp_ctx_launch_count(kicp_ctx *ctx);
 /* Tuning knobs (defaults are the measured best): "assoc_variant" 0 = 27-voxel neighbourhood staged through shared
- * memory, 1 = exact-pruning thread-per-point kernel; "sort_bits" 0..30 = Morton key bits of the optional per-registration
+ * memory, 1 = exact-pruning thread-per-point kernel; "persistent" 1 = all IRLS iterations of a registration inside one cooperative launch
+ * (default on the single-GPU path), 0 = one launch per iteration; "sort_bits" 0..30 = Morton key bits of the optional per-registration
  * binning sort (default 0 = off).  Every setting computes the same result. */
 int kicp_ctx_set_option(kicp_ctx *ctx, const char *name, int32_t value);
 /* Per-kernel device timing with CUDA events recorded on the context stream around (a) the binning of each
@@ -91,6 +92,7 @@ typedef struct kicp_profile {
     int64_t idle_launches;
     double prep_ms;           /* init + keys + sort + gather, summed over registrations */
     int64_t registrations;
+    int64_t assoc_iterations; /* IRLS iterations executed by those launches (a persistent launch runs several) */
 } kicp_profile;
 int kicp_ctx_profile_begin(kicp_ctx *ctx);
 int kicp_ctx_profile_end(kicp_ctx *ctx, kicp_profile *out);
@@ -148,6 +150,14 @@ int kicp_register_scan_async(kicp_map *map, kicp_scan *scan, const double last_r
 int kicp_comm_unique_id(uint8_t id[KICP_UNIQUE_ID_BYTES]); /* ncclGetUniqueId on rank 0; broadcast it out of band */
 int kicp_comm_init(kicp_ctx *ctx, const uint8_t id[KICP_UNIQUE_ID_BYTES], int32_t nranks, int32_t rank);
 int kicp_comm_destroy(kicp_ctx *ctx);
+/* Fused exchange over NVLink peer memory (preferred over NCCL when available): every rank allocates a mailbox and
+ * publishes its CUDA-IPC handle; after kicp_comm_p2p_init the sharded registration runs as ONE persistent kernel per GPU
+ * whose grid barrier also writes the 8 partial sums into every peer's mailbox and waits for theirs — no collective
+ * kernels, no extra launches.  All ranks must issue the same sequence of sharded registrations. */
+#define KICP_IPC_HANDLE_BYTES 64
+#define KICP_MAX_RANKS 8
+int kicp_comm_p2p_handle(kicp_ctx *ctx, uint8_t handle[KICP_IPC_HANDLE_BYTES]);
+int kicp_comm_p2p_init(kicp_ctx *ctx, const uint8_t *handles /* nranks x 64 bytes, rank order */, int32_t nranks, int32_t rank);
 /* Every rank calls this with ITS shard (frame_xyz / n are the local range).  All ranks return the same pose. */
 int kicp_register_sharded(kicp_map *map, const double *frame_xyz, int64_t n_local, const double last_robot_pose[7],
                           const double relative_wheel_odometry[7], double max_correspondence_distance,

@@ -93,6 +93,16 @@ extern "C" int kicp_comm_destroy(kicp_ctx *ctx) {
         nccl().CommDestroy((ncclComm_t)ctx->nccl_comm);
         ctx->nccl_comm = nullptr;
     }
+    if (ctx->p2p_ready) {
+        cudaStreamSynchronize(ctx->stream);
+        for (int r = 0; r < ctx->nranks; ++r)
+            if (r != ctx->rank && ctx->p2p_peer[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+        ctx->p2p_ready = false;
+    }
+    if (ctx->p2p_local) {
+        cudaFree(ctx->p2p_local);
+        ctx->p2p_local = nullptr;
+    }
     ctx->nranks = 1, ctx->rank = 0;
     return KICP_OK;
 }
@@ -103,5 +113,44 @@ int kicp_comm_allreduce8(kicp_ctx *ctx, double *d_buf) {
     ncclResult_t r = nccl().AllReduce(d_buf, d_buf, 8, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream);
     if (r != 0) return nccl_fail(r, "ncclAllReduce");
     ctx->launches++;
+    return KICP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused peer-memory exchange: mailbox allocation, CUDA-IPC export / import.
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int kicp_comm_p2p_handle(kicp_ctx *ctx, uint8_t handle[KICP_IPC_HANDLE_BYTES]) {
+    if (!ctx || !handle) return KICP_ERR_INVALID;
+    KICP_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->p2p_local) {
+        KICP_CUDA(cudaMalloc(&ctx->p2p_local, sizeof(P2PMailbox)));
+        KICP_CUDA(cudaMemset(ctx->p2p_local, 0, sizeof(P2PMailbox)));
+        KICP_CUDA(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    KICP_CUDA(cudaIpcGetMemHandle(&h, ctx->p2p_local));
+    static_assert(sizeof(h) == KICP_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    memcpy(handle, &h, sizeof(h));
+    return KICP_OK;
+}
+
+extern "C" int kicp_comm_p2p_init(kicp_ctx *ctx, const uint8_t *handles, int32_t nranks, int32_t rank) {
+    if (!ctx || !handles || nranks < 1 || nranks > KICP_MAX_RANKS || rank < 0 || rank >= nranks || !ctx->p2p_local)
+        return KICP_ERR_INVALID;
+    KICP_CUDA(cudaSetDevice(ctx->device));
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) {
+            ctx->p2p_peer[r] = ctx->p2p_local;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * KICP_IPC_HANDLE_BYTES, sizeof(h));
+        void *p = nullptr;
+        KICP_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->p2p_peer[r] = (P2PMailbox *)p;
+    }
+    ctx->nranks = nranks, ctx->rank = rank;
+    ctx->p2p_seq = 0;
+    ctx->p2p_ready = true;
     return KICP_OK;
 }

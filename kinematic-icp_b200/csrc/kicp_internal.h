@@ -32,6 +32,13 @@ struct MapView {
     double voxel_size;
 };
 
+// Mailbox of the fused cross-GPU exchange: rank r writes its 8 partial sums of iteration `it` into data[parity][it][r] of
+// EVERY rank's mailbox, then raises flag[parity][it][r] to a monotonically increasing tag.
+struct P2PMailbox {
+    unsigned long long flag[2][KICP_MAX_ITERATIONS][KICP_MAX_RANKS];
+    double data[2][KICP_MAX_ITERATIONS][KICP_MAX_RANKS][8];
+};
+
 struct kicp_ctx {
     int device = 0;
     int sm_count = 148;
@@ -39,6 +46,7 @@ struct kicp_ctx {
     int64_t launches = 0;
     // registration scratch (grown on demand)
     struct RegState *d_state = nullptr;
+    double *d_partials = nullptr;  // per-CTA partial sums of the association kernels [grid][8]
     double *d_sorted = nullptr;   // scan reordered by Morton key of the voxel at the initial guess
     uint32_t *d_keys = nullptr, *d_keys_alt = nullptr;
     int32_t *d_idx = nullptr, *d_idx_alt = nullptr;
@@ -47,7 +55,11 @@ struct kicp_ctx {
     int64_t scratch_cap = 0;
     int assoc_ctas_per_sm = 1;  // resident CTAs of the association kernel per SM (occupancy query)
     int pruned_ctas_per_sm = 1;
-    int assoc_variant = 1;  // 0 = staged (27-voxel neighbourhood through shared memory), 1 = pruned (thread per point)
+    int persistent_ctas_per_sm = 1;
+    int group4_ctas_per_sm = 1;
+    int persistent = 1;     // 1 = all IRLS iterations inside one cooperative launch (single-GPU pruned path)
+    int assoc_variant = 1;  // 0 = staged (27-voxel neighbourhood through shared memory), 1 = pruned (thread per point),
+                            // 2 = pruned with 4 lanes per point
     int sort_bits = 0;      // Morton key bits of the optional binning sort (0 = off, the measured best: DESIGN.md §5)
     kicp_scan *upload_scan = nullptr;  // staging scan used by the host-pointer entry points
     kicp_reg_result *h_result = nullptr;  // pinned bounce buffer for synchronous calls
@@ -56,6 +68,7 @@ struct kicp_ctx {
     struct ProfReg {
         cudaEvent_t prep0, prep1;
         std::vector<cudaEvent_t> it;  // 2 per association launch
+        bool persistent = false;      // one launch covers every iteration
         int32_t *d_iters;             // device word receiving the registration's iteration count
     };
     std::vector<ProfReg> prof;
@@ -64,6 +77,10 @@ struct kicp_ctx {
     // multi-GPU
     void *nccl_comm = nullptr;
     int nranks = 1, rank = 0;
+    struct P2PMailbox *p2p_local = nullptr;      // this rank's mailbox (cudaMalloc, exported through CUDA IPC)
+    struct P2PMailbox *p2p_peer[KICP_MAX_RANKS] = {nullptr};  // every rank's mailbox as mapped into this process
+    bool p2p_ready = false;
+    unsigned long long p2p_seq = 0;              // sharded registrations issued so far (identical on all ranks)
 };
 
 struct kicp_map {

@@ -57,7 +57,8 @@ extern "C" int kicp_ctx_create(int device, kicp_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     KICP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     KICP_CUDA(cudaMallocHost(&c->h_result, sizeof(kicp_reg_result)));
-    if (const char *e = getenv("KICP_ASSOC")) c->assoc_variant = strcmp(e, "staged") ? 1 : 0;
+    if (const char *e = getenv("KICP_ASSOC")) c->assoc_variant = !strcmp(e, "staged") ? 0 : (!strcmp(e, "group4") ? 2 : 1);
+    if (const char *e = getenv("KICP_PERSISTENT")) c->persistent = atoi(e) ? 1 : 0;
     if (const char *e = getenv("KICP_SORT_BITS")) c->sort_bits = std::min(30, std::max(0, atoi(e)));
     *out = c;
     return KICP_OK;
@@ -135,6 +136,7 @@ extern "C" int kicp_ctx_destroy(kicp_ctx *ctx) {
     kicp_comm_destroy(ctx);
     if (ctx->upload_scan) kicp_scan_destroy(ctx->upload_scan);
     cudaFree(ctx->d_state);
+    cudaFree(ctx->d_partials);
     cudaFree(ctx->d_sorted);
     cudaFree(ctx->d_keys);
     cudaFree(ctx->d_keys_alt);

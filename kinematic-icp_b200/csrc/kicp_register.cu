@@ -12,6 +12,7 @@
 // (Registration.cpp:119-125, 159-167, 181-184) — so the iteration loop never returns to the host.
 // The correspondence list of the reference is never materialised: association and linearisation use the same T.
 #include <cfloat>
+#include <cmath>
 #include <chrono>
 #include <cstddef>
 #include <cstdio>
@@ -24,6 +25,10 @@
 using namespace kicp_dev;
 
 #define KICP_WARPS 8     // warps per CTA in k_assoc
+#ifndef KICP_MINB
+#define KICP_MINB 2   // resident CTAs per SM the pruned kernels are compiled for (register cap = 65536 / (256 * MINB));
+                      // measured: 2 (128 registers, no spills, 4-wide scans) beats 3 and 4
+#endif
 #define KICP_CH 192      // candidates staged in shared memory per pass (27 voxels x 20 points = 540 worst case)
 
 struct RegState {
@@ -34,9 +39,11 @@ struct RegState {
     int adaptive, max_iter;
     int iter, done, status;
     unsigned int ticket, window_counter;
+    unsigned int generation;  // grid-barrier generation of the persistent kernel (= iterations completed)
     int fused_tail;
     int *iters_out;  // optional: where to publish the iteration count when the registration finishes (profiling)
     double acc[8];  // JTJ00 JTJ01 JTJ11 JTr0 JTr1 N sum|r|^2 (unused)
+    double dbg[KICP_MAX_ITERATIONS][4];  // per iteration, ns: windows phase of CTA 0, barrier wait of the last CTA, partial sum, solve
     kicp_reg_result result;
 };
 
@@ -83,8 +90,10 @@ __device__ void se3_exp_planar(double ux, double uy, double theta_in, double oq[
     } else {
         theta = sqrt(theta_sq);
         const double half_theta = 0.5 * theta;
-        imag = sin(half_theta) / theta;
-        real = cos(half_theta);
+        double sh, ch;
+        sincos(half_theta, &sh, &ch);
+        imag = sh / theta;
+        real = ch;
     }
     oq[0] = imag * wx, oq[1] = imag * wy, oq[2] = imag * wz, oq[3] = real;
     // V = I + (1-cos)/th^2 W + (th - sin)/th^3 W^2, or V = R when theta < eps;  W = hat(0, 0, wz)
@@ -92,8 +101,10 @@ __device__ void se3_exp_planar(double ux, double uy, double theta_in, double oq[
     if (theta < eps) {
         quat_to_matrix(oq, V);
     } else {
-        const double c1 = (1.0 - cos(theta)) / (theta * theta);
-        const double c2 = (theta - sin(theta)) / (theta * theta * theta);
+        double st_, ct_;
+        sincos(theta, &st_, &ct_);
+        const double c1 = (1.0 - ct_) / (theta * theta);
+        const double c2 = (theta - st_) / (theta * theta * theta);
         const double w2 = wz * wz;
         V[0] = 1.0 + c2 * (-w2), V[1] = c1 * (-wz), V[2] = 0.0;
         V[3] = c1 * wz, V[4] = 1.0 + c2 * (-w2), V[5] = 0.0;
@@ -122,7 +133,7 @@ __global__ void k_reg_init(RegState *st, RegArgs a) {
     st->tau = a.tau, st->conv = a.conv, st->fixed_reg = a.fixed_reg, st->beta = 0.0;
     st->adaptive = a.adaptive, st->max_iter = a.max_iter, st->fused_tail = a.fused_tail;
     st->iter = 0, st->done = a.max_iter <= 0 ? 1 : 0, st->status = KICP_OK;
-    st->ticket = 0, st->window_counter = 0;
+    st->ticket = 0, st->window_counter = 0, st->generation = 0;
     st->iters_out = a.iters_out;
     if (a.iters_out) *a.iters_out = 0;
     for (int k = 0; k < 8; ++k) st->acc[k] = 0.0;
@@ -170,6 +181,12 @@ __global__ void k_gather(const double *__restrict__ xyz, const int32_t *__restri
 
 // ComputePerturbation's tail + motion model + pose update + convergence test (one thread).
 // `acc` holds the (all-reduced) sums of this iteration.
+__device__ __forceinline__ unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ void solve_and_update(RegState *st) {
     double s[8];
     for (int k = 0; k < 8; ++k) s[k] = __ldcg(&st->acc[k]);  // written by other CTAs' atomics: read through L2
@@ -191,8 +208,10 @@ __device__ void solve_and_update(RegState *st) {
     const double i00 = d * invdet, i01 = -b * invdet, i10 = -b * invdet, i11 = a * invdet;
     const double dx0 = -(i00 * r0 + i01 * r1), dx1 = -(i10 * r0 + i11 * r1);
     // motion_model (Registration.cpp:159-167), epsilon = DBL_MIN
-    const double ux = dx0 * sin(dx1) / (dx1 + DBL_MIN);
-    const double uy = dx0 * (1.0 - cos(dx1)) / (dx1 + DBL_MIN);
+    double sn, cs;
+    sincos(dx1, &sn, &cs);
+    const double ux = dx0 * sn / (dx1 + DBL_MIN);
+    const double uy = dx0 * (1.0 - cs) / (dx1 + DBL_MIN);
     double dq[4], dt[3], nq[4], nt[3];
     se3_exp_planar(ux, uy, dx1, dq, dt);
     se3_compose(st->q, st->t, dq, dt, nq, nt);  // current_estimate = current_estimate * delta_motion  (:182)
@@ -211,6 +230,7 @@ __device__ void solve_and_update(RegState *st) {
         st->status = KICP_WARN_NO_CORRESPONDENCES;
         done = 1;
     }
+    if (st->status == KICP_ERR_NCCL) done = 1;  // a peer of the fused exchange never arrived
     res->status = st->status;
     st->done = done;
     if (st->iters_out) *st->iters_out = j + 1;
@@ -400,22 +420,26 @@ __device__ __forceinline__ void candidate_step(const double2 xy, const double2 z
     if (d2 < best) best = d2, bestp = p;
 }
 
-// Scan the `cnt` points of one voxel, two per step (four independent 16-byte loads in flight per lane).  The loop is
-// per-lane (no warp vote): lanes with fewer points simply leave earlier and reconverge behind it.
+// Scan the `cnt` points of one voxel, KICP_SCANW per step: 2*KICP_SCANW independent 16-byte loads are in flight per lane
+// before the first distance is formed (the path is bound by dependent memory round trips).  Indices past
+// the end are clamped to the last point, which is harmless: re-evaluating a point cannot change a strict minimum.
+// The loop is per-lane (no warp vote): lanes with fewer points leave earlier and reconverge behind it.
+#ifndef KICP_SCANW
+#define KICP_SCANW 4
+#endif
 __device__ __forceinline__ void scan_voxel(const double *vp, int cnt, double qx, double qy, double qz, double &best,
                                            const double *&bestp) {
-    int j = 0;
-    for (; j + 1 < cnt; j += 2) {
-        const double *p0 = vp + (size_t)j * KICP_PSTRIDE, *p1 = p0 + KICP_PSTRIDE;
-        const double2 a0 = __ldg(reinterpret_cast<const double2 *>(p0)), b0 = __ldg(reinterpret_cast<const double2 *>(p0) + 1);
-        const double2 a1 = __ldg(reinterpret_cast<const double2 *>(p1)), b1 = __ldg(reinterpret_cast<const double2 *>(p1) + 1);
-        candidate_step(a0, b0, p0, qx, qy, qz, best, bestp);
-        candidate_step(a1, b1, p1, qx, qy, qz, best, bestp);
-    }
-    if (j < cnt) {
-        const double *p0 = vp + (size_t)j * KICP_PSTRIDE;
-        const double2 a0 = __ldg(reinterpret_cast<const double2 *>(p0)), b0 = __ldg(reinterpret_cast<const double2 *>(p0) + 1);
-        candidate_step(a0, b0, p0, qx, qy, qz, best, bestp);
+    for (int j = 0; j < cnt; j += KICP_SCANW) {
+        const double *p[KICP_SCANW];
+        double2 a[KICP_SCANW], b[KICP_SCANW];
+#pragma unroll
+        for (int u = 0; u < KICP_SCANW; ++u) {
+            p[u] = vp + (size_t)min(j + u, cnt - 1) * KICP_PSTRIDE;
+            a[u] = __ldg(reinterpret_cast<const double2 *>(p[u]));
+            b[u] = __ldg(reinterpret_cast<const double2 *>(p[u]) + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < KICP_SCANW; ++u) candidate_step(a[u], b[u], p[u], qx, qy, qz, best, bestp);
     }
 }
 
@@ -436,22 +460,173 @@ __device__ __forceinline__ void scan_voxel(const double *vp, int cnt, double qx,
 // every voxel's points are read four at a time (eight independent 16-byte loads per lane).  Map data is read
 // straight from L1/L2 (the map fits the 126 MB L2).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(KICP_WARPS * 32, 3) k_assoc_pruned(RegState *st, const double *__restrict__ scan, int n, MapView map) {
+// PERSISTENT = true: launched cooperatively with every CTA resident; all IRLS iterations run inside this one launch,
+// separated by a grid barrier whose last arriver solves the 2x2 system and updates the pose (no launches after
+// convergence, no per-iteration launch gap).  PERSISTENT = false: one launch per iteration (used by the NCCL-sharded
+// path, where the allreduce sits between association and solve).
+struct P2PArgs {
+    P2PMailbox *peer[KICP_MAX_RANKS];
+    int nranks, rank, parity;
+    unsigned long long tag_base;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Cross-GPU exchange fused into the grid barrier (executed by the last CTA of every rank): write the local sums of
+// iteration `it` into every peer's mailbox over NVLink, raise the flags, wait for all peers, and replace st->acc by the
+// sum over ranks IN RANK ORDER — every rank adds the same values in the same order, so all ranks solve for the
+// identical pose.  A rank that never shows up turns into an error status after ~2 s instead of a hung GPU.
+__device__ __forceinline__ void p2p_exchange(RegState *st, const P2PArgs &px, unsigned it) {
+    const unsigned long long tag = px.tag_base + it + 1ull;
+    const int t = threadIdx.x;
+    if (t < 32) {  // warp 0 only; the loops over ranks are warp-synchronous (see kicp_device.cuh on divergence safety)
+        const double mine = t < 7 ? __ldcg(&st->acc[t]) : 0.0;
+        for (int r = 0; r < px.nranks; ++r) {
+            if (t < 8) {
+                volatile double *dst = &px.peer[r]->data[px.parity][it][px.rank][t];
+                *dst = mine;
+            }
+            __syncwarp();
+        }
+        __threadfence_system();
+        __syncwarp();
+        if (t < px.nranks) st_release_sys(&px.peer[t]->flag[px.parity][it][px.rank], tag);
+        if (t < px.nranks) {
+            const unsigned long long *f = &px.peer[px.rank]->flag[px.parity][it][t];
+            const long long t0 = clock64();
+            while (ld_acquire_sys(f) < tag) {
+                if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer is missing
+                    st->status = KICP_ERR_NCCL;
+                    break;
+                }
+            }
+        }
+        __syncwarp();
+        double s = 0.0;
+        for (int r = 0; r < px.nranks; ++r) {
+            if (t < 8) s += *(volatile double *)&px.peer[px.rank]->data[px.parity][it][r][t];
+            __syncwarp();
+        }
+        if (t < 8) __stcg(&st->acc[t], s);
+    }
+    __syncthreads();
+}
+
+// Warp-shuffle reduction of the 7 per-thread sums -> one partial per warp -> one partial per CTA, written with plain
+// stores to partials[blockIdx.x][8].  The last CTA to arrive (ticket) sums the partials in a fixed order — no contended
+// floating-point atomics, and the result does not depend on the arrival order — and then either runs the multi-launch
+// tail or releases the grid barrier of the persistent kernel after solving for the next pose.
+// Returns true when the kernel must return (non-persistent launch, or converged).
+template <bool PERSISTENT>
+__device__ __forceinline__ bool reduce_and_finish(RegState *st, double *partials, double (&v)[7], unsigned it, double (*s_part)[8],
+                                                  int *s_last, const P2PArgs &px) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned FULL = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) s_part[wid][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double s = 0.0;
+        if (threadIdx.x < 7)
+            for (int k = 0; k < KICP_WARPS; ++k) s += s_part[k][threadIdx.x];
+        __stcg(&partials[(size_t)blockIdx.x * 8 + threadIdx.x], s);
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicAdd(&st->ticket, 1u);
+        *s_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    const bool last = *s_last != 0;
+    const unsigned long long tb0 = gtime_ns();
+    if (last) {
+        __threadfence();
+        if (wid < 7) {  // warp `wid` sums column `wid` over the CTAs, lanes striding, fixed tree
+            double s = 0.0;
+            for (unsigned b0 = 0; b0 < gridDim.x; b0 += 32) {  // warp-uniform trip count
+                const unsigned b = b0 + lane;
+                if (b < gridDim.x) s += __ldcg(&partials[(size_t)b * 8 + wid]);
+                __syncwarp();
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+            if (lane == 0) __stcg(&st->acc[wid], s);
+        }
+        __syncthreads();
+        if (PERSISTENT && px.nranks > 1) p2p_exchange(st, px, it);
+        if (threadIdx.x == 0) {
+            __threadfence();
+            st->ticket = 0;
+            st->window_counter = 0;
+            const unsigned long long tb1 = gtime_ns();
+            const int jdbg = st->iter;
+            if (PERSISTENT || st->fused_tail) solve_and_update(st);
+            if (jdbg < KICP_MAX_ITERATIONS) st->dbg[jdbg][2] = (double)(tb1 - tb0), st->dbg[jdbg][3] = (double)(gtime_ns() - tb1);
+            if (PERSISTENT) {
+                __threadfence();
+                atomicExch(&st->generation, it + 1u);
+            }
+        }
+    }
+    if (!PERSISTENT) return true;
+    if (threadIdx.x == 0) {
+        if (!last) {
+            while (*(volatile unsigned *)&st->generation <= it) {
+            }
+            __threadfence();
+        }
+        *s_last = __ldcg(&st->done);
+    }
+    __syncthreads();
+    return *s_last != 0;
+}
+
+template <bool PERSISTENT>
+__global__ void __launch_bounds__(KICP_WARPS * 32, KICP_MINB) k_assoc_pruned(RegState *st, const double *__restrict__ scan, int n, MapView map, double *partials,
+                                                                                 P2PArgs px) {
     if (st->done) return;
     __shared__ double s_T[12];
     __shared__ double s_part[KICP_WARPS][8];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned FULL = 0xFFFFFFFFu;
-    if (threadIdx.x < 9) s_T[threadIdx.x] = st->R[threadIdx.x];
-    if (threadIdx.x >= 9 && threadIdx.x < 12) s_T[threadIdx.x] = st->t[threadIdx.x - 9];
-    __syncthreads();
     __shared__ MapView s_map[32];
     const MapRegs mr = map_regs(map, s_map);  // per-thread copy of the map view (divergence safety, kicp_device.cuh)
-    const double tau = st->tau, vs = map.voxel_size;
+    __shared__ double s_tau[32];
+    if (threadIdx.x < 32) s_tau[threadIdx.x] = st->tau;
+    __syncthreads();
+    const double tau = ((const volatile double *)s_tau)[lane], vs = map.voxel_size;
     const int num_windows = (n + 31) >> 5;
+    // the iteration counter is read inside thread 0's spin loop of the grid barrier: keep it in a per-thread register
+    // (loaded from a lane-dependent shared address, see kicp_device.cuh) rather than in a uniform register
+    __shared__ unsigned s_zero[32];
+    if (threadIdx.x < 32) s_zero[threadIdx.x] = 0u;
+    __syncthreads();
+    unsigned it = ((const volatile unsigned *)s_zero)[lane];
+  for (;; ++it) {
+    // the current estimate: written by k_reg_init or by the last CTA of the previous iteration -> read through L2
+    if (threadIdx.x < 9) s_T[threadIdx.x] = __ldcg(&st->R[threadIdx.x]);
+    if (threadIdx.x >= 9 && threadIdx.x < 12) s_T[threadIdx.x] = __ldcg(&st->t[threadIdx.x - 9]);
+    __syncthreads();
     double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0, cntN = 0, ssq = 0;
+    const unsigned long long t_iter0 = gtime_ns();
 
+    // dynamic window fetch (measured 15-20 % faster than a static round-robin at cfg4: windows differ in cost)
     while (true) {
         int w = 0;
         if (lane == 0) w = (int)atomicAdd(&st->window_counter, 1u);
@@ -571,35 +746,203 @@ __global__ void __launch_bounds__(KICP_WARPS * 32, 3) k_assoc_pruned(RegState *s
         }
     }
 
+    if (blockIdx.x == 0 && threadIdx.x == 0 && it < KICP_MAX_ITERATIONS) st->dbg[it][0] = (double)(gtime_ns() - t_iter0);
     double v[7] = {a00, a01, a11, b0, b1, cntN, ssq};
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o);
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 7; ++k) s_part[wid][k] = v[k];
-    }
+    if (reduce_and_finish<PERSISTENT>(st, partials, v, it, s_part, &s_last, px)) return;
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_assoc_group4 (variant 2): the same exact-pruning search with FOUR LANES PER SCAN POINT (a warp-window = 8 points).
+// The pruned path is bound by the serial latency of one window (cfg2: 43 us per iteration with less than one window
+// per warp), so the search of one point is spread over a 4-lane group:
+//   - every lane of the group probes a different neighbour voxel (4 hash probes in flight per point, 1 per lane);
+//   - the group strides over a voxel's points (lane s takes points s, s+4, ...: one coalesced 128-byte row per step);
+//   - the best squared distance is min-reduced over the group (2 shuffles) between rounds so pruning stays tight.
+// The winner is the minimum of (d2, order key) with order key = (KISS shift index, index in voxel), i.e. the first
+// minimum in the reference's visiting order.  Windows are 4x smaller, so the end-of-launch tail shrinks as well.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double group4_min(double x) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    x = fmin(x, __shfl_xor_sync(FULL, x, 1));
+    x = fmin(x, __shfl_xor_sync(FULL, x, 2));
+    return x;
+}
+
+template <bool PERSISTENT>
+__global__ void __launch_bounds__(KICP_WARPS * 32, KICP_MINB) k_assoc_group4(RegState *st, const double *__restrict__ scan, int n, MapView map,
+                                                                      double *partials, int pow2_voxel, P2PArgs px) {
+    if (st->done) return;
+    __shared__ double s_T[12];
+    __shared__ double s_part[KICP_WARPS][8];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & 3;
+    const unsigned FULL = 0xFFFFFFFFu;
+    __shared__ MapView s_map[32];
+    const MapRegs mr = map_regs(map, s_map);  // per-thread copy of the map view (divergence safety, kicp_device.cuh)
+    __shared__ double s_tau[32];
+    if (threadIdx.x < 32) s_tau[threadIdx.x] = st->tau;
     __syncthreads();
-    if (threadIdx.x < 7) {
-        double s = 0.0;
-        for (int k = 0; k < KICP_WARPS; ++k) s += s_part[k][threadIdx.x];
-        atomicAdd(&st->acc[threadIdx.x], s);
-        __threadfence();
-    }
+    const double tau = ((const volatile double *)s_tau)[lane], vs = map.voxel_size, inv_vs = 1.0 / map.voxel_size;
+    const int num_windows = (n + 7) >> 3;
+    __shared__ unsigned s_zero[32];
+    if (threadIdx.x < 32) s_zero[threadIdx.x] = 0u;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned ticket = atomicAdd(&st->ticket, 1u);
-        s_last = (ticket == gridDim.x - 1);
-    }
+    unsigned it = ((const volatile unsigned *)s_zero)[lane];
+    const uint32_t tmask = mr.mask;
+    const int4 *tslots = mr.slots;
+    const double *tpts = mr.pts;
+    const size_t tstride = (size_t)mr.cap * KICP_PSTRIDE;
+  for (;; ++it) {
+    if (threadIdx.x < 9) s_T[threadIdx.x] = __ldcg(&st->R[threadIdx.x]);
+    if (threadIdx.x >= 9 && threadIdx.x < 12) s_T[threadIdx.x] = __ldcg(&st->t[threadIdx.x - 9]);
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-        __threadfence();
-        st->ticket = 0;
-        st->window_counter = 0;
-        if (st->fused_tail) solve_and_update(st);
+    double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0, cntN = 0, ssq = 0;
+    const unsigned long long t_iter0 = gtime_ns();
+
+    while (true) {
+        int w = 0;
+        if (lane == 0) w = (int)atomicAdd(&st->window_counter, 1u);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= num_windows) break;
+        const int i = w * 8 + (lane >> 2);
+        const bool valid = i < n;
+        double px = 0, py = 0, pz = 0;
+        if (valid) px = scan[3 * (size_t)i], py = scan[3 * (size_t)i + 1], pz = scan[3 * (size_t)i + 2];
+        const double qx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[9];
+        const double qy = s_T[3] * px + s_T[4] * py + s_T[5] * pz + s_T[10];
+        const double qz = s_T[6] * px + s_T[7] * py + s_T[8] * pz + s_T[11];
+        // PointToVoxel: floor(q / voxel_size); for a power-of-two voxel size the product with the (exact) reciprocal
+        // is the same double as the quotient, so the cheaper form is used
+        int vx, vy, vz;
+        if (pow2_voxel) {
+            vx = (int)floor(qx * inv_vs), vy = (int)floor(qy * inv_vs), vz = (int)floor(qz * inv_vs);
+        } else {
+            vx = voxel_coord(qx, vs), vy = voxel_coord(qy, vs), vz = voxel_coord(qz, vs);
+        }
+        double t;
+        t = (double)(vx + 1) * vs - qx; const double gxp = t * t;
+        t = qx - (double)vx * vs;       const double gxm = t * t;
+        t = (double)(vy + 1) * vs - qy; const double gyp = t * t;
+        t = qy - (double)vy * vs;       const double gym = t * t;
+        t = (double)(vz + 1) * vs - qz; const double gzp = t * t;
+        t = qz - (double)vz * vs;       const double gzm = t * t;
+
+        double best = DBL_MAX;            // this lane's best
+        unsigned bestkey = 0xFFFFFFFFu;   // (shift index << 8) | index in voxel of this lane's best
+        const double *bestp = nullptr;
+        // round 0: the query's own voxel, its points strided over the 4 lanes
+        if (valid) {
+            const uint32_t meta = map_probe(mr, vx, vy, vz);
+            if (meta != KICP_SLOT_EMPTY) {
+                const double *vp = tpts + (size_t)(meta >> 8) * tstride;
+                const int cnt = (int)(meta & 0xFFu);
+                for (int j = sub; j < cnt; j += 4) {
+                    const double *p0 = vp + (size_t)j * KICP_PSTRIDE;
+                    const double2 a = __ldg(reinterpret_cast<const double2 *>(p0)), b = __ldg(reinterpret_cast<const double2 *>(p0) + 1);
+                    const double dx = a.x - qx, dy = a.y - qy, dz = b.x - qz;
+                    const double d2 = dx * dx + dy * dy + dz * dz;
+                    if (d2 < best) best = d2, bestkey = (unsigned)j, bestp = p0;
+                }
+            }
+        }
+        __syncwarp();
+        double gbest = group4_min(best);
+        unsigned mask = valid ? 0x07FFFFFEu : 0u;  // identical in the 4 lanes of a group
+        while (__any_sync(FULL, mask != 0u)) {
+            uint32_t meta = KICP_SLOT_EMPTY;
+            int myk = 0;
+            double lb[4] = {0.0, 0.0, 0.0, 0.0};
+            if (mask) {
+                const double bound = gbest * (1.0 + 1e-6) + 1e-10;
+                mask &= (kX0 | (gxp <= bound ? kXP : 0u) | (gxm <= bound ? kXM : 0u)) &
+                        (kY0 | (gyp <= bound ? kYP : 0u) | (gym <= bound ? kYM : 0u)) &
+                        (kZ0 | (gzp <= bound ? kZP : 0u) | (gzm <= bound ? kZM : 0u));
+                // the next (up to) 4 shifts in KISS order that survive the exact bound; lane `sub` probes the sub-th one
+                int kxs = 0, kys = 0, kzs = 0;
+                bool use = false;
+                int found = 0;
+                while (mask && found < 4) {
+                    const int k = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int sx = shift_x(k), sy = shift_y(k), sz = shift_z(k);
+                    const double lb2 = (sx > 0 ? gxp : (sx < 0 ? gxm : 0.0)) + (sy > 0 ? gyp : (sy < 0 ? gym : 0.0)) +
+                                       (sz > 0 ? gzp : (sz < 0 ? gzm : 0.0));
+                    if (lb2 > bound) continue;
+                    if (found == 0) lb[0] = lb2;
+                    if (found == 1) lb[1] = lb2;
+                    if (found == 2) lb[2] = lb2;
+                    if (found == 3) lb[3] = lb2;
+                    if (found == sub) use = true, myk = k, kxs = vx + sx, kys = vy + sy, kzs = vz + sz;
+                    ++found;
+                }
+                if (use) {
+                    uint32_t h = voxel_hash(kxs, kys, kzs) & tmask;
+                    while (true) {
+                        const int4 sl = __ldg(&tslots[h]);
+                        if ((uint32_t)sl.w == KICP_SLOT_EMPTY) break;
+                        if (sl.x == kxs && sl.y == kys && sl.z == kzs) {
+                            meta = (uint32_t)sl.w;
+                            break;
+                        }
+                        h = (h + 1) & tmask;
+                    }
+                }
+            }
+            __syncwarp();
+            // every lane of the group learns the 4 probe results, then the group scans the found voxels in KISS order
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t mu = __shfl_sync(FULL, meta, (lane & ~3) | u);
+                const int ku = __shfl_sync(FULL, myk, (lane & ~3) | u);
+                if (mu != KICP_SLOT_EMPTY && !(lb[u] > best * (1.0 + 1e-6) + 1e-10)) {
+                    const double *vp = tpts + (size_t)(mu >> 8) * tstride;
+                    const int cnt = (int)(mu & 0xFFu);
+                    for (int j = sub; j < cnt; j += 4) {
+                        const double *p0 = vp + (size_t)j * KICP_PSTRIDE;
+                        const double2 a = __ldg(reinterpret_cast<const double2 *>(p0)), b = __ldg(reinterpret_cast<const double2 *>(p0) + 1);
+                        const double dx = a.x - qx, dy = a.y - qy, dz = b.x - qz;
+                        const double d2 = dx * dx + dy * dy + dz * dz;
+                        if (d2 < best) best = d2, bestkey = ((unsigned)ku << 8) | (unsigned)j, bestp = p0;
+                    }
+                }
+                __syncwarp();
+            }
+            gbest = group4_min(best);
+        }
+        // the group's winner: minimum of (d2, order key) — the first minimum in the reference's visiting order
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            const double od = __shfl_xor_sync(FULL, best, o);
+            const unsigned ok = __shfl_xor_sync(FULL, bestkey, o);
+            const unsigned long long op = __shfl_xor_sync(FULL, (unsigned long long)bestp, o);
+            if (od < best || (od == best && ok < bestkey)) best = od, bestkey = ok, bestp = (const double *)op;
+        }
+        if (sub == 0 && bestp != nullptr) {
+            const double2 a = __ldg(reinterpret_cast<const double2 *>(bestp)), b = __ldg(reinterpret_cast<const double2 *>(bestp) + 1);
+            const double rx = qx - a.x, ry = qy - a.y, rz = qz - b.x;  // r = T p - n
+            const double rr = rx * rx + ry * ry + rz * rz;
+            if (sqrt(rr) < tau) {  // distance < max_correspondance_distance   (Registration.cpp:75)
+                const double c0x = s_T[0], c0y = s_T[3], c0z = s_T[6];
+                const double c1x = s_T[1] * px - s_T[0] * py, c1y = s_T[4] * px - s_T[3] * py, c1z = s_T[7] * px - s_T[6] * py;
+                a00 += c0x * c0x + c0y * c0y + c0z * c0z;
+                a01 += c0x * c1x + c0y * c1y + c0z * c1z;
+                a11 += c1x * c1x + c1y * c1y + c1z * c1z;
+                b0 += c0x * rx + c0y * ry + c0z * rz;
+                b1 += c1x * rx + c1y * ry + c1z * rz;
+                cntN += 1.0;
+                ssq += rr;
+            }
+        }
+        __syncwarp();
     }
+
+    if (blockIdx.x == 0 && threadIdx.x == 0 && it < KICP_MAX_ITERATIONS) st->dbg[it][0] = (double)(gtime_ns() - t_iter0);
+    double v[7] = {a00, a01, a11, b0, b1, cntN, ssq};
+    if (reduce_and_finish<PERSISTENT>(st, partials, v, it, s_part, &s_last, px)) return;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------- host
@@ -609,8 +952,11 @@ __global__ void __launch_bounds__(KICP_WARPS * 32, 3) k_assoc_pruned(RegState *s
 extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value) {
     if (!c || !name) return KICP_ERR_INVALID;
     if (!strcmp(name, "assoc_variant")) {
-        if (value != 0 && value != 1) return KICP_ERR_INVALID;
+        if (value < 0 || value > 2) return KICP_ERR_INVALID;
         c->assoc_variant = value;
+    } else if (!strcmp(name, "persistent")) {
+        if (value != 0 && value != 1) return KICP_ERR_INVALID;
+        c->persistent = value;
     } else if (!strcmp(name, "sort_bits")) {
         if (value < 0 || value > 30) return KICP_ERR_INVALID;
         c->sort_bits = value;
@@ -627,12 +973,22 @@ static size_t assoc_smem_bytes() {
 static int reg_reserve(kicp_ctx *c, int64_t n) {
     if (!c->d_state) {
         KICP_CUDA(cudaMalloc(&c->d_state, sizeof(RegState)));
+        KICP_CUDA(cudaMalloc(&c->d_partials, (size_t)c->sm_count * 16 * 8 * sizeof(double)));
         KICP_CUDA(cudaFuncSetAttribute(k_assoc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)assoc_smem_bytes()));
         int per_sm = 0;
         KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc, KICP_WARPS * 32, assoc_smem_bytes()));
         c->assoc_ctas_per_sm = std::max(per_sm, 1);
-        KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc_pruned, KICP_WARPS * 32, 0));
+        KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc_pruned<false>, KICP_WARPS * 32, 0));
         c->pruned_ctas_per_sm = std::max(per_sm, 1);
+        KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc_pruned<true>, KICP_WARPS * 32, 0));
+        c->persistent_ctas_per_sm = std::max(per_sm, 1);
+        KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc_group4<true>, KICP_WARPS * 32, 0));
+        c->group4_ctas_per_sm = std::max(per_sm, 1);
+        KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc_group4<false>, KICP_WARPS * 32, 0));
+        c->group4_ctas_per_sm = std::min(c->group4_ctas_per_sm, std::max(per_sm, 1));
+        int coop = 0;
+        KICP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
+        if (!coop) c->persistent = 0;
     }
     if (n <= c->scratch_cap) return KICP_OK;
     KICP_CUDA(cudaStreamSynchronize(c->stream));
@@ -672,8 +1028,8 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
     kicp_ctx *c = m->ctx;
     if (scan->ctx != c) return KICP_ERR_INVALID;
     if (scan->n > 0x7FFFFFE0ll) return KICP_ERR_CAPACITY;
-    if (sharded && !c->nccl_comm) {
-        kicp_set_error("kicp_register_sharded: kicp_comm_init has not been called on this context");
+    if (sharded && !c->nccl_comm && !c->p2p_ready) {
+        kicp_set_error("kicp_register_sharded: neither kicp_comm_p2p_init nor kicp_comm_init has been called on this context");
         return KICP_ERR_INVALID;
     }
     KICP_CUDA(cudaSetDevice(c->device));
@@ -686,7 +1042,7 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
     a.adaptive = p->use_adaptive_odometry_regularization ? 1 : 0;
     // an empty map returns the prediction (Registration.cpp:157): no association, no solve
     a.max_iter = m->num_blocks == 0 ? 0 : p->max_num_iterations;
-    a.fused_tail = sharded ? 0 : 1;
+    a.fused_tail = (sharded && !(c->p2p_ready && c->assoc_variant >= 1 && c->persistent)) ? 0 : 1;
     a.iters_out = nullptr;
     kicp_ctx::ProfReg *pr = nullptr;
     if (c->profiling && (int64_t)c->prof.size() < c->prof_cap) {
@@ -718,46 +1074,101 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
         if (pr) KICP_CUDA(cudaEventRecord(pr->prep1, c->stream));
         const int num_windows = (n + 31) / 32;
         // persistent-style grid: every CTA is resident and pulls windows from a device-side counter
-        const bool pruned = c->assoc_variant == 1;
-        const int per_sm = pruned ? c->pruned_ctas_per_sm : c->assoc_ctas_per_sm;
-        int grid = std::max(1, std::min((num_windows + KICP_WARPS - 1) / KICP_WARPS, c->sm_count * per_sm));
-        for (int j = 0; j < a.max_iter; ++j) {
+        const bool group4 = c->assoc_variant == 2;
+        const bool pruned = c->assoc_variant >= 1;
+        const bool p2p = sharded && c->p2p_ready && pruned;
+        const bool persistent = pruned && c->persistent && (!sharded || p2p);
+        P2PArgs px{};
+        px.nranks = 1;
+        if (p2p) {
+            for (int r = 0; r < c->nranks; ++r) px.peer[r] = c->p2p_peer[r];
+            px.nranks = c->nranks, px.rank = c->rank;
+            px.parity = (int)(c->p2p_seq & 1ull);
+            px.tag_base = (c->p2p_seq + 1ull) * 128ull;
+            c->p2p_seq++;
+        }
+        const int per_sm = group4 ? c->group4_ctas_per_sm
+                                  : (persistent ? c->persistent_ctas_per_sm : (pruned ? c->pruned_ctas_per_sm : c->assoc_ctas_per_sm));
+        const int units = group4 ? (n + 7) / 8 : num_windows;  // warp-windows of 8 or 32 points
+        int grid = std::max(1, std::min((units + KICP_WARPS - 1) / KICP_WARPS, c->sm_count * std::min(per_sm, 16)));
+        int pow2_voxel = 0;
+        {
+            int e = 0;
+            pow2_voxel = std::frexp(m->voxel_size, &e) == 0.5 ? 1 : 0;
+        }
+        const bool dbg = getenv("KICP_DEBUG_SYNC") != nullptr;
+        if (persistent) {
+            // one cooperative launch runs every iteration (grid barrier inside the kernel)
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (pr) {
                 KICP_CUDA(cudaEventCreate(&e0));
                 KICP_CUDA(cudaEventCreate(&e1));
                 pr->it.push_back(e0), pr->it.push_back(e1);
+                pr->persistent = true;
                 KICP_CUDA(cudaEventRecord(e0, c->stream));
             }
-            if (pruned)
-                k_assoc_pruned<<<grid, KICP_WARPS * 32, 0, c->stream>>>(c->d_state, d_pts, n, m->view());
-            else
-                k_assoc<<<grid, KICP_WARPS * 32, assoc_smem_bytes(), c->stream>>>(c->d_state, d_pts, n, m->view());
-            KICP_CHECK_LAUNCH(c);
+            RegState *st_arg = c->d_state;
+            const double *pts_arg = d_pts;
+            int n_arg = n;
+            MapView mv = m->view();
+            double *part_arg = c->d_partials;
+            int pow2_arg = pow2_voxel;
+            void *args_g4[] = {&st_arg, &pts_arg, &n_arg, &mv, &part_arg, &pow2_arg, &px};
+            void *args_pr[] = {&st_arg, &pts_arg, &n_arg, &mv, &part_arg, &px};
+            void **args = group4 ? args_g4 : args_pr;
+            KICP_CUDA(cudaLaunchCooperativeKernel(group4 ? (const void *)k_assoc_group4<true> : (const void *)k_assoc_pruned<true>,
+                                                  dim3(grid), dim3(KICP_WARPS * 32), args, 0, c->stream));
+            c->launches++;
             if (pr) KICP_CUDA(cudaEventRecord(e1, c->stream));
-            if (getenv("KICP_DEBUG_SYNC")) {  // debugging aid: locate a misbehaving launch
-                fprintf(stderr, "[kicp] assoc launch %d (variant %d, grid %d, n %d, d_pts %p) ...", j, pruned ? 1 : 0, grid, n,
-                        (const void *)d_pts);
-                cudaEvent_t t0 = pr ? nullptr : nullptr;
-                (void)t0;
-                const auto wall0 = std::chrono::steady_clock::now();
+            if (dbg) {
                 cudaError_t e = cudaStreamSynchronize(c->stream);
-                const double wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
-                fprintf(stderr, " [%.3f ms]", wall_ms);
-                RegState hs;
-                cudaMemcpy(&hs, c->d_state, offsetof(RegState, result), cudaMemcpyDeviceToHost);
-                fprintf(stderr, " %s iter=%d done=%d ticket=%u wc=%u N=%.0f\n", cudaGetErrorString(e), hs.iter, hs.done, hs.ticket,
-                        hs.window_counter, hs.acc[5]);
+                fprintf(stderr, "[kicp] persistent launch (grid %d, n %d): %s\n", grid, n, cudaGetErrorString(e));
             }
-            if (sharded) {
-                KICP_TRY(kicp_comm_allreduce8(c, c->d_state->acc));
-                k_solve<<<1, 32, 0, c->stream>>>(c->d_state);
+        } else {
+            for (int j = 0; j < a.max_iter; ++j) {
+                cudaEvent_t e0 = nullptr, e1 = nullptr;
+                if (pr) {
+                    KICP_CUDA(cudaEventCreate(&e0));
+                    KICP_CUDA(cudaEventCreate(&e1));
+                    pr->it.push_back(e0), pr->it.push_back(e1);
+                    KICP_CUDA(cudaEventRecord(e0, c->stream));
+                }
+                if (group4)
+                    k_assoc_group4<false><<<grid, KICP_WARPS * 32, 0, c->stream>>>(c->d_state, d_pts, n, m->view(), c->d_partials,
+                                                                                   pow2_voxel, px);
+                else if (pruned)
+                    k_assoc_pruned<false><<<grid, KICP_WARPS * 32, 0, c->stream>>>(c->d_state, d_pts, n, m->view(), c->d_partials, px);
+                else
+                    k_assoc<<<grid, KICP_WARPS * 32, assoc_smem_bytes(), c->stream>>>(c->d_state, d_pts, n, m->view());
                 KICP_CHECK_LAUNCH(c);
+                if (pr) KICP_CUDA(cudaEventRecord(e1, c->stream));
+                if (dbg) {  // debugging aid: locate a misbehaving launch
+                    fprintf(stderr, "[kicp] assoc launch %d (variant %d, grid %d, n %d) ...", j, pruned ? 1 : 0, grid, n);
+                    cudaError_t e = cudaStreamSynchronize(c->stream);
+                    RegState hs;
+                    cudaMemcpy(&hs, c->d_state, offsetof(RegState, result), cudaMemcpyDeviceToHost);
+                    fprintf(stderr, " %s iter=%d done=%d ticket=%u wc=%u\n", cudaGetErrorString(e), hs.iter, hs.done, hs.ticket,
+                            hs.window_counter);
+                }
+                if (sharded) {
+                    KICP_TRY(kicp_comm_allreduce8(c, c->d_state->acc));
+                    k_solve<<<1, 32, 0, c->stream>>>(c->d_state);
+                    KICP_CHECK_LAUNCH(c);
+                }
             }
         }
     }
     if (result)
         KICP_CUDA(cudaMemcpyAsync(result, &c->d_state->result, sizeof(kicp_reg_result), cudaMemcpyDeviceToHost, c->stream));
+    return KICP_OK;
+}
+
+// debugging aid (not part of the public header): per-iteration device timings of the last registration
+extern "C" int kicp_debug_last_timing(kicp_ctx *c, double *out /* [KICP_MAX_ITERATIONS][4] */) {
+    if (!c || !c->d_state) return KICP_ERR_INVALID;
+    KICP_CUDA(cudaStreamSynchronize(c->stream));
+    KICP_CUDA(cudaMemcpy(out, (const char *)c->d_state + offsetof(RegState, dbg), sizeof(double) * KICP_MAX_ITERATIONS * 4,
+                         cudaMemcpyDeviceToHost));
     return KICP_OK;
 }
 
@@ -787,10 +1198,11 @@ extern "C" int kicp_ctx_profile_end(kicp_ctx *c, kicp_profile *out) {
         kicp_ctx::ProfReg &pr = c->prof[r];
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, pr.prep0, pr.prep1) == cudaSuccess) p.prep_ms += ms;
+        p.assoc_iterations += iters[r];
         for (size_t k = 0; k + 1 < pr.it.size(); k += 2) {
             ms = 0.f;
             cudaEventElapsedTime(&ms, pr.it[k], pr.it[k + 1]);
-            if ((int)(k / 2) < iters[r]) {
+            if (pr.persistent || (int)(k / 2) < iters[r]) {
                 p.assoc_ms += ms, p.assoc_launches++;
             } else {
                 p.idle_ms += ms, p.idle_launches++;

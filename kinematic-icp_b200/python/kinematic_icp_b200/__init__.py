@@ -54,6 +54,18 @@ class Context:
         buf = (C.c_uint8 * _capi.KICP_UNIQUE_ID_BYTES).from_buffer_copy(bytes(unique_id))
         check(lib().kicp_comm_init(self.h, buf, int(nranks), int(rank)), "kicp_comm_init")
 
+    def p2p_handle(self):
+        """CUDA-IPC handle of this rank's mailbox (64 bytes) for the fused NVLink exchange."""
+        buf = (C.c_uint8 * _capi.KICP_IPC_HANDLE_BYTES)()
+        check(lib().kicp_comm_p2p_handle(self.h, buf), "kicp_comm_p2p_handle")
+        return bytes(buf)
+
+    def p2p_init(self, handles, nranks, rank):
+        """handles: the nranks 64-byte handles in rank order (all-gathered out of band)."""
+        blob = b"".join(bytes(h) for h in handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        check(lib().kicp_comm_p2p_init(self.h, buf, int(nranks), int(rank)), "kicp_comm_p2p_init")
+
     def close(self):
         if self.h:
             lib().kicp_ctx_destroy(self.h)

@@ -7,9 +7,10 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.normpath(os.path.join(_PKG, "..", ".."))  # kinematic-icp_b200/
-LIB_PATH = os.path.join(_ROOT, "lib", "libkicp_b200.so")
+LIB_PATH = os.environ.get("KICP_LIB", os.path.join(_ROOT, "lib", "libkicp_b200.so"))  # KICP_LIB: A/B builds of the same ABI
 KICP_MAX_ITERATIONS = 64
 KICP_UNIQUE_ID_BYTES = 128
+KICP_IPC_HANDLE_BYTES = 64
 
 KICP_OK = 0
 KICP_ERR_CUDA, KICP_ERR_INVALID, KICP_ERR_UNSUPPORTED, KICP_ERR_NCCL, KICP_ERR_CAPACITY = 1, 2, 3, 4, 5
@@ -44,7 +45,8 @@ class RegResult(C.Structure):
 class Profile(C.Structure):
     """kicp_profile"""
     _fields_ = [("assoc_ms", C.c_double), ("assoc_launches", C.c_int64), ("idle_ms", C.c_double),
-                ("idle_launches", C.c_int64), ("prep_ms", C.c_double), ("registrations", C.c_int64)]
+                ("idle_launches", C.c_int64), ("prep_ms", C.c_double), ("registrations", C.c_int64),
+                ("assoc_iterations", C.c_int64)]
 
 
 class KicpError(RuntimeError):
@@ -97,6 +99,8 @@ SYMBOLS = [
     ("kicp_comm_unique_id", C.c_int, [C.POINTER(C.c_uint8)]),
     ("kicp_comm_init", C.c_int, [_P, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]),
     ("kicp_comm_destroy", C.c_int, [_P]),
+    ("kicp_comm_p2p_handle", C.c_int, [_P, C.POINTER(C.c_uint8)]),
+    ("kicp_comm_p2p_init", C.c_int, [_P, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]),
     ("kicp_register_sharded", C.c_int, [_P, c_dp, C.c_int64, c_dp, c_dp, C.c_double, C.POINTER(RegParams), c_dp,
                                         C.POINTER(RegResult)]),
     ("kicp_register_scan_sharded_async", C.c_int, [_P, _P, c_dp, c_dp, C.c_double, C.POINTER(RegParams),

@@ -1,8 +1,10 @@
 #!/usr/bin/env python
-"""Static check of a kernel's SASS: list uniform-register (URx) READS inside loop bodies (a backward branch to an
-earlier address) whose defining write is outside the loop.  Such reads are only safe if the loop is warp-uniform; for
-per-lane loops they are the hazard documented in kicp_device.cuh.  UR used as memory descriptors (desc[URx]) are
-reported separately (they hold a constant descriptor for the whole kernel)."""
+"""Static check of a kernel's SASS for the hazard documented in kicp_device.cuh: a uniform register (URx, shared by
+the 32 lanes of a warp) that is READ inside a loop body, not written inside it, and WRITTEN AGAIN LATER in the kernel
+(at an address after the loop).  Lanes that leave a per-lane loop early can reach that later write while their siblings
+are still looping and still reading the old value.  A uniform register with no write after the loop (kernel
+parameters loaded once, e.g. the state pointer) cannot be clobbered and is not reported.  Memory descriptors
+(desc[URx]) are ignored."""
 import re, subprocess, sys
 lib, fun = sys.argv[1], sys.argv[2]
 sass = subprocess.run(["cuobjdump", "-sass", "-fun", fun, lib], capture_output=True, text=True).stdout
@@ -25,16 +27,23 @@ def writes(t):
 bad = 0
 for lo, hi in sorted(set(loops)):
     body = [(a, t) for a, t in ins if lo <= a <= hi]
+    # a loop that contains a full-warp or CTA barrier is warp-synchronous by construction: no lane can leave it early
+    # (__syncwarp() compiles to WARPSYNC.ALL, or to BRA.DIV -> a warpsync stub when the compiler expects convergence)
+    if any(("WARPSYNC.ALL" in t) or ("BRA.DIV" in t) or t.startswith("BAR.SYNC") or (" BAR.SYNC" in t) for a, t in body):
+        continue
     defs = set()
     for a, t in body: defs |= writes(t)
+    later = set()
+    for a, t in ins:
+        if a > hi: later |= writes(t)
     reads = {}
     for a, t in body:
         t2 = re.sub(r"^(?:@!?U?P\d+\s+)?\S+\s+UR\d+", "", t) if writes(t) else t
         for r in re.findall(r"(?<!desc\[)UR\d+", t2):
-            if r not in defs: reads.setdefault(r, []).append((a, t))
+            if r not in defs and r in later: reads.setdefault(r, []).append((a, t))
     if reads:
         bad += 1
-        print("loop 0x%x..0x%x (%d instr) reads loop-invariant uniform regs:" % (lo, hi, len(body)))
+        print("loop 0x%x..0x%x (%d instr) reads uniform regs that are rewritten after the loop:" % (lo, hi, len(body)))
         for r, uses in reads.items():
             print("   %s: %s" % (r, "; ".join("0x%x %s" % (a, t[:50]) for a, t in uses[:2])))
-print("loops: %d, with loop-invariant UR reads: %d" % (len(set(loops)), bad))
+print("loops: %d, hazardous: %d" % (len(set(loops)), bad))

@@ -32,7 +32,14 @@ ctx = kb.Context(local)
 uid = torch.tensor(list(kb.comm_unique_id()), dtype=torch.uint8, device=dev) if rank == 0 else torch.empty(
     _capi.KICP_UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
 dist.broadcast(uid, 0)
-ctx.comm_init(bytes(uid.cpu().tolist()), world, rank)
+mode = sys.argv[2] if len(sys.argv) > 2 else "p2p"
+if mode == "nccl":
+    ctx.comm_init(bytes(uid.cpu().tolist()), world, rank)
+else:  # fused NVLink exchange: all-gather the CUDA-IPC handles of the mailboxes
+    mine = torch.tensor(list(ctx.p2p_handle()), dtype=torch.uint8, device=dev)
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    ctx.p2p_init([bytes(h.cpu().tolist()) for h in allh], world, rank)
 gm = kb.VoxelHashMap(ctx, w.voxel_size, w.max_range, w.max_points_per_voxel)
 gm.load_voxels(*w.map.export_voxels())
 lo, hi = kb.shard_range(w.N, world, rank)
@@ -48,8 +55,8 @@ if rank == 0:
     ref, st = w.map.register(w.scan, w.last_pose, w.rel_odom, w.tau, threads=os.cpu_count() or 1)
     dt, ang = ko.pose_delta(pose, ref)
     sums_ok = np.array_equal(res.sums_np()[:, 5], st.sums_np()[:, 5])
-    print("SHARDED cfg%d world=%d iterations gpu=%d cpu=%d identical_on_all_ranks=%s N_match=%s pose delta %.3e m %.3e rad" %
-          (cfg, world, res.iterations, st.iterations, ok, sums_ok, dt, ang), flush=True)
+    print("SHARDED[%s] cfg%d world=%d iterations gpu=%d cpu=%d identical_on_all_ranks=%s N_match=%s pose delta %.3e m %.3e rad" %
+          (mode, cfg, world, res.iterations, st.iterations, ok, sums_ok, dt, ang), flush=True)
     assert ok and sums_ok and res.iterations == st.iterations and dt <= 1e-6 and ang <= 1e-7
 gm.close()
 ctx.close()

@@ -142,15 +142,17 @@ def test_registration_configs_vs_oracle(oracle, gpu_ctx, workload, cfg):
     w = workload(cfg)
     gm = gpu_map_from_oracle(kb, gpu_ctx, w.map)
     try:
-        for variant, sort_bits in ((1, 30), (0, 30), (1, 0), (1, 12)):
+        for variant, sort_bits, persistent in ((2, 0, 1), (2, 0, 0), (2, 30, 1), (1, 0, 1), (1, 0, 0), (0, 30, 0), (1, 30, 1), (1, 12, 0)):
             gpu_ctx.set_option("assoc_variant", variant)
             gpu_ctx.set_option("sort_bits", sort_bits)
+            gpu_ctx.set_option("persistent", persistent)
             pose, dt, ang = check_registration(ko, kb, gpu_ctx, w.map, gm, w.scan, w.last_pose, w.rel_odom, w.tau)
-            print("cfg%d variant=%d sort_bits=%d N=%d M=%d pose delta %.3e m %.3e rad" %
-                  (cfg, variant, sort_bits, w.N, w.map.num_points(), dt, ang))
+            print("cfg%d variant=%d sort_bits=%d persistent=%d N=%d M=%d pose delta %.3e m %.3e rad" %
+                  (cfg, variant, sort_bits, persistent, w.N, w.map.num_points(), dt, ang))
     finally:
         gpu_ctx.set_option("assoc_variant", 1)
         gpu_ctx.set_option("sort_bits", 0)
+        gpu_ctx.set_option("persistent", 1)
     gm.close()
 
 

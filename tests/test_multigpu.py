@@ -65,14 +65,15 @@ def test_sharded_logic_gloo_world2(oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
 @pytest.mark.parametrize("cfg", [2])
-def test_sharded_registration_nccl(cfg):
+def test_sharded_registration(cfg, mode):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     n = min(torch.cuda.device_count(), 8)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
-                        "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "scripts", "sharded_check.py"), str(cfg)],
+                        "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "scripts", "sharded_check.py"), str(cfg), mode],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARDED" in r.stdout
