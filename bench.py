@@ -323,22 +323,35 @@ def main():
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         roofline = None
         if prof is not None and prof.assoc_launches > 0:
-            # average duration of ONE association pass: launches that run several iterations count each of them
-            t_k = prof.assoc_ms / max(prof.assoc_iterations, 1) * 1e-3
-            achieved = n_local * a_pt / t_k / 1e9
-            traffic = None
+            # one launch of the association kernel = all IRLS iterations of one registration (persistent kernel) or one
+            # iteration (multi-launch paths); algorithmic bytes per launch = passes per launch x N x A_pt
+            passes_per_launch = prof.assoc_iterations / float(prof.assoc_launches)
+            t_launch = prof.assoc_ms / prof.assoc_launches * 1e-3
+            bytes_per_launch = passes_per_launch * n_local * a_pt
+            achieved = bytes_per_launch / t_launch / 1e9
+            traffic, traffic_note = None, None
             ncu_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-            if os.path.exists(ncu_path):
-                traffic = json.load(open(ncu_path)).get("dram_bytes_per_launch")
+            if os.path.exists(ncu_path) and args.workload == 4 and world == 1:
+                tj = json.load(open(ncu_path))
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_note = "dram__bytes_read+write per launch from %s" % tj.get("source")
+            kernel_name = {0: "k_assoc", 1: "k_assoc_pruned", 2: "k_assoc_group4"}.get(
+                {"staged": 0, "group4": 2}.get(os.environ.get("KICP_ASSOC", "pruned"), 1))
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": traffic, "kernel": "k_assoc", "kernel_us": t_k * 1e6,
+                        "traffic": traffic, "traffic_note": traffic_note, "kernel": kernel_name,
+                        "launch_us": t_launch * 1e6, "passes_per_launch": passes_per_launch,
+                        "kernel_us": t_launch * 1e6 / max(passes_per_launch, 1e-9),
                         "launches_timed": int(prof.assoc_launches), "iterations_timed": int(prof.assoc_iterations),
+                        "algorithmic_bytes_per_launch": bytes_per_launch,
                         "algorithmic_bytes_per_point": a_pt, "mean_candidates_per_point": cbar,
                         "mean_occupied_voxels_of_27": kbar, "peak_source": peak_src,
-                        "note": "logical gather bytes N*A_pt per launch; the map (%.0f MB) fits the 126 MB L2 and each "
-                                "27-voxel neighbourhood is staged once per voxel group in shared memory, so a "
-                                "fraction above 1 is L2/shared-memory-served, not HBM traffic" %
-                                (w.map.num_voxels() * w.max_points_per_voxel * 24 / 1e6)}
+                        "note": "achieved = LOGICAL gather bytes (SURVEY.md 8(d): 16 + 27*16 + c*16 per point per pass) / "
+                                "CUDA-event duration of the launch. The kernel prunes the 27-voxel neighbourhood exactly "
+                                "(about 26 of the %.0f candidates per point are evaluated) and the map (%.0f MB) is served "
+                                "from L2 after the first touch, so the logical figure exceeds what HBM carries: ncu "
+                                "dram bytes per launch are in `traffic`. The kernel is latency/issue-bound, not "
+                                "bandwidth-bound (profiles/)." %
+                                (cbar, w.map.num_voxels() * w.max_points_per_voxel * 32 / 1e6)}
         ms_per_step = total_ms / args.steps
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -11,6 +11,7 @@
 #define KICP_SLOT_EMPTY 0xFFFFFFFFu
 #define KICP_SLOT_LOCKED 0xFFFFFFFEu
 #define KICP_PSTRIDE 4    // doubles per stored map point: {x, y, z, pad} = one 32-byte sector, two 16-byte loads
+#define KICP_UPLOAD_CHUNKS 8
 #define KICP_MAX_CAP 255  // max_points_per_voxel: the count shares the slot's meta word (low 8 bits)
 
 // ---------------------------------------------------------------------------------------------------------
@@ -62,6 +63,12 @@ struct kicp_ctx {
                             // 2 = pruned with 4 lanes per point
     int sort_bits = 0;      // Morton key bits of the optional binning sort (0 = off, the measured best: DESIGN.md §5)
     kicp_scan *upload_scan = nullptr;  // staging scan used by the host-pointer entry points
+    // chunked upload overlapped with the first IRLS iteration (host-pointer entry points, persistent kernel)
+    cudaStream_t copy_stream = nullptr;
+    uint32_t *d_chunk_flags = nullptr;   // [KICP_UPLOAD_CHUNKS] raised (to the upload sequence number) chunk by chunk
+    uint32_t *h_chunk_tags = nullptr;    // pinned source of the flag copies
+    uint32_t upload_seq = 0;
+    int overlap_upload = 1;
     kicp_reg_result *h_result = nullptr;  // pinned bounce buffer for synchronous calls
     // profiling (kicp_ctx_profile_begin/end): event pairs per registration
     bool profiling = false;

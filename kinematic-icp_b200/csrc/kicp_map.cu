@@ -57,6 +57,11 @@ extern "C" int kicp_ctx_create(int device, kicp_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     KICP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     KICP_CUDA(cudaMallocHost(&c->h_result, sizeof(kicp_reg_result)));
+    KICP_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    KICP_CUDA(cudaMalloc(&c->d_chunk_flags, KICP_UPLOAD_CHUNKS * sizeof(uint32_t)));
+    KICP_CUDA(cudaMemset(c->d_chunk_flags, 0, KICP_UPLOAD_CHUNKS * sizeof(uint32_t)));
+    KICP_CUDA(cudaMallocHost(&c->h_chunk_tags, KICP_UPLOAD_CHUNKS * sizeof(uint32_t)));
+    if (const char *e = getenv("KICP_OVERLAP_UPLOAD")) c->overlap_upload = atoi(e) ? 1 : 0;
     if (const char *e = getenv("KICP_ASSOC")) c->assoc_variant = !strcmp(e, "staged") ? 0 : (!strcmp(e, "group4") ? 2 : 1);
     if (const char *e = getenv("KICP_PERSISTENT")) c->persistent = atoi(e) ? 1 : 0;
     if (const char *e = getenv("KICP_SORT_BITS")) c->sort_bits = std::min(30, std::max(0, atoi(e)));
@@ -145,6 +150,9 @@ extern "C" int kicp_ctx_destroy(kicp_ctx *ctx) {
     cudaFree(ctx->d_sort_tmp);
     cudaFree(ctx->d_prof_iters);
     cudaFreeHost(ctx->h_result);
+    cudaFreeHost(ctx->h_chunk_tags);
+    cudaFree(ctx->d_chunk_flags);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream), cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return KICP_OK;

@@ -464,12 +464,25 @@ __device__ __forceinline__ void scan_voxel(const double *vp, int cnt, double qx,
 // separated by a grid barrier whose last arriver solves the 2x2 system and updates the pose (no launches after
 // convergence, no per-iteration launch gap).  PERSISTENT = false: one launch per iteration (used by the NCCL-sharded
 // path, where the allreduce sits between association and solve).
+// Chunked upload overlapped with the first iteration: chunk c (windows [c*windows_per_chunk, ...)) may be read once
+// flags[c] == seq — the flag is copied by the same copy stream right after the chunk's data.
+struct UploadArgs {
+    const uint32_t *flags;  // nullptr: the scan is already resident
+    uint32_t seq;
+    int windows_per_chunk;  // in 32-point windows
+};
+
 struct P2PArgs {
     P2PMailbox *peer[KICP_MAX_RANKS];
     int nranks, rank, parity;
     unsigned long long tag_base;
 };
 
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -598,7 +611,7 @@ __device__ __forceinline__ bool reduce_and_finish(RegState *st, double *partials
 
 template <bool PERSISTENT>
 __global__ void __launch_bounds__(KICP_WARPS * 32, KICP_MINB) k_assoc_pruned(RegState *st, const double *__restrict__ scan, int n, MapView map, double *partials,
-                                                                                 P2PArgs px) {
+                                                                                 P2PArgs px, UploadArgs up) {
     if (st->done) return;
     __shared__ double s_T[12];
     __shared__ double s_part[KICP_WARPS][8];
@@ -632,6 +645,20 @@ __global__ void __launch_bounds__(KICP_WARPS * 32, KICP_MINB) k_assoc_pruned(Reg
         if (lane == 0) w = (int)atomicAdd(&st->window_counter, 1u);
         w = __shfl_sync(FULL, w, 0);
         if (w >= num_windows) break;
+        if (PERSISTENT && up.flags != nullptr && it == 0u) {
+            // first pass over a frame that is still being uploaded: wait until this window's chunk has landed
+            if (lane == 0) {
+                const uint32_t *f = up.flags + min(w / up.windows_per_chunk, KICP_UPLOAD_CHUNKS - 1);
+                const long long t0 = clock64();
+                while (ld_acquire_sys_u32(f) != up.seq) {
+                    if (clock64() - t0 > 4000000000ll) {  // ~2 s: the copy never arrived
+                        st->status = KICP_ERR_CUDA;
+                        break;
+                    }
+                }
+            }
+            __syncwarp();
+        }
         const int i = w * 32 + lane;
         const bool valid = i < n;
         double px = 0, py = 0, pz = 0;
@@ -1022,7 +1049,7 @@ static int check_params(const kicp_reg_params *p) {
 // Enqueue one full registration on the context stream.  `sharded` inserts the 8-double allreduce between the
 // association and the solve of every iteration.
 static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[7], const double odom[7], double tau,
-                                const kicp_reg_params *p, kicp_reg_result *result, bool sharded) {
+                                const kicp_reg_params *p, kicp_reg_result *result, bool sharded, const UploadArgs *upload = nullptr) {
     if (!m || !scan || !last || !odom) return KICP_ERR_INVALID;
     KICP_TRY(check_params(p));
     kicp_ctx *c = m->ctx;
@@ -1059,6 +1086,15 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
     if (a.max_iter > 0) {
         const double *d_pts = scan->d_xyz;
         const int sbits = c->sort_bits;
+        if (upload && (sbits > 0 || !(c->assoc_variant == 1 && c->persistent && (!sharded || c->p2p_ready)))) {
+            // this configuration reads the whole frame up front: wait for the upload instead of overlapping it
+            cudaEvent_t ev;
+            KICP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            KICP_CUDA(cudaEventRecord(ev, c->copy_stream));
+            KICP_CUDA(cudaStreamWaitEvent(c->stream, ev, 0));
+            KICP_CUDA(cudaEventDestroy(ev));
+            upload = nullptr;
+        }
         if (n > 0 && sbits > 0) {
             const int threads = 256, blocks = (n + threads - 1) / threads;
             k_morton_keys<<<blocks, threads, 0, c->stream>>>(c->d_state, scan->d_xyz, n, m->voxel_size, c->d_keys, c->d_idx);
@@ -1114,7 +1150,9 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
             double *part_arg = c->d_partials;
             int pow2_arg = pow2_voxel;
             void *args_g4[] = {&st_arg, &pts_arg, &n_arg, &mv, &part_arg, &pow2_arg, &px};
-            void *args_pr[] = {&st_arg, &pts_arg, &n_arg, &mv, &part_arg, &px};
+            UploadArgs up_arg = upload ? *upload : UploadArgs{nullptr, 0u, 1};
+            if (group4 || sbits > 0) up_arg.flags = nullptr;
+            void *args_pr[] = {&st_arg, &pts_arg, &n_arg, &mv, &part_arg, &px, &up_arg};
             void **args = group4 ? args_g4 : args_pr;
             KICP_CUDA(cudaLaunchCooperativeKernel(group4 ? (const void *)k_assoc_group4<true> : (const void *)k_assoc_pruned<true>,
                                                   dim3(grid), dim3(KICP_WARPS * 32), args, 0, c->stream));
@@ -1137,7 +1175,8 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
                     k_assoc_group4<false><<<grid, KICP_WARPS * 32, 0, c->stream>>>(c->d_state, d_pts, n, m->view(), c->d_partials,
                                                                                    pow2_voxel, px);
                 else if (pruned)
-                    k_assoc_pruned<false><<<grid, KICP_WARPS * 32, 0, c->stream>>>(c->d_state, d_pts, n, m->view(), c->d_partials, px);
+                    k_assoc_pruned<false><<<grid, KICP_WARPS * 32, 0, c->stream>>>(c->d_state, d_pts, n, m->view(), c->d_partials, px,
+                                                                                   UploadArgs{nullptr, 0u, 1});
                 else
                     k_assoc<<<grid, KICP_WARPS * 32, assoc_smem_bytes(), c->stream>>>(c->d_state, d_pts, n, m->view());
                 KICP_CHECK_LAUNCH(c);
@@ -1231,10 +1270,38 @@ static int register_host(kicp_map *map, const double *frame_xyz, int64_t n, cons
                          double tau, const kicp_reg_params *params, double out_pose[7], kicp_reg_result *result, bool sharded) {
     if (!map || n < 0 || (n > 0 && !frame_xyz) || !out_pose) return KICP_ERR_INVALID;
     kicp_ctx *c = map->ctx;
+    KICP_CUDA(cudaSetDevice(c->device));
     if (!c->upload_scan) KICP_TRY(kicp_scan_create(c, n, &c->upload_scan));
-    KICP_TRY(kicp_scan_upload_async(c->upload_scan, frame_xyz, n));
-    KICP_TRY(enqueue_registration(map, c->upload_scan, last, odom, tau, params, c->h_result, sharded));
+    kicp_scan *s = c->upload_scan;
+    KICP_TRY(kicp_scan_reserve(s, n));
+    s->n = n;
+    // Upload in KICP_UPLOAD_CHUNKS pieces on the copy stream, each followed by a 4-byte flag copy; the persistent kernel's
+    // first pass waits per chunk on the flag, so the association starts while later chunks are still on the bus.
+    UploadArgs up{nullptr, 0u, 1};
+    const UploadArgs *upp = nullptr;
+    if (n > 0) {
+        const int64_t windows = (n + 31) / 32;
+        const int64_t wpc = (windows + KICP_UPLOAD_CHUNKS - 1) / KICP_UPLOAD_CHUNKS;
+        const uint32_t seq = ++c->upload_seq ? c->upload_seq : ++c->upload_seq;  // never 0
+        for (int k = 0; k < KICP_UPLOAD_CHUNKS; ++k) c->h_chunk_tags[k] = seq;
+        for (int k = 0; k < KICP_UPLOAD_CHUNKS; ++k) {
+            const int64_t lo = std::min<int64_t>(n, k * wpc * 32), hi = std::min<int64_t>(n, (k + 1) * wpc * 32);
+            if (hi > lo)
+                KICP_CUDA(cudaMemcpyAsync(s->d_xyz + 3 * lo, frame_xyz + 3 * lo, (size_t)(hi - lo) * 3 * sizeof(double),
+                                          cudaMemcpyHostToDevice, c->copy_stream));
+            KICP_CUDA(cudaMemcpyAsync(c->d_chunk_flags + k, c->h_chunk_tags + k, sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                      c->copy_stream));
+        }
+        up = UploadArgs{c->d_chunk_flags, seq, (int)wpc};
+        upp = &up;
+        if (!c->overlap_upload) {
+            KICP_CUDA(cudaStreamSynchronize(c->copy_stream));
+            upp = nullptr;
+        }
+    }
+    KICP_TRY(enqueue_registration(map, s, last, odom, tau, params, c->h_result, sharded, upp));
     KICP_CUDA(cudaStreamSynchronize(c->stream));
+    KICP_CUDA(cudaStreamSynchronize(c->copy_stream));
     for (int k = 0; k < 7; ++k) out_pose[k] = c->h_result->pose[k];
     if (result) *result = *c->h_result;
     return c->h_result->status;
