@@ -603,10 +603,10 @@ __device__ __forceinline__ bool reduce_and_finish(RegState *st, double *partials
             }
             __threadfence();
         }
-        *s_last = __ldcg(&st->done);
+        s_last[1] = __ldcg(&st->done);  // a different word than the ticket flag s_last[0] (other warps may still read it)
     }
     __syncthreads();
-    return *s_last != 0;
+    return s_last[1] != 0;
 }
 
 template <bool PERSISTENT>
@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(KICP_WARPS * 32, KICP_MINB) k_assoc_pruned(Reg
     if (st->done) return;
     __shared__ double s_T[12];
     __shared__ double s_part[KICP_WARPS][8];
-    __shared__ int s_last;
+    __shared__ int s_last[2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned FULL = 0xFFFFFFFFu;
     __shared__ MapView s_map[32];
@@ -775,7 +775,7 @@ __global__ void __launch_bounds__(KICP_WARPS * 32, KICP_MINB) k_assoc_pruned(Reg
 
     if (blockIdx.x == 0 && threadIdx.x == 0 && it < KICP_MAX_ITERATIONS) st->dbg[it][0] = (double)(gtime_ns() - t_iter0);
     double v[7] = {a00, a01, a11, b0, b1, cntN, ssq};
-    if (reduce_and_finish<PERSISTENT>(st, partials, v, it, s_part, &s_last, px)) return;
+    if (reduce_and_finish<PERSISTENT>(st, partials, v, it, s_part, s_last, px)) return;
   }
 }
 
@@ -803,7 +803,7 @@ __global__ void __launch_bounds__(KICP_WARPS * 32, KICP_MINB) k_assoc_group4(Reg
     if (st->done) return;
     __shared__ double s_T[12];
     __shared__ double s_part[KICP_WARPS][8];
-    __shared__ int s_last;
+    __shared__ int s_last[2];
     const int lane = threadIdx.x & 31;
     const int sub = lane & 3;
     const unsigned FULL = 0xFFFFFFFFu;
@@ -968,7 +968,7 @@ __global__ void __launch_bounds__(KICP_WARPS * 32, KICP_MINB) k_assoc_group4(Reg
 
     if (blockIdx.x == 0 && threadIdx.x == 0 && it < KICP_MAX_ITERATIONS) st->dbg[it][0] = (double)(gtime_ns() - t_iter0);
     double v[7] = {a00, a01, a11, b0, b1, cntN, ssq};
-    if (reduce_and_finish<PERSISTENT>(st, partials, v, it, s_part, &s_last, px)) return;
+    if (reduce_and_finish<PERSISTENT>(st, partials, v, it, s_part, s_last, px)) return;
   }
 }
 
