@@ -144,6 +144,17 @@ int kicp_register_scan_async(kicp_map *map, kicp_scan *scan, const double last_r
                              const double relative_wheel_odometry[7], double max_correspondence_distance,
                              const kicp_reg_params *params, kicp_reg_result *result);
 
+/* ---- front end of KinematicICP::RegisterFrame (pipeline/KinematicICP.cpp:38-44,54-59; KISS-ICP v1.2.0) ---------------- */
+/* kiss_icp::VoxelDownsample(frame, voxel_size): the first point (input order) of every voxel, in input order. */
+int kicp_voxel_downsample(kicp_ctx *ctx, const double *xyz, int64_t n, double voxel_size, double *out_xyz, int64_t cap,
+                          int64_t *m);
+/* kiss_icp::Preprocessor::Preprocess(frame, timestamps, relative_motion) — de-skew with exp((s-1) log(relative_motion))
+ * when `deskew` and stamps are given (n_stamps == n), keep min_range < |p| < max_range — followed by the transform of
+ * the survivors by lidar_to_base (KinematicICP.cpp:59).  Pass the identity pose to get Preprocess alone. */
+int kicp_preprocess(kicp_ctx *ctx, const double *xyz, int64_t n, const double *stamps, int64_t n_stamps,
+                    const double relative_motion[7], const double lidar_to_base[7], double max_range, double min_range,
+                    int32_t deskew, double *out_xyz, int64_t cap, int64_t *m);
+
 /* ---- multi-GPU: the scan's points shard by contiguous index range, the map is replicated, and each IRLS
  *      iteration ends with one sum-allreduce of the 8 accumulated doubles. ------------------- */
 #define KICP_UNIQUE_ID_BYTES 128

@@ -1,10 +1,12 @@
 // kiss_icp/core/Preprocessing.hpp surface (KISS-ICP v1.2.0): Preprocessor(max_range, min_range, deskew, threads).
-// Host-side stand-in for the step before the hot path (pipeline/KinematicICP.cpp:54-57); SURVEY.md §8(f)#2.
+// Preprocess runs on the device (kicp_preprocess, include/kicp.h): de-skew by exp((s-1) log(relative_motion)) with the
+// stamps normalised to [0,1], then the range filter min_range < |p| < max_range; survivors keep their input order.
 #pragma once
 #include <Eigen/Core>
-#include <algorithm>
 #include <sophus/se3.hpp>
 #include <vector>
+
+#include "kicp/runtime.hpp"
 
 namespace kiss_icp {
 struct Preprocessor {
@@ -13,25 +15,17 @@ struct Preprocessor {
 
     std::vector<Eigen::Vector3d> Preprocess(const std::vector<Eigen::Vector3d> &frame, const std::vector<double> &timestamps,
                                             const Sophus::SE3d &relative_motion) const {
-        std::vector<Eigen::Vector3d> deskewed;
-        const std::vector<Eigen::Vector3d> *src = &frame;
-        if (deskew_ && !timestamps.empty()) {
-            const auto mm = std::minmax_element(timestamps.cbegin(), timestamps.cend());
-            const double min_time = *mm.first, max_time = *mm.second;
-            const Sophus::SE3d::Tangent omega = relative_motion.log();
-            deskewed.resize(frame.size());
-            for (size_t i = 0; i < frame.size(); ++i) {
-                const double stamp = (timestamps[i] - min_time) / (max_time - min_time);
-                deskewed[i] = Sophus::SE3d::exp(omega * (stamp - 1.0)) * frame[i];
-            }
-            src = &deskewed;
-        }
-        std::vector<Eigen::Vector3d> out;
-        out.reserve(src->size());
-        for (const auto &p : *src) {
-            const double r = p.norm();
-            if (r < max_range_ && r > min_range_) out.push_back(p);
-        }
+        double motion[7];
+        const double identity[7] = {0, 0, 0, 1, 0, 0, 0};
+        kicp::to_pose7(relative_motion, motion);
+        std::vector<Eigen::Vector3d> out(frame.size());
+        int64_t m = 0;
+        kicp::check(kicp_preprocess(kicp::default_context(), kicp::xyz(frame), (int64_t)frame.size(),
+                                    timestamps.empty() ? nullptr : timestamps.data(), (int64_t)timestamps.size(), motion, identity,
+                                    max_range_, min_range_, deskew_ ? 1 : 0, out.empty() ? nullptr : out.front().data(),
+                                    (int64_t)out.size(), &m),
+                    "kicp_preprocess");
+        out.resize(static_cast<size_t>(m));
         return out;
     }
     double max_range_;

@@ -1,0 +1,288 @@
+// Device-side front end of KinematicICP::RegisterFrame: the two operations the reference runs
+// immediately before the hot path (pipeline/KinematicICP.cpp:38-44, 54-59), both from KISS-ICP v1.2.0:
+//   kiss_icp::VoxelDownsample(frame, voxel_size)          first point (input order) of every voxel
+//   kiss_icp::Preprocessor::Preprocess(frame, stamps, T)  de-skew p <- exp((s-1) log T) p, then keep min < |p| < max
+// followed by the transform to the robot base frame.  Output order is the input order of the survivors (stable stream
+// compaction), which is what the CPU restatement produces.  Compiled with -fmad=false like kicp_map.cu: voxel floors and
+// range tests are evaluated in plain IEEE order.
+#include <cfloat>
+#include <cmath>
+#include <cub/device/device_reduce.cuh>
+#include <cub/device/device_select.cuh>
+
+#include "kicp_device.cuh"
+
+using namespace kicp_dev;
+
+struct P3 {
+    double x, y, z;
+};
+
+// ------------------------------------------------------------------------------------------------ VoxelDownsample
+__global__ void k_ds_insert(const P3 *__restrict__ pts, int n, double vs, int4 *slots, uint32_t mask_in, int *first_idx,
+                            int *slot_of) {
+    __shared__ uint32_t s_mask[32];
+    const uint32_t mask = lane_private(mask_in, s_mask);  // divergence safety, see kicp_device.cuh
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const P3 p = pts[i];
+    const int kx = voxel_coord(p.x, vs), ky = voxel_coord(p.y, vs), kz = voxel_coord(p.z, vs);
+    uint32_t h = voxel_hash(kx, ky, kz) & mask;
+    volatile int4 *vsl = slots;
+    while (true) {
+        uint32_t st = (uint32_t)vsl[h].w;
+        if (st == KICP_SLOT_EMPTY) {
+            const uint32_t old = atomicCAS((unsigned int *)&slots[h].w, KICP_SLOT_EMPTY, KICP_SLOT_LOCKED);
+            if (old == KICP_SLOT_EMPTY) {
+                vsl[h].x = kx, vsl[h].y = ky, vsl[h].z = kz;
+                __threadfence();
+                atomicExch((unsigned int *)&slots[h].w, 0u);
+                break;
+            }
+            st = old;
+        }
+        if (st == KICP_SLOT_LOCKED) continue;
+        __threadfence();
+        if (vsl[h].x == kx && vsl[h].y == ky && vsl[h].z == kz) break;
+        h = (h + 1) & mask;
+    }
+    atomicMin(&first_idx[h], i);  // the voxel keeps the point with the smallest input index
+    slot_of[i] = (int)h;
+}
+
+__global__ void k_ds_flag(int n, const int *__restrict__ first_idx, const int *__restrict__ slot_of, unsigned char *flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = first_idx[slot_of[i]] == i ? 1 : 0;
+}
+
+__global__ void k_fill_int(int *p, int v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------------ Preprocess
+struct PreArgs {
+    double omega[6];       // log(relative_motion) as (upsilon, omega), computed on the host once per frame
+    Pose lidar_to_base;
+    double max_range, min_range, t_min, t_span;  // stamps are normalised as (t - t_min) / t_span
+    int deskew;
+};
+
+// Sophus SE3::exp applied to a point (same operation order as the CPU restatement)
+__device__ void se3_exp_apply(const double a[6], double px, double py, double pz, double &ox, double &oy, double &oz) {
+    const double eps = 1e-10;
+    const double wx = a[3], wy = a[4], wz = a[5];
+    const double theta_sq = wx * wx + wy * wy + wz * wz;
+    double theta, imag, real;
+    if (theta_sq < eps * eps) {
+        theta = 0.0;
+        const double theta_po4 = theta_sq * theta_sq;
+        imag = 0.5 - (1.0 / 48.0) * theta_sq + (1.0 / 3840.0) * theta_po4;
+        real = 1.0 - (1.0 / 8.0) * theta_sq + (1.0 / 384.0) * theta_po4;
+    } else {
+        theta = sqrt(theta_sq);
+        const double half_theta = 0.5 * theta;
+        imag = sin(half_theta) / theta;
+        real = cos(half_theta);
+    }
+    const double qx = imag * wx, qy = imag * wy, qz = imag * wz, qw = real;
+    // V = I + c1 W + c2 W^2 (or the rotation matrix when theta < eps), t = V * upsilon
+    double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0}, O2[9], V[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) O2[3 * i + j] = O[3 * i] * O[j] + O[3 * i + 1] * O[3 + j] + O[3 * i + 2] * O[6 + j];
+    if (theta < eps) {
+        const double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz;
+        const double twx = tx * qw, twy = ty * qw, twz = tz * qw, txx = tx * qx, txy = ty * qx, txz = tz * qx;
+        const double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+        V[0] = 1 - (tyy + tzz), V[1] = txy - twz, V[2] = txz + twy;
+        V[3] = txy + twz, V[4] = 1 - (txx + tzz), V[5] = tyz - twx;
+        V[6] = txz - twy, V[7] = tyz + twx, V[8] = 1 - (txx + tyy);
+    } else {
+        const double theta2 = theta * theta;
+        const double c1 = (1.0 - cos(theta)) / theta2, c2 = (theta - sin(theta)) / (theta2 * theta);
+        for (int i = 0; i < 9; ++i) V[i] = ((i % 4 == 0) ? 1.0 : 0.0) + c1 * O[i] + c2 * O2[i];
+    }
+    const double tx = V[0] * a[0] + V[1] * a[1] + V[2] * a[2];
+    const double ty = V[3] * a[0] + V[4] * a[1] + V[5] * a[2];
+    const double tz = V[6] * a[0] + V[7] * a[1] + V[8] * a[2];
+    double rx, ry, rz;
+    quat_rotate(qx, qy, qz, qw, px, py, pz, rx, ry, rz);
+    ox = rx + tx, oy = ry + ty, oz = rz + tz;
+}
+
+__global__ void k_preprocess(const P3 *__restrict__ pts, const double *__restrict__ stamps, int n, PreArgs a, P3 *out,
+                             unsigned char *flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    P3 p = pts[i];
+    if (a.deskew) {
+        const double stamp = (stamps[i] - a.t_min) / a.t_span;
+        double w[6];
+        for (int k = 0; k < 6; ++k) w[k] = (stamp - 1.0) * a.omega[k];
+        double ox, oy, oz;
+        se3_exp_apply(w, p.x, p.y, p.z, ox, oy, oz);
+        p.x = ox, p.y = oy, p.z = oz;
+    }
+    const double r = sqrt(p.x * p.x + p.y * p.y + p.z * p.z);
+    flags[i] = (r < a.max_range && r > a.min_range) ? 1 : 0;
+    double bx, by, bz;
+    pose_apply(a.lidar_to_base, p.x, p.y, p.z, bx, by, bz);  // preprocessed_frame_in_base (KinematicICP.cpp:59)
+    out[i] = P3{bx, by, bz};
+}
+
+// ------------------------------------------------------------------------------------------------------------ host
+namespace {
+struct Scratch {
+    P3 *in = nullptr, *mid = nullptr, *out = nullptr;
+    double *stamps = nullptr;
+    unsigned char *flags = nullptr;
+    int *first_idx = nullptr, *slot_of = nullptr, *d_count = nullptr;
+    int4 *slots = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int64_t cap = 0;
+    uint32_t nslots = 0;
+};
+Scratch &scratch(kicp_ctx *c) {
+    static thread_local Scratch s[16];
+    return s[c->device & 15];
+}
+
+int reserve(kicp_ctx *c, Scratch &s, int64_t n) {
+    if (n <= s.cap) return KICP_OK;
+    KICP_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(s.in), cudaFree(s.mid), cudaFree(s.out), cudaFree(s.stamps), cudaFree(s.flags), cudaFree(s.first_idx);
+    cudaFree(s.slot_of), cudaFree(s.slots), cudaFree(s.tmp), cudaFree(s.d_count);
+    s = Scratch();
+    const int64_t cap = std::max<int64_t>(n + n / 4, 4096);
+    uint32_t nslots = 1;
+    while (nslots < (uint64_t)cap * 2) nslots <<= 1;
+    KICP_CUDA(cudaMalloc(&s.in, cap * sizeof(P3)));
+    KICP_CUDA(cudaMalloc(&s.mid, cap * sizeof(P3)));
+    KICP_CUDA(cudaMalloc(&s.out, cap * sizeof(P3)));
+    KICP_CUDA(cudaMalloc(&s.stamps, cap * sizeof(double)));
+    KICP_CUDA(cudaMalloc(&s.flags, cap));
+    KICP_CUDA(cudaMalloc(&s.first_idx, (size_t)nslots * sizeof(int)));
+    KICP_CUDA(cudaMalloc(&s.slot_of, cap * sizeof(int)));
+    KICP_CUDA(cudaMalloc(&s.slots, (size_t)nslots * sizeof(int4)));
+    KICP_CUDA(cudaMalloc(&s.d_count, sizeof(int)));
+    size_t b1 = 0, b2 = 0, b3 = 0;
+    KICP_CUDA(cub::DeviceSelect::Flagged(nullptr, b1, s.in, s.flags, s.out, s.d_count, (int)cap, c->stream));
+    KICP_CUDA(cub::DeviceReduce::Min(nullptr, b2, s.stamps, s.stamps, (int)cap, c->stream));
+    KICP_CUDA(cub::DeviceReduce::Max(nullptr, b3, s.stamps, s.stamps, (int)cap, c->stream));
+    s.tmp_bytes = std::max(b1, std::max(b2, b3));
+    KICP_CUDA(cudaMalloc(&s.tmp, s.tmp_bytes));
+    s.cap = cap, s.nslots = nslots;
+    return KICP_OK;
+}
+
+// Sophus SE3::log of a pose7 (host, once per frame)
+void se3_log_host(const double p[7], double out[6]) {
+    const double eps = 1e-10;
+    const double qx = p[0], qy = p[1], qz = p[2], qw = p[3];
+    const double squared_n = qx * qx + qy * qy + qz * qz;
+    double two_atan_nbyw_by_n, theta;
+    if (squared_n < eps * eps) {
+        two_atan_nbyw_by_n = 2.0 / qw - (2.0 / 3.0) * squared_n / (qw * qw * qw);
+        theta = 2.0 * squared_n / qw;
+    } else {
+        const double nn = std::sqrt(squared_n);
+        const double at = qw < 0.0 ? std::atan2(-nn, -qw) : std::atan2(nn, qw);
+        two_atan_nbyw_by_n = 2.0 * at / nn;
+        theta = two_atan_nbyw_by_n * nn;
+    }
+    const double w[3] = {two_atan_nbyw_by_n * qx, two_atan_nbyw_by_n * qy, two_atan_nbyw_by_n * qz};
+    const double O[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+    double O2[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) O2[3 * i + j] = O[3 * i] * O[j] + O[3 * i + 1] * O[3 + j] + O[3 * i + 2] * O[6 + j];
+    double cc;
+    if (std::abs(theta) < eps) {
+        cc = 1.0 / 12.0;
+    } else {
+        const double half = 0.5 * theta;
+        cc = (1.0 - theta * std::cos(half) / (2.0 * std::sin(half))) / (theta * theta);
+    }
+    double Vinv[9];
+    for (int i = 0; i < 9; ++i) Vinv[i] = ((i % 4 == 0) ? 1.0 : 0.0) - 0.5 * O[i] + cc * O2[i];
+    for (int i = 0; i < 3; ++i) out[i] = Vinv[3 * i] * p[4] + Vinv[3 * i + 1] * p[5] + Vinv[3 * i + 2] * p[6];
+    out[3] = w[0], out[4] = w[1], out[5] = w[2];
+}
+}  // namespace
+
+extern "C" int kicp_voxel_downsample(kicp_ctx *c, const double *xyz, int64_t n, double voxel_size, double *out_xyz, int64_t cap,
+                                     int64_t *m) {
+    if (!c || !m || n < 0 || (n > 0 && (!xyz || !out_xyz)) || !(voxel_size > 0.0) || n > 0x3FFFFFFF) return KICP_ERR_INVALID;
+    *m = 0;
+    if (n == 0) return KICP_OK;
+    KICP_CUDA(cudaSetDevice(c->device));
+    Scratch &s = scratch(c);
+    KICP_TRY(reserve(c, s, n));
+    KICP_CUDA(cudaMemcpyAsync(s.in, xyz, (size_t)n * sizeof(P3), cudaMemcpyHostToDevice, c->stream));
+    KICP_CUDA(cudaMemsetAsync(s.slots, 0xFF, (size_t)s.nslots * sizeof(int4), c->stream));
+    const int threads = 256, blocks = (int)((n + threads - 1) / threads);
+    k_fill_int<<<(s.nslots + 255) / 256, 256, 0, c->stream>>>(s.first_idx, 0x7FFFFFFF, (int)s.nslots);
+    KICP_CHECK_LAUNCH(c);
+    k_ds_insert<<<blocks, threads, 0, c->stream>>>(s.in, (int)n, voxel_size, s.slots, s.nslots - 1, s.first_idx, s.slot_of);
+    KICP_CHECK_LAUNCH(c);
+    k_ds_flag<<<blocks, threads, 0, c->stream>>>((int)n, s.first_idx, s.slot_of, s.flags);
+    KICP_CHECK_LAUNCH(c);
+    size_t bytes = s.tmp_bytes;
+    KICP_CUDA(cub::DeviceSelect::Flagged(s.tmp, bytes, s.in, s.flags, s.out, s.d_count, (int)n, c->stream));
+    c->launches += 2;
+    int count = 0;
+    KICP_CUDA(cudaMemcpyAsync(&count, s.d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    KICP_CUDA(cudaStreamSynchronize(c->stream));
+    *m = count;
+    if (count > cap) return KICP_ERR_CAPACITY;
+    KICP_CUDA(cudaMemcpy(out_xyz, s.out, (size_t)count * sizeof(P3), cudaMemcpyDeviceToHost));
+    return KICP_OK;
+}
+
+extern "C" int kicp_preprocess(kicp_ctx *c, const double *xyz, int64_t n, const double *stamps, int64_t n_stamps,
+                               const double relative_motion[7], const double lidar_to_base[7], double max_range, double min_range,
+                               int deskew, double *out_xyz, int64_t cap, int64_t *m) {
+    if (!c || !m || n < 0 || (n > 0 && (!xyz || !out_xyz)) || !relative_motion || !lidar_to_base || n > 0x3FFFFFFF)
+        return KICP_ERR_INVALID;
+    if (deskew && n_stamps > 0 && (n_stamps != n || !stamps)) return KICP_ERR_INVALID;
+    *m = 0;
+    if (n == 0) return KICP_OK;
+    KICP_CUDA(cudaSetDevice(c->device));
+    Scratch &s = scratch(c);
+    KICP_TRY(reserve(c, s, n));
+    PreArgs a;
+    a.deskew = (deskew && n_stamps > 0) ? 1 : 0;  // Preprocessing.cpp: `!deskew_ || timestamps.empty()` returns the frame as is
+    a.max_range = max_range, a.min_range = min_range, a.t_min = 0.0, a.t_span = 1.0;
+    a.lidar_to_base = Pose{lidar_to_base[0], lidar_to_base[1], lidar_to_base[2], lidar_to_base[3], lidar_to_base[4], lidar_to_base[5],
+                           lidar_to_base[6]};
+    for (int k = 0; k < 6; ++k) a.omega[k] = 0.0;
+    KICP_CUDA(cudaMemcpyAsync(s.in, xyz, (size_t)n * sizeof(P3), cudaMemcpyHostToDevice, c->stream));
+    if (a.deskew) {
+        KICP_CUDA(cudaMemcpyAsync(s.stamps, stamps, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        double *d_mm = reinterpret_cast<double *>(s.mid);  // two doubles of scratch
+        size_t bytes = s.tmp_bytes;
+        KICP_CUDA(cub::DeviceReduce::Min(s.tmp, bytes, s.stamps, d_mm, (int)n, c->stream));
+        bytes = s.tmp_bytes;
+        KICP_CUDA(cub::DeviceReduce::Max(s.tmp, bytes, s.stamps, d_mm + 1, (int)n, c->stream));
+        c->launches += 2;
+        double mm[2];
+        KICP_CUDA(cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, c->stream));
+        KICP_CUDA(cudaStreamSynchronize(c->stream));
+        a.t_min = mm[0];
+        a.t_span = mm[1] - mm[0];
+        se3_log_host(relative_motion, a.omega);
+    }
+    const int threads = 256, blocks = (int)((n + threads - 1) / threads);
+    k_preprocess<<<blocks, threads, 0, c->stream>>>(s.in, s.stamps, (int)n, a, s.mid, s.flags);
+    KICP_CHECK_LAUNCH(c);
+    size_t bytes = s.tmp_bytes;
+    KICP_CUDA(cub::DeviceSelect::Flagged(s.tmp, bytes, s.mid, s.flags, s.out, s.d_count, (int)n, c->stream));
+    c->launches += 2;
+    int count = 0;
+    KICP_CUDA(cudaMemcpyAsync(&count, s.d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    KICP_CUDA(cudaStreamSynchronize(c->stream));
+    *m = count;
+    if (count > cap) return KICP_ERR_CAPACITY;
+    KICP_CUDA(cudaMemcpy(out_xyz, s.out, (size_t)count * sizeof(P3), cudaMemcpyDeviceToHost));
+    return KICP_OK;
+}

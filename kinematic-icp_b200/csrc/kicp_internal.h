@@ -58,9 +58,10 @@ struct kicp_ctx {
     int pruned_ctas_per_sm = 1;
     int persistent_ctas_per_sm = 1;
     int group4_ctas_per_sm = 1;
+    int hybrid_ctas_per_sm = 1;
     int persistent = 1;     // 1 = all IRLS iterations inside one cooperative launch (single-GPU pruned path)
     int assoc_variant = 1;  // 0 = staged (27-voxel neighbourhood through shared memory), 1 = pruned (thread per point),
-                            // 2 = pruned with 4 lanes per point
+                            // 2 = pruned with 4 lanes per point, 3 = hybrid (32-point windows + 8-point tail)
     int sort_bits = 0;      // Morton key bits of the optional binning sort (0 = off, the measured best: DESIGN.md §5)
     kicp_scan *upload_scan = nullptr;  // staging scan used by the host-pointer entry points
     // chunked upload overlapped with the first IRLS iteration (host-pointer entry points, persistent kernel)

@@ -972,6 +972,326 @@ __global__ void __launch_bounds__(KICP_WARPS * 32, KICP_MINB) k_assoc_group4(Reg
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_assoc_hybrid (variant 3, default): one pass = 32-point windows (k_assoc_pruned's body, the efficient one for the
+// bulk) followed by 8-point group windows (k_assoc_group4's body) for the last KICP_TAIL_PERCENT of the points.  Work
+// units are handed out in increasing order from one counter, so the small units come last and the end-of-pass tail is
+// the duration of an 8-point window (about 5 us) instead of a 32-point one (about 18 us).
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef KICP_TAIL_PERCENT
+#define KICP_TAIL_PERCENT 15
+#endif
+template <bool PERSISTENT>
+__global__ void __launch_bounds__(KICP_WARPS * 32, KICP_MINB) k_assoc_hybrid(RegState *st, const double *__restrict__ scan, int n, MapView map,
+                                                                              double *partials, int pow2_voxel, P2PArgs px, UploadArgs up) {
+    if (st->done) return;
+    __shared__ double s_T[12];
+    __shared__ double s_part[KICP_WARPS][8];
+    __shared__ int s_last[2];
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & 3;
+    const unsigned FULL = 0xFFFFFFFFu;
+    __shared__ MapView s_map[32];
+    const MapRegs mr = map_regs(map, s_map);  // per-thread copy of the map view (divergence safety, kicp_device.cuh)
+    __shared__ double s_tau[32];
+    if (threadIdx.x < 32) s_tau[threadIdx.x] = st->tau;
+    __syncthreads();
+    const double tau = ((const volatile double *)s_tau)[lane], vs = map.voxel_size, inv_vs = 1.0 / map.voxel_size;
+    // bulk: 32-point windows over the first points; tail: 8-point units over the rest
+    const int all32 = (n + 31) >> 5;
+    const int num_big = n >= 4096 ? (int)((long long)all32 * (100 - KICP_TAIL_PERCENT) / 100) : all32;
+    const int base8 = min(n, num_big * 32);
+    const int num_units = num_big + ((n - base8 + 7) >> 3);
+    __shared__ unsigned s_zero[32];
+    if (threadIdx.x < 32) s_zero[threadIdx.x] = 0u;
+    __syncthreads();
+    unsigned it = ((const volatile unsigned *)s_zero)[lane];
+    const uint32_t tmask = mr.mask;
+    const int4 *tslots = mr.slots;
+    const double *tpts = mr.pts;
+    const size_t tstride = (size_t)mr.cap * KICP_PSTRIDE;
+  for (;; ++it) {
+    if (threadIdx.x < 9) s_T[threadIdx.x] = __ldcg(&st->R[threadIdx.x]);
+    if (threadIdx.x >= 9 && threadIdx.x < 12) s_T[threadIdx.x] = __ldcg(&st->t[threadIdx.x - 9]);
+    __syncthreads();
+    double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0, cntN = 0, ssq = 0;
+    const unsigned long long t_iter0 = gtime_ns();
+
+    while (true) {
+        int w = 0;
+        if (lane == 0) w = (int)atomicAdd(&st->window_counter, 1u);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= num_units) break;
+        if (PERSISTENT && up.flags != nullptr && it == 0u) {
+            // first pass over a frame that is still being uploaded: wait until this unit's chunk has landed
+            if (lane == 0) {
+                const int w32 = w < num_big ? w : (base8 + (w - num_big) * 8) >> 5;
+                const uint32_t *f = up.flags + min(w32 / up.windows_per_chunk, KICP_UPLOAD_CHUNKS - 1);
+                const long long t0 = clock64();
+                while (ld_acquire_sys_u32(f) != up.seq) {
+                    if (clock64() - t0 > 4000000000ll) {
+                        st->status = KICP_ERR_CUDA;
+                        break;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (w < num_big) {
+        const int i = w * 32 + lane;
+        const bool valid = i < n;
+        double px = 0, py = 0, pz = 0;
+        if (valid) px = scan[3 * (size_t)i], py = scan[3 * (size_t)i + 1], pz = scan[3 * (size_t)i + 2];
+        const double qx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[9];
+        const double qy = s_T[3] * px + s_T[4] * py + s_T[5] * pz + s_T[10];
+        const double qz = s_T[6] * px + s_T[7] * py + s_T[8] * pz + s_T[11];
+        const int vx = voxel_coord(qx, vs), vy = voxel_coord(qy, vs), vz = voxel_coord(qz, vs);
+        // squared gaps to the six faces of the query voxel
+        double t;
+        t = (double)(vx + 1) * vs - qx; const double gxp = t * t;
+        t = qx - (double)vx * vs;       const double gxm = t * t;
+        t = (double)(vy + 1) * vs - qy; const double gyp = t * t;
+        t = qy - (double)vy * vs;       const double gym = t * t;
+        t = (double)(vz + 1) * vs - qz; const double gzp = t * t;
+        t = qz - (double)vz * vs;       const double gzm = t * t;
+
+        double best = DBL_MAX;
+        const double *bestp = nullptr;
+        const uint32_t tmask = mr.mask;
+        const int4 *tslots = mr.slots;
+        const double *tpts = mr.pts;
+        const size_t tstride = (size_t)mr.cap * KICP_PSTRIDE;
+        // round 0: the query's own voxel — it usually yields a best distance that prunes most of the other 26
+        if (valid) {
+            const uint32_t meta = map_probe(mr, vx, vy, vz);
+            if (meta != KICP_SLOT_EMPTY) scan_voxel(tpts + (size_t)(meta >> 8) * tstride, (int)(meta & 0xFFu), qx, qy, qz, best, bestp);
+        }
+        __syncwarp();
+        unsigned mask = valid ? 0x07FFFFFEu : 0u;  // shifts still to consider, bit k <-> voxel_shifts[k]
+        while (__any_sync(FULL, mask != 0u)) {  // warp-uniform loop; inside a round every lane walks its own voxels
+            if (mask) {
+                // drop every shift whose cube is provably too far, then take the next (up to) 4 in KISS order
+                const double bound = best * (1.0 + 1e-6) + 1e-10;
+                mask &= (kX0 | (gxp <= bound ? kXP : 0u) | (gxm <= bound ? kXM : 0u)) &
+                        (kY0 | (gyp <= bound ? kYP : 0u) | (gym <= bound ? kYM : 0u)) &
+                        (kZ0 | (gzp <= bound ? kZP : 0u) | (gzm <= bound ? kZM : 0u));
+                int kx[4], ky[4], kz[4];
+                uint32_t hh[4];
+                double lb[4];
+                bool use[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    use[u] = false;
+                    kx[u] = ky[u] = kz[u] = 0, hh[u] = 0, lb[u] = 0.0;
+                    while (mask) {
+                        const int k = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const int sx = shift_x(k), sy = shift_y(k), sz = shift_z(k);
+                        const double lb2 = (sx > 0 ? gxp : (sx < 0 ? gxm : 0.0)) + (sy > 0 ? gyp : (sy < 0 ? gym : 0.0)) +
+                                           (sz > 0 ? gzp : (sz < 0 ? gzm : 0.0));
+                        if (lb2 > bound) continue;
+                        use[u] = true, lb[u] = lb2;
+                        kx[u] = vx + sx, ky[u] = vy + sy, kz[u] = vz + sz;
+                        hh[u] = voxel_hash(kx[u], ky[u], kz[u]) & tmask;
+                        break;
+                    }
+                }
+                // four independent home-slot loads in flight, then resolve the (rare) longer probe chains
+                int4 s0[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (use[u]) s0[u] = __ldg(&tslots[hh[u]]);
+                uint32_t metas[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    uint32_t meta = KICP_SLOT_EMPTY;
+                    if (use[u]) {
+                        int4 sl = s0[u];
+                        uint32_t h = hh[u];
+                        while (true) {
+                            if ((uint32_t)sl.w == KICP_SLOT_EMPTY) break;
+                            if (sl.x == kx[u] && sl.y == ky[u] && sl.z == kz[u]) {
+                                meta = (uint32_t)sl.w;
+                                break;
+                            }
+                            h = (h + 1) & tmask;
+                            sl = __ldg(&tslots[h]);
+                        }
+                    }
+                    metas[u] = meta;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    // re-check against the best found meanwhile; KISS order is kept, so strict < resolves ties identically
+                    if (metas[u] != KICP_SLOT_EMPTY && !(lb[u] > best * (1.0 + 1e-6) + 1e-10))
+                        scan_voxel(tpts + (size_t)(metas[u] >> 8) * tstride, (int)(metas[u] & 0xFFu), qx, qy, qz, best, bestp);
+                }
+            }
+            __syncwarp();
+        }
+        const bool have = bestp != nullptr;
+        double bx = 0, by = 0, bz = 0;
+        if (have) {
+            const double2 a = __ldg(reinterpret_cast<const double2 *>(bestp)), b = __ldg(reinterpret_cast<const double2 *>(bestp) + 1);
+            bx = a.x, by = a.y, bz = b.x;
+        }
+        if (have) {
+            const double rx = qx - bx, ry = qy - by, rz = qz - bz;  // r = T p - n
+            const double rr = rx * rx + ry * ry + rz * rz;
+            if (sqrt(rr) < tau) {  // distance < max_correspondance_distance   (Registration.cpp:75)
+                const double c0x = s_T[0], c0y = s_T[3], c0z = s_T[6];
+                const double c1x = s_T[1] * px - s_T[0] * py, c1y = s_T[4] * px - s_T[3] * py, c1z = s_T[7] * px - s_T[6] * py;
+                a00 += c0x * c0x + c0y * c0y + c0z * c0z;
+                a01 += c0x * c1x + c0y * c1y + c0z * c1z;
+                a11 += c1x * c1x + c1y * c1y + c1z * c1z;
+                b0 += c0x * rx + c0y * ry + c0z * rz;
+                b1 += c1x * rx + c1y * ry + c1z * rz;
+                cntN += 1.0;
+                ssq += rr;
+            }
+        }
+
+        } else {
+        const int i = base8 + (w - num_big) * 8 + (lane >> 2);
+        const bool valid = i < n;
+        double px = 0, py = 0, pz = 0;
+        if (valid) px = scan[3 * (size_t)i], py = scan[3 * (size_t)i + 1], pz = scan[3 * (size_t)i + 2];
+        const double qx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[9];
+        const double qy = s_T[3] * px + s_T[4] * py + s_T[5] * pz + s_T[10];
+        const double qz = s_T[6] * px + s_T[7] * py + s_T[8] * pz + s_T[11];
+        // PointToVoxel: floor(q / voxel_size); for a power-of-two voxel size the product with the (exact) reciprocal
+        // is the same double as the quotient, so the cheaper form is used
+        int vx, vy, vz;
+        if (pow2_voxel) {
+            vx = (int)floor(qx * inv_vs), vy = (int)floor(qy * inv_vs), vz = (int)floor(qz * inv_vs);
+        } else {
+            vx = voxel_coord(qx, vs), vy = voxel_coord(qy, vs), vz = voxel_coord(qz, vs);
+        }
+        double t;
+        t = (double)(vx + 1) * vs - qx; const double gxp = t * t;
+        t = qx - (double)vx * vs;       const double gxm = t * t;
+        t = (double)(vy + 1) * vs - qy; const double gyp = t * t;
+        t = qy - (double)vy * vs;       const double gym = t * t;
+        t = (double)(vz + 1) * vs - qz; const double gzp = t * t;
+        t = qz - (double)vz * vs;       const double gzm = t * t;
+
+        double best = DBL_MAX;            // this lane's best
+        unsigned bestkey = 0xFFFFFFFFu;   // (shift index << 8) | index in voxel of this lane's best
+        const double *bestp = nullptr;
+        // round 0: the query's own voxel, its points strided over the 4 lanes
+        if (valid) {
+            const uint32_t meta = map_probe(mr, vx, vy, vz);
+            if (meta != KICP_SLOT_EMPTY) {
+                const double *vp = tpts + (size_t)(meta >> 8) * tstride;
+                const int cnt = (int)(meta & 0xFFu);
+                for (int j = sub; j < cnt; j += 4) {
+                    const double *p0 = vp + (size_t)j * KICP_PSTRIDE;
+                    const double2 a = __ldg(reinterpret_cast<const double2 *>(p0)), b = __ldg(reinterpret_cast<const double2 *>(p0) + 1);
+                    const double dx = a.x - qx, dy = a.y - qy, dz = b.x - qz;
+                    const double d2 = dx * dx + dy * dy + dz * dz;
+                    if (d2 < best) best = d2, bestkey = (unsigned)j, bestp = p0;
+                }
+            }
+        }
+        __syncwarp();
+        double gbest = group4_min(best);
+        unsigned mask = valid ? 0x07FFFFFEu : 0u;  // identical in the 4 lanes of a group
+        while (__any_sync(FULL, mask != 0u)) {
+            uint32_t meta = KICP_SLOT_EMPTY;
+            int myk = 0;
+            double lb[4] = {0.0, 0.0, 0.0, 0.0};
+            if (mask) {
+                const double bound = gbest * (1.0 + 1e-6) + 1e-10;
+                mask &= (kX0 | (gxp <= bound ? kXP : 0u) | (gxm <= bound ? kXM : 0u)) &
+                        (kY0 | (gyp <= bound ? kYP : 0u) | (gym <= bound ? kYM : 0u)) &
+                        (kZ0 | (gzp <= bound ? kZP : 0u) | (gzm <= bound ? kZM : 0u));
+                // the next (up to) 4 shifts in KISS order that survive the exact bound; lane `sub` probes the sub-th one
+                int kxs = 0, kys = 0, kzs = 0;
+                bool use = false;
+                int found = 0;
+                while (mask && found < 4) {
+                    const int k = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int sx = shift_x(k), sy = shift_y(k), sz = shift_z(k);
+                    const double lb2 = (sx > 0 ? gxp : (sx < 0 ? gxm : 0.0)) + (sy > 0 ? gyp : (sy < 0 ? gym : 0.0)) +
+                                       (sz > 0 ? gzp : (sz < 0 ? gzm : 0.0));
+                    if (lb2 > bound) continue;
+                    if (found == 0) lb[0] = lb2;
+                    if (found == 1) lb[1] = lb2;
+                    if (found == 2) lb[2] = lb2;
+                    if (found == 3) lb[3] = lb2;
+                    if (found == sub) use = true, myk = k, kxs = vx + sx, kys = vy + sy, kzs = vz + sz;
+                    ++found;
+                }
+                if (use) {
+                    uint32_t h = voxel_hash(kxs, kys, kzs) & tmask;
+                    while (true) {
+                        const int4 sl = __ldg(&tslots[h]);
+                        if ((uint32_t)sl.w == KICP_SLOT_EMPTY) break;
+                        if (sl.x == kxs && sl.y == kys && sl.z == kzs) {
+                            meta = (uint32_t)sl.w;
+                            break;
+                        }
+                        h = (h + 1) & tmask;
+                    }
+                }
+            }
+            __syncwarp();
+            // every lane of the group learns the 4 probe results, then the group scans the found voxels in KISS order
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t mu = __shfl_sync(FULL, meta, (lane & ~3) | u);
+                const int ku = __shfl_sync(FULL, myk, (lane & ~3) | u);
+                if (mu != KICP_SLOT_EMPTY && !(lb[u] > best * (1.0 + 1e-6) + 1e-10)) {
+                    const double *vp = tpts + (size_t)(mu >> 8) * tstride;
+                    const int cnt = (int)(mu & 0xFFu);
+                    for (int j = sub; j < cnt; j += 4) {
+                        const double *p0 = vp + (size_t)j * KICP_PSTRIDE;
+                        const double2 a = __ldg(reinterpret_cast<const double2 *>(p0)), b = __ldg(reinterpret_cast<const double2 *>(p0) + 1);
+                        const double dx = a.x - qx, dy = a.y - qy, dz = b.x - qz;
+                        const double d2 = dx * dx + dy * dy + dz * dz;
+                        if (d2 < best) best = d2, bestkey = ((unsigned)ku << 8) | (unsigned)j, bestp = p0;
+                    }
+                }
+                __syncwarp();
+            }
+            gbest = group4_min(best);
+        }
+        // the group's winner: minimum of (d2, order key) — the first minimum in the reference's visiting order
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            const double od = __shfl_xor_sync(FULL, best, o);
+            const unsigned ok = __shfl_xor_sync(FULL, bestkey, o);
+            const unsigned long long op = __shfl_xor_sync(FULL, (unsigned long long)bestp, o);
+            if (od < best || (od == best && ok < bestkey)) best = od, bestkey = ok, bestp = (const double *)op;
+        }
+        if (sub == 0 && bestp != nullptr) {
+            const double2 a = __ldg(reinterpret_cast<const double2 *>(bestp)), b = __ldg(reinterpret_cast<const double2 *>(bestp) + 1);
+            const double rx = qx - a.x, ry = qy - a.y, rz = qz - b.x;  // r = T p - n
+            const double rr = rx * rx + ry * ry + rz * rz;
+            if (sqrt(rr) < tau) {  // distance < max_correspondance_distance   (Registration.cpp:75)
+                const double c0x = s_T[0], c0y = s_T[3], c0z = s_T[6];
+                const double c1x = s_T[1] * px - s_T[0] * py, c1y = s_T[4] * px - s_T[3] * py, c1z = s_T[7] * px - s_T[6] * py;
+                a00 += c0x * c0x + c0y * c0y + c0z * c0z;
+                a01 += c0x * c1x + c0y * c1y + c0z * c1z;
+                a11 += c1x * c1x + c1y * c1y + c1z * c1z;
+                b0 += c0x * rx + c0y * ry + c0z * rz;
+                b1 += c1x * rx + c1y * ry + c1z * rz;
+                cntN += 1.0;
+                ssq += rr;
+            }
+        }
+        __syncwarp();
+
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && it < KICP_MAX_ITERATIONS) st->dbg[it][0] = (double)(gtime_ns() - t_iter0);
+    double v[7] = {a00, a01, a11, b0, b1, cntN, ssq};
+    if (reduce_and_finish<PERSISTENT>(st, partials, v, it, s_part, s_last, px)) return;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------- host
 // Kernel variant and binning granularity are per-context options (kicp_ctx_set_option); the defaults are the
 // measured best (profiles/) and can be overridden with KICP_ASSOC=staged|pruned and KICP_SORT_BITS=0..30 so that
@@ -979,7 +1299,7 @@ __global__ void __launch_bounds__(KICP_WARPS * 32, KICP_MINB) k_assoc_group4(Reg
 extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value) {
     if (!c || !name) return KICP_ERR_INVALID;
     if (!strcmp(name, "assoc_variant")) {
-        if (value < 0 || value > 2) return KICP_ERR_INVALID;
+        if (value < 0 || value > 3) return KICP_ERR_INVALID;
         c->assoc_variant = value;
     } else if (!strcmp(name, "persistent")) {
         if (value != 0 && value != 1) return KICP_ERR_INVALID;
@@ -1013,6 +1333,10 @@ static int reg_reserve(kicp_ctx *c, int64_t n) {
         c->group4_ctas_per_sm = std::max(per_sm, 1);
         KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc_group4<false>, KICP_WARPS * 32, 0));
         c->group4_ctas_per_sm = std::min(c->group4_ctas_per_sm, std::max(per_sm, 1));
+        KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc_hybrid<true>, KICP_WARPS * 32, 0));
+        c->hybrid_ctas_per_sm = std::max(per_sm, 1);
+        KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc_hybrid<false>, KICP_WARPS * 32, 0));
+        c->hybrid_ctas_per_sm = std::min(c->hybrid_ctas_per_sm, std::max(per_sm, 1));
         int coop = 0;
         KICP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
         if (!coop) c->persistent = 0;
@@ -1086,7 +1410,7 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
     if (a.max_iter > 0) {
         const double *d_pts = scan->d_xyz;
         const int sbits = c->sort_bits;
-        if (upload && (sbits > 0 || !(c->assoc_variant == 1 && c->persistent && (!sharded || c->p2p_ready)))) {
+        if (upload && (sbits > 0 || !((c->assoc_variant == 1 || c->assoc_variant == 3) && c->persistent && (!sharded || c->p2p_ready)))) {
             // this configuration reads the whole frame up front: wait for the upload instead of overlapping it
             cudaEvent_t ev;
             KICP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1111,6 +1435,7 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
         const int num_windows = (n + 31) / 32;
         // persistent-style grid: every CTA is resident and pulls windows from a device-side counter
         const bool group4 = c->assoc_variant == 2;
+        const bool hybrid = c->assoc_variant == 3;
         const bool pruned = c->assoc_variant >= 1;
         const bool p2p = sharded && c->p2p_ready && pruned;
         const bool persistent = pruned && c->persistent && (!sharded || p2p);
@@ -1123,7 +1448,7 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
             px.tag_base = (c->p2p_seq + 1ull) * 128ull;
             c->p2p_seq++;
         }
-        const int per_sm = group4 ? c->group4_ctas_per_sm
+        const int per_sm = hybrid ? c->hybrid_ctas_per_sm : group4 ? c->group4_ctas_per_sm
                                   : (persistent ? c->persistent_ctas_per_sm : (pruned ? c->pruned_ctas_per_sm : c->assoc_ctas_per_sm));
         const int units = group4 ? (n + 7) / 8 : num_windows;  // warp-windows of 8 or 32 points
         int grid = std::max(1, std::min((units + KICP_WARPS - 1) / KICP_WARPS, c->sm_count * std::min(per_sm, 16)));
@@ -1152,9 +1477,12 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
             void *args_g4[] = {&st_arg, &pts_arg, &n_arg, &mv, &part_arg, &pow2_arg, &px};
             UploadArgs up_arg = upload ? *upload : UploadArgs{nullptr, 0u, 1};
             if (group4 || sbits > 0) up_arg.flags = nullptr;
+            void *args_hy[] = {&st_arg, &pts_arg, &n_arg, &mv, &part_arg, &pow2_arg, &px, &up_arg};
             void *args_pr[] = {&st_arg, &pts_arg, &n_arg, &mv, &part_arg, &px, &up_arg};
-            void **args = group4 ? args_g4 : args_pr;
-            KICP_CUDA(cudaLaunchCooperativeKernel(group4 ? (const void *)k_assoc_group4<true> : (const void *)k_assoc_pruned<true>,
+            void **args = hybrid ? args_hy : (group4 ? args_g4 : args_pr);
+            KICP_CUDA(cudaLaunchCooperativeKernel(hybrid   ? (const void *)k_assoc_hybrid<true>
+                                                  : group4 ? (const void *)k_assoc_group4<true>
+                                                           : (const void *)k_assoc_pruned<true>,
                                                   dim3(grid), dim3(KICP_WARPS * 32), args, 0, c->stream));
             c->launches++;
             if (pr) KICP_CUDA(cudaEventRecord(e1, c->stream));
@@ -1171,7 +1499,10 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
                     pr->it.push_back(e0), pr->it.push_back(e1);
                     KICP_CUDA(cudaEventRecord(e0, c->stream));
                 }
-                if (group4)
+                if (hybrid)
+                    k_assoc_hybrid<false><<<grid, KICP_WARPS * 32, 0, c->stream>>>(c->d_state, d_pts, n, m->view(), c->d_partials,
+                                                                                   pow2_voxel, px, UploadArgs{nullptr, 0u, 1});
+                else if (group4)
                     k_assoc_group4<false><<<grid, KICP_WARPS * 32, 0, c->stream>>>(c->d_state, d_pts, n, m->view(), c->d_partials,
                                                                                    pow2_voxel, px);
                 else if (pruned)

@@ -17,7 +17,7 @@ from ._capi import (KICP_OK, KICP_WARN_NO_CORRESPONDENCES, KicpError, RegParams,
                     lib)
 
 __all__ = ["Context", "VoxelHashMap", "Scan", "KinematicRegistration", "KicpError", "RegParams", "RegResult",
-           "pinned_empty"]
+           "pinned_empty", "VoxelDownsample", "Preprocess"]
 
 
 class Context:
@@ -257,6 +257,30 @@ class KinematicRegistration:
         f = lib().kicp_register_scan_sharded_async if sharded else lib().kicp_register_scan_async
         check(f(voxel_map.h, scan.h, dp(as_pose(last_robot_pose)), dp(as_pose(relative_wheel_odometry)),
                 float(max_correspondence_distance), C.byref(p), C.byref(result)), "kicp_register_scan_async")
+
+
+def VoxelDownsample(ctx, frame, voxel_size):
+    """kiss_icp::VoxelDownsample on the device: first point (input order) per voxel, in input order."""
+    frame = as_points(frame)
+    out = np.empty_like(frame)
+    m = C.c_int64()
+    check(lib().kicp_voxel_downsample(ctx.h, dp(frame), len(frame), float(voxel_size), dp(out), len(out), C.byref(m)),
+          "kicp_voxel_downsample")
+    return out[: m.value].copy()
+
+
+def Preprocess(ctx, frame, timestamps, relative_motion, max_range, min_range, deskew, lidar_to_base=None):
+    """kiss_icp::Preprocessor::Preprocess (+ optional transform to the base frame) on the device."""
+    frame = as_points(frame)
+    ts = np.ascontiguousarray(timestamps, dtype=np.float64)
+    ident = np.array([0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
+    l2b = ident if lidar_to_base is None else as_pose(lidar_to_base)
+    out = np.empty_like(frame)
+    m = C.c_int64()
+    check(lib().kicp_preprocess(ctx.h, dp(frame), len(frame), dp(ts), len(ts), dp(as_pose(relative_motion)), dp(l2b),
+                                float(max_range), float(min_range), int(bool(deskew)), dp(out), len(out), C.byref(m)),
+          "kicp_preprocess")
+    return out[: m.value].copy()
 
 
 def shard_range(n, nranks, rank):

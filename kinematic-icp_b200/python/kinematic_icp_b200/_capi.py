@@ -96,6 +96,9 @@ SYMBOLS = [
     ("kicp_scan_upload", C.c_int, [_P, c_dp, C.c_int64]),
     ("kicp_scan_upload_async", C.c_int, [_P, c_dp, C.c_int64]),
     ("kicp_register_scan_async", C.c_int, [_P, _P, c_dp, c_dp, C.c_double, C.POINTER(RegParams), C.POINTER(RegResult)]),
+    ("kicp_voxel_downsample", C.c_int, [_P, c_dp, C.c_int64, C.c_double, c_dp, C.c_int64, C.POINTER(C.c_int64)]),
+    ("kicp_preprocess", C.c_int, [_P, c_dp, C.c_int64, c_dp, C.c_int64, c_dp, c_dp, C.c_double, C.c_double, C.c_int32, c_dp,
+                                  C.c_int64, C.POINTER(C.c_int64)]),
     ("kicp_comm_unique_id", C.c_int, [C.POINTER(C.c_uint8)]),
     ("kicp_comm_init", C.c_int, [_P, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]),
     ("kicp_comm_destroy", C.c_int, [_P]),

@@ -142,7 +142,7 @@ def test_registration_configs_vs_oracle(oracle, gpu_ctx, workload, cfg):
     w = workload(cfg)
     gm = gpu_map_from_oracle(kb, gpu_ctx, w.map)
     try:
-        for variant, sort_bits, persistent in ((2, 0, 1), (2, 0, 0), (2, 30, 1), (1, 0, 1), (1, 0, 0), (0, 30, 0), (1, 30, 1), (1, 12, 0)):
+        for variant, sort_bits, persistent in ((3, 0, 1), (3, 0, 0), (3, 30, 1), (2, 0, 1), (2, 0, 0), (2, 30, 1), (1, 0, 1), (1, 0, 0), (0, 30, 0), (1, 30, 1), (1, 12, 0)):
             gpu_ctx.set_option("assoc_variant", variant)
             gpu_ctx.set_option("sort_bits", sort_bits)
             gpu_ctx.set_option("persistent", persistent)
