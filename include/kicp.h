@@ -79,7 +79,8 @@ int64_t kicp_ctx_launch_count(kicp_ctx *ctx);
 /* Tuning knobs (defaults are the measured best): "assoc_variant" 0 = 27-voxel neighbourhood staged through shared
  * memory, 1 = exact-pruning thread-per-point kernel; "persistent" 1 = all IRLS iterations of a registration inside one cooperative launch
  * (default on the single-GPU path), 0 = one launch per iteration; "sort_bits" 0..30 = Morton key bits of the optional per-registration
- * binning sort (default 0 = off).  Every setting computes the same result. */
+ * binning sort (default 0 = off); "group4_below" = scans of at most this many points run the 8-point-window kernel (variant 2) when
+ * variant 1 is selected (default 49152, 0 = never).  Every setting computes the same result up to the summation order. */
 int kicp_ctx_set_option(kicp_ctx *ctx, const char *name, int32_t value);
 /* Per-kernel device timing with CUDA events recorded on the context stream around (a) the binning of each
  * registration (init + Morton keys + radix sort + gather) and (b) every launch of the association kernel.  Only
@@ -105,6 +106,10 @@ int kicp_host_free(void *p);
 /* VoxelHashMap(voxel_size, max_distance, max_points_per_voxel) */
 int kicp_map_create(kicp_ctx *ctx, double voxel_size, double max_distance, uint32_t max_points_per_voxel, kicp_map **out);
 int kicp_map_destroy(kicp_map *map);
+/* Pre-size the map's device storage for `voxels` occupied voxels (like tsl::robin_map::reserve on the reference's
+ * map_ member).  Optional: kicp_map_create already sizes for a disc of radius max_distance, and the storage doubles
+ * when exceeded — but growth re-allocates, which is the one slow (milliseconds) event of a drive. */
+int kicp_map_reserve(kicp_map *map, int64_t voxels);
 int kicp_map_clear(kicp_map *map);                         /* Clear(), KinematicICP.hpp:88 */
 int kicp_map_empty(kicp_map *map, int32_t *empty);         /* Empty(), Registration.cpp:157 */
 int kicp_map_num_points(kicp_map *map, int64_t *n);
@@ -154,6 +159,42 @@ int kicp_voxel_downsample(kicp_ctx *ctx, const double *xyz, int64_t n, double vo
 int kicp_preprocess(kicp_ctx *ctx, const double *xyz, int64_t n, const double *stamps, int64_t n_stamps,
                     const double relative_motion[7], const double lidar_to_base[7], double max_range, double min_range,
                     int32_t deskew, double *out_xyz, int64_t cap, int64_t *m);
+
+/* ---- whole frame: KinematicICP::RegisterFrame (pipeline/KinematicICP.cpp:48-85) as ONE call, the frame staying in HBM
+ *      from ingest to map update: ingest (float32/float64 fields at a PointCloud2-style stride, RosUtils.cpp:30-39) ->
+ *      Preprocess (de-skew by `deskew_motion` = lidar_to_base^-1 * relative_odometry * lidar_to_base, range filter) ->
+ *      transform to base -> VoxelDownsample(0.5 vs) -> VoxelDownsample(1.5 vs) -> ComputeRobotMotion(source, map,
+ *      last_pose, relative_odometry, tau) -> map.Update(frame_downsample, new_pose).  The scalar CorrespondenceThreshold
+ *      stays with the caller (tau in, pose out).  out_frame / out_source receive the two clouds RegisterFrame returns
+ *      (preprocessed frame in base, registration source); either may be NULL to skip its download.  On zero
+ *      correspondences the pose is NaN like the reference's, KICP_WARN_NO_CORRESPONDENCES is returned and the map is
+ *      left untouched. ------------------------------------------------------------------------------------------- */
+#define KICP_DTYPE_F64 0
+#define KICP_DTYPE_F32 1
+typedef struct kicp_frame_input {
+    const void *data;   /* host pointer: n points */
+    int64_t n;
+    int32_t dtype;      /* KICP_DTYPE_F64 (std::vector<Eigen::Vector3d>) or KICP_DTYPE_F32 (PointCloud2 FLOAT32 fields) */
+    int32_t point_step; /* bytes between consecutive points; 0 = tightly packed x,y,z (offsets ignored) */
+    int32_t offset_x, offset_y, offset_z; /* byte offsets of the fields inside a point (used when point_step > 0) */
+    const double *stamps; /* per-point times in any affine scale (normalised to [0,1] on the device, like          */
+    int64_t n_stamps;     /* TimeStampHandler.cpp:129-135 does); 0 = no de-skewing                                 */
+} kicp_frame_input;
+typedef struct kicp_frame_params {
+    double max_range, min_range; /* kiss_icp::Preprocessor, pipeline/KinematicICP.hpp:40-41 */
+    int32_t deskew;              /* pipeline::Config::deskew */
+    double voxel_size;           /* pipeline::Config::voxel_size: the two down-sample sizes are 0.5x and 1.5x of it */
+    int32_t stage_clouds;        /* keep the two clouds in context-owned pinned host memory for kicp_frame_clouds() */
+    kicp_reg_params reg;
+} kicp_frame_params;
+int kicp_register_frame(kicp_map *map, const kicp_frame_input *in, const double deskew_motion[7], const double lidar_to_base[7],
+                        const double last_pose[7], const double relative_odometry[7], double tau, const kicp_frame_params *fp,
+                        double out_pose[7], double *out_frame, int64_t cap_frame, int64_t *n_frame, double *out_source,
+                        int64_t cap_source, int64_t *n_source, kicp_reg_result *result);
+/* The two clouds of the last kicp_register_frame on this context (fp->stage_clouds != 0 or out_* given): pointers into
+ * context-owned pinned host memory, valid until the next front-end call on the same device.  Lets a caller build its
+ * own containers in one pass instead of pre-sizing worst-case output buffers. */
+int kicp_frame_clouds(kicp_ctx *ctx, const double **frame, int64_t *n_frame, const double **source, int64_t *n_source);
 
 /* ---- multi-GPU: the scan's points shard by contiguous index range, the map is replicated, and each IRLS
  *      iteration ends with one sum-allreduce of the 8 accumulated doubles. ------------------- */

@@ -2,6 +2,7 @@
 // ROS 2 workspace links instead of kinematic_icp_registration / _threshold / _pipeline.
 #include <cstdlib>
 #include <mutex>
+#include <utility>
 
 #include "kicp/runtime.hpp"
 #include "kinematic_icp/correspondence_threshold/CorrespondenceThreshold.hpp"
@@ -76,24 +77,49 @@ void CorrespondenceThreshold::UpdateOdometryError(const Sophus::SE3d &odometry_e
 
 #ifndef KICP_FACADE_NO_PIPELINE  // the reference's own pipeline/KinematicICP.cpp can be compiled in its place
 namespace pipeline {
-// pipeline/KinematicICP.cpp:48-85
-KinematicICP::Vector3dVectorTuple KinematicICP::RegisterFrame(const std::vector<Eigen::Vector3d> &frame, const std::vector<double> &timestamps,
-                                                              const Sophus::SE3d &lidar_to_base, const Sophus::SE3d &relative_odometry) {
-    // deskew in the lidar frame, range filter
+// pipeline/KinematicICP.cpp:48-85: one kicp_register_frame call does the per-point work (ingest, de-skew, range filter,
+// base transform, both voxel down-samples, registration, map update) with the frame resident in HBM throughout; the
+// scalar threshold model and the pose bookkeeping stay here.
+KinematicICP::Vector3dVectorTuple KinematicICP::RegisterFrame(const kicp_frame_input &input, const Sophus::SE3d &lidar_to_base,
+                                                              const Sophus::SE3d &relative_odometry) {
+    // deskew in the lidar frame
     const Sophus::SE3d relative_odometry_in_lidar = lidar_to_base.inverse() * relative_odometry * lidar_to_base;
-    const Vector3dVector preprocessed = preprocessor_.Preprocess(frame, timestamps, relative_odometry_in_lidar);
-    Vector3dVector in_base(preprocessed.size());
-    for (size_t i = 0; i < preprocessed.size(); ++i) in_base[i] = lidar_to_base * preprocessed[i];
-    // two voxel down-samples: 0.5 vs for the map update, then 1.5 vs for the registration source
-    const Vector3dVector frame_downsample = kiss_icp::VoxelDownsample(in_base, config_.voxel_size * 0.5);
-    const Vector3dVector source = kiss_icp::VoxelDownsample(frame_downsample, config_.voxel_size * 1.5);
+    double motion[7], l2b[7], last[7], odom[7], out[7];
+    kicp::to_pose7(relative_odometry_in_lidar, motion);
+    kicp::to_pose7(lidar_to_base, l2b);
+    kicp::to_pose7(last_pose_, last);
+    kicp::to_pose7(relative_odometry, odom);
+    kicp_frame_params fp;
+    fp.max_range = preprocessor_.max_range_, fp.min_range = preprocessor_.min_range_, fp.deskew = preprocessor_.deskew_ ? 1 : 0;
+    fp.voxel_size = config_.voxel_size;
+    fp.reg.max_num_iterations = registration_.max_num_iterations_;
+    fp.reg.use_adaptive_odometry_regularization = registration_.use_adaptive_odometry_regularization_ ? 1 : 0;
+    fp.reg.convergence_criterion = registration_.convergence_criterion_;
+    fp.reg.fixed_regularization = registration_.fixed_regularization_;
     const double tau = correspondence_threshold_.ComputeThreshold();
-    const Sophus::SE3d new_pose = registration_.ComputeRobotMotion(source, local_map_, last_pose_, relative_odometry, tau);
+    fp.stage_clouds = 1;  // the two returned clouds are built below, in one pass each, from the library's pinned staging
+    kicp::check(kicp_register_frame(local_map_.handle_, &input, motion, l2b, last, odom, tau, &fp, out, nullptr, 0, nullptr, nullptr, 0,
+                                    nullptr, nullptr),
+                "kicp_register_frame");
+    const double *frame_xyz = nullptr, *source_xyz = nullptr;
+    int64_t n_frame = 0, n_source = 0;
+    kicp::check(kicp_frame_clouds(kicp::default_context(), &frame_xyz, &n_frame, &source_xyz, &n_source), "kicp_frame_clouds");
+    const auto *fb = reinterpret_cast<const Eigen::Vector3d *>(frame_xyz);
+    const auto *sb = reinterpret_cast<const Eigen::Vector3d *>(source_xyz);
+    Vector3dVector in_base(fb, fb + n_frame), source(sb, sb + n_source);
+    const Sophus::SE3d new_pose = kicp::from_pose7(out);
     const Sophus::SE3d odometry_error = (last_pose_ * relative_odometry).inverse() * new_pose;
     correspondence_threshold_.UpdateOdometryError(odometry_error);
-    local_map_.Update(frame_downsample, new_pose);
     last_pose_ = new_pose;
-    return {in_base, source};
+    return {std::move(in_base), std::move(source)};
+}
+
+KinematicICP::Vector3dVectorTuple KinematicICP::RegisterFrame(const std::vector<Eigen::Vector3d> &frame, const std::vector<double> &timestamps,
+                                                              const Sophus::SE3d &lidar_to_base, const Sophus::SE3d &relative_odometry) {
+    kicp_frame_input input{};
+    input.data = kicp::xyz(frame), input.n = (int64_t)frame.size(), input.dtype = KICP_DTYPE_F64, input.point_step = 0;
+    input.stamps = timestamps.empty() ? nullptr : timestamps.data(), input.n_stamps = (int64_t)timestamps.size();
+    return RegisterFrame(input, lidar_to_base, relative_odometry);
 }
 }  // namespace pipeline
 #endif

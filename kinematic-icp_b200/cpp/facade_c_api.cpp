@@ -2,6 +2,7 @@
 #include <cstdint>
 #include <vector>
 
+#include "kicp/tum.hpp"
 #include "kinematic_icp/pipeline/KinematicICP.hpp"
 
 namespace {
@@ -39,7 +40,27 @@ int64_t kfac_pipeline_register_frame(void *h, const double *xyz, int64_t n, cons
     kicp::to_pose7(p->pose(), out_pose7);
     return static_cast<int64_t>(source.size());
 }
+// the caller's buffer goes to the device as it is: float64 (dtype 0) or float32 (dtype 1) x,y,z records at `point_step` bytes
+// (PointCloud2 layout; 0 = packed), no intermediate std::vector and no host-side widening
+int64_t kfac_pipeline_register_frame_raw(void *h, const void *data, int64_t n, int32_t dtype, int32_t point_step, int32_t ox, int32_t oy,
+                                         int32_t oz, const double *stamps, int64_t n_stamps, const double *lidar_to_base7,
+                                         const double *rel_odom7, double *out_pose7) {
+    auto *p = static_cast<kinematic_icp::pipeline::KinematicICP *>(h);
+    kicp_frame_input in{};
+    in.data = data, in.n = n, in.dtype = dtype, in.point_step = point_step, in.offset_x = ox, in.offset_y = oy, in.offset_z = oz;
+    in.stamps = n_stamps ? stamps : nullptr, in.n_stamps = n_stamps;
+    const auto [frame, source] = p->RegisterFrame(in, kicp::from_pose7(lidar_to_base7), kicp::from_pose7(rel_odom7));
+    kicp::to_pose7(p->pose(), out_pose7);
+    return static_cast<int64_t>(source.size());
+}
 int64_t kfac_pipeline_num_map_points(void *h) {
     return static_cast<int64_t>(static_cast<kinematic_icp::pipeline::KinematicICP *>(h)->LocalMap().size());
+}
+// poses7[n][7] + stamps[n] -> TUM file (offline_node.cpp:76-97)
+int kfac_write_tum(const char *path, const double *stamps, const double *poses7, int64_t n) {
+    std::vector<std::pair<double, Sophus::SE3d>> v;
+    v.reserve(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i) v.emplace_back(stamps[i], kicp::from_pose7(poses7 + 7 * i));
+    return kicp::write_poses_tum(path, v) ? 0 : 1;
 }
 }

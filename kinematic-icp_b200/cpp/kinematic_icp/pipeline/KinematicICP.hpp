@@ -45,6 +45,10 @@ public:
 
     Vector3dVectorTuple RegisterFrame(const std::vector<Eigen::Vector3d> &frame, const std::vector<double> &timestamps,
                                       const Sophus::SE3d &lidar_to_base, const Sophus::SE3d &relative_odometry);
+    // Extension (not in the reference): the same frame straight from a PointCloud2-shaped buffer (float32 or float64 fields
+    // at a byte stride, include/kicp.h kicp_frame_input), skipping the host-side widening of RosUtils.cpp:30-39.
+    Vector3dVectorTuple RegisterFrame(const kicp_frame_input &input, const Sophus::SE3d &lidar_to_base,
+                                      const Sophus::SE3d &relative_odometry);
 
     inline void SetPose(const Sophus::SE3d &pose) {
         last_pose_ = pose;

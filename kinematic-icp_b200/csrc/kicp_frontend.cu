@@ -6,7 +6,9 @@
 // compaction), which is what the CPU restatement produces.  Compiled with -fmad=false like kicp_map.cu: voxel floors and
 // range tests are evaluated in plain IEEE order.
 #include <cfloat>
+#include <chrono>
 #include <cmath>
+#include <cstring>
 #include <cub/device/device_reduce.cuh>
 #include <cub/device/device_select.cuh>
 
@@ -19,11 +21,14 @@ struct P3 {
 };
 
 // ------------------------------------------------------------------------------------------------ VoxelDownsample
-__global__ void k_ds_insert(const P3 *__restrict__ pts, int n, double vs, int4 *slots, uint32_t mask_in, int *first_idx,
-                            int *slot_of) {
+// `d_n` (optional) is the device-resident point count of a stage whose input was compacted on the device: the grid is sized
+// for the host-side upper bound `n_max` and the tail threads retire, so chained stages need no host round trip.
+__global__ void k_ds_insert(const P3 *__restrict__ pts, int n_max, const int *__restrict__ d_n, double vs, int4 *slots, uint32_t mask_in,
+                            int *first_idx, int *slot_of) {
     __shared__ uint32_t s_mask[32];
     const uint32_t mask = lane_private(mask_in, s_mask);  // divergence safety, see kicp_device.cuh
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = d_n ? min(*d_n, n_max) : n_max;
     if (i >= n) return;
     const P3 p = pts[i];
     const int kx = voxel_coord(p.x, vs), ky = voxel_coord(p.y, vs), kz = voxel_coord(p.z, vs);
@@ -50,9 +55,12 @@ __global__ void k_ds_insert(const P3 *__restrict__ pts, int n, double vs, int4 *
     slot_of[i] = (int)h;
 }
 
-__global__ void k_ds_flag(int n, const int *__restrict__ first_idx, const int *__restrict__ slot_of, unsigned char *flags) {
+__global__ void k_ds_flag(int n_max, const int *__restrict__ d_n, const int *__restrict__ first_idx, const int *__restrict__ slot_of,
+                          unsigned char *flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flags[i] = first_idx[slot_of[i]] == i ? 1 : 0;
+    if (i >= n_max) return;
+    const int n = d_n ? min(*d_n, n_max) : n_max;
+    flags[i] = (i < n && first_idx[slot_of[i]] == i) ? 1 : 0;
 }
 
 __global__ void k_fill_int(int *p, int v, int n) {
@@ -60,11 +68,32 @@ __global__ void k_fill_int(int *p, int v, int n) {
     if (i < n) p[i] = v;
 }
 
+// ---------------------------------------------------------------------------------------------------------- ingest
+// PointCloud2-shaped input (RosUtils.cpp:30-39 reads float32 x,y,z through an iterator with the message's point_step and
+// widens to double): the raw bytes are uploaded once and widened here.
+struct IngestArgs {
+    int is_f32, step, ox, oy, oz;
+};
+__global__ void k_ingest(const unsigned char *__restrict__ raw, int n, IngestArgs a, P3 *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char *p = raw + (size_t)i * a.step;
+    P3 o;
+    if (a.is_f32) {
+        float x, y, z;  // fields need not be 4-byte aligned inside the message: assemble from bytes
+        memcpy(&x, p + a.ox, 4), memcpy(&y, p + a.oy, 4), memcpy(&z, p + a.oz, 4);
+        o = P3{(double)x, (double)y, (double)z};
+    } else {
+        memcpy(&o.x, p + a.ox, 8), memcpy(&o.y, p + a.oy, 8), memcpy(&o.z, p + a.oz, 8);
+    }
+    out[i] = o;
+}
+
 // ------------------------------------------------------------------------------------------------------ Preprocess
 struct PreArgs {
     double omega[6];       // log(relative_motion) as (upsilon, omega), computed on the host once per frame
     Pose lidar_to_base;
-    double max_range, min_range, t_min, t_span;  // stamps are normalised as (t - t_min) / t_span
+    double max_range, min_range;  // stamps are normalised as (t - t_min) / (t_max - t_min)
     int deskew;
 };
 
@@ -110,13 +139,15 @@ __device__ void se3_exp_apply(const double a[6], double px, double py, double pz
     ox = rx + tx, oy = ry + ty, oz = rz + tz;
 }
 
-__global__ void k_preprocess(const P3 *__restrict__ pts, const double *__restrict__ stamps, int n, PreArgs a, P3 *out,
-                             unsigned char *flags) {
+// `d_mm` = {min, max} of the stamps, reduced on the device just before (no host round trip)
+__global__ void k_preprocess(const P3 *__restrict__ pts, const double *__restrict__ stamps, const double *__restrict__ d_mm, int n,
+                             PreArgs a, P3 *out, unsigned char *flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     P3 p = pts[i];
     if (a.deskew) {
-        const double stamp = (stamps[i] - a.t_min) / a.t_span;
+        const double t_min = d_mm[0], t_span = d_mm[1] - d_mm[0];
+        const double stamp = (stamps[i] - t_min) / t_span;
         double w[6];
         for (int k = 0; k < 6; ++k) w[k] = (stamp - 1.0) * a.omega[k];
         double ox, oy, oz;
@@ -133,8 +164,14 @@ __global__ void k_preprocess(const P3 *__restrict__ pts, const double *__restric
 // ------------------------------------------------------------------------------------------------------------ host
 namespace {
 struct Scratch {
-    P3 *in = nullptr, *mid = nullptr, *out = nullptr;
-    double *stamps = nullptr;
+    P3 *in = nullptr, *mid = nullptr, *out = nullptr, *out2 = nullptr, *out3 = nullptr;
+    double *stamps = nullptr, *d_mm = nullptr;
+    unsigned char *raw = nullptr;
+    size_t raw_cap = 0;
+    int *h_count = nullptr;  // pinned, 4 ints
+    P3 *h_frame = nullptr, *h_source = nullptr;  // pinned staging of the two clouds RegisterFrame returns (cap points each)
+    int64_t staged_frame = 0, staged_source = 0;
+    double timing[8] = {0};  // host-side stage times of the last kicp_register_frame, milliseconds (debug export)
     unsigned char *flags = nullptr;
     int *first_idx = nullptr, *slot_of = nullptr, *d_count = nullptr;
     int4 *slots = nullptr;
@@ -143,16 +180,18 @@ struct Scratch {
     int64_t cap = 0;
     uint32_t nslots = 0;
 };
-Scratch &scratch(kicp_ctx *c) {
+Scratch &scratch_of_device(int device) {
     static thread_local Scratch s[16];
-    return s[c->device & 15];
+    return s[device & 15];
 }
+Scratch &scratch(kicp_ctx *c) { return scratch_of_device(c->device); }
 
 int reserve(kicp_ctx *c, Scratch &s, int64_t n) {
     if (n <= s.cap) return KICP_OK;
     KICP_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(s.in), cudaFree(s.mid), cudaFree(s.out), cudaFree(s.stamps), cudaFree(s.flags), cudaFree(s.first_idx);
-    cudaFree(s.slot_of), cudaFree(s.slots), cudaFree(s.tmp), cudaFree(s.d_count);
+    cudaFree(s.in), cudaFree(s.mid), cudaFree(s.out), cudaFree(s.out2), cudaFree(s.out3), cudaFree(s.stamps), cudaFree(s.flags);
+    cudaFree(s.first_idx), cudaFree(s.slot_of), cudaFree(s.slots), cudaFree(s.tmp), cudaFree(s.d_count), cudaFree(s.d_mm);
+    cudaFree(s.raw), cudaFreeHost(s.h_count), cudaFreeHost(s.h_frame), cudaFreeHost(s.h_source);
     s = Scratch();
     const int64_t cap = std::max<int64_t>(n + n / 4, 4096);
     uint32_t nslots = 1;
@@ -160,12 +199,18 @@ int reserve(kicp_ctx *c, Scratch &s, int64_t n) {
     KICP_CUDA(cudaMalloc(&s.in, cap * sizeof(P3)));
     KICP_CUDA(cudaMalloc(&s.mid, cap * sizeof(P3)));
     KICP_CUDA(cudaMalloc(&s.out, cap * sizeof(P3)));
+    KICP_CUDA(cudaMalloc(&s.out2, cap * sizeof(P3)));
+    KICP_CUDA(cudaMalloc(&s.out3, cap * sizeof(P3)));
+    KICP_CUDA(cudaMalloc(&s.d_mm, 2 * sizeof(double)));
+    KICP_CUDA(cudaMallocHost(&s.h_count, 4 * sizeof(int)));
+    KICP_CUDA(cudaMallocHost(&s.h_frame, cap * sizeof(P3)));
+    KICP_CUDA(cudaMallocHost(&s.h_source, cap * sizeof(P3)));
     KICP_CUDA(cudaMalloc(&s.stamps, cap * sizeof(double)));
     KICP_CUDA(cudaMalloc(&s.flags, cap));
     KICP_CUDA(cudaMalloc(&s.first_idx, (size_t)nslots * sizeof(int)));
     KICP_CUDA(cudaMalloc(&s.slot_of, cap * sizeof(int)));
     KICP_CUDA(cudaMalloc(&s.slots, (size_t)nslots * sizeof(int4)));
-    KICP_CUDA(cudaMalloc(&s.d_count, sizeof(int)));
+    KICP_CUDA(cudaMalloc(&s.d_count, 4 * sizeof(int)));
     size_t b1 = 0, b2 = 0, b3 = 0;
     KICP_CUDA(cub::DeviceSelect::Flagged(nullptr, b1, s.in, s.flags, s.out, s.d_count, (int)cap, c->stream));
     KICP_CUDA(cub::DeviceReduce::Min(nullptr, b2, s.stamps, s.stamps, (int)cap, c->stream));
@@ -208,6 +253,49 @@ void se3_log_host(const double p[7], double out[6]) {
     for (int i = 0; i < 3; ++i) out[i] = Vinv[3 * i] * p[4] + Vinv[3 * i + 1] * p[5] + Vinv[3 * i + 2] * p[6];
     out[3] = w[0], out[4] = w[1], out[5] = w[2];
 }
+
+// VoxelDownsample of src[0, n) (n = *d_n when given, else n_max) into dst, survivor count to d_count_out; all on the stream
+int enqueue_downsample(kicp_ctx *c, Scratch &s, const P3 *src, int n_max, const int *d_n, double voxel_size, P3 *dst, int *d_count_out) {
+    KICP_CUDA(cudaMemsetAsync(s.slots, 0xFF, (size_t)s.nslots * sizeof(int4), c->stream));
+    const int threads = 256, blocks = (n_max + threads - 1) / threads;
+    k_fill_int<<<(s.nslots + 255) / 256, 256, 0, c->stream>>>(s.first_idx, 0x7FFFFFFF, (int)s.nslots);
+    KICP_CHECK_LAUNCH(c);
+    k_ds_insert<<<blocks, threads, 0, c->stream>>>(src, n_max, d_n, voxel_size, s.slots, s.nslots - 1, s.first_idx, s.slot_of);
+    KICP_CHECK_LAUNCH(c);
+    k_ds_flag<<<blocks, threads, 0, c->stream>>>(n_max, d_n, s.first_idx, s.slot_of, s.flags);
+    KICP_CHECK_LAUNCH(c);
+    size_t bytes = s.tmp_bytes;
+    KICP_CUDA(cub::DeviceSelect::Flagged(s.tmp, bytes, src, s.flags, dst, d_count_out, n_max, c->stream));
+    c->launches += 2;  // CUB's select passes (library kernels)
+    return KICP_OK;
+}
+
+// Preprocess of s.in[0, n) (stamps still on the host) + transform to the base frame, compacted into dst
+int enqueue_preprocess(kicp_ctx *c, Scratch &s, int n, const double *stamps, int64_t n_stamps, const double relative_motion[7],
+                       const double lidar_to_base[7], double max_range, double min_range, int deskew, P3 *dst, int *d_count_out) {
+    PreArgs a;
+    a.deskew = (deskew && n_stamps > 0) ? 1 : 0;  // Preprocessing.cpp: `!deskew_ || timestamps.empty()` returns the frame as is
+    a.max_range = max_range, a.min_range = min_range;
+    a.lidar_to_base = Pose{lidar_to_base[0], lidar_to_base[1], lidar_to_base[2], lidar_to_base[3], lidar_to_base[4], lidar_to_base[5],
+                           lidar_to_base[6]};
+    for (int k = 0; k < 6; ++k) a.omega[k] = 0.0;
+    if (a.deskew) {
+        KICP_CUDA(cudaMemcpyAsync(s.stamps, stamps, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        size_t bytes = s.tmp_bytes;
+        KICP_CUDA(cub::DeviceReduce::Min(s.tmp, bytes, s.stamps, s.d_mm, n, c->stream));
+        bytes = s.tmp_bytes;
+        KICP_CUDA(cub::DeviceReduce::Max(s.tmp, bytes, s.stamps, s.d_mm + 1, n, c->stream));
+        c->launches += 2;
+        se3_log_host(relative_motion, a.omega);
+    }
+    const int threads = 256, blocks = (n + threads - 1) / threads;
+    k_preprocess<<<blocks, threads, 0, c->stream>>>(s.in, s.stamps, s.d_mm, n, a, s.mid, s.flags);
+    KICP_CHECK_LAUNCH(c);
+    size_t bytes = s.tmp_bytes;
+    KICP_CUDA(cub::DeviceSelect::Flagged(s.tmp, bytes, s.mid, s.flags, dst, d_count_out, n, c->stream));
+    c->launches += 2;
+    return KICP_OK;
+}
 }  // namespace
 
 extern "C" int kicp_voxel_downsample(kicp_ctx *c, const double *xyz, int64_t n, double voxel_size, double *out_xyz, int64_t cap,
@@ -219,17 +307,7 @@ extern "C" int kicp_voxel_downsample(kicp_ctx *c, const double *xyz, int64_t n, 
     Scratch &s = scratch(c);
     KICP_TRY(reserve(c, s, n));
     KICP_CUDA(cudaMemcpyAsync(s.in, xyz, (size_t)n * sizeof(P3), cudaMemcpyHostToDevice, c->stream));
-    KICP_CUDA(cudaMemsetAsync(s.slots, 0xFF, (size_t)s.nslots * sizeof(int4), c->stream));
-    const int threads = 256, blocks = (int)((n + threads - 1) / threads);
-    k_fill_int<<<(s.nslots + 255) / 256, 256, 0, c->stream>>>(s.first_idx, 0x7FFFFFFF, (int)s.nslots);
-    KICP_CHECK_LAUNCH(c);
-    k_ds_insert<<<blocks, threads, 0, c->stream>>>(s.in, (int)n, voxel_size, s.slots, s.nslots - 1, s.first_idx, s.slot_of);
-    KICP_CHECK_LAUNCH(c);
-    k_ds_flag<<<blocks, threads, 0, c->stream>>>((int)n, s.first_idx, s.slot_of, s.flags);
-    KICP_CHECK_LAUNCH(c);
-    size_t bytes = s.tmp_bytes;
-    KICP_CUDA(cub::DeviceSelect::Flagged(s.tmp, bytes, s.in, s.flags, s.out, s.d_count, (int)n, c->stream));
-    c->launches += 2;
+    KICP_TRY(enqueue_downsample(c, s, s.in, (int)n, nullptr, voxel_size, s.out, s.d_count));
     int count = 0;
     KICP_CUDA(cudaMemcpyAsync(&count, s.d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     KICP_CUDA(cudaStreamSynchronize(c->stream));
@@ -250,39 +328,121 @@ extern "C" int kicp_preprocess(kicp_ctx *c, const double *xyz, int64_t n, const 
     KICP_CUDA(cudaSetDevice(c->device));
     Scratch &s = scratch(c);
     KICP_TRY(reserve(c, s, n));
-    PreArgs a;
-    a.deskew = (deskew && n_stamps > 0) ? 1 : 0;  // Preprocessing.cpp: `!deskew_ || timestamps.empty()` returns the frame as is
-    a.max_range = max_range, a.min_range = min_range, a.t_min = 0.0, a.t_span = 1.0;
-    a.lidar_to_base = Pose{lidar_to_base[0], lidar_to_base[1], lidar_to_base[2], lidar_to_base[3], lidar_to_base[4], lidar_to_base[5],
-                           lidar_to_base[6]};
-    for (int k = 0; k < 6; ++k) a.omega[k] = 0.0;
     KICP_CUDA(cudaMemcpyAsync(s.in, xyz, (size_t)n * sizeof(P3), cudaMemcpyHostToDevice, c->stream));
-    if (a.deskew) {
-        KICP_CUDA(cudaMemcpyAsync(s.stamps, stamps, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        double *d_mm = reinterpret_cast<double *>(s.mid);  // two doubles of scratch
-        size_t bytes = s.tmp_bytes;
-        KICP_CUDA(cub::DeviceReduce::Min(s.tmp, bytes, s.stamps, d_mm, (int)n, c->stream));
-        bytes = s.tmp_bytes;
-        KICP_CUDA(cub::DeviceReduce::Max(s.tmp, bytes, s.stamps, d_mm + 1, (int)n, c->stream));
-        c->launches += 2;
-        double mm[2];
-        KICP_CUDA(cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, c->stream));
-        KICP_CUDA(cudaStreamSynchronize(c->stream));
-        a.t_min = mm[0];
-        a.t_span = mm[1] - mm[0];
-        se3_log_host(relative_motion, a.omega);
-    }
-    const int threads = 256, blocks = (int)((n + threads - 1) / threads);
-    k_preprocess<<<blocks, threads, 0, c->stream>>>(s.in, s.stamps, (int)n, a, s.mid, s.flags);
-    KICP_CHECK_LAUNCH(c);
-    size_t bytes = s.tmp_bytes;
-    KICP_CUDA(cub::DeviceSelect::Flagged(s.tmp, bytes, s.mid, s.flags, s.out, s.d_count, (int)n, c->stream));
-    c->launches += 2;
+    KICP_TRY(enqueue_preprocess(c, s, (int)n, stamps, n_stamps, relative_motion, lidar_to_base, max_range, min_range, deskew, s.out,
+                                s.d_count));
     int count = 0;
     KICP_CUDA(cudaMemcpyAsync(&count, s.d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     KICP_CUDA(cudaStreamSynchronize(c->stream));
     *m = count;
     if (count > cap) return KICP_ERR_CAPACITY;
     KICP_CUDA(cudaMemcpy(out_xyz, s.out, (size_t)count * sizeof(P3), cudaMemcpyDeviceToHost));
+    return KICP_OK;
+}
+
+// ------------------------------------------------------------------------------------------- fused RegisterFrame
+// KinematicICP::RegisterFrame (pipeline/KinematicICP.cpp:48-85) with every per-point stage on the device and the frame
+// resident in HBM from ingest to map update: one upload of the raw scan, one pose-sized download, plus the two point
+// clouds the reference returns by value.  The scalar threshold model (CorrespondenceThreshold) stays with the caller:
+// it needs tau before and the pose after, both of which cross this boundary anyway.
+extern "C" int kicp_register_frame(kicp_map *map, const kicp_frame_input *in, const double deskew_motion[7], const double lidar_to_base[7],
+                                   const double last_pose[7], const double relative_odometry[7], double tau, const kicp_frame_params *fp,
+                                   double out_pose[7], double *out_frame, int64_t cap_frame, int64_t *n_frame, double *out_source,
+                                   int64_t cap_source, int64_t *n_source, kicp_reg_result *result) {
+    if (!map || !in || !deskew_motion || !lidar_to_base || !last_pose || !relative_odometry || !fp || !out_pose) return KICP_ERR_INVALID;
+    const int64_t n = in->n;
+    if (n < 0 || n > 0x3FFFFFFF || (n > 0 && !in->data) || !(fp->voxel_size > 0.0)) return KICP_ERR_INVALID;
+    if (in->dtype != KICP_DTYPE_F64 && in->dtype != KICP_DTYPE_F32) return KICP_ERR_INVALID;
+    const int elem = in->dtype == KICP_DTYPE_F32 ? 4 : 8;
+    const int step = in->point_step > 0 ? in->point_step : 3 * elem;
+    const int ox = in->point_step > 0 ? in->offset_x : 0, oy = in->point_step > 0 ? in->offset_y : elem,
+              oz = in->point_step > 0 ? in->offset_z : 2 * elem;
+    if (ox < 0 || oy < 0 || oz < 0 || ox + elem > step || oy + elem > step || oz + elem > step) return KICP_ERR_INVALID;
+    const int deskew = fp->deskew && in->n_stamps > 0;
+    if (deskew && (in->n_stamps != n || !in->stamps)) return KICP_ERR_INVALID;
+    if (n_frame) *n_frame = 0;
+    if (n_source) *n_source = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms_since = [&t0]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+    kicp_ctx *c = map->ctx;
+    KICP_CUDA(cudaSetDevice(c->device));
+    Scratch &s = scratch(c);
+    int counts[3] = {0, 0, 0};
+    if (n > 0) {
+        KICP_TRY(reserve(c, s, n));
+        const bool packed_f64 = in->dtype == KICP_DTYPE_F64 && step == 24 && ox == 0 && oy == 8 && oz == 16;
+        if (packed_f64) {
+            KICP_CUDA(cudaMemcpyAsync(s.in, in->data, (size_t)n * sizeof(P3), cudaMemcpyHostToDevice, c->stream));
+        } else {
+            const size_t raw_bytes = (size_t)n * step;
+            if (raw_bytes > s.raw_cap) {
+                KICP_CUDA(cudaStreamSynchronize(c->stream));
+                cudaFree(s.raw);
+                s.raw = nullptr, s.raw_cap = 0;
+                KICP_CUDA(cudaMalloc(&s.raw, raw_bytes + raw_bytes / 4));
+                s.raw_cap = raw_bytes + raw_bytes / 4;
+            }
+            KICP_CUDA(cudaMemcpyAsync(s.raw, in->data, raw_bytes, cudaMemcpyHostToDevice, c->stream));
+            k_ingest<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(s.raw, (int)n, IngestArgs{in->dtype == KICP_DTYPE_F32, step, ox, oy, oz},
+                                                                       s.in);
+            KICP_CHECK_LAUNCH(c);
+        }
+        // s.out = preprocessed frame in base, s.out2 = frame_downsample (0.5 vs), s.out3 = source (1.5 vs); each stage reads
+        // the previous stage's survivor count from device memory (KinematicICP.cpp:38-44, 54-62)
+        KICP_TRY(enqueue_preprocess(c, s, (int)n, in->stamps, in->n_stamps, deskew_motion, lidar_to_base, fp->max_range, fp->min_range,
+                                    fp->deskew, s.out, s.d_count));
+        KICP_TRY(enqueue_downsample(c, s, s.out, (int)n, s.d_count, fp->voxel_size * 0.5, s.out2, s.d_count + 1));
+        KICP_TRY(enqueue_downsample(c, s, s.out2, (int)n, s.d_count + 1, fp->voxel_size * 1.5, s.out3, s.d_count + 2));
+        KICP_CUDA(cudaMemcpyAsync(s.h_count, s.d_count, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        KICP_CUDA(cudaStreamSynchronize(c->stream));  // the one mid-frame round trip: 12 bytes, sizes the registration grid
+        for (int k = 0; k < 3; ++k) counts[k] = s.h_count[k];
+    }
+    s.timing[0] = ms_since();  // upload + front end (ingest, de-skew, filter, transform, both down-samples)
+    if (n_frame) *n_frame = counts[0];
+    if (n_source) *n_source = counts[2];
+    if ((out_frame && counts[0] > cap_frame) || (out_source && counts[2] > cap_source)) return KICP_ERR_CAPACITY;
+    // registration of the source against the local map, enqueued first so that the downloads below overlap it
+    KICP_TRY(kicp_enqueue_registration_device(map, counts[2] ? reinterpret_cast<const double *>(s.out3) : nullptr, counts[2], last_pose,
+                                              relative_odometry, tau, &fp->reg));
+    s.timing[1] = ms_since();  // + registration enqueued
+    // the two clouds go to pinned staging on the copy stream while the registration runs
+    const bool stage = fp->stage_clouds || out_frame || out_source;
+    s.staged_frame = s.staged_source = 0;
+    if (stage && counts[0]) KICP_CUDA(cudaMemcpyAsync(s.h_frame, s.out, (size_t)counts[0] * sizeof(P3), cudaMemcpyDeviceToHost, c->copy_stream));
+    if (stage && counts[2])
+        KICP_CUDA(cudaMemcpyAsync(s.h_source, s.out3, (size_t)counts[2] * sizeof(P3), cudaMemcpyDeviceToHost, c->copy_stream));
+    KICP_CUDA(cudaStreamSynchronize(c->stream));
+    s.timing[2] = ms_since();  // + registration finished
+    const kicp_reg_result &r = *c->h_result;
+    for (int k = 0; k < 7; ++k) out_pose[k] = r.pose[k];
+    if (result) *result = r;
+    int status = r.status;
+    // local_map_.Update(frame_downsample, new_pose) (KinematicICP.cpp:79); a NaN pose (zero correspondences, which the
+    // reference does not defend against) is reported and leaves the map untouched
+    if (status == KICP_OK && counts[1] > 0)
+        status = kicp_map_update_pose_device(map, reinterpret_cast<const double *>(s.out2), counts[1], r.pose);
+    s.timing[3] = ms_since();  // + map update
+    KICP_CUDA(cudaStreamSynchronize(c->copy_stream));
+    if (stage) s.staged_frame = counts[0], s.staged_source = counts[2];
+    if (out_frame && counts[0]) memcpy(out_frame, s.h_frame, (size_t)counts[0] * sizeof(P3));
+    if (out_source && counts[2]) memcpy(out_source, s.h_source, (size_t)counts[2] * sizeof(P3));
+    s.timing[4] = ms_since();  // + clouds delivered
+    return status;
+}
+
+/* The clouds of the last kicp_register_frame on this context (fp->stage_clouds), in context-owned pinned host memory, valid
+ * until the next kicp_register_frame / kicp_preprocess / kicp_voxel_downsample call on a context of the same device. */
+extern "C" int kicp_frame_clouds(kicp_ctx *c, const double **frame, int64_t *n_frame, const double **source, int64_t *n_source) {
+    if (!c || !frame || !n_frame || !source || !n_source) return KICP_ERR_INVALID;
+    Scratch &s = scratch(c);
+    *frame = reinterpret_cast<const double *>(s.h_frame), *n_frame = s.staged_frame;
+    *source = reinterpret_cast<const double *>(s.h_source), *n_source = s.staged_source;
+    return KICP_OK;
+}
+
+// debugging aid (not part of the public header): cumulative host-side stage times of the last kicp_register_frame, ms
+extern "C" int kicp_debug_frame_timing(int device, double out[8]) {
+    if (!out) return KICP_ERR_INVALID;
+    for (int k = 0; k < 8; ++k) out[k] = scratch_of_device(device).timing[k];
     return KICP_OK;
 }

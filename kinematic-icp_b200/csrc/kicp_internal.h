@@ -62,6 +62,8 @@ struct kicp_ctx {
     int persistent = 1;     // 1 = all IRLS iterations inside one cooperative launch (single-GPU pruned path)
     int assoc_variant = 1;  // 0 = staged (27-voxel neighbourhood through shared memory), 1 = pruned (thread per point),
                             // 2 = pruned with 4 lanes per point, 3 = hybrid (32-point windows + 8-point tail)
+    int group4_below = 49152;  // scans of at most this many points use variant 2 when variant 1 is selected (0 = never);
+                               // measured: +24 % at 2k points, +10 % at 29k, -13 % at 131k (profiles/r01_replay.md)
     int sort_bits = 0;      // Morton key bits of the optional binning sort (0 = off, the measured best: DESIGN.md §5)
     kicp_scan *upload_scan = nullptr;  // staging scan used by the host-pointer entry points
     // chunked upload overlapped with the first IRLS iteration (host-pointer entry points, persistent kernel)
@@ -108,6 +110,17 @@ struct kicp_map {
     double *d_in = nullptr, *d_xyz_t = nullptr;
     int32_t *d_next = nullptr, *d_touched = nullptr;
     int64_t in_cap = 0;
+    // one allocation holds every array above and below (kicp_map.cu, map_alloc_storage)
+    void *slab = nullptr;
+    size_t slab_bytes = 0;
+    uint32_t slots_cap = 0;  // slots allocated (power of two); nslots <= slots_cap are in use
+    // scratch of RemovePointsFarFromLocation: survivor flags / new ids, and the spare header+point arrays the
+    // survivors are compacted into (swapped with blk/pts afterwards)
+    uint32_t *d_keep = nullptr, *d_new_id = nullptr;
+    void *d_scan_tmp = nullptr;  // cub::DeviceScan workspace
+    size_t scan_tmp_bytes = 0;
+    int4 *blk_spare = nullptr;
+    double *pts_spare = nullptr;
     MapView view() const { return MapView{slots, nslots - 1, pts, (int)cap, voxel_size}; }
 };
 
@@ -142,5 +155,11 @@ int kicp_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 
 // defined in kicp_map.cu, used by the registration entry points
 int kicp_scan_reserve(kicp_scan *scan, int64_t n);
+// VoxelHashMap::Update(points, pose) with `d_xyz` already resident in HBM (packed xyz doubles): used by kicp_register_frame
+int kicp_map_update_pose_device(kicp_map *m, const double *d_xyz, int64_t n, const double pose[7]);
+// defined in kicp_register.cu: enqueue one registration of n device-resident points on the context stream; the result
+// lands in ctx->h_result (pinned) once the stream has drained
+int kicp_enqueue_registration_device(kicp_map *m, const double *d_xyz, int64_t n, const double last[7], const double odom[7],
+                                     double tau, const kicp_reg_params *p);
 // defined in kicp_comm.cu
 int kicp_comm_allreduce8(kicp_ctx *ctx, double *d_buf);

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <cub/device/device_scan.cuh>
 
 #include "kicp_device.cuh"
 
@@ -62,6 +63,7 @@ extern "C" int kicp_ctx_create(int device, kicp_ctx **out) {
     KICP_CUDA(cudaMemset(c->d_chunk_flags, 0, KICP_UPLOAD_CHUNKS * sizeof(uint32_t)));
     KICP_CUDA(cudaMallocHost(&c->h_chunk_tags, KICP_UPLOAD_CHUNKS * sizeof(uint32_t)));
     if (const char *e = getenv("KICP_OVERLAP_UPLOAD")) c->overlap_upload = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("KICP_GROUP4_BELOW")) c->group4_below = std::max(0, atoi(e));
     if (const char *e = getenv("KICP_ASSOC")) c->assoc_variant = !strcmp(e, "staged") ? 0 : (!strcmp(e, "group4") ? 2 : (!strcmp(e, "hybrid") ? 3 : 1));
     if (const char *e = getenv("KICP_PERSISTENT")) c->persistent = atoi(e) ? 1 : 0;
     if (const char *e = getenv("KICP_SORT_BITS")) c->sort_bits = std::min(30, std::max(0, atoi(e)));
@@ -310,41 +312,6 @@ __global__ void k_mark_far(const int4 *blk, const double *pts, int cap, uint32_t
     }
 }
 
-// single-CTA exclusive scan (maintenance path, a few hundred thousand elements at most)
-__global__ void k_exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (uint32_t base = 0; base < n; base += blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < n ? in[i] : 0u;
-        uint32_t x = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) warp_sums[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t w = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0u;
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o);
-                if (lane >= o) w += y;
-            }
-            warp_sums[lane] = w;  // inclusive
-        }
-        __syncthreads();
-        const uint32_t prefix = carry + (wid ? warp_sums[wid - 1] : 0u);
-        if (i < n) out[i] = prefix + x - v;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry = prefix + x;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *total = carry;
-}
-
 __global__ void k_compact_blocks(const int4 *blk, const double *pts, int cap, uint32_t num_blocks, const uint32_t *keep,
                                  const uint32_t *new_id, int4 *blk_out, double *pts_out) {
     // one warp per block: header by lane 0, points copied cooperatively
@@ -410,14 +377,14 @@ static uint32_t next_pow2(uint64_t v) {
     return (uint32_t)p;
 }
 
+// (Re)build the open-addressed table over the first `nslots` slots of the slab's table region (nslots <= slots_cap)
 static int map_rebuild_table(kicp_map *m, uint32_t nslots) {
     kicp_ctx *c = m->ctx;
-    if (nslots != m->nslots) {
-        if (m->slots) KICP_CUDA(cudaFree(m->slots));
-        m->slots = nullptr;
-        KICP_CUDA(cudaMalloc(&m->slots, (size_t)nslots * sizeof(int4)));
-        m->nslots = nslots;
+    if (nslots > m->slots_cap) {
+        kicp_set_error("voxel map: internal error, table larger than its slab region");
+        return KICP_ERR_CAPACITY;
     }
+    m->nslots = nslots;
     KICP_CUDA(cudaMemsetAsync(m->slots, 0xFF, (size_t)m->nslots * sizeof(int4), c->stream));
     if (m->num_blocks) {
         k_table_rebuild<<<(m->num_blocks + 255) / 256, 256, 0, c->stream>>>(m->slots, m->nslots - 1, m->blk, m->num_blocks);
@@ -426,35 +393,69 @@ static int map_rebuild_table(kicp_map *m, uint32_t nslots) {
     return KICP_OK;
 }
 
+// All of a map's device storage is ONE allocation (the slab), carved into the arrays below for a capacity of `ncap` voxels.
+// Steady-state frames therefore never call cudaMalloc/cudaFree (measured: a growth event costs 0.4 - 240 ms on the B200
+// boxes, a steady-state Update 0.1 ms; profiles/r01_replay.md); growth doubles the capacity and migrates the contents.
+static int map_alloc_storage(kicp_map *m, uint32_t ncap) {
+    kicp_ctx *c = m->ctx;
+    const uint32_t slots_cap = std::max<uint32_t>(next_pow2((uint64_t)ncap * 4), 1024u);
+    size_t scan_bytes = 0;
+    KICP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)ncap, c->stream));
+    const size_t pts_bytes = (size_t)ncap * m->cap * KICP_PSTRIDE * sizeof(double);
+    size_t off = 0;
+    auto carve = [&off](size_t bytes) {
+        const size_t at = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return at;
+    };
+    const size_t o_blk = carve((size_t)ncap * sizeof(int4)), o_pts = carve(pts_bytes), o_head = carve((size_t)ncap * sizeof(int32_t));
+    const size_t o_blk2 = carve((size_t)ncap * sizeof(int4)), o_pts2 = carve(pts_bytes);
+    const size_t o_keep = carve((size_t)ncap * sizeof(uint32_t)), o_id = carve((size_t)ncap * sizeof(uint32_t));
+    const size_t o_slots = carve((size_t)slots_cap * sizeof(int4)), o_scan = carve(scan_bytes);
+    char *slab = nullptr;
+    KICP_CUDA(cudaMalloc(&slab, off));
+    int4 *nblk = reinterpret_cast<int4 *>(slab + o_blk);
+    double *npts = reinterpret_cast<double *>(slab + o_pts);
+    int32_t *nhead = reinterpret_cast<int32_t *>(slab + o_head);
+    if (m->num_blocks) {
+        KICP_CUDA(cudaMemcpyAsync(nblk, m->blk, (size_t)m->num_blocks * sizeof(int4), cudaMemcpyDeviceToDevice, c->stream));
+        KICP_CUDA(cudaMemcpyAsync(npts, m->pts, (size_t)m->num_blocks * m->cap * KICP_PSTRIDE * sizeof(double), cudaMemcpyDeviceToDevice,
+                                  c->stream));
+    }
+    k_fill_i32<<<(ncap + 255) / 256, 256, 0, c->stream>>>(nhead, -1, ncap);
+    KICP_CHECK_LAUNCH(c);
+    KICP_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(m->slab);
+    m->slab = slab, m->slab_bytes = off;
+    m->blk = nblk, m->pts = npts, m->pend_head = nhead, m->blocks_cap = ncap;
+    m->blk_spare = reinterpret_cast<int4 *>(slab + o_blk2), m->pts_spare = reinterpret_cast<double *>(slab + o_pts2);
+    m->d_keep = reinterpret_cast<uint32_t *>(slab + o_keep), m->d_new_id = reinterpret_cast<uint32_t *>(slab + o_id);
+    m->slots = reinterpret_cast<int4 *>(slab + o_slots), m->slots_cap = slots_cap;
+    m->d_scan_tmp = slab + o_scan, m->scan_tmp_bytes = scan_bytes;
+    // the table moved with the slab: rebuild it at its previous size (or the minimum for a new map)
+    return map_rebuild_table(m, std::max<uint32_t>(std::min(m->nslots, slots_cap), 1024u));
+}
+
 // make room for `extra` more voxels (blocks) and keep the table load factor <= 0.25
 static int map_reserve(kicp_map *m, uint64_t extra) {
-    kicp_ctx *c = m->ctx;
     const uint64_t need = (uint64_t)m->num_blocks + extra;
     if (need >= (1ull << 24)) {
         kicp_set_error("voxel map: more than 2^24 voxels");
         return KICP_ERR_CAPACITY;
     }
     if (need > m->blocks_cap) {
-        const uint32_t ncap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(need + need / 2, 4096), (1ull << 24));
-        int4 *nblk = nullptr;
-        double *npts = nullptr;
-        int32_t *nhead = nullptr;
-        KICP_CUDA(cudaMalloc(&nblk, (size_t)ncap * sizeof(int4)));
-        KICP_CUDA(cudaMalloc(&npts, (size_t)ncap * m->cap * KICP_PSTRIDE * sizeof(double)));
-        KICP_CUDA(cudaMalloc(&nhead, (size_t)ncap * sizeof(int32_t)));
-        if (m->num_blocks) {
-            KICP_CUDA(cudaMemcpyAsync(nblk, m->blk, (size_t)m->num_blocks * sizeof(int4), cudaMemcpyDeviceToDevice, c->stream));
-            KICP_CUDA(cudaMemcpyAsync(npts, m->pts, (size_t)m->num_blocks * m->cap * KICP_PSTRIDE * sizeof(double),
-                                      cudaMemcpyDeviceToDevice, c->stream));
-        }
-        k_fill_i32<<<(ncap + 255) / 256, 256, 0, c->stream>>>(nhead, -1, ncap);
-        KICP_CHECK_LAUNCH(c);
-        KICP_CUDA(cudaStreamSynchronize(c->stream));
-        cudaFree(m->blk), cudaFree(m->pts), cudaFree(m->pend_head);
-        m->blk = nblk, m->pts = npts, m->pend_head = nhead, m->blocks_cap = ncap;
+        const uint64_t grown = std::max<uint64_t>(std::max<uint64_t>(2ull * m->blocks_cap, need + need / 2), 4096);
+        KICP_TRY(map_alloc_storage(m, (uint32_t)std::min<uint64_t>(grown, 1ull << 24)));
     }
     const uint32_t want_slots = std::max<uint32_t>(next_pow2(need * 4), 1024u);
     if (want_slots > m->nslots) KICP_TRY(map_rebuild_table(m, want_slots));
+    return KICP_OK;
+}
+
+extern "C" int kicp_map_reserve(kicp_map *m, int64_t voxels) {
+    if (!m || voxels < 0 || voxels >= (1ll << 24)) return KICP_ERR_INVALID;
+    KICP_CUDA(cudaSetDevice(m->ctx->device));
+    if ((uint64_t)voxels > m->blocks_cap) KICP_TRY(map_alloc_storage(m, (uint32_t)voxels));
     return KICP_OK;
 }
 
@@ -489,7 +490,14 @@ extern "C" int kicp_map_create(kicp_ctx *ctx, double voxel_size, double max_dist
         delete m;
         return kicp_cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
     }
-    int st = map_reserve(m, 1024);
+    // Initial capacity: a local map is a disc of roughly pi (max_distance / voxel_size)^2 columns, a handful of voxels each.  Sized
+    // generously (HBM is 180 GB; a voxel of capacity costs ~1.4 KB at 20 points) so that a drive never re-allocates;
+    // KICP_MAP_VOXELS overrides, kicp_map_reserve() raises it, growth by doubling remains as the fallback.
+    double guess = 8.0 * 3.141592653589793 * (max_distance / voxel_size) * (max_distance / voxel_size);
+    if (const char *e = getenv("KICP_MAP_VOXELS")) guess = atof(e);
+    if (!(guess >= 16384.0)) guess = 16384.0;
+    if (guess > 1048576.0) guess = 1048576.0;
+    int st = map_alloc_storage(m, (uint32_t)guess);
     if (st != KICP_OK) {
         kicp_map_destroy(m);
         return st;
@@ -502,7 +510,7 @@ extern "C" int kicp_map_destroy(kicp_map *m) {
     if (!m) return KICP_OK;
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
-    cudaFree(m->slots), cudaFree(m->blk), cudaFree(m->pts), cudaFree(m->pend_head), cudaFree(m->d_counters);
+    cudaFree(m->slab), cudaFree(m->d_counters);
     cudaFree(m->d_in), cudaFree(m->d_xyz_t), cudaFree(m->d_next), cudaFree(m->d_touched);
     delete m;
     return KICP_OK;
@@ -532,14 +540,19 @@ extern "C" int kicp_map_num_voxels(kicp_map *m, int64_t *n) {
     return KICP_OK;
 }
 
-static int map_add_points_impl(kicp_map *m, const double *xyz, int64_t n, const double *pose7) {
+// `src_on_device`: xyz is a device pointer (packed doubles) that stays valid until the stream drains
+static int map_add_points_impl(kicp_map *m, const double *xyz, int64_t n, const double *pose7, bool src_on_device = false) {
     if (!m || n < 0 || (n > 0 && !xyz)) return KICP_ERR_INVALID;
     if (n == 0) return KICP_OK;
     kicp_ctx *c = m->ctx;
     KICP_CUDA(cudaSetDevice(c->device));
     KICP_TRY(map_reserve_input(m, n));
     KICP_TRY(map_reserve(m, (uint64_t)n));  // worst case: every point opens a new voxel
-    KICP_CUDA(cudaMemcpyAsync(m->d_in, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const double *d_src = xyz;
+    if (!src_on_device) {
+        KICP_CUDA(cudaMemcpyAsync(m->d_in, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        d_src = m->d_in;
+    }
     uint32_t init[8] = {m->num_blocks, 0, 0, 0, 0, 0, 0, 0};
     KICP_CUDA(cudaMemcpyAsync(m->d_counters, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
     MapRW rw{m->slots, m->nslots - 1, m->blk, m->pts, m->pend_head, m->blocks_cap, (int)m->cap, m->voxel_size};
@@ -547,7 +560,7 @@ static int map_add_points_impl(kicp_map *m, const double *xyz, int64_t n, const 
     if (pose7) pose = Pose{pose7[0], pose7[1], pose7[2], pose7[3], pose7[4], pose7[5], pose7[6]};
     const int threads = 256;
     k_add_find_or_create<<<(unsigned)((n + threads - 1) / threads), threads, 0, c->stream>>>(
-        rw, m->d_in, n, pose7 ? 1 : 0, pose, m->d_xyz_t, m->d_next, m->d_counters, m->d_touched);
+        rw, d_src, n, pose7 ? 1 : 0, pose, m->d_xyz_t, m->d_next, m->d_counters, m->d_touched);
     KICP_CHECK_LAUNCH(c);
     // KISS AddPoints: map_resolution = sqrt(voxel_size^2 / max_points_per_voxel)
     const double map_resolution = std::sqrt(m->voxel_size * m->voxel_size / (double)m->cap);
@@ -573,9 +586,7 @@ extern "C" int kicp_map_remove_far(kicp_map *m, const double origin[3]) {
     if (m->num_blocks == 0) return KICP_OK;
     kicp_ctx *c = m->ctx;
     KICP_CUDA(cudaSetDevice(c->device));
-    uint32_t *keep = nullptr, *new_id = nullptr;
-    KICP_CUDA(cudaMalloc(&keep, (size_t)m->num_blocks * sizeof(uint32_t)));
-    KICP_CUDA(cudaMalloc(&new_id, (size_t)m->num_blocks * sizeof(uint32_t)));
+    uint32_t *keep = m->d_keep, *new_id = m->d_new_id;
     uint32_t init[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     KICP_CUDA(cudaMemcpyAsync(m->d_counters, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
     k_mark_far<<<(m->num_blocks + 255) / 256, 256, 0, c->stream>>>(m->blk, m->pts, (int)m->cap, m->num_blocks, origin[0], origin[1],
@@ -585,37 +596,22 @@ extern "C" int kicp_map_remove_far(kicp_map *m, const double origin[3]) {
     uint32_t res[8];
     KICP_CUDA(cudaMemcpyAsync(res, m->d_counters, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
     KICP_CUDA(cudaStreamSynchronize(c->stream));
-    int st = KICP_OK;
     if (res[4] > 0) {
-        // compact surviving blocks (order preserved) into fresh storage and rebuild the table
+        // compact surviving blocks (order preserved) into the spare arrays, swap, and rebuild the table
         const uint32_t survivors = m->num_blocks - res[4];
-        int4 *nblk = nullptr;
-        double *npts = nullptr;
-        cudaError_t e1 = cudaMalloc(&nblk, (size_t)m->blocks_cap * sizeof(int4));
-        cudaError_t e2 = cudaMalloc(&npts, (size_t)m->blocks_cap * m->cap * KICP_PSTRIDE * sizeof(double));
-        if (e1 != cudaSuccess || e2 != cudaSuccess) {
-            cudaFree(nblk), cudaFree(npts), cudaFree(keep), cudaFree(new_id);
-            return kicp_cuda_fail(e1 != cudaSuccess ? e1 : e2, "cudaMalloc", __FILE__, __LINE__);
-        }
-        k_exclusive_scan<<<1, 1024, 0, c->stream>>>(keep, new_id, m->num_blocks, &m->d_counters[5]);
-        c->launches++;
+        size_t scan_bytes = m->scan_tmp_bytes;
+        KICP_CUDA(cub::DeviceScan::ExclusiveSum(m->d_scan_tmp, scan_bytes, keep, new_id, (int)m->num_blocks, c->stream));
+        c->launches += 2;  // CUB's scan passes (library kernels)
         k_compact_blocks<<<(unsigned)(((uint64_t)m->num_blocks * 32 + 255) / 256), 256, 0, c->stream>>>(
-            m->blk, m->pts, (int)m->cap, m->num_blocks, keep, new_id, nblk, npts);
-        c->launches++;
-        cudaError_t e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) {
-            cudaFree(nblk), cudaFree(npts), cudaFree(keep), cudaFree(new_id);
-            return kicp_cuda_fail(e, "compact", __FILE__, __LINE__);
-        }
-        cudaFree(m->blk), cudaFree(m->pts);
-        m->blk = nblk, m->pts = npts;
+            m->blk, m->pts, (int)m->cap, m->num_blocks, keep, new_id, m->blk_spare, m->pts_spare);
+        KICP_CHECK_LAUNCH(c);
+        std::swap(m->blk, m->blk_spare);
+        std::swap(m->pts, m->pts_spare);
         m->num_blocks = survivors;
         m->num_points -= res[3];
-        st = map_rebuild_table(m, m->nslots);
-        if (st == KICP_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) st = KICP_ERR_CUDA;
+        KICP_TRY(map_rebuild_table(m, m->nslots));  // stream-ordered after the compaction
     }
-    cudaFree(keep), cudaFree(new_id);
-    return st;
+    return KICP_OK;
 }
 
 extern "C" int kicp_map_update(kicp_map *m, const double *xyz, int64_t n, const double origin[3]) {
@@ -625,6 +621,11 @@ extern "C" int kicp_map_update(kicp_map *m, const double *xyz, int64_t n, const 
 extern "C" int kicp_map_update_pose(kicp_map *m, const double *xyz, int64_t n, const double pose[7]) {
     if (!pose) return KICP_ERR_INVALID;
     KICP_TRY(map_add_points_impl(m, xyz, n, pose));
+    return kicp_map_remove_far(m, pose + 4);
+}
+int kicp_map_update_pose_device(kicp_map *m, const double *d_xyz, int64_t n, const double pose[7]) {
+    if (!pose) return KICP_ERR_INVALID;
+    KICP_TRY(map_add_points_impl(m, d_xyz, n, pose, true));
     return kicp_map_remove_far(m, pose + 4);
 }
 

@@ -1307,6 +1307,9 @@ extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value)
     } else if (!strcmp(name, "sort_bits")) {
         if (value < 0 || value > 30) return KICP_ERR_INVALID;
         c->sort_bits = value;
+    } else if (!strcmp(name, "group4_below")) {
+        if (value < 0) return KICP_ERR_INVALID;
+        c->group4_below = value;
     } else {
         return KICP_ERR_INVALID;
     }
@@ -1393,7 +1396,9 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
     a.adaptive = p->use_adaptive_odometry_regularization ? 1 : 0;
     // an empty map returns the prediction (Registration.cpp:157): no association, no solve
     a.max_iter = m->num_blocks == 0 ? 0 : p->max_num_iterations;
-    a.fused_tail = (sharded && !(c->p2p_ready && c->assoc_variant >= 1 && c->persistent)) ? 0 : 1;
+    // small scans leave most warps without a 32-point window: the 8-point-window kernel spreads them over the whole machine
+    const int variant = (c->assoc_variant == 1 && !sharded && n > 0 && n <= c->group4_below) ? 2 : c->assoc_variant;
+    a.fused_tail = (sharded && !(c->p2p_ready && variant >= 1 && c->persistent)) ? 0 : 1;
     a.iters_out = nullptr;
     kicp_ctx::ProfReg *pr = nullptr;
     if (c->profiling && (int64_t)c->prof.size() < c->prof_cap) {
@@ -1410,7 +1415,7 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
     if (a.max_iter > 0) {
         const double *d_pts = scan->d_xyz;
         const int sbits = c->sort_bits;
-        if (upload && (sbits > 0 || !((c->assoc_variant == 1 || c->assoc_variant == 3) && c->persistent && (!sharded || c->p2p_ready)))) {
+        if (upload && (sbits > 0 || !((variant == 1 || variant == 3) && c->persistent && (!sharded || c->p2p_ready)))) {
             // this configuration reads the whole frame up front: wait for the upload instead of overlapping it
             cudaEvent_t ev;
             KICP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1434,9 +1439,9 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
         if (pr) KICP_CUDA(cudaEventRecord(pr->prep1, c->stream));
         const int num_windows = (n + 31) / 32;
         // persistent-style grid: every CTA is resident and pulls windows from a device-side counter
-        const bool group4 = c->assoc_variant == 2;
-        const bool hybrid = c->assoc_variant == 3;
-        const bool pruned = c->assoc_variant >= 1;
+        const bool group4 = variant == 2;
+        const bool hybrid = variant == 3;
+        const bool pruned = variant >= 1;
         const bool p2p = sharded && c->p2p_ready && pruned;
         const bool persistent = pruned && c->persistent && (!sharded || p2p);
         P2PArgs px{};
@@ -1595,6 +1600,14 @@ extern "C" int kicp_register_scan_async(kicp_map *map, kicp_scan *scan, const do
 extern "C" int kicp_register_scan_sharded_async(kicp_map *map, kicp_scan *scan, const double last[7], const double odom[7],
                                                 double tau, const kicp_reg_params *params, kicp_reg_result *result) {
     return enqueue_registration(map, scan, last, odom, tau, params, result, true);
+}
+
+int kicp_enqueue_registration_device(kicp_map *m, const double *d_xyz, int64_t n, const double last[7], const double odom[7],
+                                     double tau, const kicp_reg_params *p) {
+    if (!m || n < 0 || (n > 0 && !d_xyz)) return KICP_ERR_INVALID;
+    kicp_scan view;  // non-owning alias of the caller's device buffer
+    view.ctx = m->ctx, view.d_xyz = const_cast<double *>(d_xyz), view.cap = n, view.n = n;
+    return enqueue_registration(m, &view, last, odom, tau, p, m->ctx->h_result, false);
 }
 
 static int register_host(kicp_map *map, const double *frame_xyz, int64_t n, const double last[7], const double odom[7],

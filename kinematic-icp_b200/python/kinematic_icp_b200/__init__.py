@@ -118,6 +118,10 @@ class VoxelHashMap:
     def Clear(self):
         check(lib().kicp_map_clear(self.h), "kicp_map_clear")
 
+    def reserve(self, voxels):
+        """Pre-size the device storage (kicp_map_reserve); growth beyond it still works, by doubling."""
+        check(lib().kicp_map_reserve(self.h, int(voxels)), "kicp_map_reserve")
+
     def Empty(self):
         e = C.c_int32()
         check(lib().kicp_map_empty(self.h, C.byref(e)), "kicp_map_empty")
@@ -281,6 +285,55 @@ def Preprocess(ctx, frame, timestamps, relative_motion, max_range, min_range, de
                                 float(max_range), float(min_range), int(bool(deskew)), dp(out), len(out), C.byref(m)),
           "kicp_preprocess")
     return out[: m.value].copy()
+
+
+def RegisterFrame(voxel_map, frame, timestamps, deskew_motion, lidar_to_base, last_pose, relative_odometry, tau, *, max_range=100.0,
+                  min_range=0.0, deskew=True, voxel_size=1.0, max_num_iterations=10, convergence_criterion=0.001,
+                  use_adaptive_odometry_regularization=True, fixed_regularization=0.0, point_step=0, offsets=(0, 0, 0),
+                  want_clouds=True):
+    """kicp_register_frame: the per-point part of KinematicICP::RegisterFrame (pipeline/KinematicICP.cpp:48-85) in one call.
+    `frame` is float64 [n,3], float32 [n,3], or (with point_step/offsets) a uint8 buffer of PointCloud2-style records with
+    float32 x,y,z fields.  Returns (new_pose, preprocessed_frame_in_base, source, result)."""
+    from ._capi import KICP_DTYPE_F32, KICP_DTYPE_F64, FrameInput, FrameParams
+    inp = FrameInput()
+    if point_step:
+        raw = np.ascontiguousarray(frame).view(np.uint8).reshape(-1)
+        n = raw.size // point_step
+        inp.data, inp.n, inp.dtype, inp.point_step = raw.ctypes.data, n, KICP_DTYPE_F32, point_step
+        inp.offset_x, inp.offset_y, inp.offset_z = offsets
+        keep = raw
+    else:
+        arr = np.asarray(frame)
+        if arr.dtype == np.float32:
+            keep = np.ascontiguousarray(arr.reshape(-1, 3))
+            inp.dtype = KICP_DTYPE_F32
+        else:
+            keep = as_points(arr)
+            inp.dtype = KICP_DTYPE_F64
+        n = len(keep)
+        inp.data, inp.n, inp.point_step = keep.ctypes.data, n, 0
+    ts = np.ascontiguousarray(timestamps, dtype=np.float64)
+    inp.stamps, inp.n_stamps = dp(ts), len(ts)
+    fp = FrameParams()
+    fp.max_range, fp.min_range, fp.deskew, fp.voxel_size = float(max_range), float(min_range), int(bool(deskew)), float(voxel_size)
+    fp.reg.max_num_iterations = int(max_num_iterations)
+    fp.reg.use_adaptive_odometry_regularization = int(bool(use_adaptive_odometry_regularization))
+    fp.reg.convergence_criterion, fp.reg.fixed_regularization = float(convergence_criterion), float(fixed_regularization)
+    out_pose = np.empty(7)
+    res = RegResult()
+    nf, ns = C.c_int64(), C.c_int64()
+    out_frame = np.empty((n, 3)) if want_clouds else None
+    out_source = np.empty((n, 3)) if want_clouds else None
+    st = lib().kicp_register_frame(voxel_map.h, C.byref(inp), dp(as_pose(deskew_motion)), dp(as_pose(lidar_to_base)), dp(as_pose(last_pose)),
+                                   dp(as_pose(relative_odometry)), float(tau), C.byref(fp), dp(out_pose),
+                                   dp(out_frame) if want_clouds else None, n, C.byref(nf), dp(out_source) if want_clouds else None, n,
+                                   C.byref(ns), C.byref(res))
+    if st not in (KICP_OK, KICP_WARN_NO_CORRESPONDENCES):
+        check(st, "kicp_register_frame")
+    del keep
+    if want_clouds:
+        return out_pose, out_frame[: nf.value].copy(), out_source[: ns.value].copy(), res
+    return out_pose, nf.value, ns.value, res
 
 
 def shard_range(n, nranks, rank):

@@ -49,6 +49,21 @@ class Profile(C.Structure):
                 ("assoc_iterations", C.c_int64)]
 
 
+class FrameInput(C.Structure):
+    """kicp_frame_input"""
+    _fields_ = [("data", C.c_void_p), ("n", C.c_int64), ("dtype", C.c_int32), ("point_step", C.c_int32), ("offset_x", C.c_int32),
+                ("offset_y", C.c_int32), ("offset_z", C.c_int32), ("stamps", c_dp), ("n_stamps", C.c_int64)]
+
+
+class FrameParams(C.Structure):
+    """kicp_frame_params"""
+    _fields_ = [("max_range", C.c_double), ("min_range", C.c_double), ("deskew", C.c_int32), ("voxel_size", C.c_double),
+                ("stage_clouds", C.c_int32), ("reg", RegParams)]
+
+
+KICP_DTYPE_F64, KICP_DTYPE_F32 = 0, 1
+
+
 class KicpError(RuntimeError):
     def __init__(self, status, where):
         self.status = status
@@ -76,6 +91,7 @@ SYMBOLS = [
     ("kicp_host_free", C.c_int, [_P]),
     ("kicp_map_create", C.c_int, [_P, C.c_double, C.c_double, C.c_uint32, C.POINTER(_P)]),
     ("kicp_map_destroy", C.c_int, [_P]),
+    ("kicp_map_reserve", C.c_int, [_P, C.c_int64]),
     ("kicp_map_clear", C.c_int, [_P]),
     ("kicp_map_empty", C.c_int, [_P, c_ip]),
     ("kicp_map_num_points", C.c_int, [_P, C.POINTER(C.c_int64)]),
@@ -99,6 +115,10 @@ SYMBOLS = [
     ("kicp_voxel_downsample", C.c_int, [_P, c_dp, C.c_int64, C.c_double, c_dp, C.c_int64, C.POINTER(C.c_int64)]),
     ("kicp_preprocess", C.c_int, [_P, c_dp, C.c_int64, c_dp, C.c_int64, c_dp, c_dp, C.c_double, C.c_double, C.c_int32, c_dp,
                                   C.c_int64, C.POINTER(C.c_int64)]),
+    ("kicp_register_frame", C.c_int, [_P, C.POINTER(FrameInput), c_dp, c_dp, c_dp, c_dp, C.c_double, C.POINTER(FrameParams), c_dp,
+                                      c_dp, C.c_int64, C.POINTER(C.c_int64), c_dp, C.c_int64, C.POINTER(C.c_int64),
+                                      C.POINTER(RegResult)]),
+    ("kicp_frame_clouds", C.c_int, [_P, C.POINTER(c_dp), C.POINTER(C.c_int64), C.POINTER(c_dp), C.POINTER(C.c_int64)]),
     ("kicp_comm_unique_id", C.c_int, [C.POINTER(C.c_uint8)]),
     ("kicp_comm_init", C.c_int, [_P, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]),
     ("kicp_comm_destroy", C.c_int, [_P]),

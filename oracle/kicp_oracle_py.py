@@ -393,6 +393,20 @@ class _Pipeline:
                                                                      _dp(pose7(lidar_to_base)), _dp(pose7(rel_odom)), _dp(out))
         return out, int(n_src)
 
+    def register_frame_raw(self, pts, stamps, lidar_to_base, rel_odom):
+        """Facade only: a packed float64 or float32 [n,3] buffer straight to the device (kicp_frame_input), no std::vector copy."""
+        pts = np.ascontiguousarray(pts).reshape(-1, 3)
+        assert pts.dtype in (np.float32, np.float64)
+        stamps = np.ascontiguousarray(stamps, dtype=np.float64)
+        out = np.empty(7)
+        g = getattr(self.L, self.p + "pipeline_register_frame_raw")
+        g.restype = C.c_int64
+        g.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_dp, C.c_int64, c_dp,
+                      c_dp, c_dp]
+        n_src = g(self.h, pts.ctypes.data, len(pts), 1 if pts.dtype == np.float32 else 0, 0, 0, 0, 0, _dp(stamps), len(stamps),
+                  _dp(pose7(lidar_to_base)), _dp(pose7(rel_odom)), _dp(out))
+        return out, int(n_src)
+
     def num_map_points(self):
         return int(getattr(self.L, self.p + "pipeline_num_map_points")(self.h))
 

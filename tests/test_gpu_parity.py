@@ -142,6 +142,7 @@ def test_registration_configs_vs_oracle(oracle, gpu_ctx, workload, cfg):
     w = workload(cfg)
     gm = gpu_map_from_oracle(kb, gpu_ctx, w.map)
     try:
+        gpu_ctx.set_option("group4_below", 0)  # the matrix names its kernel explicitly; the default choice is checked last
         for variant, sort_bits, persistent in ((3, 0, 1), (3, 0, 0), (3, 30, 1), (2, 0, 1), (2, 0, 0), (2, 30, 1), (1, 0, 1), (1, 0, 0), (0, 30, 0), (1, 30, 1), (1, 12, 0)):
             gpu_ctx.set_option("assoc_variant", variant)
             gpu_ctx.set_option("sort_bits", sort_bits)
@@ -153,6 +154,9 @@ def test_registration_configs_vs_oracle(oracle, gpu_ctx, workload, cfg):
         gpu_ctx.set_option("assoc_variant", 1)
         gpu_ctx.set_option("sort_bits", 0)
         gpu_ctx.set_option("persistent", 1)
+        gpu_ctx.set_option("group4_below", 49152)
+    pose, dt, ang = check_registration(ko, kb, gpu_ctx, w.map, gm, w.scan, w.last_pose, w.rel_odom, w.tau)
+    print("cfg%d defaults (kernel chosen by scan size) pose delta %.3e m %.3e rad" % (cfg, dt, ang))
     gm.close()
 
 
@@ -209,3 +213,31 @@ def test_device_resident_async_path(oracle, gpu_ctx, workload):
     assert gpu_ctx.launch_count > 0
     scan.close()
     gm.close()
+
+
+def test_map_storage_growth_and_reserve_bit_exact(oracle, gpu_ctx, monkeypatch):
+    """The map's single device slab doubles when a batch could exceed it (contents migrate, table rebuilt) and
+    kicp_map_reserve pre-sizes it: contents stay identical to the CPU map through growth, eviction and further inserts."""
+    import kinematic_icp_b200 as kb
+    ko = oracle
+    monkeypatch.setenv("KICP_MAP_VOXELS", "16384")  # smallest initial capacity
+    rng = np.random.default_rng(77)
+    om = ko.OracleMap(1.0, 60.0, 5)
+    gm = kb.VoxelHashMap(gpu_ctx, 1.0, 60.0, 5)
+    monkeypatch.delenv("KICP_MAP_VOXELS")
+    for it in range(5):
+        origin = np.array([15.0 * it, -4.0 * it, 0.0])
+        pts = rng.uniform(-70, 70, size=(30000, 3)) * [1, 1, 0.1] + origin  # almost every point opens its own voxel
+        om.update_origin(pts, origin)
+        gm.Update(pts, origin)
+        if it == 2:
+            gm.reserve(400000)  # explicit re-size in the middle of a drive
+        assert gm.num_points() == om.num_points() and gm.num_voxels() == om.num_voxels()
+    assert om.num_voxels() > 16384 * 2
+    k1, c1, p1 = sorted_voxels(*gm.export_voxels())
+    k0, c0, p0 = sorted_voxels(*om.export_voxels())
+    assert np.array_equal(k1, k0) and np.array_equal(c1, c0) and np.array_equal(p1, p0)
+    q = rng.uniform(-60, 120, size=(4000, 3)) * [1, 1, 0.1]
+    gp, gd = gm.GetClosestNeighbor(q)
+    op, od = om.nearest(q)
+    assert np.array_equal(gp, op) and np.array_equal(gd, od)
