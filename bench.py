@@ -106,6 +106,78 @@ class ClockSampler:
         return out
 
 
+class NvmlSampler:
+    """SM clock and throttle reasons sampled every millisecond by a thread, through NVML (nvidia_ml_py), only while the
+    main thread is inside a timed region (`active`): the timed regions of this bench last milliseconds, shorter than one
+    nvidia-smi start-up.  Falls back to the nvidia-smi loop above when NVML is unavailable."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+
+    def __init__(self, gpu_index, uuid=None):
+        import threading
+        self.fallback = None
+        self.samples, self.active, self.stop_flag = [], False, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = None
+            if uuid is not None:
+                try:
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+                except Exception:
+                    self.h = None
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
+        except Exception:
+            self.nv = None
+            self.fallback = ClockSampler(gpu_index)
+
+    def _reasons(self):
+        for name in ("nvmlDeviceGetCurrentClocksEventReasons", "nvmlDeviceGetCurrentClocksThrottleReasons"):
+            f = getattr(self.nv, name, None)
+            if f is not None:
+                try:
+                    return int(f(self.h))
+                except Exception:
+                    continue
+        return 0
+
+    def _run(self):
+        import time as _t
+        while not self.stop_flag:
+            if self.active:
+                try:
+                    self.samples.append((float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)), self._reasons()))
+                except Exception:
+                    pass
+            _t.sleep(0.001)
+
+    def start(self):
+        if self.fallback is not None:
+            self.fallback.start()
+        else:
+            self.thread.start()
+
+    def stop(self):
+        if self.fallback is not None:
+            out = self.fallback.stop()
+            out["source"] = "nvidia-smi -lms 100 over the whole run"
+            return out
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": len(self.samples),
+               "source": "NVML, 1 ms period, timed regions only"}
+        if self.samples:
+            out["sm_mhz"] = statistics.median(x[0] for x in self.samples)
+            mask = 0
+            for _, r in self.samples:
+                mask |= r
+            out["reasons"] = [name for bit, name in self.REASONS if mask & bit]
+        return out
+
+
 # -------------------------------------------------------------------------------------------------- CPU baseline
 def cpu_registration_runner(w):
     """Returns (callable running one full registration on the host cores, kind, cores)."""
@@ -243,6 +315,13 @@ def main():
         return float(t.item())
 
     results = [kb.pinned_result() for _ in range(args.steps + args.warmup)]
+    try:
+        gpu_uuid = torch.cuda.get_device_properties(dev).uuid
+    except Exception:
+        gpu_uuid = None
+    sampler = NvmlSampler(local_rank, gpu_uuid)
+    if rank == 0:
+        sampler.start()
 
     def timed_loop(enqueue, steps, warmup, profile=False):
         """W untimed warm-up steps, then K steps each bracketed by CUDA events on the launching stream, with an
@@ -254,6 +333,7 @@ def main():
         barrier()
         if profile:
             ctx.profile_begin()
+        sampler.active = True  # clocks are sampled only inside timed regions
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for i in range(steps):
             flush_l2(i)
@@ -262,6 +342,7 @@ def main():
             ev[i][1].record(stream)
         prof = ctx.profile_end() if profile else None
         ctx.synchronize()
+        sampler.active = False
         barrier()
         step_ms = [a.elapsed_time(b) for a, b in ev]
         return max_over_ranks(sum(step_ms)), prof, step_ms
@@ -270,15 +351,11 @@ def main():
     def enqueue_resident(i):
         reg.enqueue(scan, gm, w.last_pose, w.rel_odom, w.tau, results[i], sharded=sharded)
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = ctx.launch_count
     total_ms, prof, step_ms = timed_loop(enqueue_resident, args.steps, args.warmup, profile=True)
     gpu_launches = ctx.launch_count - launches0
     # warm-up launches are included in launch_count; subtract them proportionally
     gpu_launches = int(round(gpu_launches * args.steps / float(args.steps + args.warmup)))
-    clocks = sampler.stop() if rank == 0 else None
     jobs = world if (world > 1 and not sharded) else 1  # replicas: every rank finishes its own registrations
     value = jobs * args.steps / (total_ms * 1e-3)
     iters = results[args.warmup].iterations
@@ -296,6 +373,7 @@ def main():
         assert st == 0, st
 
     e2e_ms, _, _ = timed_loop(e2e_call, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
     e2e_value = jobs * args.steps / (e2e_ms * 1e-3)
 
     # ---- parity of what was just timed ------------------------------------------------------------------------

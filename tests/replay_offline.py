@@ -86,9 +86,12 @@ if rank == 0:
     parity = None
     if ko.ref_available():
         ref = ko.ref_pipeline(deskew=True, max_num_threads=os.cpu_count() or 1)
+        tr = time.perf_counter()
         rposes, _, _ = S.run_pipeline(ref, seq)
+        cpu_fps = frames / (time.perf_counter() - tr)
         worst = [max(d) for d in zip(*[ko.pose_delta(a, b) for a, b in zip(poses, rposes)])]
-        parity = {"translation_m": worst[0], "rotation_rad": worst[1]}
+        parity = {"translation_m": worst[0], "rotation_rad": worst[1], "cpu_reference_frames_per_s": cpu_fps,
+                  "cpu_threads": os.cpu_count()}
     print(json.dumps({"metric": "offline replay: frames/s through KinematicICP::RegisterFrame (aggregate)",
                       "value": world * frames / elapsed, "unit": "frames/s", "n_gpus": world, "frames_per_sequence": frames, "ingest": ingest, "variant": variant, "host_buffers": host,
                       "points_per_frame": int(np.mean([len(f) for f in seq["frames"]])), "ms_per_frame": 1e3 * elapsed / frames,
