@@ -192,7 +192,7 @@ int kicp_register_frame(kicp_map *map, const kicp_frame_input *in, const double 
                         double out_pose[7], double *out_frame, int64_t cap_frame, int64_t *n_frame, double *out_source,
                         int64_t cap_source, int64_t *n_source, kicp_reg_result *result);
 /* The two clouds of the last kicp_register_frame on this context (fp->stage_clouds != 0 or out_* given): pointers into
- * context-owned pinned host memory, valid until the next front-end call on the same device.  Lets a caller build its
+ * context-owned pinned host memory, valid until the next front-end call on the same context.  Lets a caller build its
  * own containers in one pass instead of pre-sizing worst-case output buffers. */
 int kicp_frame_clouds(kicp_ctx *ctx, const double **frame, int64_t *n_frame, const double **source, int64_t *n_source);
 

@@ -56,6 +56,9 @@ int64_t kfac_pipeline_register_frame_raw(void *h, const void *data, int64_t n, i
 int64_t kfac_pipeline_num_map_points(void *h) {
     return static_cast<int64_t>(static_cast<kinematic_icp::pipeline::KinematicICP *>(h)->LocalMap().size());
 }
+// host-side stage times (ms, cumulative) of the last RegisterFrame on the process-wide context (library debug export)
+extern "C" int kicp_debug_frame_timing(kicp_ctx *, double *);
+int kfac_debug_frame_timing(double *out8) { return kicp_debug_frame_timing(kicp::default_context(), out8); }
 // poses7[n][7] + stamps[n] -> TUM file (offline_node.cpp:76-97)
 int kfac_write_tum(const char *path, const double *stamps, const double *poses7, int64_t n) {
     std::vector<std::pair<double, Sophus::SE3d>> v;

@@ -180,19 +180,33 @@ struct Scratch {
     int64_t cap = 0;
     uint32_t nslots = 0;
 };
-Scratch &scratch_of_device(int device) {
-    static thread_local Scratch s[16];
-    return s[device & 15];
-}
-Scratch &scratch(kicp_ctx *c) { return scratch_of_device(c->device); }
-
-int reserve(kicp_ctx *c, Scratch &s, int64_t n) {
-    if (n <= s.cap) return KICP_OK;
-    KICP_CUDA(cudaStreamSynchronize(c->stream));
+void release(Scratch &s) {
     cudaFree(s.in), cudaFree(s.mid), cudaFree(s.out), cudaFree(s.out2), cudaFree(s.out3), cudaFree(s.stamps), cudaFree(s.flags);
     cudaFree(s.first_idx), cudaFree(s.slot_of), cudaFree(s.slots), cudaFree(s.tmp), cudaFree(s.d_count), cudaFree(s.d_mm);
     cudaFree(s.raw), cudaFreeHost(s.h_count), cudaFreeHost(s.h_frame), cudaFreeHost(s.h_source);
     s = Scratch();
+}
+void free_scratch(kicp_ctx *c) {
+    if (!c->frontend) return;
+    release(*static_cast<Scratch *>(c->frontend));
+    delete static_cast<Scratch *>(c->frontend);
+    c->frontend = nullptr;
+}
+// the scratch belongs to the context (created on first use, freed by kicp_ctx_destroy); like every other object of the
+// library it is not thread-safe
+Scratch &scratch(kicp_ctx *c) {
+    if (!c->frontend) {
+        c->frontend = new Scratch();
+        c->frontend_free = free_scratch;
+    }
+    return *static_cast<Scratch *>(c->frontend);
+}
+
+int reserve(kicp_ctx *c, Scratch &s, int64_t n) {
+    if (n <= s.cap) return KICP_OK;
+    KICP_CUDA(cudaStreamSynchronize(c->stream));
+    KICP_CUDA(cudaStreamSynchronize(c->copy_stream));
+    release(s);
     const int64_t cap = std::max<int64_t>(n + n / 4, 4096);
     uint32_t nslots = 1;
     while (nslots < (uint64_t)cap * 2) nslots <<= 1;
@@ -431,7 +445,7 @@ extern "C" int kicp_register_frame(kicp_map *map, const kicp_frame_input *in, co
 }
 
 /* The clouds of the last kicp_register_frame on this context (fp->stage_clouds), in context-owned pinned host memory, valid
- * until the next kicp_register_frame / kicp_preprocess / kicp_voxel_downsample call on a context of the same device. */
+ * until the next kicp_register_frame / kicp_preprocess / kicp_voxel_downsample call on the same context. */
 extern "C" int kicp_frame_clouds(kicp_ctx *c, const double **frame, int64_t *n_frame, const double **source, int64_t *n_source) {
     if (!c || !frame || !n_frame || !source || !n_source) return KICP_ERR_INVALID;
     Scratch &s = scratch(c);
@@ -441,8 +455,8 @@ extern "C" int kicp_frame_clouds(kicp_ctx *c, const double **frame, int64_t *n_f
 }
 
 // debugging aid (not part of the public header): cumulative host-side stage times of the last kicp_register_frame, ms
-extern "C" int kicp_debug_frame_timing(int device, double out[8]) {
-    if (!out) return KICP_ERR_INVALID;
-    for (int k = 0; k < 8; ++k) out[k] = scratch_of_device(device).timing[k];
+extern "C" int kicp_debug_frame_timing(kicp_ctx *c, double out[8]) {
+    if (!c || !out) return KICP_ERR_INVALID;
+    for (int k = 0; k < 8; ++k) out[k] = scratch(c).timing[k];
     return KICP_OK;
 }

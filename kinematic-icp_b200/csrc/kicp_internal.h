@@ -84,6 +84,9 @@ struct kicp_ctx {
     std::vector<ProfReg> prof;
     int32_t *d_prof_iters = nullptr;
     int64_t prof_cap = 0;
+    // front-end scratch (kicp_frontend.cu owns the type): frame buffers, down-sample hash, pinned staging of the clouds
+    void *frontend = nullptr;
+    void (*frontend_free)(kicp_ctx *) = nullptr;
     // multi-GPU
     void *nccl_comm = nullptr;
     int nranks = 1, rank = 0;

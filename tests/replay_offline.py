@@ -58,14 +58,14 @@ if world > 1:
     dist.barrier()
 t0 = time.perf_counter()
 poses, stage_ms = [], []
-KL = C.CDLL(os.path.join(ROOT, "kinematic-icp_b200", "lib", "libkicp_b200.so"))  # same library instance the facade links
-KL.kicp_debug_frame_timing.argtypes = [C.c_int, ko.c_dp]
+KL = C.CDLL(os.path.join(ROOT, "kinematic-icp_b200", "lib", "libkinematic_icp_b200.so"))
+KL.kfac_debug_frame_timing.argtypes = [ko.c_dp]
 tbuf = np.zeros(8)
 for f, s, o in zip(frames_in, stamps_in, seq["odoms"]):
     p, _ = step(f, s, seq["lidar_to_base"], o)
     poses.append(p)
     if variant == "fused":
-        KL.kicp_debug_frame_timing(local, tbuf.ctypes.data_as(ko.c_dp))
+        KL.kfac_debug_frame_timing(tbuf.ctypes.data_as(ko.c_dp))
         stage_ms.append(np.diff(np.concatenate([[0.0], tbuf[:5]])))
 elapsed = time.perf_counter() - t0
 if world > 1:
