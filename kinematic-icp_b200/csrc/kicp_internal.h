@@ -72,6 +72,8 @@ struct kicp_ctx {
     uint32_t *h_chunk_tags = nullptr;    // pinned source of the flag copies
     uint32_t upload_seq = 0;
     int overlap_upload = 1;
+    int launch_first = 0;                // 1 = issue only the first upload chunk before the persistent launch, the rest after it
+                                         // (measured: no gain at cfg4, -6 % e2e at cfg3: the first pass is bound by the copy itself)
     kicp_reg_result *h_result = nullptr;  // pinned bounce buffer for synchronous calls
     // profiling (kicp_ctx_profile_begin/end): event pairs per registration
     bool profiling = false;

@@ -63,6 +63,7 @@ extern "C" int kicp_ctx_create(int device, kicp_ctx **out) {
     KICP_CUDA(cudaMemset(c->d_chunk_flags, 0, KICP_UPLOAD_CHUNKS * sizeof(uint32_t)));
     KICP_CUDA(cudaMallocHost(&c->h_chunk_tags, KICP_UPLOAD_CHUNKS * sizeof(uint32_t)));
     if (const char *e = getenv("KICP_OVERLAP_UPLOAD")) c->overlap_upload = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("KICP_LAUNCH_FIRST")) c->launch_first = atoi(e) ? 1 : 0;
     if (const char *e = getenv("KICP_GROUP4_BELOW")) c->group4_below = std::max(0, atoi(e));
     if (const char *e = getenv("KICP_ASSOC")) c->assoc_variant = !strcmp(e, "staged") ? 0 : (!strcmp(e, "group4") ? 2 : (!strcmp(e, "hybrid") ? 3 : 1));
     if (const char *e = getenv("KICP_PERSISTENT")) c->persistent = atoi(e) ? 1 : 0;

@@ -472,6 +472,28 @@ struct UploadArgs {
     int windows_per_chunk;  // in 32-point windows
 };
 
+// Host side of the same upload: the chunks still to be issued on the copy stream.  With the "launch_first" option only the
+// first chunk goes out before the persistent kernel is launched and the rest right after the launch call; measured on B200
+// this does not pay (cfg4 e2e +-0, cfg3 -6 %: the first pass is bound by the 6 MB copy itself, not by the ~16 driver
+// calls in front of the launch), so the default issues every chunk first.
+struct HostUpload {
+    const double *src;
+    double *dst;
+    int64_t n, wpc;
+    int issued;
+};
+static int issue_chunks(kicp_ctx *c, HostUpload *hu, int upto) {
+    for (int k = hu->issued; k < upto; ++k) {
+        const int64_t lo = std::min<int64_t>(hu->n, k * hu->wpc * 32), hi = std::min<int64_t>(hu->n, (k + 1) * hu->wpc * 32);
+        hu->issued = k + 1;
+        if (hi > lo)
+            KICP_CUDA(cudaMemcpyAsync(hu->dst + 3 * lo, hu->src + 3 * lo, (size_t)(hi - lo) * 3 * sizeof(double), cudaMemcpyHostToDevice,
+                                      c->copy_stream));
+        KICP_CUDA(cudaMemcpyAsync(c->d_chunk_flags + k, c->h_chunk_tags + k, sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
+    }
+    return KICP_OK;
+}
+
 struct P2PArgs {
     P2PMailbox *peer[KICP_MAX_RANKS];
     int nranks, rank, parity;
@@ -1307,6 +1329,9 @@ extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value)
     } else if (!strcmp(name, "sort_bits")) {
         if (value < 0 || value > 30) return KICP_ERR_INVALID;
         c->sort_bits = value;
+    } else if (!strcmp(name, "launch_first")) {
+        if (value != 0 && value != 1) return KICP_ERR_INVALID;
+        c->launch_first = value;
     } else if (!strcmp(name, "group4_below")) {
         if (value < 0) return KICP_ERR_INVALID;
         c->group4_below = value;
@@ -1376,7 +1401,8 @@ static int check_params(const kicp_reg_params *p) {
 // Enqueue one full registration on the context stream.  `sharded` inserts the 8-double allreduce between the
 // association and the solve of every iteration.
 static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[7], const double odom[7], double tau,
-                                const kicp_reg_params *p, kicp_reg_result *result, bool sharded, const UploadArgs *upload = nullptr) {
+                                const kicp_reg_params *p, kicp_reg_result *result, bool sharded, const UploadArgs *upload = nullptr,
+                                HostUpload *host_upload = nullptr) {
     if (!m || !scan || !last || !odom) return KICP_ERR_INVALID;
     KICP_TRY(check_params(p));
     kicp_ctx *c = m->ctx;
@@ -1417,6 +1443,7 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
         const int sbits = c->sort_bits;
         if (upload && (sbits > 0 || !((variant == 1 || variant == 3) && c->persistent && (!sharded || c->p2p_ready)))) {
             // this configuration reads the whole frame up front: wait for the upload instead of overlapping it
+            if (host_upload) KICP_TRY(issue_chunks(c, host_upload, KICP_UPLOAD_CHUNKS));
             cudaEvent_t ev;
             KICP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             KICP_CUDA(cudaEventRecord(ev, c->copy_stream));
@@ -1490,6 +1517,7 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
                                                            : (const void *)k_assoc_pruned<true>,
                                                   dim3(grid), dim3(KICP_WARPS * 32), args, 0, c->stream));
             c->launches++;
+            if (host_upload) KICP_TRY(issue_chunks(c, host_upload, KICP_UPLOAD_CHUNKS));  // the kernel is already waiting on the flags
             if (pr) KICP_CUDA(cudaEventRecord(e1, c->stream));
             if (dbg) {
                 cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -1533,6 +1561,7 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
             }
         }
     }
+    if (host_upload) KICP_TRY(issue_chunks(c, host_upload, KICP_UPLOAD_CHUNKS));  // paths that did not need the frame yet
     if (result)
         KICP_CUDA(cudaMemcpyAsync(result, &c->d_state->result, sizeof(kicp_reg_result), cudaMemcpyDeviceToHost, c->stream));
     return KICP_OK;
@@ -1623,27 +1652,26 @@ static int register_host(kicp_map *map, const double *frame_xyz, int64_t n, cons
     // first pass waits per chunk on the flag, so the association starts while later chunks are still on the bus.
     UploadArgs up{nullptr, 0u, 1};
     const UploadArgs *upp = nullptr;
+    HostUpload hu{frame_xyz, s->d_xyz, n, 1, KICP_UPLOAD_CHUNKS};
+    HostUpload *hup = nullptr;
     if (n > 0) {
         const int64_t windows = (n + 31) / 32;
         const int64_t wpc = (windows + KICP_UPLOAD_CHUNKS - 1) / KICP_UPLOAD_CHUNKS;
         const uint32_t seq = ++c->upload_seq ? c->upload_seq : ++c->upload_seq;  // never 0
         for (int k = 0; k < KICP_UPLOAD_CHUNKS; ++k) c->h_chunk_tags[k] = seq;
-        for (int k = 0; k < KICP_UPLOAD_CHUNKS; ++k) {
-            const int64_t lo = std::min<int64_t>(n, k * wpc * 32), hi = std::min<int64_t>(n, (k + 1) * wpc * 32);
-            if (hi > lo)
-                KICP_CUDA(cudaMemcpyAsync(s->d_xyz + 3 * lo, frame_xyz + 3 * lo, (size_t)(hi - lo) * 3 * sizeof(double),
-                                          cudaMemcpyHostToDevice, c->copy_stream));
-            KICP_CUDA(cudaMemcpyAsync(c->d_chunk_flags + k, c->h_chunk_tags + k, sizeof(uint32_t), cudaMemcpyHostToDevice,
-                                      c->copy_stream));
-        }
+        hu.wpc = wpc, hu.issued = 0;
+        hup = &hu;
         up = UploadArgs{c->d_chunk_flags, seq, (int)wpc};
         upp = &up;
+        // first chunk now; the others follow the kernel launch (launch_first) or precede it (the older order, kept for A/B)
+        KICP_TRY(issue_chunks(c, hup, c->launch_first ? 1 : KICP_UPLOAD_CHUNKS));
         if (!c->overlap_upload) {
+            KICP_TRY(issue_chunks(c, hup, KICP_UPLOAD_CHUNKS));
             KICP_CUDA(cudaStreamSynchronize(c->copy_stream));
             upp = nullptr;
         }
     }
-    KICP_TRY(enqueue_registration(map, s, last, odom, tau, params, c->h_result, sharded, upp));
+    KICP_TRY(enqueue_registration(map, s, last, odom, tau, params, c->h_result, sharded, upp, hup));
     KICP_CUDA(cudaStreamSynchronize(c->stream));
     KICP_CUDA(cudaStreamSynchronize(c->copy_stream));
     for (int k = 0; k < 7; ++k) out_pose[k] = c->h_result->pose[k];
