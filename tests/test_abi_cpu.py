@@ -27,10 +27,30 @@ def test_library_exports_every_declared_symbol():
     assert declared == {s[0] for s in _capi.SYMBOLS}, "python binding and header disagree"
 
 
-def test_struct_layout_matches_header():
+def test_struct_layout_matches_header(tmp_path):
+    """sizeof / offsetof of every struct of include/kicp.h as gcc lays it out == the ctypes mirror (and the header is plain C)."""
+    import subprocess
     from kinematic_icp_b200 import _capi
+    structs = {"kicp_reg_params": _capi.RegParams, "kicp_reg_result": _capi.RegResult, "kicp_profile": _capi.Profile,
+               "kicp_frame_input": _capi.FrameInput, "kicp_frame_params": _capi.FrameParams}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "kicp.h"', 'int main(void) {']
+    for cname, ct in structs.items():
+        lines.append('printf("%s.sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in ct._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in structs.items():
+        assert int(out[cname + ".sizeof"]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(out["%s.%s" % (cname, fname)]) == getattr(ct, fname).offset, (cname, fname)
     assert C.sizeof(_capi.RegParams) == 24
     assert C.sizeof(_capi.RegResult) == 7 * 8 + 8 + 8 + 4 + 4 + 64 * 8 * 8 + 64 * 2 * 8
+    assert _capi.KICP_MAX_ITERATIONS == 64 and _capi.KICP_DTYPE_F32 == 1
 
 
 def test_no_cpu_fallback_without_device():
