@@ -4,10 +4,11 @@
 #include <mutex>
 #include <utility>
 
+#include "kicp/facade_core.hpp"
 #include "kicp/runtime.hpp"
-#include "kinematic_icp/correspondence_threshold/CorrespondenceThreshold.hpp"
-#include "kinematic_icp/pipeline/KinematicICP.hpp"
-#include "kinematic_icp/registration/Registration.hpp"
+#ifndef KICP_FACADE_NO_PIPELINE
+#include "kicp/facade_pipeline.hpp"
+#endif
 
 namespace kicp {
 kicp_ctx *default_context() {
@@ -66,6 +67,11 @@ double CorrespondenceThreshold::ComputeThreshold() const {
     return 3.0 * (map_discretization_error_ + sigma_odom);
 }
 
+void CorrespondenceThreshold::Reset() {
+    odom_sse_ = 0.0;
+    num_samples_ = 1e-8;
+}
+
 void CorrespondenceThreshold::UpdateOdometryError(const Sophus::SE3d &odometry_error) {
     if (!use_adaptive_threshold_) return;
     // odometry error expressed in point space (:29-34): translation plus the chord a max_range lever arm sweeps
@@ -77,6 +83,22 @@ void CorrespondenceThreshold::UpdateOdometryError(const Sophus::SE3d &odometry_e
 
 #ifndef KICP_FACADE_NO_PIPELINE  // the reference's own pipeline/KinematicICP.cpp can be compiled in its place
 namespace pipeline {
+// pipeline/KinematicICP.hpp:73-79
+KinematicICP::KinematicICP(const Config &config)
+    : solver_(config.max_num_iterations, config.convergence_criterion, config.max_num_threads,
+                    config.use_adaptive_odometry_regularization, config.fixed_regularization),
+      threshold_(config.map_resolution(), config.max_range, config.use_adaptive_threshold, config.fixed_threshold),
+      settings_(config),
+      front_end_(config.max_range, config.min_range, config.deskew, config.max_num_threads),
+      map_(config.voxel_size, config.max_range, config.max_points_per_voxel) {}
+
+// pipeline/KinematicICP.hpp:85-89
+void KinematicICP::SetPose(const Sophus::SE3d &pose) {
+    last_pose_ = pose;
+    map_.Clear();
+    threshold_.Reset();
+}
+
 // pipeline/KinematicICP.cpp:48-85: one kicp_register_frame call does the per-point work (ingest, de-skew, range filter,
 // base transform, both voxel down-samples, registration, map update) with the frame resident in HBM throughout; the
 // scalar threshold model and the pose bookkeeping stay here.
@@ -90,15 +112,15 @@ KinematicICP::Vector3dVectorTuple KinematicICP::RegisterFrame(const kicp_frame_i
     kicp::to_pose7(last_pose_, last);
     kicp::to_pose7(relative_odometry, odom);
     kicp_frame_params fp;
-    fp.max_range = preprocessor_.max_range_, fp.min_range = preprocessor_.min_range_, fp.deskew = preprocessor_.deskew_ ? 1 : 0;
-    fp.voxel_size = config_.voxel_size;
-    fp.reg.max_num_iterations = registration_.max_num_iterations_;
-    fp.reg.use_adaptive_odometry_regularization = registration_.use_adaptive_odometry_regularization_ ? 1 : 0;
-    fp.reg.convergence_criterion = registration_.convergence_criterion_;
-    fp.reg.fixed_regularization = registration_.fixed_regularization_;
-    const double tau = correspondence_threshold_.ComputeThreshold();
+    fp.max_range = front_end_.max_range_, fp.min_range = front_end_.min_range_, fp.deskew = front_end_.deskew_ ? 1 : 0;
+    fp.voxel_size = settings_.voxel_size;
+    fp.reg.max_num_iterations = solver_.max_num_iterations_;
+    fp.reg.use_adaptive_odometry_regularization = solver_.use_adaptive_odometry_regularization_ ? 1 : 0;
+    fp.reg.convergence_criterion = solver_.convergence_criterion_;
+    fp.reg.fixed_regularization = solver_.fixed_regularization_;
+    const double tau = threshold_.ComputeThreshold();
     fp.stage_clouds = 1;  // the two returned clouds are built below, in one pass each, from the library's pinned staging
-    kicp::check(kicp_register_frame(local_map_.handle_, &input, motion, l2b, last, odom, tau, &fp, out, nullptr, 0, nullptr, nullptr, 0,
+    kicp::check(kicp_register_frame(map_.handle_, &input, motion, l2b, last, odom, tau, &fp, out, nullptr, 0, nullptr, nullptr, 0,
                                     nullptr, nullptr),
                 "kicp_register_frame");
     const double *frame_xyz = nullptr, *source_xyz = nullptr;
@@ -109,7 +131,7 @@ KinematicICP::Vector3dVectorTuple KinematicICP::RegisterFrame(const kicp_frame_i
     Vector3dVector in_base(fb, fb + n_frame), source(sb, sb + n_source);
     const Sophus::SE3d new_pose = kicp::from_pose7(out);
     const Sophus::SE3d odometry_error = (last_pose_ * relative_odometry).inverse() * new_pose;
-    correspondence_threshold_.UpdateOdometryError(odometry_error);
+    threshold_.UpdateOdometryError(odometry_error);
     last_pose_ = new_pose;
     return {std::move(in_base), std::move(source)};
 }
