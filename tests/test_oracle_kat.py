@@ -221,3 +221,60 @@ def test_threaded_oracle_matches_sequential(oracle, workload):
     dt, ang = ko.pose_delta(p1, p4)
     assert dt < 1e-12 and ang < 1e-12 and s1.iterations == s4.iterations
     assert np.array_equal(s1.sums_np()[:, 5], s4.sums_np()[:, 5])
+
+
+def test_front_end_voxel_downsample_semantics(oracle):
+    """kiss_icp::VoxelDownsample (KISS-ICP v1.2.0, call sites pipeline/KinematicICP.cpp:38-44): floor voxelisation, the FIRST
+    point of the input order wins its voxel, survivors keep their input order."""
+    ko = oracle
+    pts = np.array([[0.10, 0.10, 0.10],    # voxel (0,0,0)   kept
+                    [0.90, 0.90, 0.90],    # voxel (0,0,0)   dropped (later)
+                    [-0.10, 0.10, 0.10],   # voxel (-1,0,0)  kept: floor, not truncation
+                    [1.00, 0.00, 0.00],    # voxel (1,0,0)   kept: the upper face belongs to the next voxel
+                    [-1.00, 0.0, 0.0],     # voxel (-1,0,0)  dropped
+                    [0.999999, 0.5, 0.5]])  # voxel (0,0,0)  dropped
+    out = ko.voxel_downsample(pts, 1.0)
+    assert np.array_equal(out, pts[[0, 2, 3]])
+    # a permutation changes the winners, not the voxel set
+    out2 = ko.voxel_downsample(pts[::-1].copy(), 1.0)
+    assert np.array_equal(out2, pts[::-1][[0, 1, 2]])
+    # the pipeline's double down-sample is idempotent per level and never grows
+    rng = np.random.default_rng(8)
+    cloud = rng.normal(size=(5000, 3)) * [10, 10, 2]
+    a = ko.voxel_downsample(cloud, 0.5)
+    b = ko.voxel_downsample(a, 1.5)
+    assert np.array_equal(ko.voxel_downsample(a, 0.5), a) and len(b) <= len(a) <= len(cloud)
+    keys = np.floor(b / 1.5).astype(np.int64)
+    assert len(np.unique(keys, axis=0)) == len(b)  # one survivor per voxel
+    assert ko.voxel_downsample(np.zeros((0, 3)), 1.0).shape == (0, 3)
+
+
+def test_front_end_preprocess_semantics(oracle):
+    """kiss_icp::Preprocessor::Preprocess (call site pipeline/KinematicICP.cpp:54-57): strict range gate on both sides;
+    de-skew p <- exp((s - 1) log T) p with stamps normalised to [0, 1] (any affine time scale gives the same result)."""
+    ko = oracle
+    pts = np.array([[0.5, 0, 0], [0.5 + 1e-12, 0, 0], [100.0, 0, 0], [100.0 - 1e-9, 0, 0], [3.0, 4.0, 0.0], [0, 0, 0]])
+    out = ko.preprocess(pts, np.zeros(0), ko.IDENTITY, 100.0, 0.5, False)
+    assert np.array_equal(out, pts[[1, 3, 4]])  # r == min and r == max are both rejected
+    # deskew requested without stamps, or stamps without deskew: the frame is only range-filtered
+    T = ko.se3_exp([0.8, 0.05, 0.0, 0.0, 0.0, 0.04])
+    assert np.array_equal(ko.preprocess(pts, np.zeros(0), T, 100.0, 0.5, True), out)
+    assert np.array_equal(ko.preprocess(pts, np.linspace(0, 1, len(pts)), T, 100.0, 0.5, False), out)
+    # closed form at the ends of the sweep: stamp 1 -> identity, stamp 0 -> T^-1
+    cloud = np.random.default_rng(9).uniform(-20, 20, size=(64, 3))
+    stamps = np.linspace(0.0, 1.0, len(cloud))
+    d = ko.preprocess(cloud, stamps, T, 1e9, 0.0, True)
+    assert np.allclose(d[-1], cloud[-1], atol=1e-13)
+    assert np.allclose(d[0], ko.se3_transform(ko.se3_inverse(T), cloud[:1])[0], atol=1e-12)
+    # mid-sweep: exp(-0.5 log T) = the inverse of the half motion
+    half = ko.se3_exp(0.5 * np.asarray(ko.se3_log(T)))
+    k = len(cloud) // 2
+    s = stamps[k]
+    mid = ko.se3_exp((s - 1.0) * np.asarray(ko.se3_log(T)))
+    assert np.allclose(d[k], ko.se3_transform(mid, cloud[k:k + 1])[0], atol=1e-12)
+    assert np.allclose(ko.se3_compose(half, half), T, atol=1e-12)
+    # time scale invariance (TimeStampHandler.cpp:129-135 normalises as well; doing it twice is harmless)
+    d2 = ko.preprocess(cloud, 1.7e9 + 0.1 * stamps, T, 1e9, 0.0, True)
+    assert np.allclose(d2, d, atol=1e-6)  # 0.1 s on 1.7e9 s keeps ~7 digits of the stamp
+    d3 = ko.preprocess(cloud, 5.0 + 0.25 * stamps, T, 1e9, 0.0, True)
+    assert np.allclose(d3, d, atol=1e-12)
