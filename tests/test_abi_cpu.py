@@ -86,3 +86,36 @@ def test_shard_range_partitions_the_scan():
             assert r[0][0] == 0 and r[-1][1] == n
             assert all(r[k][1] == r[k + 1][0] for k in range(g - 1))
             assert max(hi - lo for lo, hi in r) - min(hi - lo for lo, hi in r) <= 1
+
+
+def test_null_arguments_are_rejected_before_any_device_work():
+    """Every entry point validates its arguments first: KICP_ERR_INVALID for null handles, with or without a GPU."""
+    _build()
+    from kinematic_icp_b200 import _capi
+    L = _capi.lib()
+    INVALID = _capi.KICP_ERR_INVALID
+    z7 = np.array([0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
+    pts = np.zeros((4, 3))
+    out = np.zeros((4, 3))
+    m = C.c_int64()
+    p = _capi.RegParams(10, 1, 1e-3, 0.0)
+    dp = _capi.dp
+    assert L.kicp_map_create(None, 1.0, 100.0, 20, C.byref(C.c_void_p())) == INVALID
+    assert L.kicp_map_reserve(None, 1000) == INVALID
+    assert L.kicp_map_clear(None) == INVALID
+    assert L.kicp_map_add_points(None, dp(pts), 4) == INVALID
+    assert L.kicp_map_update_pose(None, dp(pts), 4, dp(z7)) == INVALID
+    assert L.kicp_map_nearest(None, dp(pts), 4, dp(out), dp(np.zeros(4))) == INVALID
+    assert L.kicp_register(None, dp(pts), 4, dp(z7), dp(z7), 1.0, C.byref(p), dp(np.zeros(7)), None) == INVALID
+    assert L.kicp_register_sharded(None, dp(pts), 4, dp(z7), dp(z7), 1.0, C.byref(p), dp(np.zeros(7)), None) == INVALID
+    assert L.kicp_voxel_downsample(None, dp(pts), 4, 0.5, dp(out), 4, C.byref(m)) == INVALID
+    assert L.kicp_preprocess(None, dp(pts), 4, None, 0, dp(z7), dp(z7), 100.0, 0.0, 0, dp(out), 4, C.byref(m)) == INVALID
+    fi, fp = _capi.FrameInput(), _capi.FrameParams()
+    fp.voxel_size = 1.0
+    assert L.kicp_register_frame(None, C.byref(fi), dp(z7), dp(z7), dp(z7), dp(z7), 1.0, C.byref(fp), dp(np.zeros(7)), None, 0, None, None,
+                                 0, None, None) == INVALID
+    assert L.kicp_frame_clouds(None, None, None, None, None) == INVALID
+    assert L.kicp_ctx_set_option(None, b"assoc_variant", 1) == INVALID
+    assert L.kicp_scan_create(None, 16, C.byref(C.c_void_p())) == INVALID
+    assert L.kicp_comm_p2p_handle(None, None) == INVALID
+    assert L.kicp_status_string(INVALID) and L.kicp_status_string(_capi.KICP_WARN_NO_CORRESPONDENCES)
