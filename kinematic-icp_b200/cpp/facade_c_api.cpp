@@ -2,6 +2,7 @@
 #include <cstdint>
 #include <vector>
 
+#include "kicp/pointcloud2.hpp"
 #include "kicp/tum.hpp"
 #include "kinematic_icp/pipeline/KinematicICP.hpp"
 
@@ -59,6 +60,40 @@ int64_t kfac_pipeline_num_map_points(void *h) {
 // host-side stage times (ms, cumulative) of the last RegisterFrame on the process-wide context (library debug export)
 extern "C" int kicp_debug_frame_timing(kicp_ctx *, double *);
 int kfac_debug_frame_timing(double *out8) { return kicp_debug_frame_timing(kicp::default_context(), out8); }
+// PointCloud2-shaped buffer -> ingest layout + per-point stamps (kicp/pointcloud2.hpp).  Fields arrive as parallel arrays, names
+// joined by ','.  layout5 = {dtype, point_step, offset_x, offset_y, offset_z}; returns the number of stamps written (0 = none),
+// -1 on a decoding error.
+int64_t kfac_pc2_decode(const uint8_t *data, uint32_t width, uint32_t height, uint32_t point_step, const char *names_csv,
+                        const uint32_t *offsets, const uint8_t *datatypes, const uint32_t *counts, int32_t n_fields, int32_t *layout5,
+                        double *stamps_out) {
+    try {
+        kicp::PointCloud2View m;
+        m.data = data, m.width = width, m.height = height, m.point_step = point_step;
+        std::string names(names_csv);
+        size_t pos = 0;
+        for (int32_t i = 0; i < n_fields; ++i) {
+            const size_t next = names.find(',', pos);
+            kicp::PointFieldView f;
+            f.name = names.substr(pos, next == std::string::npos ? std::string::npos : next - pos);
+            f.offset = offsets[i], f.datatype = datatypes[i], f.count = counts[i];
+            m.fields.push_back(f);
+            pos = next == std::string::npos ? names.size() : next + 1;
+        }
+        const kicp_frame_input in = kicp::make_frame_input(m);
+        layout5[0] = in.dtype, layout5[1] = in.point_step, layout5[2] = in.offset_x, layout5[3] = in.offset_y, layout5[4] = in.offset_z;
+        const std::vector<double> stamps = kicp::extract_timestamps(m);
+        for (size_t i = 0; i < stamps.size(); ++i) stamps_out[i] = stamps[i];
+        return static_cast<int64_t>(stamps.size());
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+void kfac_process_timestamps(double *stamps, int64_t n, double header_stamp, double *last_processed, double *begin_end2) {
+    std::vector<double> v(stamps, stamps + n);
+    const kicp::SweepTiming t = kicp::process_timestamps(v, header_stamp, *last_processed);
+    for (int64_t i = 0; i < n; ++i) stamps[i] = v[static_cast<size_t>(i)];
+    begin_end2[0] = t.begin, begin_end2[1] = t.end;
+}
 // poses7[n][7] + stamps[n] -> TUM file (offline_node.cpp:76-97)
 int kfac_write_tum(const char *path, const double *stamps, const double *poses7, int64_t n) {
     std::vector<std::pair<double, Sophus::SE3d>> v;
