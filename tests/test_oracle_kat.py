@@ -278,3 +278,31 @@ def test_front_end_preprocess_semantics(oracle):
     assert np.allclose(d2, d, atol=1e-6)  # 0.1 s on 1.7e9 s keeps ~7 digits of the stamp
     d3 = ko.preprocess(cloud, 5.0 + 0.25 * stamps, T, 1e9, 0.0, True)
     assert np.allclose(d3, d, atol=1e-12)
+
+
+def test_map_invariants_after_random_updates(oracle):
+    """Size-independent properties of the restated VoxelHashMap (KISS-ICP v1.2.0 semantics) that the bit-exact
+    GPU comparison inherits: per-voxel cap, floor keys, min spacing inside a voxel, first-point eviction rule."""
+    ko = oracle
+    rng = np.random.default_rng(31)
+    vs, max_d, cap = 0.8, 25.0, 6
+    m = ko.OracleMap(vs, max_d, cap)
+    res = math.sqrt(vs * vs / cap)
+    origin = np.zeros(3)
+    for it in range(12):
+        origin = origin + [2.5, 0.7, 0.0]
+        pts = rng.normal(size=(4000, 3)) * [12.0, 12.0, 1.0] + origin
+        m.update_origin(pts, origin)
+        keys, counts, stored = m.export_voxels()
+        assert counts.min() >= 1 and counts.max() <= cap and counts.sum() == len(stored) == m.num_points()
+        off = np.concatenate([[0], np.cumsum(counts)])
+        vox = np.repeat(keys, counts, axis=0)
+        assert np.array_equal(np.floor(stored / vs).astype(np.int64), vox.astype(np.int64))  # every point lies in its voxel
+        first = stored[off[:-1]]
+        assert (np.linalg.norm(first - origin, axis=1) < max_d).all()  # survivors: FIRST point strictly inside max_distance
+        for v in rng.integers(0, len(counts), 200):  # spacing rule inside a voxel: later points keep >= map_resolution
+            p = stored[off[v]:off[v + 1]]
+            if len(p) > 1:
+                d = np.linalg.norm(p[:, None, :] - p[None, :, :], axis=2)[np.triu_indices(len(p), 1)]
+                assert (d >= res * (1 - 1e-12)).all()
+    assert len(np.unique(keys, axis=0)) == len(keys)  # one block per voxel
