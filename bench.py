@@ -413,10 +413,7 @@ def main():
                 tj = json.load(open(ncu_path))
                 traffic = tj.get("dram_bytes_per_launch")
                 traffic_note = "dram__bytes_read+write per launch from %s" % tj.get("source")
-            variant = {"staged": 0, "group4": 2, "hybrid": 3}.get(os.environ.get("KICP_ASSOC", "pruned"), 1)
-            if variant == 1 and world == 1 and n_local <= int(os.environ.get("KICP_GROUP4_BELOW", "49152")):
-                variant = 2  # the library's default choice for small scans (kicp_ctx_set_option "group4_below")
-            kernel_name = {0: "k_assoc", 1: "k_assoc_pruned", 2: "k_assoc_group4", 3: "k_assoc_hybrid"}[variant]
+            kernel_name = "k_register"
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "traffic_note": traffic_note, "kernel": kernel_name,
                         "launch_us": t_launch * 1e6, "passes_per_launch": passes_per_launch,

@@ -39,6 +39,9 @@ enum kicp_status {
     KICP_WARN_NO_CORRESPONDENCES = 16
 };
 
+#define KICP_DTYPE_F64 0 /* std::vector<Eigen::Vector3d> storage */
+#define KICP_DTYPE_F32 1 /* PointCloud2 FLOAT32 fields */
+
 typedef struct kicp_ctx kicp_ctx;   /* one GPU: device id, stream, scratch, optional NCCL communicator */
 typedef struct kicp_map kicp_map;   /* kiss_icp::VoxelHashMap resident in HBM */
 typedef struct kicp_scan kicp_scan; /* a scan (the `frame` argument of ComputeRobotMotion) resident in HBM */
@@ -76,14 +79,15 @@ int kicp_ctx_synchronize(kicp_ctx *ctx);
 void *kicp_ctx_stream(kicp_ctx *ctx);
 /* Number of this library's kernels launched on the context since creation (bench.py reports gpu_launches). */
 int64_t kicp_ctx_launch_count(kicp_ctx *ctx);
-/* Tuning knobs (defaults are the measured best): "assoc_variant" 0 = 27-voxel neighbourhood staged through shared
- * memory, 1 = exact-pruning thread-per-point kernel; "persistent" 1 = all IRLS iterations of a registration inside one cooperative launch
- * (default on the single-GPU path), 0 = one launch per iteration; "sort_bits" 0..30 = Morton key bits of the optional per-registration
- * binning sort (default 0 = off); "group4_below" = scans of at most this many points run the 8-point-window kernel (variant 2) when
- * variant 1 is selected (default 49152, 0 = never).  Every setting computes the same result up to the summation order. */
+/* Options: "persistent" 1 = all IRLS iterations of a registration inside ONE cooperative launch (default), 0 = one launch per
+ * iteration; "stats" 1 = count hash probes / candidate points / 128-byte lines on the device (bench.py's touched-bytes figure);
+ * "ctas_per_sm" = cap of the resident CTAs per SM the grid is sized for (0 = occupancy limit); "overlap_upload" 1 = the
+ * host-pointer entry points overlap the frame's upload with the first pass (default); "spin_timeout_ms" = bound of every
+ * device-side wait (upload flags, peers of the fused exchange; default 20000).  Unknown names fail with KICP_ERR_INVALID.
+ * Every setting computes the same result up to the summation order. */
 int kicp_ctx_set_option(kicp_ctx *ctx, const char *name, int32_t value);
-/* Per-kernel device timing with CUDA events recorded on the context stream around (a) the binning of each
- * registration (init + Morton keys + radix sort + gather) and (b) every launch of the association kernel.  Only
+/* Per-kernel device timing with CUDA events recorded on the context stream around (a) the set-up of each registration
+ * (k_reg_init, multi-launch path only) and (b) every launch of the registration kernel.  Only
  * launches that did work are counted in assoc_* (a launch issued after convergence exits at its first instruction
  * and is reported under idle_*).  kicp_ctx_profile_end synchronises the stream. */
 typedef struct kicp_profile {
@@ -91,7 +95,7 @@ typedef struct kicp_profile {
     int64_t assoc_launches;
     double idle_ms;           /* launches issued after convergence (early exit) */
     int64_t idle_launches;
-    double prep_ms;           /* init + keys + sort + gather, summed over registrations */
+    double prep_ms;           /* set-up launches, summed over registrations (0 on the persistent path) */
     int64_t registrations;
     int64_t assoc_iterations; /* IRLS iterations executed by those launches (a persistent launch runs several) */
 } kicp_profile;
@@ -145,6 +149,19 @@ int kicp_scan_create(kicp_ctx *ctx, int64_t capacity, kicp_scan **out);
 int kicp_scan_destroy(kicp_scan *scan);
 int kicp_scan_upload(kicp_scan *scan, const double *xyz, int64_t n);       /* synchronous host -> HBM copy */
 int kicp_scan_upload_async(kicp_scan *scan, const double *xyz, int64_t n); /* enqueued on the context stream */
+/* The same two uploads for a frame held as float32 or float64 x,y,z fields at a byte stride (dtype / point_step / offsets as in
+ * kicp_frame_input below; point_step 0 = tightly packed): the bytes cross PCIe as they are — half the traffic for the float32
+ * clouds the reference's callers actually hold (RosUtils.cpp:30-39 widens float32 PointCloud2 fields to double) — and the
+ * registration kernel widens while it reads.  Field offsets and point_step must be multiples of the field width. */
+int kicp_scan_upload_points(kicp_scan *scan, const void *data, int64_t n, int32_t dtype, int32_t point_step, int32_t offset_x,
+                            int32_t offset_y, int32_t offset_z);
+int kicp_scan_upload_points_async(kicp_scan *scan, const void *data, int64_t n, int32_t dtype, int32_t point_step, int32_t offset_x,
+                                  int32_t offset_y, int32_t offset_z);
+/* kicp_register for such a frame (host pointer). */
+int kicp_register_points(kicp_map *map, const void *data, int64_t n, int32_t dtype, int32_t point_step, int32_t offset_x,
+                         int32_t offset_y, int32_t offset_z, const double last_robot_pose[7],
+                         const double relative_wheel_odometry[7], double max_correspondence_distance,
+                         const kicp_reg_params *params, double out_pose[7], kicp_reg_result *result);
 int kicp_register_scan_async(kicp_map *map, kicp_scan *scan, const double last_robot_pose[7],
                              const double relative_wheel_odometry[7], double max_correspondence_distance,
                              const kicp_reg_params *params, kicp_reg_result *result);
@@ -169,8 +186,6 @@ int kicp_preprocess(kicp_ctx *ctx, const double *xyz, int64_t n, const double *s
  *      (preprocessed frame in base, registration source); either may be NULL to skip its download.  On zero
  *      correspondences the pose is NaN like the reference's, KICP_WARN_NO_CORRESPONDENCES is returned and the map is
  *      left untouched. ------------------------------------------------------------------------------------------- */
-#define KICP_DTYPE_F64 0
-#define KICP_DTYPE_F32 1
 typedef struct kicp_frame_input {
     const void *data;   /* host pointer: n points */
     int64_t n;
@@ -214,6 +229,10 @@ int kicp_comm_p2p_init(kicp_ctx *ctx, const uint8_t *handles /* nranks x 64 byte
 int kicp_register_sharded(kicp_map *map, const double *frame_xyz, int64_t n_local, const double last_robot_pose[7],
                           const double relative_wheel_odometry[7], double max_correspondence_distance,
                           const kicp_reg_params *params, double out_pose[7], kicp_reg_result *result);
+int kicp_register_points_sharded(kicp_map *map, const void *data, int64_t n_local, int32_t dtype, int32_t point_step, int32_t offset_x,
+                                 int32_t offset_y, int32_t offset_z, const double last_robot_pose[7],
+                                 const double relative_wheel_odometry[7], double max_correspondence_distance,
+                                 const kicp_reg_params *params, double out_pose[7], kicp_reg_result *result);
 int kicp_register_scan_sharded_async(kicp_map *map, kicp_scan *scan_shard, const double last_robot_pose[7],
                                      const double relative_wheel_odometry[7], double max_correspondence_distance,
                                      const kicp_reg_params *params, kicp_reg_result *result);

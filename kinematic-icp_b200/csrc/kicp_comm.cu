@@ -68,14 +68,36 @@ extern "C" int kicp_comm_unique_id(uint8_t id[KICP_UNIQUE_ID_BYTES]) {
     return KICP_OK;
 }
 
+// NCCL and the peer-memory mailboxes are torn down separately: (re-)initialising one never invalidates the other.
+static void nccl_teardown(kicp_ctx *ctx) {
+    if (ctx->nccl_comm) {
+        cudaStreamSynchronize(ctx->stream);
+        nccl().CommDestroy((ncclComm_t)ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+}
+static void p2p_close_peers(kicp_ctx *ctx) {
+    if (!ctx->p2p_ready) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (int r = 0; r < KICP_MAX_RANKS; ++r) {
+        if (r != ctx->rank && ctx->p2p_peer[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+        ctx->p2p_peer[r] = nullptr;
+    }
+    ctx->p2p_ready = false;
+}
+
 extern "C" int kicp_comm_init(kicp_ctx *ctx, const uint8_t id[KICP_UNIQUE_ID_BYTES], int32_t nranks, int32_t rank) {
     if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return KICP_ERR_INVALID;
+    if (ctx->p2p_ready && (ctx->nranks != nranks || ctx->rank != rank)) {
+        kicp_set_error("kicp_comm_init: rank layout differs from the one given to kicp_comm_p2p_init");
+        return KICP_ERR_INVALID;
+    }
     if (!nccl().ok) {
         kicp_set_error("libnccl.so.2 could not be loaded");
         return KICP_ERR_NCCL;
     }
     KICP_CUDA(cudaSetDevice(ctx->device));
-    kicp_comm_destroy(ctx);
+    nccl_teardown(ctx);
     ncclUniqueId uid;
     memcpy(&uid, id, sizeof(uid));
     ncclComm_t comm = nullptr;
@@ -88,18 +110,10 @@ extern "C" int kicp_comm_init(kicp_ctx *ctx, const uint8_t id[KICP_UNIQUE_ID_BYT
 
 extern "C" int kicp_comm_destroy(kicp_ctx *ctx) {
     if (!ctx) return KICP_ERR_INVALID;
-    if (ctx->nccl_comm) {
-        cudaStreamSynchronize(ctx->stream);
-        nccl().CommDestroy((ncclComm_t)ctx->nccl_comm);
-        ctx->nccl_comm = nullptr;
-    }
-    if (ctx->p2p_ready) {
-        cudaStreamSynchronize(ctx->stream);
-        for (int r = 0; r < ctx->nranks; ++r)
-            if (r != ctx->rank && ctx->p2p_peer[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
-        ctx->p2p_ready = false;
-    }
+    nccl_teardown(ctx);
+    p2p_close_peers(ctx);
     if (ctx->p2p_local) {
+        cudaStreamSynchronize(ctx->stream);
         cudaFree(ctx->p2p_local);
         ctx->p2p_local = nullptr;
     }
@@ -137,7 +151,13 @@ extern "C" int kicp_comm_p2p_handle(kicp_ctx *ctx, uint8_t handle[KICP_IPC_HANDL
 extern "C" int kicp_comm_p2p_init(kicp_ctx *ctx, const uint8_t *handles, int32_t nranks, int32_t rank) {
     if (!ctx || !handles || nranks < 1 || nranks > KICP_MAX_RANKS || rank < 0 || rank >= nranks || !ctx->p2p_local)
         return KICP_ERR_INVALID;
+    if (ctx->nccl_comm && (ctx->nranks != nranks || ctx->rank != rank)) {
+        kicp_set_error("kicp_comm_p2p_init: rank layout differs from the one given to kicp_comm_init");
+        return KICP_ERR_INVALID;
+    }
     KICP_CUDA(cudaSetDevice(ctx->device));
+    p2p_close_peers(ctx);  // a second init must not leak the handles of the first
+    ctx->rank = rank;
     for (int r = 0; r < nranks; ++r) {
         if (r == rank) {
             ctx->p2p_peer[r] = ctx->p2p_local;
@@ -149,8 +169,8 @@ extern "C" int kicp_comm_p2p_init(kicp_ctx *ctx, const uint8_t *handles, int32_t
         KICP_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
         ctx->p2p_peer[r] = (P2PMailbox *)p;
     }
-    ctx->nranks = nranks, ctx->rank = rank;
-    ctx->p2p_seq = 0;
+    ctx->nranks = nranks;
+    // p2p_seq is NOT reset: the words left in the mailboxes carry tags of earlier registrations, and tags only grow
     ctx->p2p_ready = true;
     return KICP_OK;
 }

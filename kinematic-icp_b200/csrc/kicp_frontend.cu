@@ -416,8 +416,8 @@ extern "C" int kicp_register_frame(kicp_map *map, const kicp_frame_input *in, co
     if (n_source) *n_source = counts[2];
     if ((out_frame && counts[0] > cap_frame) || (out_source && counts[2] > cap_source)) return KICP_ERR_CAPACITY;
     // registration of the source against the local map, enqueued first so that the downloads below overlap it
-    KICP_TRY(kicp_enqueue_registration_device(map, counts[2] ? reinterpret_cast<const double *>(s.out3) : nullptr, counts[2], last_pose,
-                                              relative_odometry, tau, &fp->reg));
+    KICP_TRY(kicp_enqueue_registration_device(map, counts[2] ? reinterpret_cast<const double *>(s.out3) : nullptr, counts[2], nullptr,
+                                              last_pose, relative_odometry, tau, &fp->reg));
     s.timing[1] = ms_since();  // + registration enqueued
     // the two clouds go to pinned staging on the copy stream while the registration runs
     const bool stage = fp->stage_clouds || out_frame || out_source;

@@ -33,11 +33,13 @@ struct MapView {
     double voxel_size;
 };
 
-// Mailbox of the fused cross-GPU exchange: rank r writes its 8 partial sums of iteration `it` into data[parity][it][r] of
-// EVERY rank's mailbox, then raises flag[parity][it][r] to a monotonically increasing tag.
+// Mailbox of the fused cross-GPU exchange (NCCL-LL style): rank r writes its 8 partial sums of pass `it` as sixteen 8-byte
+// words {32 data bits | 32-bit tag << 32} into ll[parity][it][r] of EVERY rank's mailbox.  An aligned 8-byte store arrives
+// whole, so a word whose tag matches is valid data: no fence, no separate flag.  Tags grow monotonically per registration
+// and pass, so nothing is ever cleared; `parity` (registration sequence number & 1) keeps a fast rank from overwriting
+// words a slow rank has not read yet.
 struct P2PMailbox {
-    unsigned long long flag[2][KICP_MAX_ITERATIONS][KICP_MAX_RANKS];
-    double data[2][KICP_MAX_ITERATIONS][KICP_MAX_RANKS][8];
+    unsigned long long ll[2][KICP_MAX_ITERATIONS][KICP_MAX_RANKS][16];
 };
 
 struct kicp_ctx {
@@ -45,26 +47,15 @@ struct kicp_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
-    // registration scratch (grown on demand)
+    // registration scratch
     struct RegState *d_state = nullptr;
-    double *d_partials = nullptr;  // per-CTA partial sums of the association kernels [grid][8]
-    double *d_sorted = nullptr;   // scan reordered by Morton key of the voxel at the initial guess
-    uint32_t *d_keys = nullptr, *d_keys_alt = nullptr;
-    int32_t *d_idx = nullptr, *d_idx_alt = nullptr;
-    void *d_sort_tmp = nullptr;
-    size_t sort_tmp_bytes = 0;
-    int64_t scratch_cap = 0;
-    int assoc_ctas_per_sm = 1;  // resident CTAs of the association kernel per SM (occupancy query)
-    int pruned_ctas_per_sm = 1;
-    int persistent_ctas_per_sm = 1;
-    int group4_ctas_per_sm = 1;
-    int hybrid_ctas_per_sm = 1;
-    int persistent = 1;     // 1 = all IRLS iterations inside one cooperative launch (single-GPU pruned path)
-    int assoc_variant = 1;  // 0 = staged (27-voxel neighbourhood through shared memory), 1 = pruned (thread per point),
-                            // 2 = pruned with 4 lanes per point, 3 = hybrid (32-point windows + 8-point tail)
-    int group4_below = 49152;  // scans of at most this many points use variant 2 when variant 1 is selected (0 = never);
-                               // measured: +24 % at 2k points, +10 % at 29k, -13 % at 131k (profiles/r01_replay.md)
-    int sort_bits = 0;      // Morton key bits of the optional binning sort (0 = off, the measured best: DESIGN.md §5)
+    double *d_partials = nullptr;  // per-CTA partial sums of the registration kernel [2][grid][8]
+    int pruned_ctas_per_sm = 1;      // resident CTAs per SM of k_register<false> (occupancy query)
+    int persistent_ctas_per_sm = 1;  // ... of k_register<true>
+    int ctas_per_sm_cap = 0;         // option "ctas_per_sm": 0 = use the occupancy limit
+    int persistent = 1;     // 1 = all IRLS iterations inside one cooperative launch, 0 = one launch per iteration
+    int collect_stats = 0;  // option "stats": count probes / candidate points / lines on the device
+    int spin_timeout_ms = 20000;  // bound of every device-side wait (upload flags, peers of the fused exchange)
     kicp_scan *upload_scan = nullptr;  // staging scan used by the host-pointer entry points
     // chunked upload overlapped with the first IRLS iteration (host-pointer entry points, persistent kernel)
     cudaStream_t copy_stream = nullptr;
@@ -72,8 +63,6 @@ struct kicp_ctx {
     uint32_t *h_chunk_tags = nullptr;    // pinned source of the flag copies
     uint32_t upload_seq = 0;
     int overlap_upload = 1;
-    int launch_first = 0;                // 1 = issue only the first upload chunk before the persistent launch, the rest after it
-                                         // (measured: no gain at cfg4, -6 % e2e at cfg3: the first pass is bound by the copy itself)
     kicp_reg_result *h_result = nullptr;  // pinned bounce buffer for synchronous calls
     // profiling (kicp_ctx_profile_begin/end): event pairs per registration
     bool profiling = false;
@@ -129,10 +118,15 @@ struct kicp_map {
     MapView view() const { return MapView{slots, nslots - 1, pts, (int)cap, voxel_size}; }
 };
 
+// A frame resident in HBM exactly as the caller holds it: float64 or float32 x,y,z fields at a byte stride
+// (std::vector<Eigen::Vector3d> = {F64, 24, 0, 8, 16}; a PointCloud2 message = F32 at point_step with its field offsets,
+// ros/src/kinematic_icp_ros/utils/RosUtils.cpp:30-39).  The registration kernel widens float32 while it reads.
 struct kicp_scan {
     kicp_ctx *ctx = nullptr;
-    double *d_xyz = nullptr;
-    int64_t cap = 0, n = 0;
+    void *d_data = nullptr;
+    int64_t cap_bytes = 0, n = 0;
+    const int *d_n = nullptr;  // optional device-resident point count (frames compacted on the device); n is then an upper bound
+    int dtype = KICP_DTYPE_F64, stride = 24, ox = 0, oy = 8, oz = 16;
 };
 
 // error plumbing ------------------------------------------------------------------------------------------
@@ -159,12 +153,15 @@ int kicp_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
     } while (0)
 
 // defined in kicp_map.cu, used by the registration entry points
-int kicp_scan_reserve(kicp_scan *scan, int64_t n);
+int kicp_scan_reserve_bytes(kicp_scan *scan, int64_t bytes);
+// dtype / point_step / field offsets as in kicp_frame_input (point_step 0 = tightly packed x,y,z); fields must be aligned
+int kicp_scan_set_layout(kicp_scan *scan, int32_t dtype, int32_t point_step, int32_t ox, int32_t oy, int32_t oz);
 // VoxelHashMap::Update(points, pose) with `d_xyz` already resident in HBM (packed xyz doubles): used by kicp_register_frame
 int kicp_map_update_pose_device(kicp_map *m, const double *d_xyz, int64_t n, const double pose[7]);
 // defined in kicp_register.cu: enqueue one registration of n device-resident points on the context stream; the result
 // lands in ctx->h_result (pinned) once the stream has drained
-int kicp_enqueue_registration_device(kicp_map *m, const double *d_xyz, int64_t n, const double last[7], const double odom[7],
-                                     double tau, const kicp_reg_params *p);
+// (`d_n`, optional: device-resident point count written earlier on the same stream; n_max is then the upper bound)
+int kicp_enqueue_registration_device(kicp_map *m, const double *d_xyz, int64_t n_max, const int *d_n, const double last[7],
+                                     const double odom[7], double tau, const kicp_reg_params *p);
 // defined in kicp_comm.cu
 int kicp_comm_allreduce8(kicp_ctx *ctx, double *d_buf);

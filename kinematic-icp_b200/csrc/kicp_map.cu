@@ -63,11 +63,9 @@ extern "C" int kicp_ctx_create(int device, kicp_ctx **out) {
     KICP_CUDA(cudaMemset(c->d_chunk_flags, 0, KICP_UPLOAD_CHUNKS * sizeof(uint32_t)));
     KICP_CUDA(cudaMallocHost(&c->h_chunk_tags, KICP_UPLOAD_CHUNKS * sizeof(uint32_t)));
     if (const char *e = getenv("KICP_OVERLAP_UPLOAD")) c->overlap_upload = atoi(e) ? 1 : 0;
-    if (const char *e = getenv("KICP_LAUNCH_FIRST")) c->launch_first = atoi(e) ? 1 : 0;
-    if (const char *e = getenv("KICP_GROUP4_BELOW")) c->group4_below = std::max(0, atoi(e));
-    if (const char *e = getenv("KICP_ASSOC")) c->assoc_variant = !strcmp(e, "staged") ? 0 : (!strcmp(e, "group4") ? 2 : (!strcmp(e, "hybrid") ? 3 : 1));
     if (const char *e = getenv("KICP_PERSISTENT")) c->persistent = atoi(e) ? 1 : 0;
-    if (const char *e = getenv("KICP_SORT_BITS")) c->sort_bits = std::min(30, std::max(0, atoi(e)));
+    if (const char *e = getenv("KICP_CTAS_PER_SM")) c->ctas_per_sm_cap = std::min(16, std::max(0, atoi(e)));
+    if (const char *e = getenv("KICP_SPIN_TIMEOUT_MS")) c->spin_timeout_ms = std::max(1, atoi(e));
     *out = c;
     return KICP_OK;
 }
@@ -91,22 +89,35 @@ extern "C" int kicp_host_free(void *p) {
 }
 
 // ------------------------------------------------------------------------------------------------------ scans
-int kicp_scan_reserve(kicp_scan *s, int64_t n) {
-    if (n <= s->cap) return KICP_OK;
+int kicp_scan_reserve_bytes(kicp_scan *s, int64_t bytes) {
+    if (bytes <= s->cap_bytes) return KICP_OK;
     KICP_CUDA(cudaSetDevice(s->ctx->device));
     KICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
-    if (s->d_xyz) KICP_CUDA(cudaFree(s->d_xyz));
-    s->d_xyz = nullptr;
-    const int64_t cap = std::max<int64_t>(n + n / 4, 1024);
-    KICP_CUDA(cudaMalloc(&s->d_xyz, (size_t)cap * 3 * sizeof(double)));
-    s->cap = cap;
+    if (s->d_data) KICP_CUDA(cudaFree(s->d_data));
+    s->d_data = nullptr, s->cap_bytes = 0;
+    const int64_t cap = std::max<int64_t>(bytes + bytes / 4, 32768);
+    KICP_CUDA(cudaMalloc(&s->d_data, (size_t)cap));
+    s->cap_bytes = cap;
+    return KICP_OK;
+}
+int kicp_scan_set_layout(kicp_scan *s, int32_t dtype, int32_t point_step, int32_t ox, int32_t oy, int32_t oz) {
+    if (dtype != KICP_DTYPE_F64 && dtype != KICP_DTYPE_F32) return KICP_ERR_INVALID;
+    const int w = dtype == KICP_DTYPE_F32 ? 4 : 8;
+    if (point_step == 0) point_step = 3 * w, ox = 0, oy = w, oz = 2 * w;
+    // the registration kernel reads the fields with aligned loads (a PointCloud2 message keeps its fields aligned)
+    if (point_step < 3 * w || point_step % w || ox < 0 || oy < 0 || oz < 0 || ox % w || oy % w || oz % w || ox + w > point_step ||
+        oy + w > point_step || oz + w > point_step) {
+        kicp_set_error("scan layout: point_step / field offsets must be multiples of the field width and lie inside the point");
+        return KICP_ERR_INVALID;
+    }
+    s->dtype = dtype, s->stride = point_step, s->ox = ox, s->oy = oy, s->oz = oz;
     return KICP_OK;
 }
 extern "C" int kicp_scan_create(kicp_ctx *ctx, int64_t capacity, kicp_scan **out) {
     if (!ctx || !out || capacity < 0) return KICP_ERR_INVALID;
     kicp_scan *s = new kicp_scan();
     s->ctx = ctx;
-    int st = kicp_scan_reserve(s, capacity);
+    int st = kicp_scan_reserve_bytes(s, capacity * 24);
     if (st != KICP_OK) {
         delete s;
         return st;
@@ -118,23 +129,31 @@ extern "C" int kicp_scan_destroy(kicp_scan *s) {
     if (!s) return KICP_OK;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
-    cudaFree(s->d_xyz);
+    cudaFree(s->d_data);
     delete s;
     return KICP_OK;
 }
-extern "C" int kicp_scan_upload_async(kicp_scan *s, const double *xyz, int64_t n) {
-    if (!s || n < 0 || (n > 0 && !xyz)) return KICP_ERR_INVALID;
+extern "C" int kicp_scan_upload_points_async(kicp_scan *s, const void *data, int64_t n, int32_t dtype, int32_t point_step,
+                                             int32_t offset_x, int32_t offset_y, int32_t offset_z) {
+    if (!s || n < 0 || (n > 0 && !data)) return KICP_ERR_INVALID;
     KICP_CUDA(cudaSetDevice(s->ctx->device));
-    KICP_TRY(kicp_scan_reserve(s, n));
-    if (n > 0)
-        KICP_CUDA(cudaMemcpyAsync(s->d_xyz, xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, s->ctx->stream));
-    s->n = n;
+    KICP_TRY(kicp_scan_set_layout(s, dtype, point_step, offset_x, offset_y, offset_z));
+    KICP_TRY(kicp_scan_reserve_bytes(s, n * (int64_t)s->stride));
+    if (n > 0) KICP_CUDA(cudaMemcpyAsync(s->d_data, data, (size_t)(n * s->stride), cudaMemcpyHostToDevice, s->ctx->stream));
+    s->n = n, s->d_n = nullptr;
     return KICP_OK;
 }
-extern "C" int kicp_scan_upload(kicp_scan *s, const double *xyz, int64_t n) {
-    KICP_TRY(kicp_scan_upload_async(s, xyz, n));
+extern "C" int kicp_scan_upload_points(kicp_scan *s, const void *data, int64_t n, int32_t dtype, int32_t point_step, int32_t offset_x,
+                                       int32_t offset_y, int32_t offset_z) {
+    KICP_TRY(kicp_scan_upload_points_async(s, data, n, dtype, point_step, offset_x, offset_y, offset_z));
     KICP_CUDA(cudaStreamSynchronize(s->ctx->stream));
     return KICP_OK;
+}
+extern "C" int kicp_scan_upload_async(kicp_scan *s, const double *xyz, int64_t n) {
+    return kicp_scan_upload_points_async(s, xyz, n, KICP_DTYPE_F64, 0, 0, 0, 0);
+}
+extern "C" int kicp_scan_upload(kicp_scan *s, const double *xyz, int64_t n) {
+    return kicp_scan_upload_points(s, xyz, n, KICP_DTYPE_F64, 0, 0, 0, 0);
 }
 
 extern "C" int kicp_ctx_destroy(kicp_ctx *ctx) {
@@ -146,12 +165,6 @@ extern "C" int kicp_ctx_destroy(kicp_ctx *ctx) {
     if (ctx->upload_scan) kicp_scan_destroy(ctx->upload_scan);
     cudaFree(ctx->d_state);
     cudaFree(ctx->d_partials);
-    cudaFree(ctx->d_sorted);
-    cudaFree(ctx->d_keys);
-    cudaFree(ctx->d_keys_alt);
-    cudaFree(ctx->d_idx);
-    cudaFree(ctx->d_idx_alt);
-    cudaFree(ctx->d_sort_tmp);
     cudaFree(ctx->d_prof_iters);
     cudaFreeHost(ctx->h_result);
     cudaFreeHost(ctx->h_chunk_tags);

@@ -1,49 +1,77 @@
 // kinematic_icp::KinematicRegistration::ComputeRobotMotion on the device
 // (reference: cpp/kinematic_icp/registration/Registration.cpp:48-190 + kiss_icp::VoxelHashMap::GetClosestNeighbor).
 //
-// One registration = k_reg_init, a Morton binning of the scan (keys -> radix sort -> gather, once, at the initial
-// guess), then up to max_num_iterations launches of k_assoc.  k_assoc fuses, for every scan point,
+// One registration = ONE cooperative launch of k_register<true>.  Every IRLS iteration ("pass") fuses, for every scan point,
 //   q = T p                                          Registration.cpp:74
 //   27-voxel probe + nearest neighbour               GetClosestNeighbor (KISS-ICP v1.2.0)
 //   gate d < tau                                     Registration.cpp:75
 //   r = T p - n,  J = [R e_x | R (-p_y, p_x, 0)]     Registration.cpp:86-93
 //   sum of J^T J, J^T r, N, |r|^2                    Registration.cpp:95-118, 48-60
-// and its last CTA solves the 2x2 system, applies the unicycle motion model and decides convergence
-// (Registration.cpp:119-125, 159-167, 181-184) — so the iteration loop never returns to the host.
-// The correspondence list of the reference is never materialised: association and linearisation use the same T.
+// and ends in a grid barrier after which EVERY CTA sums the per-CTA partials in the same fixed order and solves the 2x2
+// system, applies the unicycle motion model and decides convergence redundantly (Registration.cpp:119-125, 159-167,
+// 181-184): identical inputs give identical poses, so there is no serial section and no broadcast.  The correspondence
+// list of the reference is never materialised: association and linearisation use the same T.
+//
+// THE SEARCH (pooled, warp-cooperative).  A warp owns a window of 32 consecutive scan points ("owners").  The work of the
+// window is turned into flat streams that all 32 lanes consume together, so no lane waits for the slowest owner:
+//   tasks      (owner, neighbour shift k): one hash probe each.  Batch -1 is the 32 own voxels (k = 0); its result gives
+//              every owner an exact pruning bound, after which the surviving neighbour voxels of ALL owners form one
+//              stream that is processed 32 tasks at a time (lane = task);
+//   lines      a found voxel's points are one contiguous run of 32-byte records, 4 per 128-byte line.  The lines of a
+//              batch are numbered by a warp prefix sum; a quad (4 lanes) takes one line, each lane loads ONE point with a
+//              single 256-bit load (a warp instruction touches 8 full lines), KR_G line-rounds are in flight together;
+//   reduction  d^2 goes to the owner's slot in shared memory with an atomicMin on the IEEE bit pattern (non-negative
+//              doubles order like integers); exact ties resolve by a second atomicMin on the visiting-order key
+//              (shift index, index in voxel), i.e. the first minimum in the reference's order wins.
+// Exact pruning: with q in voxel v the cube of v + s is at least lb^2 = sum of the squared face gaps along the shifted axes
+// away, so a voxel with lb^2 > best (1 + 1e-6) + 1e-10 cannot hold the answer (the margin covers the rounding of the face
+// coordinates by 9 orders of magnitude).  Everything that could tie or win is still evaluated, so the result is the
+// reference's, bit for bit in the choice of the neighbour.
 #include <cfloat>
 #include <cmath>
-#include <chrono>
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
 
 #include "kicp_device.cuh"
 
 using namespace kicp_dev;
 
-#define KICP_WARPS 8     // warps per CTA in k_assoc
-#ifndef KICP_MINB
-#define KICP_MINB 2   // resident CTAs per SM the pruned kernels are compiled for (register cap = 65536 / (256 * MINB));
-                      // measured: 2 (128 registers, no spills, 4-wide scans) beats 3 and 4
+#define KR_WARPS 8                    // warps per CTA
+#define KR_THREADS (KR_WARPS * 32)
+#ifndef KR_MINB
+#define KR_MINB 2                     // resident CTAs per SM the kernel is compiled for
 #endif
-#define KICP_CH 192      // candidates staged in shared memory per pass (27 voxels x 20 points = 540 worst case)
+#define KR_LCAP 160                   // line-map entries per chunk (32 tasks x 5 lines at 20 points per voxel)
+#ifndef KR_G
+#define KR_G 4                        // line-rounds (of 8 lines = 32 points) in flight together
+#endif
+#define KR_DBLMAX_BITS 0x7FEFFFFFFFFFFFFFull
 
-struct RegState {
+// Pose + solver state of one registration.  The persistent kernel keeps one replica per CTA in shared memory; the
+// multi-launch (NCCL) path keeps it in RegState.
+struct PoseState {
     double q[4];  // current estimate: unit quaternion (x, y, z, w) ...
     double t[3];  // ... translation ...
     double R[9];  // ... and the rotation matrix of q, row-major
     double tau, conv, fixed_reg, beta;
     int adaptive, max_iter;
     int iter, done, status;
-    unsigned int ticket, window_counter;
-    unsigned int generation;  // grid-barrier generation of the persistent kernel (= iterations completed)
-    int fused_tail;
-    int *iters_out;  // optional: where to publish the iteration count when the registration finishes (profiling)
-    double acc[8];  // JTJ00 JTJ01 JTJ11 JTr0 JTr1 N sum|r|^2 (unused)
-    double dbg[KICP_MAX_ITERATIONS][4];  // per iteration, ns: windows phase of CTA 0, barrier wait of the last CTA, partial sum, solve
+};
+
+struct RegState {
+    PoseState pose;                 // multi-launch path only
+    unsigned int win_ctr;           // window tickets handed out so far (monotonic inside a registration)
+    unsigned int arrive;            // grid-barrier arrivals so far (monotonic inside a registration)
+    unsigned int exit_ctr;          // CTAs that have left the kernel; the last one zeroes the three counters
+    unsigned int ticket;            // multi-launch path: last-CTA detection
+    int abort;                      // a device-side wait gave up (status code); every CTA leaves after the current pass
+    int *iters_out;                 // optional: where to publish the iteration count (profiling)
+    double acc[8];                  // multi-launch path: JTJ00 JTJ01 JTJ11 JTr0 JTr1 N sum|r|^2 (unused)
+    unsigned long long stats[4];    // optional work counters: probes, candidate points evaluated, lines, windows
+    double dbg[KICP_MAX_ITERATIONS][4];  // per pass, ns (CTA 0): windows phase, barrier wait, partial sum (+ exchange), solve
     kicp_reg_result result;
 };
 
@@ -115,94 +143,130 @@ __device__ void se3_exp_planar(double ux, double uy, double theta_in, double oq[
     ot[2] = V[6] * ux + V[7] * uy;
 }
 
-// ---------------------------------------------------------------------------------------------------- kernels
+// ---------------------------------------------------------------------------------------------------- arguments
 struct RegArgs {
     Pose last, odom;
     double tau, conv, fixed_reg;
-    int adaptive, max_iter, fused_tail;
+    int adaptive, max_iter;
     int *iters_out;
 };
 
-// current_estimate = last_robot_pose * relative_wheel_odometry   (Registration.cpp:156)
-__global__ void k_reg_init(RegState *st, RegArgs a) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const double lq[4] = {a.last.qx, a.last.qy, a.last.qz, a.last.qw}, lt[3] = {a.last.tx, a.last.ty, a.last.tz};
-    const double oq[4] = {a.odom.qx, a.odom.qy, a.odom.qz, a.odom.qw}, ot[3] = {a.odom.tx, a.odom.ty, a.odom.tz};
-    se3_compose(lq, lt, oq, ot, st->q, st->t);
-    quat_to_matrix(st->q, st->R);
-    st->tau = a.tau, st->conv = a.conv, st->fixed_reg = a.fixed_reg, st->beta = 0.0;
-    st->adaptive = a.adaptive, st->max_iter = a.max_iter, st->fused_tail = a.fused_tail;
-    st->iter = 0, st->done = a.max_iter <= 0 ? 1 : 0, st->status = KICP_OK;
-    st->ticket = 0, st->window_counter = 0, st->generation = 0;
-    st->iters_out = a.iters_out;
-    if (a.iters_out) *a.iters_out = 0;
-    for (int k = 0; k < 8; ++k) st->acc[k] = 0.0;
-    kicp_reg_result *r = &st->result;
-    for (int k = 0; k < 4; ++k) r->pose[k] = st->q[k];
-    for (int k = 0; k < 3; ++k) r->pose[4 + k] = st->t[k];
-    r->beta = 0.0, r->last_dx_norm = 0.0, r->iterations = 0, r->status = KICP_OK;
-}
+// The frame as it lies in HBM: float64 or float32 x,y,z fields at a byte stride (std::vector<Eigen::Vector3d> is
+// {f64, 24, 0, 8, 16}; a PointCloud2 message is f32 at point_step with its field offsets, RosUtils.cpp:30-39).
+struct ScanView {
+    const unsigned char *base;
+    int n;            // number of points (an upper bound when d_n is given)
+    const int *d_n;   // optional device-resident count produced by an earlier stage on the same stream
+    int stride, ox, oy, oz;
+    int f32;
+};
 
-__device__ __forceinline__ uint32_t spread10(uint32_t v) {  // 10 bits -> every third bit
-    v &= 1023u;
-    v = (v | (v << 16)) & 0x030000FFu;
-    v = (v | (v << 8)) & 0x0300F00Fu;
-    v = (v | (v << 4)) & 0x030C30C3u;
-    v = (v | (v << 2)) & 0x09249249u;
-    return v;
-}
+// Chunked upload overlapped with the first pass: chunk c (windows [c*windows_per_chunk, ...)) may be read once
+// flags[c] == seq — the flag is copied by the same copy stream right after the chunk's data.
+struct UploadArgs {
+    const uint32_t *flags;  // nullptr: the scan is already resident
+    uint32_t seq;
+    int windows_per_chunk;  // in 32-point windows
+};
 
-// Morton key of the voxel each point falls in at the initial guess.  The key only orders the scan so that
-// consecutive points share voxel neighbourhoods; k_assoc re-derives every voxel from the current estimate, so a
-// stale or aliased key costs locality, never correctness.
-__global__ void k_morton_keys(const RegState *st, const double *__restrict__ xyz, int n, double voxel_size,
-                              uint32_t *__restrict__ keys, int32_t *__restrict__ idx) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
-    const double *R = st->R, *t = st->t;
-    const double qx = R[0] * px + R[1] * py + R[2] * pz + t[0];
-    const double qy = R[3] * px + R[4] * py + R[5] * pz + t[1];
-    const double qz = R[6] * px + R[7] * py + R[8] * pz + t[2];
-    const int ox = voxel_coord(t[0], voxel_size) - 512, oy = voxel_coord(t[1], voxel_size) - 512,
-              oz = voxel_coord(t[2], voxel_size) - 512;
-    const uint32_t ux = (uint32_t)(voxel_coord(qx, voxel_size) - ox), uy = (uint32_t)(voxel_coord(qy, voxel_size) - oy),
-                   uz = (uint32_t)(voxel_coord(qz, voxel_size) - oz);
-    keys[i] = spread10(ux) | (spread10(uy) << 1) | (spread10(uz) << 2);
-    idx[i] = i;
-}
+struct P2PArgs {
+    P2PMailbox *peer[KICP_MAX_RANKS];
+    int nranks, rank, parity;
+    uint32_t tag_base;  // + pass index = the tag of this registration's words
+};
 
-__global__ void k_gather(const double *__restrict__ xyz, const int32_t *__restrict__ idx, int n, double *__restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int s = idx[i];
-    out[3 * i] = xyz[3 * s], out[3 * i + 1] = xyz[3 * s + 1], out[3 * i + 2] = xyz[3 * s + 2];
-}
+struct KernelArgs {
+    RegState *st;
+    ScanView scan;
+    MapView map;
+    double *partials;  // [2][grid][8]
+    P2PArgs px;
+    UploadArgs up;
+    RegArgs init;
+    int pow2_voxel;
+    int collect_stats;
+    unsigned long long timeout_ns;  // device-side waits (upload flags, peers) give up after this long
+};
 
-// ComputePerturbation's tail + motion model + pose update + convergence test (one thread).
-// `acc` holds the (all-reduced) sums of this iteration.
 __device__ __forceinline__ unsigned long long gtime_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// one stored map point {x, y, z, pad}: a single 256-bit load (LDG.E.256, sm_100)
+struct __align__(32) Point4 {
+    double x, y, z, w;
+};
+__device__ __forceinline__ Point4 ld_point(const double *p) {
+    Point4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
 
-__device__ void solve_and_update(RegState *st) {
-    double s[8];
-    for (int k = 0; k < 8; ++k) s[k] = __ldcg(&st->acc[k]);  // written by other CTAs' atomics: read through L2
-    const int j = st->iter;
-    kicp_reg_result *res = &st->result;
-    if (j < KICP_MAX_ITERATIONS)
-        for (int k = 0; k < 8; ++k) res->sums[j][k] = s[k];
+// current_estimate = last_robot_pose * relative_wheel_odometry   (Registration.cpp:156)
+__device__ void pose_init(PoseState *ps, const RegArgs &a) {
+    const double lq[4] = {a.last.qx, a.last.qy, a.last.qz, a.last.qw}, lt[3] = {a.last.tx, a.last.ty, a.last.tz};
+    const double oq[4] = {a.odom.qx, a.odom.qy, a.odom.qz, a.odom.qw}, ot[3] = {a.odom.tx, a.odom.ty, a.odom.tz};
+    double q[4], t[3], R[9];
+    se3_compose(lq, lt, oq, ot, q, t);
+    quat_to_matrix(q, R);
+    for (int k = 0; k < 4; ++k) ps->q[k] = q[k];
+    for (int k = 0; k < 3; ++k) ps->t[k] = t[k];
+    for (int k = 0; k < 9; ++k) ps->R[k] = R[k];
+    ps->tau = a.tau, ps->conv = a.conv, ps->fixed_reg = a.fixed_reg, ps->beta = 0.0;
+    ps->adaptive = a.adaptive, ps->max_iter = a.max_iter;
+    ps->iter = 0, ps->done = a.max_iter <= 0 ? 1 : 0, ps->status = KICP_OK;
+}
+__device__ void result_init(kicp_reg_result *r, const PoseState *ps) {
+    for (int k = 0; k < 4; ++k) r->pose[k] = ps->q[k];
+    for (int k = 0; k < 3; ++k) r->pose[4 + k] = ps->t[k];
+    r->beta = 0.0, r->last_dx_norm = 0.0, r->iterations = 0, r->status = ps->status;
+}
+
+// Multi-launch path and the "nothing to do" case (empty map / max_iter <= 0): state in global memory.
+__global__ void k_reg_init(RegState *st, RegArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    pose_init(&st->pose, a);
+    result_init(&st->result, &st->pose);
+    st->ticket = 0, st->win_ctr = 0, st->arrive = 0, st->exit_ctr = 0, st->abort = 0;
+    st->iters_out = a.iters_out;
+    if (a.iters_out) *a.iters_out = 0;
+    for (int k = 0; k < 8; ++k) st->acc[k] = 0.0;
+}
+
+// ComputePerturbation's tail + motion model + pose update + convergence test (one thread).  `s` holds the (all-reduced)
+// sums of this iteration; `res` (optional) receives the public result fields.
+__device__ void solve_and_update(PoseState *ps, const double *s, kicp_reg_result *res, int *iters_out) {
+    const int j = ps->iter;
+    if (res && j < KICP_MAX_ITERATIONS)
+        for (int k = 0; k < 8; ++k) res->sums[j][k] = k < 7 ? s[k] : 0.0;
     const double N = s[5];
     if (j == 0) {
         // ComputeOdometryRegularization (Registration.cpp:48-60): beta = 1 / (mean |T0 p - n|^2 + DBL_MIN), computed
         // once from the first association; the fixed value otherwise (:171-177)
-        st->beta = st->adaptive ? 1.0 / (s[6] / N + DBL_MIN) : st->fixed_reg;
-        res->beta = st->beta;
+        ps->beta = ps->adaptive ? 1.0 / (s[6] / N + DBL_MIN) : ps->fixed_reg;
+        if (res) res->beta = ps->beta;
     }
     // JTJ /= N; JTr /= N; JTJ += diag(beta, 0); dx = -(JTJ^-1 JTr)     (Registration.cpp:119-125)
-    const double a = s[0] / N + st->beta, b = s[1] / N, d = s[2] / N + 0.0;
+    const double a = s[0] / N + ps->beta, b = s[1] / N, d = s[2] / N + 0.0;
     const double r0 = s[3] / N, r1 = s[4] / N;
     const double invdet = 1.0 / (a * d - b * b);
     const double i00 = d * invdet, i01 = -b * invdet, i10 = -b * invdet, i11 = a * invdet;
@@ -212,1180 +276,567 @@ __device__ void solve_and_update(RegState *st) {
     sincos(dx1, &sn, &cs);
     const double ux = dx0 * sn / (dx1 + DBL_MIN);
     const double uy = dx0 * (1.0 - cs) / (dx1 + DBL_MIN);
-    double dq[4], dt[3], nq[4], nt[3];
+    double dq[4], dt[3], nq[4], nt[3], cq[4], ct[3], nR[9];
+    for (int k = 0; k < 4; ++k) cq[k] = ps->q[k];
+    for (int k = 0; k < 3; ++k) ct[k] = ps->t[k];
     se3_exp_planar(ux, uy, dx1, dq, dt);
-    se3_compose(st->q, st->t, dq, dt, nq, nt);  // current_estimate = current_estimate * delta_motion  (:182)
-    for (int k = 0; k < 4; ++k) st->q[k] = nq[k];
-    for (int k = 0; k < 3; ++k) st->t[k] = nt[k];
-    quat_to_matrix(st->q, st->R);
+    se3_compose(cq, ct, dq, dt, nq, nt);  // current_estimate = current_estimate * delta_motion  (:182)
+    quat_to_matrix(nq, nR);
+    for (int k = 0; k < 4; ++k) ps->q[k] = nq[k];
+    for (int k = 0; k < 3; ++k) ps->t[k] = nt[k];
+    for (int k = 0; k < 9; ++k) ps->R[k] = nR[k];
     const double dxn = sqrt(dx0 * dx0 + dx1 * dx1);
-    if (j < KICP_MAX_ITERATIONS) res->dx[j][0] = dx0, res->dx[j][1] = dx1;
-    res->last_dx_norm = dxn;
-    res->iterations = j + 1;
-    for (int k = 0; k < 4; ++k) res->pose[k] = st->q[k];
-    for (int k = 0; k < 3; ++k) res->pose[4 + k] = st->t[k];
-    st->iter = j + 1;
-    int done = (dxn < st->conv) || (j + 1 >= st->max_iter);  // break BEFORE re-association (:184)
+    ps->iter = j + 1;
+    int done = (dxn < ps->conv) || (j + 1 >= ps->max_iter);  // break BEFORE re-association (:184)
     if (!(N > 0.0)) {  // the reference has no guard: the pose is NaN from here on; stop early and say so
-        st->status = KICP_WARN_NO_CORRESPONDENCES;
+        ps->status = KICP_WARN_NO_CORRESPONDENCES;
         done = 1;
     }
-    if (st->status == KICP_ERR_NCCL) done = 1;  // a peer of the fused exchange never arrived
-    res->status = st->status;
-    st->done = done;
-    if (st->iters_out) *st->iters_out = j + 1;
-    for (int k = 0; k < 8; ++k) st->acc[k] = 0.0;
+    ps->done = done;
+    if (res) {
+        if (j < KICP_MAX_ITERATIONS) res->dx[j][0] = dx0, res->dx[j][1] = dx1;
+        res->last_dx_norm = dxn;
+        res->iterations = j + 1;
+        for (int k = 0; k < 4; ++k) res->pose[k] = nq[k];
+        for (int k = 0; k < 3; ++k) res->pose[4 + k] = nt[k];
+        res->status = ps->status;
+    }
+    if (iters_out) *iters_out = j + 1;
 }
 
+// Multi-launch path: the solve between the NCCL allreduce and the next association launch.
 __global__ void k_solve(RegState *st) {
-    if (threadIdx.x == 0 && blockIdx.x == 0 && !st->done) solve_and_update(st);
+    if (threadIdx.x == 0 && blockIdx.x == 0 && !st->pose.done) {
+        double s[8];
+        for (int k = 0; k < 8; ++k) s[k] = st->acc[k];
+        solve_and_update(&st->pose, s, &st->result, st->iters_out);
+        for (int k = 0; k < 8; ++k) st->acc[k] = 0.0;
+    }
 }
 
-// The fused association + linearisation + reduction kernel.  One warp owns a window of 32 consecutive (Morton-
-// sorted) scan points.  Lanes that fall in the same voxel form a group; for each group the warp probes the 27
-// neighbour voxels (lanes 0..26, one hash probe each), stages their points in shared memory, and scans them with
-// 32 / 2^ceil(log2 P) lanes per query point so small groups still use every lane.
-__global__ void __launch_bounds__(KICP_WARPS * 32) k_assoc(RegState *st, const double *__restrict__ scan, int n, MapView map) {
-    if (st->done) return;
-    extern __shared__ double smem_d[];
-    __shared__ double s_T[12];
-    __shared__ double s_part[KICP_WARPS][8];
-    __shared__ int s_last;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned FULL = 0xFFFFFFFFu;
-    // per-warp shared memory: candidate coordinates (SoA), their global point indices, query broadcast, results
-    double *sx = smem_d + (size_t)wid * (3 * KICP_CH + 3 * 32 + 32);
-    double *sy = sx + KICP_CH, *sz = sy + KICP_CH;
-    double *sq = sz + KICP_CH;      // [32][3] query points of the current group
-    double *sres_d = sq + 96;       // [32]    winning squared distance per query slot
-    int *sg = (int *)(smem_d + (size_t)KICP_WARPS * (3 * KICP_CH + 3 * 32 + 32)) + wid * (KICP_CH + 32);
-    int *sres_g = sg + KICP_CH;     // [32]    winning global point index per query slot
+// ------------------------------------------------------------------------------------------- per-warp shared state
+struct __align__(16) WarpSm {
+    double2 qxy[32];                 // owner's query point (map frame)
+    double qz[32];
+    unsigned long long best[32];     // bit pattern of the smallest d^2 found so far (atomicMin)
+    unsigned long long kg[32];       // (visiting-order key << 32) | global point index of the FIRST such minimum (atomicMin)
+    int vx[32], vy[32], vz[32];      // owner's voxel
+    unsigned int tend[32];           // inclusive prefix sum of the owners' surviving-neighbour counts
+    unsigned int nmask[32];          // owner's surviving neighbour shifts, bit k <-> voxel_shifts[k]
+    unsigned short lmap[KR_LCAP];    // line -> (task lane, line index inside the voxel)
+};
 
-    if (threadIdx.x < 9) s_T[threadIdx.x] = st->R[threadIdx.x];
-    if (threadIdx.x >= 9 && threadIdx.x < 12) s_T[threadIdx.x] = st->t[threadIdx.x - 9];
-    __syncthreads();
-    __shared__ MapView s_map[32];
-    const MapRegs mr = map_regs(map, s_map);  // per-thread copy of the map view (divergence safety, kicp_device.cuh)
-    const double tau = st->tau, vs = map.voxel_size;
-    const int num_windows = (n + 31) >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
+__device__ __forceinline__ void load_scan_point(const ScanView &sv, int i, double &x, double &y, double &z) {
+    const unsigned char *p = sv.base + (size_t)i * (size_t)sv.stride;
+    if (sv.f32) {
+        x = (double)__ldg(reinterpret_cast<const float *>(p + sv.ox));
+        y = (double)__ldg(reinterpret_cast<const float *>(p + sv.oy));
+        z = (double)__ldg(reinterpret_cast<const float *>(p + sv.oz));
+    } else {
+        x = __ldg(reinterpret_cast<const double *>(p + sv.ox));
+        y = __ldg(reinterpret_cast<const double *>(p + sv.oy));
+        z = __ldg(reinterpret_cast<const double *>(p + sv.oz));
+    }
+}
 
-    double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0, cntN = 0, ssq = 0;
-
-    while (true) {
-        int w = 0;
-        if (lane == 0) w = (int)atomicAdd(&st->window_counter, 1u);
-        w = __shfl_sync(FULL, w, 0);
-        if (w >= num_windows) break;
-        const int i = w * 32 + lane;
-        const bool valid = i < n;
-        double px = 0, py = 0, pz = 0;
-        if (valid) px = scan[3 * (size_t)i], py = scan[3 * (size_t)i + 1], pz = scan[3 * (size_t)i + 2];
-        const double qx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[9];
-        const double qy = s_T[3] * px + s_T[4] * py + s_T[5] * pz + s_T[10];
-        const double qz = s_T[6] * px + s_T[7] * py + s_T[8] * pz + s_T[11];
-        const int vx = voxel_coord(qx, vs), vy = voxel_coord(qy, vs), vz = voxel_coord(qz, vs);
-        const unsigned vmask = __ballot_sync(FULL, valid);
-        unsigned gmask = 0;
-        if (valid) gmask = __match_any_sync(vmask, vx) & __match_any_sync(vmask, vy) & __match_any_sync(vmask, vz);
-        double best = DBL_MAX;
-        int bestg = -1;
-        unsigned remaining = vmask;
-        while (remaining) {
-            const int leader = __ffs(remaining) - 1;
-            const unsigned gm = __shfl_sync(FULL, gmask, leader);
-            const int cvx = __shfl_sync(FULL, vx, leader), cvy = __shfl_sync(FULL, vy, leader), cvz = __shfl_sync(FULL, vz, leader);
-            const int P = __popc(gm);
-            const bool member = (gm >> lane) & 1u;
-            const int myslot = __popc(gm & lt_mask);
-            if (member) sq[3 * myslot] = qx, sq[3 * myslot + 1] = qy, sq[3 * myslot + 2] = qz;
-            // 27-neighbour probe, KISS shift order (lane k <-> voxel_shifts[k])
-            int cnt = 0;
-            unsigned blk = 0;
-            if (lane < 27) {
-                const uint32_t meta = map_probe(mr, cvx + shift_x(lane), cvy + shift_y(lane), cvz + shift_z(lane));
-                if (meta != KICP_SLOT_EMPTY) cnt = (int)(meta & 0xFFu), blk = meta >> 8;
-            }
-            __syncwarp();
-            int incl = cnt;
+// per-lane work counters (option "stats") -> warp sum -> one atomic per warp
+__device__ __forceinline__ void stats_flush(RegState *st, unsigned long long probes, unsigned long long cands, unsigned long long lines) {
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += y;
+    for (int d = 16; d > 0; d >>= 1) {
+        probes += __shfl_xor_sync(0xFFFFFFFFu, probes, d);
+        cands += __shfl_xor_sync(0xFFFFFFFFu, cands, d);
+        lines += __shfl_xor_sync(0xFFFFFFFFu, lines, d);
+    }
+    if ((threadIdx.x & 31) == 0) atomicAdd(&st->stats[0], probes), atomicAdd(&st->stats[1], cands), atomicAdd(&st->stats[2], lines);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_register.  PERSISTENT = true: cooperative launch, every CTA resident, all IRLS iterations inside the launch
+// (single GPU, and the sharded path with the exchange over NVLink peer memory fused into the barrier).
+// PERSISTENT = false: one pass per launch; the last CTA leaves the local sums in st->acc for the NCCL allreduce.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool PERSISTENT>
+__global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelArgs a) {
+    __shared__ WarpSm s_warp[KR_WARPS];
+    __shared__ PoseState s_ps;
+    __shared__ double s_part[KR_WARPS][8];
+    __shared__ double s_sum[8];
+    __shared__ MapView s_map[32];
+    __shared__ int s_flag[2];
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int quad = lane >> 2, sub = lane & 3;
+    const unsigned FULL = 0xFFFFFFFFu;
+    WarpSm &sm = s_warp[wid];
+    RegState *const st = a.st;
+    const MapRegs mr = map_regs(a.map, s_map);  // per-thread copy of the map view (divergence safety, kicp_device.cuh)
+    const double vs = a.map.voxel_size, inv_vs = 1.0 / a.map.voxel_size;
+    const int n = a.scan.d_n ? min(__ldg(a.scan.d_n), a.scan.n) : a.scan.n;
+    const int num_windows = (n + 31) >> 5;
+    const unsigned total_warps = gridDim.x * KR_WARPS;
+
+    if (threadIdx.x == 0) {
+        if (PERSISTENT) {
+            pose_init(&s_ps, a.init);
+            if (blockIdx.x == 0) {
+                result_init(&st->result, &s_ps);
+                if (a.init.iters_out) *a.init.iters_out = 0;
             }
-            const int off = incl - cnt;
-            const int C = __shfl_sync(FULL, incl, 31);
-            // lanes per query point: 32 / 2^ceil(log2 P)
-            const int lg = P <= 1 ? 0 : 32 - __clz(P - 1);
-            const int L = 32 >> lg;
-            const int slot = lane >> (5 - lg), sub = lane & (L - 1);
-            const bool worker = slot < P;
-            __syncwarp();
-            double wqx = 0, wqy = 0, wqz = 0;
-            if (worker) wqx = sq[3 * slot], wqy = sq[3 * slot + 1], wqz = sq[3 * slot + 2];
-            double wbest = DBL_MAX;
-            int wc = 0x7FFFFFFF, wg = -1;
-            for (int base = 0; base < C; base += KICP_CH) {
-                for (int j = 0; j < cnt; ++j) {
-                    const int c = off + j - base;
-                    if (c >= 0 && c < KICP_CH) sg[c] = (int)(blk * (unsigned)mr.cap) + j;
-                }
-                __syncwarp();
-                const int m = min(KICP_CH, C - base);
-                for (int c = lane; c < m; c += 32) {
-                    const double *gp = mr.pts + (size_t)sg[c] * KICP_PSTRIDE;
-                    sx[c] = __ldg(gp), sy[c] = __ldg(gp + 1), sz[c] = __ldg(gp + 2);
-                }
-                __syncwarp();
-                if (worker) {
-                    for (int c = sub; c < m; c += L) {
-                        const double dx = sx[c] - wqx, dy = sy[c] - wqy, dz = sz[c] - wqz;
-                        const double d2 = dx * dx + dy * dy + dz * dz;
-                        if (d2 < wbest) wbest = d2, wc = base + c, wg = sg[c];  // strict <: first minimum wins
+        } else {
+            s_ps = st->pose;
+        }
+    }
+    __syncthreads();
+    if (!PERSISTENT && s_ps.done) return;
+
+    unsigned long long n_probe = 0, n_cand = 0, n_line = 0;
+
+    for (unsigned it = 0; !s_ps.done; ++it) {
+        double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0, cntN = 0, ssq = 0;
+        const unsigned long long t_iter0 = gtime_ns();
+        const unsigned ticket_base = PERSISTENT ? it * ((unsigned)num_windows + total_warps) : 0u;
+        const double tau = s_ps.tau;
+
+        // dynamic window fetch (windows differ in cost); the next ticket is requested before the current window is
+        // processed so that the atomic's round trip is off the critical path
+        unsigned tk = 0;
+        if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);
+        int w = (int)(__shfl_sync(FULL, tk, 0) - ticket_base);
+        while (w < num_windows) {
+            if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);
+            if (PERSISTENT && a.up.flags != nullptr && it == 0u) {
+                // first pass over a frame that is still being uploaded: wait until this window's chunk has landed
+                if (lane == 0) {
+                    const uint32_t *f = a.up.flags + min(w / a.up.windows_per_chunk, KICP_UPLOAD_CHUNKS - 1);
+                    const unsigned long long deadline = gtime_ns() + a.timeout_ns;
+                    const uint32_t want = a.up.seq;
+                    while (ld_acquire_sys_u32(f) != want) {
+                        if (gtime_ns() > deadline) {  // the copy never arrived
+                            atomicExch(&st->abort, KICP_ERR_CUDA);
+                            break;
+                        }
                     }
                 }
                 __syncwarp();
             }
-            for (int o = L >> 1; o > 0; o >>= 1) {
-                const double od = __shfl_xor_sync(FULL, wbest, o);
-                const int oc = __shfl_xor_sync(FULL, wc, o), og = __shfl_xor_sync(FULL, wg, o);
-                if (od < wbest || (od == wbest && oc < wc)) wbest = od, wc = oc, wg = og;
+            // ---------------------------------------------------------------- owners: q = T p, voxel, face gaps
+            const int i = w * 32 + lane;
+            const bool valid = i < n;
+            double px = 0, py = 0, pz = 0;
+            if (valid) load_scan_point(a.scan, i, px, py, pz);
+            const double qx = s_ps.R[0] * px + s_ps.R[1] * py + s_ps.R[2] * pz + s_ps.t[0];
+            const double qy = s_ps.R[3] * px + s_ps.R[4] * py + s_ps.R[5] * pz + s_ps.t[1];
+            const double qz = s_ps.R[6] * px + s_ps.R[7] * py + s_ps.R[8] * pz + s_ps.t[2];
+            // PointToVoxel: floor(q / voxel_size); for a power-of-two voxel size the product with the (exact) reciprocal
+            // is the same double as the quotient, so the cheaper form is used
+            int vx, vy, vz;
+            if (a.pow2_voxel) {
+                vx = (int)floor(qx * inv_vs), vy = (int)floor(qy * inv_vs), vz = (int)floor(qz * inv_vs);
+            } else {
+                vx = voxel_coord(qx, vs), vy = voxel_coord(qy, vs), vz = voxel_coord(qz, vs);
             }
-            if (worker && sub == 0) sres_d[slot] = wbest, sres_g[slot] = wg;
+            sm.qxy[lane] = make_double2(qx, qy), sm.qz[lane] = qz;
+            sm.vx[lane] = vx, sm.vy[lane] = vy, sm.vz[lane] = vz;
+            sm.best[lane] = KR_DBLMAX_BITS, sm.kg[lane] = ~0ull;
+            unsigned long long seen = KR_DBLMAX_BITS;  // sm.best[lane] as this lane last saw it
+            unsigned total = 0;                        // neighbour tasks of the window
+            int nbatch = 0;
             __syncwarp();
-            if (member) best = sres_d[myslot], bestg = sres_g[myslot];
-            __syncwarp();
-            remaining &= ~gm;
-        }
-        if (valid && bestg >= 0) {
-            const double *gp = mr.pts + (size_t)bestg * KICP_PSTRIDE;
-            const double rx = qx - __ldg(gp), ry = qy - __ldg(gp + 1), rz = qz - __ldg(gp + 2);  // r = T p - n
-            const double rr = rx * rx + ry * ry + rz * rz;
-            if (sqrt(rr) < tau) {  // distance < max_correspondance_distance   (Registration.cpp:75)
-                // J = [R e_x | R (-p_y, p_x, 0)]      (Registration.cpp:89-91)
-                const double c0x = s_T[0], c0y = s_T[3], c0z = s_T[6];
-                const double c1x = s_T[1] * px - s_T[0] * py, c1y = s_T[4] * px - s_T[3] * py, c1z = s_T[7] * px - s_T[6] * py;
-                a00 += c0x * c0x + c0y * c0y + c0z * c0z;
-                a01 += c0x * c1x + c0y * c1y + c0z * c1z;
-                a11 += c1x * c1x + c1y * c1y + c1z * c1z;
-                b0 += c0x * rx + c0y * ry + c0z * rz;
-                b1 += c1x * rx + c1y * ry + c1z * rz;
-                cntN += 1.0;
-                ssq += rr;
-            }
-        }
-        (void)best;
-    }
 
-    // warp shuffle reduction -> one partial per warp -> one set of atomics per CTA
-    double v[7] = {a00, a01, a11, b0, b1, cntN, ssq};
+            for (int b = -1; b < nbatch; ++b) {
+                // ------------------------------------------------------------ this lane's task: (owner o, shift k)
+                int o = lane, k = 0;
+                bool act = valid;
+                if (b >= 0) {
+                    const unsigned s = (unsigned)b * 32u + (unsigned)lane;
+                    act = s < total;
+                    int lo = 0;  // owner = number of owners whose tasks end at or before s
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
+                    for (int step = 16; step > 0; step >>= 1)
+                        if (sm.tend[lo + step - 1] <= s) lo += step;
+                    o = lo;
+                    const unsigned before = o ? sm.tend[o - 1] : 0u;
+                    const unsigned mk = sm.nmask[o];
+                    k = act ? (int)__fns(mk, 0u, (int)(s - before) + 1) : 0;
+                }
+                // ------------------------------------------------------------ hash probe (warp-uniform loop)
+                uint32_t meta = KICP_SLOT_EMPTY;
+                {
+                    int kx = 0, ky = 0, kz = 0;
+                    uint32_t h = 0;
+                    if (act) {
+                        kx = sm.vx[o] + shift_x(k), ky = sm.vy[o] + shift_y(k), kz = sm.vz[o] + shift_z(k);
+                        h = voxel_hash(kx, ky, kz) & mr.mask;
+                    }
+                    bool pend = act;
+                    while (__any_sync(FULL, pend)) {
+                        if (pend) {
+                            const int4 sl = __ldg(&mr.slots[h]);
+                            if ((uint32_t)sl.w == KICP_SLOT_EMPTY) {
+                                pend = false;
+                            } else if (sl.x == kx && sl.y == ky && sl.z == kz) {
+                                meta = (uint32_t)sl.w, pend = false;
+                            } else {
+                                h = (h + 1) & mr.mask;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                // ------------------------------------------------------------ number the 128-byte lines of the batch
+                const int cnt = meta == KICP_SLOT_EMPTY ? 0 : (int)(meta & 0xFFu);
+                const int nl = (cnt + 3) >> 2;
+                int incl = nl;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o);
-    }
-    if (lane == 0) {
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int y = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= d) incl += y;
+                }
+                const int loff = incl - nl;
+                const int ltot = __shfl_sync(FULL, incl, 31);
+                const int maxnl = __reduce_max_sync(FULL, nl);
+                const unsigned okpack = ((unsigned)o << 5) | (unsigned)k;
+                if (a.collect_stats) n_probe += act ? 1 : 0, n_cand += cnt, n_line += nl;
+
+                for (int lbase = 0; lbase < ltot; lbase += KR_LCAP) {
+                    // line map of this chunk: entry = task lane | (line inside the voxel << 5)
+                    for (int li = 0; li < maxnl; ++li) {
+                        const int pos = loff + li - lbase;
+                        if (li < nl && pos >= 0 && pos < KR_LCAP) sm.lmap[pos] = (unsigned short)(lane | (li << 5));
+                    }
+                    __syncwarp();
+                    const int nr = min(KR_LCAP, ltot - lbase);
+                    for (int r0 = 0; r0 < nr; r0 += 8 * KR_G) {
+                        double d2[KR_G];
+                        unsigned long long kgv[KR_G];
+                        int own[KR_G];
+                        unsigned hasm = 0;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) s_part[wid][k] = v[k];
-    }
-    __syncthreads();
-    if (threadIdx.x < 7) {
-        double s = 0.0;
-        for (int k = 0; k < KICP_WARPS; ++k) s += s_part[k][threadIdx.x];
-        atomicAdd(&st->acc[threadIdx.x], s);
-        __threadfence();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned ticket = atomicAdd(&st->ticket, 1u);
-        s_last = (ticket == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-        __threadfence();
-        st->ticket = 0;
-        st->window_counter = 0;
-        if (st->fused_tail) solve_and_update(st);
-    }
-}
-
-
-
-// One candidate step: squared distance of the 32-byte record at `p` to the query; strict `<` keeps the first minimum
-// (candidates are visited in the reference's order).  Only (d2, pointer) are tracked; the winner is re-read once.
-__device__ __forceinline__ void candidate_step(const double2 xy, const double2 zw, const double *p, double qx, double qy, double qz,
-                                               double &best, const double *&bestp) {
-    const double dx = xy.x - qx, dy = xy.y - qy, dz = zw.x - qz;
-    const double d2 = dx * dx + dy * dy + dz * dz;
-    if (d2 < best) best = d2, bestp = p;
-}
-
-// Scan the `cnt` points of one voxel, KICP_SCANW per step: 2*KICP_SCANW independent 16-byte loads are in flight per lane
-// before the first distance is formed (the path is bound by dependent memory round trips).  Indices past
-// the end are clamped to the last point, which is harmless: re-evaluating a point cannot change a strict minimum.
-// The loop is per-lane (no warp vote): lanes with fewer points leave earlier and reconverge behind it.
-#ifndef KICP_SCANW
-#define KICP_SCANW 4
-#endif
-__device__ __forceinline__ void scan_voxel(const double *vp, int cnt, double qx, double qy, double qz, double &best,
-                                           const double *&bestp) {
-    for (int j = 0; j < cnt; j += KICP_SCANW) {
-        const double *p[KICP_SCANW];
-        double2 a[KICP_SCANW], b[KICP_SCANW];
+                        for (int g = 0; g < KR_G; ++g) {
+                            const int line = r0 + g * 8 + quad;
+                            const bool lv = line < nr;
+                            const unsigned e = lv ? (unsigned)sm.lmap[line] : 0u;
+                            const int t = (int)(e & 31u), li = (int)(e >> 5);
+                            const uint32_t m = __shfl_sync(FULL, meta, t);
+                            const unsigned ok = __shfl_sync(FULL, okpack, t);
+                            const int j = li * 4 + sub;
+                            const bool has = lv && j < (int)(m & 0xFFu);
+                            const unsigned gidx = (m >> 8) * (unsigned)mr.cap + (unsigned)j;
+                            const int oo = (int)(ok >> 5);
+                            own[g] = oo;
+                            kgv[g] = ((unsigned long long)(((ok & 31u) << 8) | (unsigned)j) << 32) | (unsigned long long)gidx;
+                            d2[g] = DBL_MAX;
+                            if (has) {
+                                const Point4 c = ld_point(mr.pts + (size_t)gidx * KICP_PSTRIDE);
+                                const double2 qq = sm.qxy[oo];
+                                const double dx = c.x - qq.x, dy = c.y - qq.y, dz = c.z - sm.qz[oo];
+                                d2[g] = dx * dx + dy * dy + dz * dz;
+                                hasm |= 1u << g;
+                            }
+                        }
+                        // phase 1: lower the owners' best; remember who could still be (or tie with) the minimum
+                        unsigned lem = 0;
 #pragma unroll
-        for (int u = 0; u < KICP_SCANW; ++u) {
-            p[u] = vp + (size_t)min(j + u, cnt - 1) * KICP_PSTRIDE;
-            a[u] = __ldg(reinterpret_cast<const double2 *>(p[u]));
-            b[u] = __ldg(reinterpret_cast<const double2 *>(p[u]) + 1);
-        }
+                        for (int g = 0; g < KR_G; ++g) {
+                            if (hasm & (1u << g)) {
+                                const unsigned long long mine = (unsigned long long)__double_as_longlong(d2[g]);
+                                const unsigned long long br = sm.best[own[g]];
+                                if (mine <= br) {
+                                    lem |= 1u << g;
+                                    if (mine < br) atomicMin(&sm.best[own[g]], mine);
+                                }
+                            }
+                        }
+                        if (__any_sync(FULL, lem != 0u)) {
+                            __syncwarp();
+                            // every lane, as an owner: a strictly smaller best invalidates the recorded first minimum
+                            const unsigned long long cur = sm.best[lane];
+                            if (cur != seen) sm.kg[lane] = ~0ull, seen = cur;
+                            __syncwarp();
+                            // phase 2: among the candidates AT the minimum, the first in visiting order wins
 #pragma unroll
-        for (int u = 0; u < KICP_SCANW; ++u) candidate_step(a[u], b[u], p[u], qx, qy, qz, best, bestp);
-    }
-}
+                            for (int g = 0; g < KR_G; ++g) {
+                                if (lem & (1u << g)) {
+                                    if ((unsigned long long)__double_as_longlong(d2[g]) == sm.best[own[g]])
+                                        atomicMin(&sm.kg[own[g]], kgv[g]);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    __syncwarp();
+                }
 
-// ---------------------------------------------------------------------------------------------------------------
-// k_assoc_pruned: one thread per scan point, exact pruning of the 27-voxel neighbourhood.
-//
-// GetClosestNeighbor returns the nearest of all points stored in the 27 voxels around the query.  A voxel whose
-// CUBE is farther from the query than the best distance found so far cannot contain that point, so it can be
-// skipped without changing the result: with q in voxel v, the gap to the cube of v + s is
-//     lb^2 = sum over axes of { (upper face - q)^2 if s = +1, (q - lower face)^2 if s = -1, 0 if s = 0 }.
-// The voxels are visited in the reference's own order (centre, faces, edges, corners), so the strict `<` keeps the
-// same point on exact ties; a voxel is skipped only when lb^2 exceeds the current best by a safety margin that
-// covers the rounding of the face coordinates (1e-6 relative + 1e-10 absolute, orders of magnitude above 1 ulp).
-// Typical result on the 0.5 m / 1.0 m maps: ~3 voxels and ~15-25 candidate distances per point instead of 27 / 145+.
-//
-// The loop is organised around memory-level parallelism, because the path is latency-bound once pruned: the
-// centre voxel first, then rounds of up to four neighbour voxels whose home hash slots are loaded together, and
-// every voxel's points are read four at a time (eight independent 16-byte loads per lane).  Map data is read
-// straight from L1/L2 (the map fits the 126 MB L2).
-// ---------------------------------------------------------------------------------------------------------------
-// PERSISTENT = true: launched cooperatively with every CTA resident; all IRLS iterations run inside this one launch,
-// separated by a grid barrier whose last arriver solves the 2x2 system and updates the pose (no launches after
-// convergence, no per-iteration launch gap).  PERSISTENT = false: one launch per iteration (used by the NCCL-sharded
-// path, where the allreduce sits between association and solve).
-// Chunked upload overlapped with the first iteration: chunk c (windows [c*windows_per_chunk, ...)) may be read once
-// flags[c] == seq — the flag is copied by the same copy stream right after the chunk's data.
-struct UploadArgs {
-    const uint32_t *flags;  // nullptr: the scan is already resident
-    uint32_t seq;
-    int windows_per_chunk;  // in 32-point windows
-};
-
-// Host side of the same upload: the chunks still to be issued on the copy stream.  With the "launch_first" option only the
-// first chunk goes out before the persistent kernel is launched and the rest right after the launch call; measured on B200
-// this does not pay (cfg4 e2e +-0, cfg3 -6 %: the first pass is bound by the 6 MB copy itself, not by the ~16 driver
-// calls in front of the launch), so the default issues every chunk first.
-struct HostUpload {
-    const double *src;
-    double *dst;
-    int64_t n, wpc;
-    int issued;
-};
-static int issue_chunks(kicp_ctx *c, HostUpload *hu, int upto) {
-    for (int k = hu->issued; k < upto; ++k) {
-        const int64_t lo = std::min<int64_t>(hu->n, k * hu->wpc * 32), hi = std::min<int64_t>(hu->n, (k + 1) * hu->wpc * 32);
-        hu->issued = k + 1;
-        if (hi > lo)
-            KICP_CUDA(cudaMemcpyAsync(hu->dst + 3 * lo, hu->src + 3 * lo, (size_t)(hi - lo) * 3 * sizeof(double), cudaMemcpyHostToDevice,
-                                      c->copy_stream));
-        KICP_CUDA(cudaMemcpyAsync(c->d_chunk_flags + k, c->h_chunk_tags + k, sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
-    }
-    return KICP_OK;
-}
-
-struct P2PArgs {
-    P2PMailbox *peer[KICP_MAX_RANKS];
-    int nranks, rank, parity;
-    unsigned long long tag_base;
-};
-
-__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// Cross-GPU exchange fused into the grid barrier (executed by the last CTA of every rank): write the local sums of
-// iteration `it` into every peer's mailbox over NVLink, raise the flags, wait for all peers, and replace st->acc by the
-// sum over ranks IN RANK ORDER — every rank adds the same values in the same order, so all ranks solve for the
-// identical pose.  A rank that never shows up turns into an error status after ~2 s instead of a hung GPU.
-__device__ __forceinline__ void p2p_exchange(RegState *st, const P2PArgs &px, unsigned it) {
-    const unsigned long long tag = px.tag_base + it + 1ull;
-    const int t = threadIdx.x;
-    if (t < 32) {  // warp 0 only; the loops over ranks are warp-synchronous (see kicp_device.cuh on divergence safety)
-        const double mine = t < 7 ? __ldcg(&st->acc[t]) : 0.0;
-        for (int r = 0; r < px.nranks; ++r) {
-            if (t < 8) {
-                volatile double *dst = &px.peer[r]->data[px.parity][it][px.rank][t];
-                *dst = mine;
-            }
-            __syncwarp();
-        }
-        __threadfence_system();
-        __syncwarp();
-        if (t < px.nranks) st_release_sys(&px.peer[t]->flag[px.parity][it][px.rank], tag);
-        if (t < px.nranks) {
-            const unsigned long long *f = &px.peer[px.rank]->flag[px.parity][it][t];
-            const long long t0 = clock64();
-            while (ld_acquire_sys(f) < tag) {
-                if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer is missing
-                    st->status = KICP_ERR_NCCL;
-                    break;
+                if (b < 0) {
+                    // ------------------------------------------------------------ exact pruning of the 26 neighbours
+                    __syncwarp();
+                    const double best = __longlong_as_double((long long)sm.best[lane]);
+                    const double bound = best * (1.0 + 1e-6) + 1e-10;
+                    double t;
+                    t = (double)(vx + 1) * vs - qx; const double gxp = t * t;
+                    t = qx - (double)vx * vs;       const double gxm = t * t;
+                    t = (double)(vy + 1) * vs - qy; const double gyp = t * t;
+                    t = qy - (double)vy * vs;       const double gym = t * t;
+                    t = (double)(vz + 1) * vs - qz; const double gzp = t * t;
+                    t = qz - (double)vz * vs;       const double gzm = t * t;
+                    unsigned mask = valid ? 0x07FFFFFEu : 0u;
+                    mask &= (kX0 | (gxp <= bound ? kXP : 0u) | (gxm <= bound ? kXM : 0u)) &
+                            (kY0 | (gyp <= bound ? kYP : 0u) | (gym <= bound ? kYM : 0u)) &
+                            (kZ0 | (gzp <= bound ? kZP : 0u) | (gzm <= bound ? kZM : 0u));
+                    // edges and corners: the summed gap decides
+#pragma unroll
+                    for (int kk = 7; kk < 27; ++kk) {
+                        const double lb2 = (shift_x(kk) > 0 ? gxp : (shift_x(kk) < 0 ? gxm : 0.0)) +
+                                           (shift_y(kk) > 0 ? gyp : (shift_y(kk) < 0 ? gym : 0.0)) +
+                                           (shift_z(kk) > 0 ? gzp : (shift_z(kk) < 0 ? gzm : 0.0));
+                        if (lb2 > bound) mask &= ~(1u << kk);
+                    }
+                    const int no = __popc(mask);
+                    int tin = no;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int y = __shfl_up_sync(FULL, tin, d);
+                        if (lane >= d) tin += y;
+                    }
+                    sm.tend[lane] = (unsigned)tin, sm.nmask[lane] = mask;
+                    total = (unsigned)__shfl_sync(FULL, tin, 31);
+                    nbatch = (int)((total + 31u) >> 5);
+                    __syncwarp();
                 }
             }
-        }
-        __syncwarp();
-        double s = 0.0;
-        for (int r = 0; r < px.nranks; ++r) {
-            if (t < 8) s += *(volatile double *)&px.peer[px.rank]->data[px.parity][it][r][t];
             __syncwarp();
-        }
-        if (t < 8) __stcg(&st->acc[t], s);
-    }
-    __syncthreads();
-}
-
-// Warp-shuffle reduction of the 7 per-thread sums -> one partial per warp -> one partial per CTA, written with plain
-// stores to partials[blockIdx.x][8].  The last CTA to arrive (ticket) sums the partials in a fixed order — no contended
-// floating-point atomics, and the result does not depend on the arrival order — and then either runs the multi-launch
-// tail or releases the grid barrier of the persistent kernel after solving for the next pose.
-// Returns true when the kernel must return (non-persistent launch, or converged).
-template <bool PERSISTENT>
-__device__ __forceinline__ bool reduce_and_finish(RegState *st, double *partials, double (&v)[7], unsigned it, double (*s_part)[8],
-                                                  int *s_last, const P2PArgs &px) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned FULL = 0xFFFFFFFFu;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o);
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 7; ++k) s_part[wid][k] = v[k];
-    }
-    __syncthreads();
-    if (threadIdx.x < 8) {
-        double s = 0.0;
-        if (threadIdx.x < 7)
-            for (int k = 0; k < KICP_WARPS; ++k) s += s_part[k][threadIdx.x];
-        __stcg(&partials[(size_t)blockIdx.x * 8 + threadIdx.x], s);
-        __threadfence();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned ticket = atomicAdd(&st->ticket, 1u);
-        *s_last = (ticket == gridDim.x - 1);
-    }
-    __syncthreads();
-    const bool last = *s_last != 0;
-    const unsigned long long tb0 = gtime_ns();
-    if (last) {
-        __threadfence();
-        if (wid < 7) {  // warp `wid` sums column `wid` over the CTAs, lanes striding, fixed tree
-            double s = 0.0;
-            for (unsigned b0 = 0; b0 < gridDim.x; b0 += 32) {  // warp-uniform trip count
-                const unsigned b = b0 + lane;
-                if (b < gridDim.x) s += __ldcg(&partials[(size_t)b * 8 + wid]);
-                __syncwarp();
+            // ---------------------------------------------------------------- gate, residual, Jacobian, sums
+            const unsigned long long bb = sm.best[lane];
+            const unsigned gwin = (unsigned)(sm.kg[lane] & 0xFFFFFFFFull);
+            if (valid && bb != KR_DBLMAX_BITS) {
+                const Point4 c = ld_point(mr.pts + (size_t)gwin * KICP_PSTRIDE);
+                const double rx = qx - c.x, ry = qy - c.y, rz = qz - c.z;  // r = T p - n
+                const double rr = rx * rx + ry * ry + rz * rz;
+                if (sqrt(rr) < tau) {  // distance < max_correspondance_distance   (Registration.cpp:75)
+                    // J = [R e_x | R (-p_y, p_x, 0)]      (Registration.cpp:89-91)
+                    const double c0x = s_ps.R[0], c0y = s_ps.R[3], c0z = s_ps.R[6];
+                    const double c1x = s_ps.R[1] * px - s_ps.R[0] * py, c1y = s_ps.R[4] * px - s_ps.R[3] * py,
+                                 c1z = s_ps.R[7] * px - s_ps.R[6] * py;
+                    a00 += c0x * c0x + c0y * c0y + c0z * c0z;
+                    a01 += c0x * c1x + c0y * c1y + c0z * c1z;
+                    a11 += c1x * c1x + c1y * c1y + c1z * c1z;
+                    b0 += c0x * rx + c0y * ry + c0z * rz;
+                    b1 += c1x * rx + c1y * ry + c1z * rz;
+                    cntN += 1.0;
+                    ssq += rr;
+                }
             }
+            __syncwarp();
+            w = (int)(__shfl_sync(FULL, tk, 0) - ticket_base);
+        }
+
+        const unsigned long long t_win = gtime_ns();
+        // ---------------------------------------------------------------- warp -> CTA partial (plain stores, fixed order)
+        double v[7] = {a00, a01, a11, b0, b1, cntN, ssq};
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-            if (lane == 0) __stcg(&st->acc[wid], s);
+        for (int k = 0; k < 7; ++k) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], d);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) s_part[wid][k] = v[k];
+            s_part[wid][7] = 0.0;
         }
         __syncthreads();
-        if (PERSISTENT && px.nranks > 1) p2p_exchange(st, px, it);
+        double *const part = a.partials + (size_t)(PERSISTENT ? (it & 1u) : 0u) * gridDim.x * 8;
+        if (threadIdx.x < 8) {
+            double s = 0.0;
+            for (int k = 0; k < KR_WARPS; ++k) s += s_part[k][threadIdx.x];
+            __stcg(&part[(size_t)blockIdx.x * 8 + threadIdx.x], s);
+            __threadfence();
+        }
+        __syncthreads();
+
+        if (!PERSISTENT) {
+            // one pass per launch: the last CTA sums the partials into st->acc (the NCCL allreduce and k_solve follow)
+            if (threadIdx.x == 0) {
+                const unsigned ticket = atomicAdd(&st->ticket, 1u);
+                s_flag[0] = (ticket == gridDim.x - 1);
+            }
+            __syncthreads();
+            if (s_flag[0]) {
+                __threadfence();
+                if (threadIdx.x < 8) {
+                    double s = 0.0;
+                    for (unsigned bb = 0; bb < gridDim.x; ++bb) s += __ldcg(&part[(size_t)bb * 8 + threadIdx.x]);
+                    st->acc[threadIdx.x] = s;
+                }
+                if (threadIdx.x == 0) st->ticket = 0, st->win_ctr = 0;
+            }
+            if (a.collect_stats) stats_flush(st, n_probe, n_cand, n_line);
+            return;
+        }
+
+        // ---------------------------------------------------------------- grid barrier: arrive, then everyone reduces
+        const bool multi = a.px.nranks > 1;
+        unsigned long long t_arr = 0, t_red = 0;
+        if (threadIdx.x == 0) {
+            atomicAdd(&st->arrive, 1u);
+            if (!multi || blockIdx.x == 0) {
+                const unsigned target = (it + 1u) * gridDim.x;
+                const unsigned long long deadline = t_win + a.timeout_ns;  // per-thread register: no uniform read inside the spin
+                while (ld_acquire_gpu_u32(&st->arrive) < target) {
+                    if (gtime_ns() > deadline) {  // a CTA of this grid never arrived: give up instead of hanging
+                        atomicExch(&st->abort, KICP_ERR_CUDA);
+                        break;
+                    }
+                }
+            }
+            t_arr = gtime_ns();
+        }
+        __syncthreads();
+        if (!multi || blockIdx.x == 0) {
+            // column k = thread & 7, rows strided by 32: fixed summation tree, identical in every CTA
+            const int col = threadIdx.x & 7, row0 = threadIdx.x >> 3;
+            double s = 0.0;
+            const unsigned nrow = (gridDim.x + KR_THREADS / 8 - 1) / (KR_THREADS / 8);  // uniform trip count, tail predicated
+            for (unsigned kr = 0; kr < nrow; ++kr) {
+                const unsigned bb = kr * (KR_THREADS / 8) + (unsigned)row0;
+                if (bb < gridDim.x) s += __ldcg(&part[(size_t)bb * 8 + col]);
+            }
+            s += __shfl_xor_sync(FULL, s, 8);
+            s += __shfl_xor_sync(FULL, s, 16);
+            if (lane < 8) s_part[wid][lane] = s;
+            __syncthreads();
+            if (threadIdx.x < 8) {
+                double tsum = 0.0;
+                for (int k = 0; k < KR_WARPS; ++k) tsum += s_part[k][threadIdx.x];
+                s_sum[threadIdx.x] = tsum;
+            }
+            __syncthreads();
+        }
+        if (multi) {
+            // Exchange fused into the barrier (NCCL-LL style): CTA 0 writes its 8 local sums as sixteen 8-byte words
+            // {32 data bits, 32-bit tag} into EVERY rank's mailbox over NVLink — an aligned 8-byte store arrives whole, so no
+            // fence and no separate flag are needed; every CTA of every rank polls its OWN GPU's mailbox until all ranks'
+            // words carry the tag and adds them IN RANK ORDER (same values, same order -> the same pose on every rank).
+            const uint32_t tag = a.px.tag_base + it;
+            if (wid == 0) {
+                if (blockIdx.x == 0) {
+                    const double val = s_sum[(lane & 15) >> 1];
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(val);
+                    const uint32_t half = (lane & 1) ? (uint32_t)(bits >> 32) : (uint32_t)bits;
+                    const unsigned long long word = ((unsigned long long)tag << 32) | half;
+                    // lanes 16..31 repeat the stores of lanes 0..15 (same address, same value): no divergent section
+                    for (int r = 0; r < a.px.nranks; ++r) {
+                        st_relaxed_sys_u64(&a.px.peer[r]->ll[a.px.parity][it][a.px.rank][lane & 15], word);
+                        __syncwarp();
+                    }
+                }
+                __syncwarp();
+                double tot = 0.0;
+                bool timed_out = false;
+                const unsigned long long deadline = gtime_ns() + a.timeout_ns;
+                for (int r = 0; r < a.px.nranks; ++r) {
+                    unsigned long long wv = 0;
+                    const unsigned long long *src = &a.px.peer[a.px.rank]->ll[a.px.parity][it][r][lane & 15];
+                    bool pend = true;
+                    while (__any_sync(FULL, pend)) {  // warp-uniform loop
+                        if (pend) {
+                            wv = ld_relaxed_sys_u64(src);
+                            if ((uint32_t)(wv >> 32) == tag) {
+                                pend = false;
+                            } else if (gtime_ns() > deadline) {  // a peer is missing
+                                timed_out = true, pend = false;
+                            }
+                        }
+                    }
+                    const uint32_t lo = __shfl_sync(FULL, (uint32_t)wv, (lane & 7) * 2);
+                    const uint32_t hi = __shfl_sync(FULL, (uint32_t)wv, (lane & 7) * 2 + 1);
+                    tot += __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+                }
+                timed_out = __any_sync(FULL, timed_out);
+                if (lane < 8) s_sum[lane] = tot;
+                if (lane == 0) s_flag[1] = timed_out ? 1 : 0;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            t_red = gtime_ns();
+            // a wait that gave up (upload flag on this GPU, a peer's words): keep the last pose, report, leave
+            int ab = (int)ld_acquire_gpu_u32((const unsigned int *)&st->abort);
+            if (!ab && multi && s_flag[1]) ab = KICP_ERR_NCCL;
+            if (ab) {
+                s_ps.status = ab, s_ps.done = 1;
+                if (blockIdx.x == 0) st->result.status = ab;
+            } else {
+                double s[8];
+                for (int k = 0; k < 8; ++k) s[k] = s_sum[k];
+                solve_and_update(&s_ps, s, blockIdx.x == 0 ? &st->result : nullptr, blockIdx.x == 0 ? a.init.iters_out : nullptr);
+            }
+            if (blockIdx.x == 0 && it < KICP_MAX_ITERATIONS) {
+                st->dbg[it][0] = (double)(t_win - t_iter0), st->dbg[it][1] = (double)(t_arr - t_win);
+                st->dbg[it][2] = (double)(t_red - t_arr), st->dbg[it][3] = (double)(gtime_ns() - t_red);
+            }
+        }
+        __syncthreads();
+    }
+
+    if (PERSISTENT) {
+        if (a.collect_stats) stats_flush(st, n_probe, n_cand, n_line);
+        // the last CTA to leave zeroes the counters for the next registration on this stream
+        __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
-            st->ticket = 0;
-            st->window_counter = 0;
-            const unsigned long long tb1 = gtime_ns();
-            const int jdbg = st->iter;
-            if (PERSISTENT || st->fused_tail) solve_and_update(st);
-            if (jdbg < KICP_MAX_ITERATIONS) st->dbg[jdbg][2] = (double)(tb1 - tb0), st->dbg[jdbg][3] = (double)(gtime_ns() - tb1);
-            if (PERSISTENT) {
+            const unsigned left = atomicAdd(&st->exit_ctr, 1u);
+            if (left == gridDim.x - 1) {
+                st->win_ctr = 0, st->arrive = 0, st->abort = 0;
                 __threadfence();
-                atomicExch(&st->generation, it + 1u);
+                st->exit_ctr = 0;
             }
         }
     }
-    if (!PERSISTENT) return true;
-    if (threadIdx.x == 0) {
-        if (!last) {
-            while (*(volatile unsigned *)&st->generation <= it) {
-            }
-            __threadfence();
-        }
-        s_last[1] = __ldcg(&st->done);  // a different word than the ticket flag s_last[0] (other warps may still read it)
-    }
-    __syncthreads();
-    return s_last[1] != 0;
-}
-
-template <bool PERSISTENT>
-__global__ void __launch_bounds__(KICP_WARPS * 32, KICP_MINB) k_assoc_pruned(RegState *st, const double *__restrict__ scan, int n, MapView map, double *partials,
-                                                                                 P2PArgs px, UploadArgs up) {
-    if (st->done) return;
-    __shared__ double s_T[12];
-    __shared__ double s_part[KICP_WARPS][8];
-    __shared__ int s_last[2];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned FULL = 0xFFFFFFFFu;
-    __shared__ MapView s_map[32];
-    const MapRegs mr = map_regs(map, s_map);  // per-thread copy of the map view (divergence safety, kicp_device.cuh)
-    __shared__ double s_tau[32];
-    if (threadIdx.x < 32) s_tau[threadIdx.x] = st->tau;
-    __syncthreads();
-    const double tau = ((const volatile double *)s_tau)[lane], vs = map.voxel_size;
-    const int num_windows = (n + 31) >> 5;
-    // the iteration counter is read inside thread 0's spin loop of the grid barrier: keep it in a per-thread register
-    // (loaded from a lane-dependent shared address, see kicp_device.cuh) rather than in a uniform register
-    __shared__ unsigned s_zero[32];
-    if (threadIdx.x < 32) s_zero[threadIdx.x] = 0u;
-    __syncthreads();
-    unsigned it = ((const volatile unsigned *)s_zero)[lane];
-  for (;; ++it) {
-    // the current estimate: written by k_reg_init or by the last CTA of the previous iteration -> read through L2
-    if (threadIdx.x < 9) s_T[threadIdx.x] = __ldcg(&st->R[threadIdx.x]);
-    if (threadIdx.x >= 9 && threadIdx.x < 12) s_T[threadIdx.x] = __ldcg(&st->t[threadIdx.x - 9]);
-    __syncthreads();
-    double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0, cntN = 0, ssq = 0;
-    const unsigned long long t_iter0 = gtime_ns();
-
-    // dynamic window fetch (measured 15-20 % faster than a static round-robin at cfg4: windows differ in cost)
-    while (true) {
-        int w = 0;
-        if (lane == 0) w = (int)atomicAdd(&st->window_counter, 1u);
-        w = __shfl_sync(FULL, w, 0);
-        if (w >= num_windows) break;
-        if (PERSISTENT && up.flags != nullptr && it == 0u) {
-            // first pass over a frame that is still being uploaded: wait until this window's chunk has landed
-            if (lane == 0) {
-                const uint32_t *f = up.flags + min(w / up.windows_per_chunk, KICP_UPLOAD_CHUNKS - 1);
-                const long long t0 = clock64();
-                while (ld_acquire_sys_u32(f) != up.seq) {
-                    if (clock64() - t0 > 4000000000ll) {  // ~2 s: the copy never arrived
-                        st->status = KICP_ERR_CUDA;
-                        break;
-                    }
-                }
-            }
-            __syncwarp();
-        }
-        const int i = w * 32 + lane;
-        const bool valid = i < n;
-        double px = 0, py = 0, pz = 0;
-        if (valid) px = scan[3 * (size_t)i], py = scan[3 * (size_t)i + 1], pz = scan[3 * (size_t)i + 2];
-        const double qx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[9];
-        const double qy = s_T[3] * px + s_T[4] * py + s_T[5] * pz + s_T[10];
-        const double qz = s_T[6] * px + s_T[7] * py + s_T[8] * pz + s_T[11];
-        const int vx = voxel_coord(qx, vs), vy = voxel_coord(qy, vs), vz = voxel_coord(qz, vs);
-        // squared gaps to the six faces of the query voxel
-        double t;
-        t = (double)(vx + 1) * vs - qx; const double gxp = t * t;
-        t = qx - (double)vx * vs;       const double gxm = t * t;
-        t = (double)(vy + 1) * vs - qy; const double gyp = t * t;
-        t = qy - (double)vy * vs;       const double gym = t * t;
-        t = (double)(vz + 1) * vs - qz; const double gzp = t * t;
-        t = qz - (double)vz * vs;       const double gzm = t * t;
-
-        double best = DBL_MAX;
-        const double *bestp = nullptr;
-        const uint32_t tmask = mr.mask;
-        const int4 *tslots = mr.slots;
-        const double *tpts = mr.pts;
-        const size_t tstride = (size_t)mr.cap * KICP_PSTRIDE;
-        // round 0: the query's own voxel — it usually yields a best distance that prunes most of the other 26
-        if (valid) {
-            const uint32_t meta = map_probe(mr, vx, vy, vz);
-            if (meta != KICP_SLOT_EMPTY) scan_voxel(tpts + (size_t)(meta >> 8) * tstride, (int)(meta & 0xFFu), qx, qy, qz, best, bestp);
-        }
-        __syncwarp();
-        unsigned mask = valid ? 0x07FFFFFEu : 0u;  // shifts still to consider, bit k <-> voxel_shifts[k]
-        while (__any_sync(FULL, mask != 0u)) {  // warp-uniform loop; inside a round every lane walks its own voxels
-            if (mask) {
-                // drop every shift whose cube is provably too far, then take the next (up to) 4 in KISS order
-                const double bound = best * (1.0 + 1e-6) + 1e-10;
-                mask &= (kX0 | (gxp <= bound ? kXP : 0u) | (gxm <= bound ? kXM : 0u)) &
-                        (kY0 | (gyp <= bound ? kYP : 0u) | (gym <= bound ? kYM : 0u)) &
-                        (kZ0 | (gzp <= bound ? kZP : 0u) | (gzm <= bound ? kZM : 0u));
-                int kx[4], ky[4], kz[4];
-                uint32_t hh[4];
-                double lb[4];
-                bool use[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    use[u] = false;
-                    kx[u] = ky[u] = kz[u] = 0, hh[u] = 0, lb[u] = 0.0;
-                    while (mask) {
-                        const int k = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const int sx = shift_x(k), sy = shift_y(k), sz = shift_z(k);
-                        const double lb2 = (sx > 0 ? gxp : (sx < 0 ? gxm : 0.0)) + (sy > 0 ? gyp : (sy < 0 ? gym : 0.0)) +
-                                           (sz > 0 ? gzp : (sz < 0 ? gzm : 0.0));
-                        if (lb2 > bound) continue;
-                        use[u] = true, lb[u] = lb2;
-                        kx[u] = vx + sx, ky[u] = vy + sy, kz[u] = vz + sz;
-                        hh[u] = voxel_hash(kx[u], ky[u], kz[u]) & tmask;
-                        break;
-                    }
-                }
-                // four independent home-slot loads in flight, then resolve the (rare) longer probe chains
-                int4 s0[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (use[u]) s0[u] = __ldg(&tslots[hh[u]]);
-                uint32_t metas[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint32_t meta = KICP_SLOT_EMPTY;
-                    if (use[u]) {
-                        int4 sl = s0[u];
-                        uint32_t h = hh[u];
-                        while (true) {
-                            if ((uint32_t)sl.w == KICP_SLOT_EMPTY) break;
-                            if (sl.x == kx[u] && sl.y == ky[u] && sl.z == kz[u]) {
-                                meta = (uint32_t)sl.w;
-                                break;
-                            }
-                            h = (h + 1) & tmask;
-                            sl = __ldg(&tslots[h]);
-                        }
-                    }
-                    metas[u] = meta;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    // re-check against the best found meanwhile; KISS order is kept, so strict < resolves ties identically
-                    if (metas[u] != KICP_SLOT_EMPTY && !(lb[u] > best * (1.0 + 1e-6) + 1e-10))
-                        scan_voxel(tpts + (size_t)(metas[u] >> 8) * tstride, (int)(metas[u] & 0xFFu), qx, qy, qz, best, bestp);
-                }
-            }
-            __syncwarp();
-        }
-        const bool have = bestp != nullptr;
-        double bx = 0, by = 0, bz = 0;
-        if (have) {
-            const double2 a = __ldg(reinterpret_cast<const double2 *>(bestp)), b = __ldg(reinterpret_cast<const double2 *>(bestp) + 1);
-            bx = a.x, by = a.y, bz = b.x;
-        }
-        if (have) {
-            const double rx = qx - bx, ry = qy - by, rz = qz - bz;  // r = T p - n
-            const double rr = rx * rx + ry * ry + rz * rz;
-            if (sqrt(rr) < tau) {  // distance < max_correspondance_distance   (Registration.cpp:75)
-                const double c0x = s_T[0], c0y = s_T[3], c0z = s_T[6];
-                const double c1x = s_T[1] * px - s_T[0] * py, c1y = s_T[4] * px - s_T[3] * py, c1z = s_T[7] * px - s_T[6] * py;
-                a00 += c0x * c0x + c0y * c0y + c0z * c0z;
-                a01 += c0x * c1x + c0y * c1y + c0z * c1z;
-                a11 += c1x * c1x + c1y * c1y + c1z * c1z;
-                b0 += c0x * rx + c0y * ry + c0z * rz;
-                b1 += c1x * rx + c1y * ry + c1z * rz;
-                cntN += 1.0;
-                ssq += rr;
-            }
-        }
-    }
-
-    if (blockIdx.x == 0 && threadIdx.x == 0 && it < KICP_MAX_ITERATIONS) st->dbg[it][0] = (double)(gtime_ns() - t_iter0);
-    double v[7] = {a00, a01, a11, b0, b1, cntN, ssq};
-    if (reduce_and_finish<PERSISTENT>(st, partials, v, it, s_part, s_last, px)) return;
-  }
-}
-
-
-// ---------------------------------------------------------------------------------------------------------------
-// k_assoc_group4 (variant 2): the same exact-pruning search with FOUR LANES PER SCAN POINT (a warp-window = 8 points).
-// The pruned path is bound by the serial latency of one window (cfg2: 43 us per iteration with less than one window
-// per warp), so the search of one point is spread over a 4-lane group:
-//   - every lane of the group probes a different neighbour voxel (4 hash probes in flight per point, 1 per lane);
-//   - the group strides over a voxel's points (lane s takes points s, s+4, ...: one coalesced 128-byte row per step);
-//   - the best squared distance is min-reduced over the group (2 shuffles) between rounds so pruning stays tight.
-// The winner is the minimum of (d2, order key) with order key = (KISS shift index, index in voxel), i.e. the first
-// minimum in the reference's visiting order.  Windows are 4x smaller, so the end-of-launch tail shrinks as well.
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double group4_min(double x) {
-    const unsigned FULL = 0xFFFFFFFFu;
-    x = fmin(x, __shfl_xor_sync(FULL, x, 1));
-    x = fmin(x, __shfl_xor_sync(FULL, x, 2));
-    return x;
-}
-
-template <bool PERSISTENT>
-__global__ void __launch_bounds__(KICP_WARPS * 32, KICP_MINB) k_assoc_group4(RegState *st, const double *__restrict__ scan, int n, MapView map,
-                                                                      double *partials, int pow2_voxel, P2PArgs px) {
-    if (st->done) return;
-    __shared__ double s_T[12];
-    __shared__ double s_part[KICP_WARPS][8];
-    __shared__ int s_last[2];
-    const int lane = threadIdx.x & 31;
-    const int sub = lane & 3;
-    const unsigned FULL = 0xFFFFFFFFu;
-    __shared__ MapView s_map[32];
-    const MapRegs mr = map_regs(map, s_map);  // per-thread copy of the map view (divergence safety, kicp_device.cuh)
-    __shared__ double s_tau[32];
-    if (threadIdx.x < 32) s_tau[threadIdx.x] = st->tau;
-    __syncthreads();
-    const double tau = ((const volatile double *)s_tau)[lane], vs = map.voxel_size, inv_vs = 1.0 / map.voxel_size;
-    const int num_windows = (n + 7) >> 3;
-    __shared__ unsigned s_zero[32];
-    if (threadIdx.x < 32) s_zero[threadIdx.x] = 0u;
-    __syncthreads();
-    unsigned it = ((const volatile unsigned *)s_zero)[lane];
-    const uint32_t tmask = mr.mask;
-    const int4 *tslots = mr.slots;
-    const double *tpts = mr.pts;
-    const size_t tstride = (size_t)mr.cap * KICP_PSTRIDE;
-  for (;; ++it) {
-    if (threadIdx.x < 9) s_T[threadIdx.x] = __ldcg(&st->R[threadIdx.x]);
-    if (threadIdx.x >= 9 && threadIdx.x < 12) s_T[threadIdx.x] = __ldcg(&st->t[threadIdx.x - 9]);
-    __syncthreads();
-    double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0, cntN = 0, ssq = 0;
-    const unsigned long long t_iter0 = gtime_ns();
-
-    while (true) {
-        int w = 0;
-        if (lane == 0) w = (int)atomicAdd(&st->window_counter, 1u);
-        w = __shfl_sync(FULL, w, 0);
-        if (w >= num_windows) break;
-        const int i = w * 8 + (lane >> 2);
-        const bool valid = i < n;
-        double px = 0, py = 0, pz = 0;
-        if (valid) px = scan[3 * (size_t)i], py = scan[3 * (size_t)i + 1], pz = scan[3 * (size_t)i + 2];
-        const double qx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[9];
-        const double qy = s_T[3] * px + s_T[4] * py + s_T[5] * pz + s_T[10];
-        const double qz = s_T[6] * px + s_T[7] * py + s_T[8] * pz + s_T[11];
-        // PointToVoxel: floor(q / voxel_size); for a power-of-two voxel size the product with the (exact) reciprocal
-        // is the same double as the quotient, so the cheaper form is used
-        int vx, vy, vz;
-        if (pow2_voxel) {
-            vx = (int)floor(qx * inv_vs), vy = (int)floor(qy * inv_vs), vz = (int)floor(qz * inv_vs);
-        } else {
-            vx = voxel_coord(qx, vs), vy = voxel_coord(qy, vs), vz = voxel_coord(qz, vs);
-        }
-        double t;
-        t = (double)(vx + 1) * vs - qx; const double gxp = t * t;
-        t = qx - (double)vx * vs;       const double gxm = t * t;
-        t = (double)(vy + 1) * vs - qy; const double gyp = t * t;
-        t = qy - (double)vy * vs;       const double gym = t * t;
-        t = (double)(vz + 1) * vs - qz; const double gzp = t * t;
-        t = qz - (double)vz * vs;       const double gzm = t * t;
-
-        double best = DBL_MAX;            // this lane's best
-        unsigned bestkey = 0xFFFFFFFFu;   // (shift index << 8) | index in voxel of this lane's best
-        const double *bestp = nullptr;
-        // round 0: the query's own voxel, its points strided over the 4 lanes
-        if (valid) {
-            const uint32_t meta = map_probe(mr, vx, vy, vz);
-            if (meta != KICP_SLOT_EMPTY) {
-                const double *vp = tpts + (size_t)(meta >> 8) * tstride;
-                const int cnt = (int)(meta & 0xFFu);
-                for (int j = sub; j < cnt; j += 4) {
-                    const double *p0 = vp + (size_t)j * KICP_PSTRIDE;
-                    const double2 a = __ldg(reinterpret_cast<const double2 *>(p0)), b = __ldg(reinterpret_cast<const double2 *>(p0) + 1);
-                    const double dx = a.x - qx, dy = a.y - qy, dz = b.x - qz;
-                    const double d2 = dx * dx + dy * dy + dz * dz;
-                    if (d2 < best) best = d2, bestkey = (unsigned)j, bestp = p0;
-                }
-            }
-        }
-        __syncwarp();
-        double gbest = group4_min(best);
-        unsigned mask = valid ? 0x07FFFFFEu : 0u;  // identical in the 4 lanes of a group
-        while (__any_sync(FULL, mask != 0u)) {
-            uint32_t meta = KICP_SLOT_EMPTY;
-            int myk = 0;
-            double lb[4] = {0.0, 0.0, 0.0, 0.0};
-            if (mask) {
-                const double bound = gbest * (1.0 + 1e-6) + 1e-10;
-                mask &= (kX0 | (gxp <= bound ? kXP : 0u) | (gxm <= bound ? kXM : 0u)) &
-                        (kY0 | (gyp <= bound ? kYP : 0u) | (gym <= bound ? kYM : 0u)) &
-                        (kZ0 | (gzp <= bound ? kZP : 0u) | (gzm <= bound ? kZM : 0u));
-                // the next (up to) 4 shifts in KISS order that survive the exact bound; lane `sub` probes the sub-th one
-                int kxs = 0, kys = 0, kzs = 0;
-                bool use = false;
-                int found = 0;
-                while (mask && found < 4) {
-                    const int k = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const int sx = shift_x(k), sy = shift_y(k), sz = shift_z(k);
-                    const double lb2 = (sx > 0 ? gxp : (sx < 0 ? gxm : 0.0)) + (sy > 0 ? gyp : (sy < 0 ? gym : 0.0)) +
-                                       (sz > 0 ? gzp : (sz < 0 ? gzm : 0.0));
-                    if (lb2 > bound) continue;
-                    if (found == 0) lb[0] = lb2;
-                    if (found == 1) lb[1] = lb2;
-                    if (found == 2) lb[2] = lb2;
-                    if (found == 3) lb[3] = lb2;
-                    if (found == sub) use = true, myk = k, kxs = vx + sx, kys = vy + sy, kzs = vz + sz;
-                    ++found;
-                }
-                if (use) {
-                    uint32_t h = voxel_hash(kxs, kys, kzs) & tmask;
-                    while (true) {
-                        const int4 sl = __ldg(&tslots[h]);
-                        if ((uint32_t)sl.w == KICP_SLOT_EMPTY) break;
-                        if (sl.x == kxs && sl.y == kys && sl.z == kzs) {
-                            meta = (uint32_t)sl.w;
-                            break;
-                        }
-                        h = (h + 1) & tmask;
-                    }
-                }
-            }
-            __syncwarp();
-            // every lane of the group learns the 4 probe results, then the group scans the found voxels in KISS order
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t mu = __shfl_sync(FULL, meta, (lane & ~3) | u);
-                const int ku = __shfl_sync(FULL, myk, (lane & ~3) | u);
-                if (mu != KICP_SLOT_EMPTY && !(lb[u] > best * (1.0 + 1e-6) + 1e-10)) {
-                    const double *vp = tpts + (size_t)(mu >> 8) * tstride;
-                    const int cnt = (int)(mu & 0xFFu);
-                    for (int j = sub; j < cnt; j += 4) {
-                        const double *p0 = vp + (size_t)j * KICP_PSTRIDE;
-                        const double2 a = __ldg(reinterpret_cast<const double2 *>(p0)), b = __ldg(reinterpret_cast<const double2 *>(p0) + 1);
-                        const double dx = a.x - qx, dy = a.y - qy, dz = b.x - qz;
-                        const double d2 = dx * dx + dy * dy + dz * dz;
-                        if (d2 < best) best = d2, bestkey = ((unsigned)ku << 8) | (unsigned)j, bestp = p0;
-                    }
-                }
-                __syncwarp();
-            }
-            gbest = group4_min(best);
-        }
-        // the group's winner: minimum of (d2, order key) — the first minimum in the reference's visiting order
-#pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {
-            const double od = __shfl_xor_sync(FULL, best, o);
-            const unsigned ok = __shfl_xor_sync(FULL, bestkey, o);
-            const unsigned long long op = __shfl_xor_sync(FULL, (unsigned long long)bestp, o);
-            if (od < best || (od == best && ok < bestkey)) best = od, bestkey = ok, bestp = (const double *)op;
-        }
-        if (sub == 0 && bestp != nullptr) {
-            const double2 a = __ldg(reinterpret_cast<const double2 *>(bestp)), b = __ldg(reinterpret_cast<const double2 *>(bestp) + 1);
-            const double rx = qx - a.x, ry = qy - a.y, rz = qz - b.x;  // r = T p - n
-            const double rr = rx * rx + ry * ry + rz * rz;
-            if (sqrt(rr) < tau) {  // distance < max_correspondance_distance   (Registration.cpp:75)
-                const double c0x = s_T[0], c0y = s_T[3], c0z = s_T[6];
-                const double c1x = s_T[1] * px - s_T[0] * py, c1y = s_T[4] * px - s_T[3] * py, c1z = s_T[7] * px - s_T[6] * py;
-                a00 += c0x * c0x + c0y * c0y + c0z * c0z;
-                a01 += c0x * c1x + c0y * c1y + c0z * c1z;
-                a11 += c1x * c1x + c1y * c1y + c1z * c1z;
-                b0 += c0x * rx + c0y * ry + c0z * rz;
-                b1 += c1x * rx + c1y * ry + c1z * rz;
-                cntN += 1.0;
-                ssq += rr;
-            }
-        }
-        __syncwarp();
-    }
-
-    if (blockIdx.x == 0 && threadIdx.x == 0 && it < KICP_MAX_ITERATIONS) st->dbg[it][0] = (double)(gtime_ns() - t_iter0);
-    double v[7] = {a00, a01, a11, b0, b1, cntN, ssq};
-    if (reduce_and_finish<PERSISTENT>(st, partials, v, it, s_part, s_last, px)) return;
-  }
-}
-
-
-// ---------------------------------------------------------------------------------------------------------------
-// k_assoc_hybrid (variant 3, default): one pass = 32-point windows (k_assoc_pruned's body, the efficient one for the
-// bulk) followed by 8-point group windows (k_assoc_group4's body) for the last KICP_TAIL_PERCENT of the points.  Work
-// units are handed out in increasing order from one counter, so the small units come last and the end-of-pass tail is
-// the duration of an 8-point window (about 5 us) instead of a 32-point one (about 18 us).
-// ---------------------------------------------------------------------------------------------------------------
-#ifndef KICP_TAIL_PERCENT
-#define KICP_TAIL_PERCENT 15
-#endif
-template <bool PERSISTENT>
-__global__ void __launch_bounds__(KICP_WARPS * 32, KICP_MINB) k_assoc_hybrid(RegState *st, const double *__restrict__ scan, int n, MapView map,
-                                                                              double *partials, int pow2_voxel, P2PArgs px, UploadArgs up) {
-    if (st->done) return;
-    __shared__ double s_T[12];
-    __shared__ double s_part[KICP_WARPS][8];
-    __shared__ int s_last[2];
-    const int lane = threadIdx.x & 31;
-    const int sub = lane & 3;
-    const unsigned FULL = 0xFFFFFFFFu;
-    __shared__ MapView s_map[32];
-    const MapRegs mr = map_regs(map, s_map);  // per-thread copy of the map view (divergence safety, kicp_device.cuh)
-    __shared__ double s_tau[32];
-    if (threadIdx.x < 32) s_tau[threadIdx.x] = st->tau;
-    __syncthreads();
-    const double tau = ((const volatile double *)s_tau)[lane], vs = map.voxel_size, inv_vs = 1.0 / map.voxel_size;
-    // bulk: 32-point windows over the first points; tail: 8-point units over the rest
-    const int all32 = (n + 31) >> 5;
-    const int num_big = n >= 4096 ? (int)((long long)all32 * (100 - KICP_TAIL_PERCENT) / 100) : all32;
-    const int base8 = min(n, num_big * 32);
-    const int num_units = num_big + ((n - base8 + 7) >> 3);
-    __shared__ unsigned s_zero[32];
-    if (threadIdx.x < 32) s_zero[threadIdx.x] = 0u;
-    __syncthreads();
-    unsigned it = ((const volatile unsigned *)s_zero)[lane];
-    const uint32_t tmask = mr.mask;
-    const int4 *tslots = mr.slots;
-    const double *tpts = mr.pts;
-    const size_t tstride = (size_t)mr.cap * KICP_PSTRIDE;
-  for (;; ++it) {
-    if (threadIdx.x < 9) s_T[threadIdx.x] = __ldcg(&st->R[threadIdx.x]);
-    if (threadIdx.x >= 9 && threadIdx.x < 12) s_T[threadIdx.x] = __ldcg(&st->t[threadIdx.x - 9]);
-    __syncthreads();
-    double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0, cntN = 0, ssq = 0;
-    const unsigned long long t_iter0 = gtime_ns();
-
-    while (true) {
-        int w = 0;
-        if (lane == 0) w = (int)atomicAdd(&st->window_counter, 1u);
-        w = __shfl_sync(FULL, w, 0);
-        if (w >= num_units) break;
-        if (PERSISTENT && up.flags != nullptr && it == 0u) {
-            // first pass over a frame that is still being uploaded: wait until this unit's chunk has landed
-            if (lane == 0) {
-                const int w32 = w < num_big ? w : (base8 + (w - num_big) * 8) >> 5;
-                const uint32_t *f = up.flags + min(w32 / up.windows_per_chunk, KICP_UPLOAD_CHUNKS - 1);
-                const long long t0 = clock64();
-                while (ld_acquire_sys_u32(f) != up.seq) {
-                    if (clock64() - t0 > 4000000000ll) {
-                        st->status = KICP_ERR_CUDA;
-                        break;
-                    }
-                }
-            }
-            __syncwarp();
-        }
-        if (w < num_big) {
-        const int i = w * 32 + lane;
-        const bool valid = i < n;
-        double px = 0, py = 0, pz = 0;
-        if (valid) px = scan[3 * (size_t)i], py = scan[3 * (size_t)i + 1], pz = scan[3 * (size_t)i + 2];
-        const double qx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[9];
-        const double qy = s_T[3] * px + s_T[4] * py + s_T[5] * pz + s_T[10];
-        const double qz = s_T[6] * px + s_T[7] * py + s_T[8] * pz + s_T[11];
-        const int vx = voxel_coord(qx, vs), vy = voxel_coord(qy, vs), vz = voxel_coord(qz, vs);
-        // squared gaps to the six faces of the query voxel
-        double t;
-        t = (double)(vx + 1) * vs - qx; const double gxp = t * t;
-        t = qx - (double)vx * vs;       const double gxm = t * t;
-        t = (double)(vy + 1) * vs - qy; const double gyp = t * t;
-        t = qy - (double)vy * vs;       const double gym = t * t;
-        t = (double)(vz + 1) * vs - qz; const double gzp = t * t;
-        t = qz - (double)vz * vs;       const double gzm = t * t;
-
-        double best = DBL_MAX;
-        const double *bestp = nullptr;
-        const uint32_t tmask = mr.mask;
-        const int4 *tslots = mr.slots;
-        const double *tpts = mr.pts;
-        const size_t tstride = (size_t)mr.cap * KICP_PSTRIDE;
-        // round 0: the query's own voxel — it usually yields a best distance that prunes most of the other 26
-        if (valid) {
-            const uint32_t meta = map_probe(mr, vx, vy, vz);
-            if (meta != KICP_SLOT_EMPTY) scan_voxel(tpts + (size_t)(meta >> 8) * tstride, (int)(meta & 0xFFu), qx, qy, qz, best, bestp);
-        }
-        __syncwarp();
-        unsigned mask = valid ? 0x07FFFFFEu : 0u;  // shifts still to consider, bit k <-> voxel_shifts[k]
-        while (__any_sync(FULL, mask != 0u)) {  // warp-uniform loop; inside a round every lane walks its own voxels
-            if (mask) {
-                // drop every shift whose cube is provably too far, then take the next (up to) 4 in KISS order
-                const double bound = best * (1.0 + 1e-6) + 1e-10;
-                mask &= (kX0 | (gxp <= bound ? kXP : 0u) | (gxm <= bound ? kXM : 0u)) &
-                        (kY0 | (gyp <= bound ? kYP : 0u) | (gym <= bound ? kYM : 0u)) &
-                        (kZ0 | (gzp <= bound ? kZP : 0u) | (gzm <= bound ? kZM : 0u));
-                int kx[4], ky[4], kz[4];
-                uint32_t hh[4];
-                double lb[4];
-                bool use[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    use[u] = false;
-                    kx[u] = ky[u] = kz[u] = 0, hh[u] = 0, lb[u] = 0.0;
-                    while (mask) {
-                        const int k = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const int sx = shift_x(k), sy = shift_y(k), sz = shift_z(k);
-                        const double lb2 = (sx > 0 ? gxp : (sx < 0 ? gxm : 0.0)) + (sy > 0 ? gyp : (sy < 0 ? gym : 0.0)) +
-                                           (sz > 0 ? gzp : (sz < 0 ? gzm : 0.0));
-                        if (lb2 > bound) continue;
-                        use[u] = true, lb[u] = lb2;
-                        kx[u] = vx + sx, ky[u] = vy + sy, kz[u] = vz + sz;
-                        hh[u] = voxel_hash(kx[u], ky[u], kz[u]) & tmask;
-                        break;
-                    }
-                }
-                // four independent home-slot loads in flight, then resolve the (rare) longer probe chains
-                int4 s0[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (use[u]) s0[u] = __ldg(&tslots[hh[u]]);
-                uint32_t metas[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint32_t meta = KICP_SLOT_EMPTY;
-                    if (use[u]) {
-                        int4 sl = s0[u];
-                        uint32_t h = hh[u];
-                        while (true) {
-                            if ((uint32_t)sl.w == KICP_SLOT_EMPTY) break;
-                            if (sl.x == kx[u] && sl.y == ky[u] && sl.z == kz[u]) {
-                                meta = (uint32_t)sl.w;
-                                break;
-                            }
-                            h = (h + 1) & tmask;
-                            sl = __ldg(&tslots[h]);
-                        }
-                    }
-                    metas[u] = meta;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    // re-check against the best found meanwhile; KISS order is kept, so strict < resolves ties identically
-                    if (metas[u] != KICP_SLOT_EMPTY && !(lb[u] > best * (1.0 + 1e-6) + 1e-10))
-                        scan_voxel(tpts + (size_t)(metas[u] >> 8) * tstride, (int)(metas[u] & 0xFFu), qx, qy, qz, best, bestp);
-                }
-            }
-            __syncwarp();
-        }
-        const bool have = bestp != nullptr;
-        double bx = 0, by = 0, bz = 0;
-        if (have) {
-            const double2 a = __ldg(reinterpret_cast<const double2 *>(bestp)), b = __ldg(reinterpret_cast<const double2 *>(bestp) + 1);
-            bx = a.x, by = a.y, bz = b.x;
-        }
-        if (have) {
-            const double rx = qx - bx, ry = qy - by, rz = qz - bz;  // r = T p - n
-            const double rr = rx * rx + ry * ry + rz * rz;
-            if (sqrt(rr) < tau) {  // distance < max_correspondance_distance   (Registration.cpp:75)
-                const double c0x = s_T[0], c0y = s_T[3], c0z = s_T[6];
-                const double c1x = s_T[1] * px - s_T[0] * py, c1y = s_T[4] * px - s_T[3] * py, c1z = s_T[7] * px - s_T[6] * py;
-                a00 += c0x * c0x + c0y * c0y + c0z * c0z;
-                a01 += c0x * c1x + c0y * c1y + c0z * c1z;
-                a11 += c1x * c1x + c1y * c1y + c1z * c1z;
-                b0 += c0x * rx + c0y * ry + c0z * rz;
-                b1 += c1x * rx + c1y * ry + c1z * rz;
-                cntN += 1.0;
-                ssq += rr;
-            }
-        }
-
-        } else {
-        const int i = base8 + (w - num_big) * 8 + (lane >> 2);
-        const bool valid = i < n;
-        double px = 0, py = 0, pz = 0;
-        if (valid) px = scan[3 * (size_t)i], py = scan[3 * (size_t)i + 1], pz = scan[3 * (size_t)i + 2];
-        const double qx = s_T[0] * px + s_T[1] * py + s_T[2] * pz + s_T[9];
-        const double qy = s_T[3] * px + s_T[4] * py + s_T[5] * pz + s_T[10];
-        const double qz = s_T[6] * px + s_T[7] * py + s_T[8] * pz + s_T[11];
-        // PointToVoxel: floor(q / voxel_size); for a power-of-two voxel size the product with the (exact) reciprocal
-        // is the same double as the quotient, so the cheaper form is used
-        int vx, vy, vz;
-        if (pow2_voxel) {
-            vx = (int)floor(qx * inv_vs), vy = (int)floor(qy * inv_vs), vz = (int)floor(qz * inv_vs);
-        } else {
-            vx = voxel_coord(qx, vs), vy = voxel_coord(qy, vs), vz = voxel_coord(qz, vs);
-        }
-        double t;
-        t = (double)(vx + 1) * vs - qx; const double gxp = t * t;
-        t = qx - (double)vx * vs;       const double gxm = t * t;
-        t = (double)(vy + 1) * vs - qy; const double gyp = t * t;
-        t = qy - (double)vy * vs;       const double gym = t * t;
-        t = (double)(vz + 1) * vs - qz; const double gzp = t * t;
-        t = qz - (double)vz * vs;       const double gzm = t * t;
-
-        double best = DBL_MAX;            // this lane's best
-        unsigned bestkey = 0xFFFFFFFFu;   // (shift index << 8) | index in voxel of this lane's best
-        const double *bestp = nullptr;
-        // round 0: the query's own voxel, its points strided over the 4 lanes
-        if (valid) {
-            const uint32_t meta = map_probe(mr, vx, vy, vz);
-            if (meta != KICP_SLOT_EMPTY) {
-                const double *vp = tpts + (size_t)(meta >> 8) * tstride;
-                const int cnt = (int)(meta & 0xFFu);
-                for (int j = sub; j < cnt; j += 4) {
-                    const double *p0 = vp + (size_t)j * KICP_PSTRIDE;
-                    const double2 a = __ldg(reinterpret_cast<const double2 *>(p0)), b = __ldg(reinterpret_cast<const double2 *>(p0) + 1);
-                    const double dx = a.x - qx, dy = a.y - qy, dz = b.x - qz;
-                    const double d2 = dx * dx + dy * dy + dz * dz;
-                    if (d2 < best) best = d2, bestkey = (unsigned)j, bestp = p0;
-                }
-            }
-        }
-        __syncwarp();
-        double gbest = group4_min(best);
-        unsigned mask = valid ? 0x07FFFFFEu : 0u;  // identical in the 4 lanes of a group
-        while (__any_sync(FULL, mask != 0u)) {
-            uint32_t meta = KICP_SLOT_EMPTY;
-            int myk = 0;
-            double lb[4] = {0.0, 0.0, 0.0, 0.0};
-            if (mask) {
-                const double bound = gbest * (1.0 + 1e-6) + 1e-10;
-                mask &= (kX0 | (gxp <= bound ? kXP : 0u) | (gxm <= bound ? kXM : 0u)) &
-                        (kY0 | (gyp <= bound ? kYP : 0u) | (gym <= bound ? kYM : 0u)) &
-                        (kZ0 | (gzp <= bound ? kZP : 0u) | (gzm <= bound ? kZM : 0u));
-                // the next (up to) 4 shifts in KISS order that survive the exact bound; lane `sub` probes the sub-th one
-                int kxs = 0, kys = 0, kzs = 0;
-                bool use = false;
-                int found = 0;
-                while (mask && found < 4) {
-                    const int k = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const int sx = shift_x(k), sy = shift_y(k), sz = shift_z(k);
-                    const double lb2 = (sx > 0 ? gxp : (sx < 0 ? gxm : 0.0)) + (sy > 0 ? gyp : (sy < 0 ? gym : 0.0)) +
-                                       (sz > 0 ? gzp : (sz < 0 ? gzm : 0.0));
-                    if (lb2 > bound) continue;
-                    if (found == 0) lb[0] = lb2;
-                    if (found == 1) lb[1] = lb2;
-                    if (found == 2) lb[2] = lb2;
-                    if (found == 3) lb[3] = lb2;
-                    if (found == sub) use = true, myk = k, kxs = vx + sx, kys = vy + sy, kzs = vz + sz;
-                    ++found;
-                }
-                if (use) {
-                    uint32_t h = voxel_hash(kxs, kys, kzs) & tmask;
-                    while (true) {
-                        const int4 sl = __ldg(&tslots[h]);
-                        if ((uint32_t)sl.w == KICP_SLOT_EMPTY) break;
-                        if (sl.x == kxs && sl.y == kys && sl.z == kzs) {
-                            meta = (uint32_t)sl.w;
-                            break;
-                        }
-                        h = (h + 1) & tmask;
-                    }
-                }
-            }
-            __syncwarp();
-            // every lane of the group learns the 4 probe results, then the group scans the found voxels in KISS order
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t mu = __shfl_sync(FULL, meta, (lane & ~3) | u);
-                const int ku = __shfl_sync(FULL, myk, (lane & ~3) | u);
-                if (mu != KICP_SLOT_EMPTY && !(lb[u] > best * (1.0 + 1e-6) + 1e-10)) {
-                    const double *vp = tpts + (size_t)(mu >> 8) * tstride;
-                    const int cnt = (int)(mu & 0xFFu);
-                    for (int j = sub; j < cnt; j += 4) {
-                        const double *p0 = vp + (size_t)j * KICP_PSTRIDE;
-                        const double2 a = __ldg(reinterpret_cast<const double2 *>(p0)), b = __ldg(reinterpret_cast<const double2 *>(p0) + 1);
-                        const double dx = a.x - qx, dy = a.y - qy, dz = b.x - qz;
-                        const double d2 = dx * dx + dy * dy + dz * dz;
-                        if (d2 < best) best = d2, bestkey = ((unsigned)ku << 8) | (unsigned)j, bestp = p0;
-                    }
-                }
-                __syncwarp();
-            }
-            gbest = group4_min(best);
-        }
-        // the group's winner: minimum of (d2, order key) — the first minimum in the reference's visiting order
-#pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {
-            const double od = __shfl_xor_sync(FULL, best, o);
-            const unsigned ok = __shfl_xor_sync(FULL, bestkey, o);
-            const unsigned long long op = __shfl_xor_sync(FULL, (unsigned long long)bestp, o);
-            if (od < best || (od == best && ok < bestkey)) best = od, bestkey = ok, bestp = (const double *)op;
-        }
-        if (sub == 0 && bestp != nullptr) {
-            const double2 a = __ldg(reinterpret_cast<const double2 *>(bestp)), b = __ldg(reinterpret_cast<const double2 *>(bestp) + 1);
-            const double rx = qx - a.x, ry = qy - a.y, rz = qz - b.x;  // r = T p - n
-            const double rr = rx * rx + ry * ry + rz * rz;
-            if (sqrt(rr) < tau) {  // distance < max_correspondance_distance   (Registration.cpp:75)
-                const double c0x = s_T[0], c0y = s_T[3], c0z = s_T[6];
-                const double c1x = s_T[1] * px - s_T[0] * py, c1y = s_T[4] * px - s_T[3] * py, c1z = s_T[7] * px - s_T[6] * py;
-                a00 += c0x * c0x + c0y * c0y + c0z * c0z;
-                a01 += c0x * c1x + c0y * c1y + c0z * c1z;
-                a11 += c1x * c1x + c1y * c1y + c1z * c1z;
-                b0 += c0x * rx + c0y * ry + c0z * rz;
-                b1 += c1x * rx + c1y * ry + c1z * rz;
-                cntN += 1.0;
-                ssq += rr;
-            }
-        }
-        __syncwarp();
-
-        }
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && it < KICP_MAX_ITERATIONS) st->dbg[it][0] = (double)(gtime_ns() - t_iter0);
-    double v[7] = {a00, a01, a11, b0, b1, cntN, ssq};
-    if (reduce_and_finish<PERSISTENT>(st, partials, v, it, s_part, s_last, px)) return;
-  }
 }
 
 // ------------------------------------------------------------------------------------------------------- host
-// Kernel variant and binning granularity are per-context options (kicp_ctx_set_option); the defaults are the
-// measured best (profiles/) and can be overridden with KICP_ASSOC=staged|pruned and KICP_SORT_BITS=0..30 so that
-// bench.py / ncu can compare variants on the same inputs.
+// Per-context options (kicp_ctx_set_option): "persistent" 1 = one cooperative launch per registration (default), 0 = one
+// launch per IRLS iteration; "stats" 1 = count probes / candidate points / lines on the device (kicp_debug_last_stats);
+// "ctas_per_sm" caps the resident CTAs per SM the grid is sized for (0 = occupancy limit); "spin_timeout_ms" bounds every
+// device-side wait (upload flags, peers of the fused exchange).
 extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value) {
     if (!c || !name) return KICP_ERR_INVALID;
-    if (!strcmp(name, "assoc_variant")) {
-        if (value < 0 || value > 3) return KICP_ERR_INVALID;
-        c->assoc_variant = value;
-    } else if (!strcmp(name, "persistent")) {
+    if (!strcmp(name, "persistent")) {
         if (value != 0 && value != 1) return KICP_ERR_INVALID;
         c->persistent = value;
-    } else if (!strcmp(name, "sort_bits")) {
-        if (value < 0 || value > 30) return KICP_ERR_INVALID;
-        c->sort_bits = value;
-    } else if (!strcmp(name, "launch_first")) {
+    } else if (!strcmp(name, "stats")) {
         if (value != 0 && value != 1) return KICP_ERR_INVALID;
-        c->launch_first = value;
-    } else if (!strcmp(name, "group4_below")) {
-        if (value < 0) return KICP_ERR_INVALID;
-        c->group4_below = value;
+        c->collect_stats = value;
+    } else if (!strcmp(name, "ctas_per_sm")) {
+        if (value < 0 || value > 16) return KICP_ERR_INVALID;
+        c->ctas_per_sm_cap = value;
+    } else if (!strcmp(name, "spin_timeout_ms")) {
+        if (value < 1) return KICP_ERR_INVALID;
+        c->spin_timeout_ms = value;
+    } else if (!strcmp(name, "overlap_upload")) {
+        if (value != 0 && value != 1) return KICP_ERR_INVALID;
+        c->overlap_upload = value;
     } else {
+        kicp_set_error(std::string("kicp_ctx_set_option: unknown option ") + name);
         return KICP_ERR_INVALID;
     }
     return KICP_OK;
 }
 
-static size_t assoc_smem_bytes() {
-    return (size_t)KICP_WARPS * ((3 * KICP_CH + 3 * 32 + 32) * sizeof(double) + (KICP_CH + 32) * sizeof(int));
-}
-
-static int reg_reserve(kicp_ctx *c, int64_t n) {
-    if (!c->d_state) {
-        KICP_CUDA(cudaMalloc(&c->d_state, sizeof(RegState)));
-        KICP_CUDA(cudaMalloc(&c->d_partials, (size_t)c->sm_count * 16 * 8 * sizeof(double)));
-        KICP_CUDA(cudaFuncSetAttribute(k_assoc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)assoc_smem_bytes()));
-        int per_sm = 0;
-        KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc, KICP_WARPS * 32, assoc_smem_bytes()));
-        c->assoc_ctas_per_sm = std::max(per_sm, 1);
-        KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc_pruned<false>, KICP_WARPS * 32, 0));
-        c->pruned_ctas_per_sm = std::max(per_sm, 1);
-        KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc_pruned<true>, KICP_WARPS * 32, 0));
-        c->persistent_ctas_per_sm = std::max(per_sm, 1);
-        KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc_group4<true>, KICP_WARPS * 32, 0));
-        c->group4_ctas_per_sm = std::max(per_sm, 1);
-        KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc_group4<false>, KICP_WARPS * 32, 0));
-        c->group4_ctas_per_sm = std::min(c->group4_ctas_per_sm, std::max(per_sm, 1));
-        KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc_hybrid<true>, KICP_WARPS * 32, 0));
-        c->hybrid_ctas_per_sm = std::max(per_sm, 1);
-        KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assoc_hybrid<false>, KICP_WARPS * 32, 0));
-        c->hybrid_ctas_per_sm = std::min(c->hybrid_ctas_per_sm, std::max(per_sm, 1));
-        int coop = 0;
-        KICP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
-        if (!coop) c->persistent = 0;
-    }
-    if (n <= c->scratch_cap) return KICP_OK;
-    KICP_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(c->d_sorted), cudaFree(c->d_keys), cudaFree(c->d_keys_alt), cudaFree(c->d_idx), cudaFree(c->d_idx_alt);
-    cudaFree(c->d_sort_tmp);
-    c->d_sorted = nullptr, c->d_keys = c->d_keys_alt = nullptr, c->d_idx = c->d_idx_alt = nullptr, c->d_sort_tmp = nullptr;
-    const int64_t cap = std::max<int64_t>(n + n / 4, 4096);
-    KICP_CUDA(cudaMalloc(&c->d_sorted, (size_t)cap * 3 * sizeof(double)));
-    KICP_CUDA(cudaMalloc(&c->d_keys, (size_t)cap * sizeof(uint32_t)));
-    KICP_CUDA(cudaMalloc(&c->d_keys_alt, (size_t)cap * sizeof(uint32_t)));
-    KICP_CUDA(cudaMalloc(&c->d_idx, (size_t)cap * sizeof(int32_t)));
-    KICP_CUDA(cudaMalloc(&c->d_idx_alt, (size_t)cap * sizeof(int32_t)));
-    size_t bytes = 0;
-    KICP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->d_keys, c->d_keys_alt, c->d_idx, c->d_idx_alt, (int)cap, 0, 30,
-                                              c->stream));
-    KICP_CUDA(cudaMalloc(&c->d_sort_tmp, bytes));
-    c->sort_tmp_bytes = bytes;
-    c->scratch_cap = cap;
+static int reg_reserve(kicp_ctx *c) {
+    if (c->d_state) return KICP_OK;
+    KICP_CUDA(cudaMalloc(&c->d_state, sizeof(RegState)));
+    KICP_CUDA(cudaMemset(c->d_state, 0, sizeof(RegState)));
+    int per_sm = 0;
+    KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_register<true>, KR_THREADS, 0));
+    c->persistent_ctas_per_sm = std::max(per_sm, 1);
+    KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_register<false>, KR_THREADS, 0));
+    c->pruned_ctas_per_sm = std::max(per_sm, 1);
+    const int max_grid = c->sm_count * std::max(c->persistent_ctas_per_sm, c->pruned_ctas_per_sm);
+    KICP_CUDA(cudaMalloc(&c->d_partials, (size_t)2 * max_grid * 8 * sizeof(double)));
+    int coop = 0;
+    KICP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
+    if (!coop) c->persistent = 0;
     return KICP_OK;
 }
 
@@ -1398,11 +849,38 @@ static int check_params(const kicp_reg_params *p) {
     return KICP_OK;
 }
 
-// Enqueue one full registration on the context stream.  `sharded` inserts the 8-double allreduce between the
-// association and the solve of every iteration.
-static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[7], const double odom[7], double tau,
-                                const kicp_reg_params *p, kicp_reg_result *result, bool sharded, const UploadArgs *upload = nullptr,
-                                HostUpload *host_upload = nullptr) {
+// Host side of the chunked upload: the frame's bytes go out in KICP_UPLOAD_CHUNKS pieces on the copy stream, each followed
+// by a 4-byte flag copy; the persistent kernel's first pass waits per chunk on the flag, so the association starts while
+// later chunks are still on the bus.
+struct HostUpload {
+    const unsigned char *src;
+    unsigned char *dst;
+    int64_t n, wpc;   // points, windows per chunk
+    int64_t stride;   // bytes per point
+};
+static int issue_chunks(kicp_ctx *c, const HostUpload &hu) {
+    for (int k = 0; k < KICP_UPLOAD_CHUNKS; ++k) {
+        const int64_t lo = std::min<int64_t>(hu.n, k * hu.wpc * 32), hi = std::min<int64_t>(hu.n, (k + 1) * hu.wpc * 32);
+        if (hi > lo)
+            KICP_CUDA(cudaMemcpyAsync(hu.dst + lo * hu.stride, hu.src + lo * hu.stride, (size_t)((hi - lo) * hu.stride),
+                                      cudaMemcpyHostToDevice, c->copy_stream));
+        KICP_CUDA(cudaMemcpyAsync(c->d_chunk_flags + k, c->h_chunk_tags + k, sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
+    }
+    return KICP_OK;
+}
+
+static ScanView scan_view(const kicp_scan *s) {
+    ScanView v;
+    v.base = (const unsigned char *)s->d_data, v.n = (int)s->n, v.d_n = s->d_n;
+    v.stride = s->stride, v.ox = s->ox, v.oy = s->oy, v.oz = s->oz, v.f32 = s->dtype == KICP_DTYPE_F32 ? 1 : 0;
+    return v;
+}
+
+// Enqueue one full registration on the context stream.  `sharded`: this rank holds a contiguous index range of the frame;
+// the 8 sums of every iteration are exchanged (fused peer-memory exchange when kicp_comm_p2p_init was called, else NCCL).
+// Everything that can fail on arguments is checked before any device work is issued.
+static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double last[7], const double odom[7], double tau,
+                                const kicp_reg_params *p, kicp_reg_result *result, bool sharded, const HostUpload *host_upload = nullptr) {
     if (!m || !scan || !last || !odom) return KICP_ERR_INVALID;
     KICP_TRY(check_params(p));
     kicp_ctx *c = m->ctx;
@@ -1413,85 +891,72 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
         return KICP_ERR_INVALID;
     }
     KICP_CUDA(cudaSetDevice(c->device));
-    const int n = (int)scan->n;
-    KICP_TRY(reg_reserve(c, n));
-    RegArgs a;
-    a.last = Pose{last[0], last[1], last[2], last[3], last[4], last[5], last[6]};
-    a.odom = Pose{odom[0], odom[1], odom[2], odom[3], odom[4], odom[5], odom[6]};
-    a.tau = tau, a.conv = p->convergence_criterion, a.fixed_reg = p->fixed_regularization;
-    a.adaptive = p->use_adaptive_odometry_regularization ? 1 : 0;
+    KICP_TRY(reg_reserve(c));
+    KernelArgs ka{};
+    ka.st = c->d_state;
+    ka.scan = scan_view(scan);
+    ka.map = m->view();
+    ka.partials = c->d_partials;
+    ka.px.nranks = 1;
+    ka.up = UploadArgs{nullptr, 0u, 1};
+    ka.init.last = Pose{last[0], last[1], last[2], last[3], last[4], last[5], last[6]};
+    ka.init.odom = Pose{odom[0], odom[1], odom[2], odom[3], odom[4], odom[5], odom[6]};
+    ka.init.tau = tau, ka.init.conv = p->convergence_criterion, ka.init.fixed_reg = p->fixed_regularization;
+    ka.init.adaptive = p->use_adaptive_odometry_regularization ? 1 : 0;
     // an empty map returns the prediction (Registration.cpp:157): no association, no solve
-    a.max_iter = m->num_blocks == 0 ? 0 : p->max_num_iterations;
-    // small scans leave most warps without a 32-point window: the 8-point-window kernel spreads them over the whole machine
-    const int variant = (c->assoc_variant == 1 && !sharded && n > 0 && n <= c->group4_below) ? 2 : c->assoc_variant;
-    a.fused_tail = (sharded && !(c->p2p_ready && variant >= 1 && c->persistent)) ? 0 : 1;
-    a.iters_out = nullptr;
+    ka.init.max_iter = m->num_blocks == 0 ? 0 : p->max_num_iterations;
+    ka.init.iters_out = nullptr;
+    {
+        int e = 0;
+        ka.pow2_voxel = std::frexp(m->voxel_size, &e) == 0.5 ? 1 : 0;
+    }
+    ka.collect_stats = c->collect_stats;
+    ka.timeout_ns = (unsigned long long)c->spin_timeout_ms * 1000000ull;
+    const int n = (int)scan->n;
+    const bool p2p = sharded && c->p2p_ready;
+    const bool persistent = c->persistent && (!sharded || p2p);
+
     kicp_ctx::ProfReg *pr = nullptr;
     if (c->profiling && (int64_t)c->prof.size() < c->prof_cap) {
         c->prof.emplace_back();
         pr = &c->prof.back();
         pr->d_iters = c->d_prof_iters + (c->prof.size() - 1);
-        a.iters_out = pr->d_iters;
+        ka.init.iters_out = pr->d_iters;
         KICP_CUDA(cudaEventCreate(&pr->prep0));
         KICP_CUDA(cudaEventCreate(&pr->prep1));
         KICP_CUDA(cudaEventRecord(pr->prep0, c->stream));
     }
-    k_reg_init<<<1, 32, 0, c->stream>>>(c->d_state, a);
-    KICP_CHECK_LAUNCH(c);
-    if (a.max_iter > 0) {
-        const double *d_pts = scan->d_xyz;
-        const int sbits = c->sort_bits;
-        if (upload && (sbits > 0 || !((variant == 1 || variant == 3) && c->persistent && (!sharded || c->p2p_ready)))) {
-            // this configuration reads the whole frame up front: wait for the upload instead of overlapping it
-            if (host_upload) KICP_TRY(issue_chunks(c, host_upload, KICP_UPLOAD_CHUNKS));
-            cudaEvent_t ev;
-            KICP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            KICP_CUDA(cudaEventRecord(ev, c->copy_stream));
-            KICP_CUDA(cudaStreamWaitEvent(c->stream, ev, 0));
-            KICP_CUDA(cudaEventDestroy(ev));
-            upload = nullptr;
-        }
-        if (n > 0 && sbits > 0) {
-            const int threads = 256, blocks = (n + threads - 1) / threads;
-            k_morton_keys<<<blocks, threads, 0, c->stream>>>(c->d_state, scan->d_xyz, n, m->voxel_size, c->d_keys, c->d_idx);
-            KICP_CHECK_LAUNCH(c);
-            size_t bytes = c->sort_tmp_bytes;
-            KICP_CUDA(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, bytes, c->d_keys, c->d_keys_alt, c->d_idx, c->d_idx_alt, n,
-                                                      30 - sbits, 30, c->stream));
-            c->launches += 3;  // CUB's histogram + onesweep passes (library kernels, not counted individually)
-            k_gather<<<blocks, threads, 0, c->stream>>>(scan->d_xyz, c->d_idx_alt, n, c->d_sorted);
-            KICP_CHECK_LAUNCH(c);
-            d_pts = c->d_sorted;
-        }
-        if (pr) KICP_CUDA(cudaEventRecord(pr->prep1, c->stream));
+    if (c->collect_stats)
+        KICP_CUDA(cudaMemsetAsync((char *)c->d_state + offsetof(RegState, stats), 0, sizeof(((RegState *)0)->stats), c->stream));
+
+    const bool dbg = getenv("KICP_DEBUG_SYNC") != nullptr;
+    if (ka.init.max_iter <= 0 || !persistent) {
+        k_reg_init<<<1, 32, 0, c->stream>>>(c->d_state, ka.init);
+        KICP_CHECK_LAUNCH(c);
+    }
+    if (pr) KICP_CUDA(cudaEventRecord(pr->prep1, c->stream));
+    if (ka.init.max_iter > 0) {
+        // every CTA is resident and pulls 32-point windows from a device-side counter; a small scan is spread one window per
+        // CTA over the whole machine (a window is a chain of dependent memory round trips: latency, not throughput)
         const int num_windows = (n + 31) / 32;
-        // persistent-style grid: every CTA is resident and pulls windows from a device-side counter
-        const bool group4 = variant == 2;
-        const bool hybrid = variant == 3;
-        const bool pruned = variant >= 1;
-        const bool p2p = sharded && c->p2p_ready && pruned;
-        const bool persistent = pruned && c->persistent && (!sharded || p2p);
-        P2PArgs px{};
-        px.nranks = 1;
-        if (p2p) {
-            for (int r = 0; r < c->nranks; ++r) px.peer[r] = c->p2p_peer[r];
-            px.nranks = c->nranks, px.rank = c->rank;
-            px.parity = (int)(c->p2p_seq & 1ull);
-            px.tag_base = (c->p2p_seq + 1ull) * 128ull;
-            c->p2p_seq++;
-        }
-        const int per_sm = hybrid ? c->hybrid_ctas_per_sm : group4 ? c->group4_ctas_per_sm
-                                  : (persistent ? c->persistent_ctas_per_sm : (pruned ? c->pruned_ctas_per_sm : c->assoc_ctas_per_sm));
-        const int units = group4 ? (n + 7) / 8 : num_windows;  // warp-windows of 8 or 32 points
-        int grid = std::max(1, std::min((units + KICP_WARPS - 1) / KICP_WARPS, c->sm_count * std::min(per_sm, 16)));
-        int pow2_voxel = 0;
-        {
-            int e = 0;
-            pow2_voxel = std::frexp(m->voxel_size, &e) == 0.5 ? 1 : 0;
-        }
-        const bool dbg = getenv("KICP_DEBUG_SYNC") != nullptr;
+        int per_sm = persistent ? c->persistent_ctas_per_sm : c->pruned_ctas_per_sm;
+        if (c->ctas_per_sm_cap > 0) per_sm = std::min(per_sm, c->ctas_per_sm_cap);
+        const int grid = std::max(1, std::min(num_windows, c->sm_count * per_sm));
         if (persistent) {
-            // one cooperative launch runs every iteration (grid barrier inside the kernel)
+            if (host_upload && c->overlap_upload) {
+                const uint32_t seq = ++c->upload_seq ? c->upload_seq : ++c->upload_seq;  // never 0
+                for (int k = 0; k < KICP_UPLOAD_CHUNKS; ++k) c->h_chunk_tags[k] = seq;
+                ka.up = UploadArgs{c->d_chunk_flags, seq, (int)host_upload->wpc};
+                KICP_TRY(issue_chunks(c, *host_upload));
+            }
+            if (p2p) {
+                for (int r = 0; r < c->nranks; ++r) ka.px.peer[r] = c->p2p_peer[r];
+                ka.px.nranks = c->nranks, ka.px.rank = c->rank;
+                ka.px.parity = (int)(c->p2p_seq & 1ull);
+                ka.px.tag_base = (uint32_t)((c->p2p_seq * KICP_MAX_ITERATIONS + 1ull) & 0xFFFFFFFFull);
+                if (ka.px.tag_base > 0xFFFFFF00u) ka.px.tag_base = 1u, c->p2p_seq = 0;  // wrap (tags stay non-zero)
+                c->p2p_seq++;
+            }
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (pr) {
                 KICP_CUDA(cudaEventCreate(&e0));
@@ -1500,31 +965,16 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
                 pr->persistent = true;
                 KICP_CUDA(cudaEventRecord(e0, c->stream));
             }
-            RegState *st_arg = c->d_state;
-            const double *pts_arg = d_pts;
-            int n_arg = n;
-            MapView mv = m->view();
-            double *part_arg = c->d_partials;
-            int pow2_arg = pow2_voxel;
-            void *args_g4[] = {&st_arg, &pts_arg, &n_arg, &mv, &part_arg, &pow2_arg, &px};
-            UploadArgs up_arg = upload ? *upload : UploadArgs{nullptr, 0u, 1};
-            if (group4 || sbits > 0) up_arg.flags = nullptr;
-            void *args_hy[] = {&st_arg, &pts_arg, &n_arg, &mv, &part_arg, &pow2_arg, &px, &up_arg};
-            void *args_pr[] = {&st_arg, &pts_arg, &n_arg, &mv, &part_arg, &px, &up_arg};
-            void **args = hybrid ? args_hy : (group4 ? args_g4 : args_pr);
-            KICP_CUDA(cudaLaunchCooperativeKernel(hybrid   ? (const void *)k_assoc_hybrid<true>
-                                                  : group4 ? (const void *)k_assoc_group4<true>
-                                                           : (const void *)k_assoc_pruned<true>,
-                                                  dim3(grid), dim3(KICP_WARPS * 32), args, 0, c->stream));
+            void *args[] = {&ka};
+            KICP_CUDA(cudaLaunchCooperativeKernel((const void *)k_register<true>, dim3(grid), dim3(KR_THREADS), args, 0, c->stream));
             c->launches++;
-            if (host_upload) KICP_TRY(issue_chunks(c, host_upload, KICP_UPLOAD_CHUNKS));  // the kernel is already waiting on the flags
             if (pr) KICP_CUDA(cudaEventRecord(e1, c->stream));
             if (dbg) {
                 cudaError_t e = cudaStreamSynchronize(c->stream);
                 fprintf(stderr, "[kicp] persistent launch (grid %d, n %d): %s\n", grid, n, cudaGetErrorString(e));
             }
         } else {
-            for (int j = 0; j < a.max_iter; ++j) {
+            for (int j = 0; j < ka.init.max_iter; ++j) {
                 cudaEvent_t e0 = nullptr, e1 = nullptr;
                 if (pr) {
                     KICP_CUDA(cudaEventCreate(&e0));
@@ -1532,47 +982,36 @@ static int enqueue_registration(kicp_map *m, kicp_scan *scan, const double last[
                     pr->it.push_back(e0), pr->it.push_back(e1);
                     KICP_CUDA(cudaEventRecord(e0, c->stream));
                 }
-                if (hybrid)
-                    k_assoc_hybrid<false><<<grid, KICP_WARPS * 32, 0, c->stream>>>(c->d_state, d_pts, n, m->view(), c->d_partials,
-                                                                                   pow2_voxel, px, UploadArgs{nullptr, 0u, 1});
-                else if (group4)
-                    k_assoc_group4<false><<<grid, KICP_WARPS * 32, 0, c->stream>>>(c->d_state, d_pts, n, m->view(), c->d_partials,
-                                                                                   pow2_voxel, px);
-                else if (pruned)
-                    k_assoc_pruned<false><<<grid, KICP_WARPS * 32, 0, c->stream>>>(c->d_state, d_pts, n, m->view(), c->d_partials, px,
-                                                                                   UploadArgs{nullptr, 0u, 1});
-                else
-                    k_assoc<<<grid, KICP_WARPS * 32, assoc_smem_bytes(), c->stream>>>(c->d_state, d_pts, n, m->view());
+                k_register<false><<<grid, KR_THREADS, 0, c->stream>>>(ka);
                 KICP_CHECK_LAUNCH(c);
                 if (pr) KICP_CUDA(cudaEventRecord(e1, c->stream));
-                if (dbg) {  // debugging aid: locate a misbehaving launch
-                    fprintf(stderr, "[kicp] assoc launch %d (variant %d, grid %d, n %d) ...", j, pruned ? 1 : 0, grid, n);
+                if (sharded) KICP_TRY(kicp_comm_allreduce8(c, c->d_state->acc));
+                k_solve<<<1, 32, 0, c->stream>>>(c->d_state);
+                KICP_CHECK_LAUNCH(c);
+                if (dbg) {
                     cudaError_t e = cudaStreamSynchronize(c->stream);
-                    RegState hs;
-                    cudaMemcpy(&hs, c->d_state, offsetof(RegState, result), cudaMemcpyDeviceToHost);
-                    fprintf(stderr, " %s iter=%d done=%d ticket=%u wc=%u\n", cudaGetErrorString(e), hs.iter, hs.done, hs.ticket,
-                            hs.window_counter);
-                }
-                if (sharded) {
-                    KICP_TRY(kicp_comm_allreduce8(c, c->d_state->acc));
-                    k_solve<<<1, 32, 0, c->stream>>>(c->d_state);
-                    KICP_CHECK_LAUNCH(c);
+                    fprintf(stderr, "[kicp] pass %d (grid %d, n %d): %s\n", j, grid, n, cudaGetErrorString(e));
                 }
             }
         }
     }
-    if (host_upload) KICP_TRY(issue_chunks(c, host_upload, KICP_UPLOAD_CHUNKS));  // paths that did not need the frame yet
     if (result)
         KICP_CUDA(cudaMemcpyAsync(result, &c->d_state->result, sizeof(kicp_reg_result), cudaMemcpyDeviceToHost, c->stream));
     return KICP_OK;
 }
 
-// debugging aid (not part of the public header): per-iteration device timings of the last registration
+// debugging aids (not part of the public header): per-pass device timings and work counters of the last registration
 extern "C" int kicp_debug_last_timing(kicp_ctx *c, double *out /* [KICP_MAX_ITERATIONS][4] */) {
-    if (!c || !c->d_state) return KICP_ERR_INVALID;
+    if (!c || !c->d_state || !out) return KICP_ERR_INVALID;
     KICP_CUDA(cudaStreamSynchronize(c->stream));
     KICP_CUDA(cudaMemcpy(out, (const char *)c->d_state + offsetof(RegState, dbg), sizeof(double) * KICP_MAX_ITERATIONS * 4,
                          cudaMemcpyDeviceToHost));
+    return KICP_OK;
+}
+extern "C" int kicp_debug_last_stats(kicp_ctx *c, uint64_t out[4] /* probes, candidate points, 128-byte lines, 0 */) {
+    if (!c || !c->d_state || !out) return KICP_ERR_INVALID;
+    KICP_CUDA(cudaStreamSynchronize(c->stream));
+    KICP_CUDA(cudaMemcpy(out, (const char *)c->d_state + offsetof(RegState, stats), sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost));
     return KICP_OK;
 }
 
@@ -1631,60 +1070,73 @@ extern "C" int kicp_register_scan_sharded_async(kicp_map *map, kicp_scan *scan, 
     return enqueue_registration(map, scan, last, odom, tau, params, result, true);
 }
 
-int kicp_enqueue_registration_device(kicp_map *m, const double *d_xyz, int64_t n, const double last[7], const double odom[7],
-                                     double tau, const kicp_reg_params *p) {
-    if (!m || n < 0 || (n > 0 && !d_xyz)) return KICP_ERR_INVALID;
-    kicp_scan view;  // non-owning alias of the caller's device buffer
-    view.ctx = m->ctx, view.d_xyz = const_cast<double *>(d_xyz), view.cap = n, view.n = n;
-    return enqueue_registration(m, &view, last, odom, tau, p, m->ctx->h_result, false);
+int kicp_enqueue_registration_device(kicp_map *m, const double *d_xyz, int64_t n_max, const int *d_n, const double last[7],
+                                     const double odom[7], double tau, const kicp_reg_params *p) {
+    if (!m || n_max < 0 || (n_max > 0 && !d_xyz)) return KICP_ERR_INVALID;
+    kicp_scan view;  // non-owning alias of the caller's device buffer (packed xyz doubles)
+    view.ctx = m->ctx, view.d_data = const_cast<double *>(d_xyz), view.cap_bytes = n_max * 24, view.n = n_max, view.d_n = d_n;
+    const int st = enqueue_registration(m, &view, last, odom, tau, p, m->ctx->h_result, false);
+    view.d_data = nullptr;  // not ours
+    return st;
 }
 
-static int register_host(kicp_map *map, const double *frame_xyz, int64_t n, const double last[7], const double odom[7],
-                         double tau, const kicp_reg_params *params, double out_pose[7], kicp_reg_result *result, bool sharded) {
-    if (!map || n < 0 || (n > 0 && !frame_xyz) || !out_pose) return KICP_ERR_INVALID;
+// Host-pointer entry points: validate, upload (chunked, overlapped with the first pass), register, read the result back.
+static int register_host(kicp_map *map, const void *data, int64_t n, int32_t dtype, int32_t point_step, int32_t ox, int32_t oy,
+                         int32_t oz, const double last[7], const double odom[7], double tau, const kicp_reg_params *params,
+                         double out_pose[7], kicp_reg_result *result, bool sharded) {
+    if (!map || n < 0 || (n > 0 && !data) || !out_pose || !last || !odom) return KICP_ERR_INVALID;
+    KICP_TRY(check_params(params));
     kicp_ctx *c = map->ctx;
+    if (sharded && !c->nccl_comm && !c->p2p_ready) {
+        kicp_set_error("kicp_register_sharded: neither kicp_comm_p2p_init nor kicp_comm_init has been called on this context");
+        return KICP_ERR_INVALID;
+    }
     KICP_CUDA(cudaSetDevice(c->device));
-    if (!c->upload_scan) KICP_TRY(kicp_scan_create(c, n, &c->upload_scan));
+    if (!c->upload_scan) KICP_TRY(kicp_scan_create(c, 0, &c->upload_scan));
     kicp_scan *s = c->upload_scan;
-    KICP_TRY(kicp_scan_reserve(s, n));
-    s->n = n;
-    // Upload in KICP_UPLOAD_CHUNKS pieces on the copy stream, each followed by a 4-byte flag copy; the persistent kernel's
-    // first pass waits per chunk on the flag, so the association starts while later chunks are still on the bus.
-    UploadArgs up{nullptr, 0u, 1};
-    const UploadArgs *upp = nullptr;
-    HostUpload hu{frame_xyz, s->d_xyz, n, 1, KICP_UPLOAD_CHUNKS};
-    HostUpload *hup = nullptr;
+    KICP_TRY(kicp_scan_set_layout(s, dtype, point_step, ox, oy, oz));
+    KICP_TRY(kicp_scan_reserve_bytes(s, n * (int64_t)s->stride));
+    s->n = n, s->d_n = nullptr;
+    const bool overlap = n > 0 && c->overlap_upload && c->persistent && (!sharded || c->p2p_ready) && map->num_blocks != 0 &&
+                         params->max_num_iterations > 0;
+    HostUpload hu{(const unsigned char *)data, (unsigned char *)s->d_data, n, 1, s->stride};
     if (n > 0) {
         const int64_t windows = (n + 31) / 32;
-        const int64_t wpc = (windows + KICP_UPLOAD_CHUNKS - 1) / KICP_UPLOAD_CHUNKS;
-        const uint32_t seq = ++c->upload_seq ? c->upload_seq : ++c->upload_seq;  // never 0
-        for (int k = 0; k < KICP_UPLOAD_CHUNKS; ++k) c->h_chunk_tags[k] = seq;
-        hu.wpc = wpc, hu.issued = 0;
-        hup = &hu;
-        up = UploadArgs{c->d_chunk_flags, seq, (int)wpc};
-        upp = &up;
-        // first chunk now; the others follow the kernel launch (launch_first) or precede it (the older order, kept for A/B)
-        KICP_TRY(issue_chunks(c, hup, c->launch_first ? 1 : KICP_UPLOAD_CHUNKS));
-        if (!c->overlap_upload) {
-            KICP_TRY(issue_chunks(c, hup, KICP_UPLOAD_CHUNKS));
-            KICP_CUDA(cudaStreamSynchronize(c->copy_stream));
-            upp = nullptr;
+        hu.wpc = (windows + KICP_UPLOAD_CHUNKS - 1) / KICP_UPLOAD_CHUNKS;
+        if (!overlap) {
+            KICP_CUDA(cudaMemcpyAsync(s->d_data, data, (size_t)(n * s->stride), cudaMemcpyHostToDevice, c->stream));
         }
     }
-    KICP_TRY(enqueue_registration(map, s, last, odom, tau, params, c->h_result, sharded, upp, hup));
-    KICP_CUDA(cudaStreamSynchronize(c->stream));
-    KICP_CUDA(cudaStreamSynchronize(c->copy_stream));
+    int st = enqueue_registration(map, s, last, odom, tau, params, c->h_result, sharded, overlap ? &hu : nullptr);
+    cudaError_t e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(c->copy_stream);  // drain on every path
+    if (st != KICP_OK) return st;
+    if (e1 != cudaSuccess) return kicp_cuda_fail(e1, "cudaStreamSynchronize(stream)", __FILE__, __LINE__);
+    if (e2 != cudaSuccess) return kicp_cuda_fail(e2, "cudaStreamSynchronize(copy_stream)", __FILE__, __LINE__);
     for (int k = 0; k < 7; ++k) out_pose[k] = c->h_result->pose[k];
     if (result) *result = *c->h_result;
+    if (c->h_result->status == KICP_ERR_CUDA || c->h_result->status == KICP_ERR_NCCL)
+        kicp_set_error("a device-side wait of the registration kernel timed out (upload flag or a peer of the fused exchange)");
     return c->h_result->status;
 }
 
 extern "C" int kicp_register(kicp_map *map, const double *frame_xyz, int64_t n, const double last[7], const double odom[7],
                              double tau, const kicp_reg_params *params, double out_pose[7], kicp_reg_result *result) {
-    return register_host(map, frame_xyz, n, last, odom, tau, params, out_pose, result, false);
+    return register_host(map, frame_xyz, n, KICP_DTYPE_F64, 0, 0, 0, 0, last, odom, tau, params, out_pose, result, false);
+}
+extern "C" int kicp_register_points(kicp_map *map, const void *data, int64_t n, int32_t dtype, int32_t point_step, int32_t offset_x,
+                                    int32_t offset_y, int32_t offset_z, const double last[7], const double odom[7], double tau,
+                                    const kicp_reg_params *params, double out_pose[7], kicp_reg_result *result) {
+    return register_host(map, data, n, dtype, point_step, offset_x, offset_y, offset_z, last, odom, tau, params, out_pose, result, false);
 }
 extern "C" int kicp_register_sharded(kicp_map *map, const double *frame_xyz, int64_t n_local, const double last[7],
                                      const double odom[7], double tau, const kicp_reg_params *params, double out_pose[7],
                                      kicp_reg_result *result) {
-    return register_host(map, frame_xyz, n_local, last, odom, tau, params, out_pose, result, true);
+    return register_host(map, frame_xyz, n_local, KICP_DTYPE_F64, 0, 0, 0, 0, last, odom, tau, params, out_pose, result, true);
+}
+extern "C" int kicp_register_points_sharded(kicp_map *map, const void *data, int64_t n_local, int32_t dtype, int32_t point_step,
+                                            int32_t offset_x, int32_t offset_y, int32_t offset_z, const double last[7],
+                                            const double odom[7], double tau, const kicp_reg_params *params, double out_pose[7],
+                                            kicp_reg_result *result) {
+    return register_host(map, data, n_local, dtype, point_step, offset_x, offset_y, offset_z, last, odom, tau, params, out_pose, result,
+                         true);
 }

@@ -42,6 +42,24 @@ class Context:
     def set_option(self, name, value):
         check(lib().kicp_ctx_set_option(self.h, name.encode(), int(value)), "kicp_ctx_set_option")
 
+    def last_timing(self):
+        """Per-pass device timings of the last registration, ns: [pass][windows phase, barrier wait, reduce(+exchange), solve]
+        measured on CTA 0 with %globaltimer (kicp_debug_last_timing; synchronises the stream)."""
+        L = lib()
+        L.kicp_debug_last_timing.argtypes = [C.c_void_p, _capi.c_dp]
+        out = np.zeros((_capi.KICP_MAX_ITERATIONS, 4))
+        check(L.kicp_debug_last_timing(self.h, dp(out)), "kicp_debug_last_timing")
+        return out
+
+    def last_stats(self):
+        """(hash probes, candidate points evaluated, 128-byte lines loaded, 0) of the last registration run with option
+        "stats" = 1 (kicp_debug_last_stats; synchronises the stream)."""
+        L = lib()
+        L.kicp_debug_last_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        out = (C.c_uint64 * 4)()
+        check(L.kicp_debug_last_stats(self.h, out), "kicp_debug_last_stats")
+        return [int(x) for x in out]
+
     def profile_begin(self):
         check(lib().kicp_ctx_profile_begin(self.h), "kicp_ctx_profile_begin")
 
@@ -198,10 +216,11 @@ class Scan:
         check(lib().kicp_scan_create(ctx.h, int(capacity), C.byref(self.h)), "kicp_scan_create")
 
     def upload(self, points, asynchronous=False):
-        points = as_points(points)
+        """float64 or float32 (N, 3): float32 clouds travel and stay as float32, the kernel widens while it reads."""
+        points, code = _capi.as_cloud(points)
         self._keepalive = points
-        f = lib().kicp_scan_upload_async if asynchronous else lib().kicp_scan_upload
-        check(f(self.h, dp(points), len(points)), "kicp_scan_upload")
+        f = lib().kicp_scan_upload_points_async if asynchronous else lib().kicp_scan_upload_points
+        check(f(self.h, points.ctypes.data, len(points), code, 0, 0, 0, 0), "kicp_scan_upload_points")
 
     def close(self):
         if self.h:
@@ -229,13 +248,18 @@ class KinematicRegistration:
 
     def ComputeRobotMotion(self, frame, voxel_map, last_robot_pose, relative_wheel_odometry, max_correspondence_distance):
         """Host points in, pose7 out (synchronous) — the reference's call at pipeline/KinematicICP.cpp:68-72."""
-        frame = as_points(frame)
+        frame, code = _capi.as_cloud(frame)
         out = np.empty(7)
         res = RegResult()
         p = self._params()
-        st = lib().kicp_register(voxel_map.h, dp(frame), len(frame), dp(as_pose(last_robot_pose)),
-                                 dp(as_pose(relative_wheel_odometry)), float(max_correspondence_distance), C.byref(p), dp(out),
-                                 C.byref(res))
+        if code == _capi.KICP_DTYPE_F64:
+            st = lib().kicp_register(voxel_map.h, dp(frame), len(frame), dp(as_pose(last_robot_pose)),
+                                     dp(as_pose(relative_wheel_odometry)), float(max_correspondence_distance), C.byref(p), dp(out),
+                                     C.byref(res))
+        else:
+            st = lib().kicp_register_points(voxel_map.h, frame.ctypes.data, len(frame), code, 0, 0, 0, 0, dp(as_pose(last_robot_pose)),
+                                            dp(as_pose(relative_wheel_odometry)), float(max_correspondence_distance), C.byref(p),
+                                            dp(out), C.byref(res))
         check(st, "kicp_register", allow=(KICP_OK, KICP_WARN_NO_CORRESPONDENCES))
         self.last_result = res
         return out

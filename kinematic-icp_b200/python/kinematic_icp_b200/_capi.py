@@ -111,6 +111,10 @@ SYMBOLS = [
     ("kicp_scan_destroy", C.c_int, [_P]),
     ("kicp_scan_upload", C.c_int, [_P, c_dp, C.c_int64]),
     ("kicp_scan_upload_async", C.c_int, [_P, c_dp, C.c_int64]),
+    ("kicp_scan_upload_points", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    ("kicp_scan_upload_points_async", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    ("kicp_register_points", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_dp, c_dp,
+                                       C.c_double, C.POINTER(RegParams), c_dp, C.POINTER(RegResult)]),
     ("kicp_register_scan_async", C.c_int, [_P, _P, c_dp, c_dp, C.c_double, C.POINTER(RegParams), C.POINTER(RegResult)]),
     ("kicp_voxel_downsample", C.c_int, [_P, c_dp, C.c_int64, C.c_double, c_dp, C.c_int64, C.POINTER(C.c_int64)]),
     ("kicp_preprocess", C.c_int, [_P, c_dp, C.c_int64, c_dp, C.c_int64, c_dp, c_dp, C.c_double, C.c_double, C.c_int32, c_dp,
@@ -126,6 +130,8 @@ SYMBOLS = [
     ("kicp_comm_p2p_init", C.c_int, [_P, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]),
     ("kicp_register_sharded", C.c_int, [_P, c_dp, C.c_int64, c_dp, c_dp, C.c_double, C.POINTER(RegParams), c_dp,
                                         C.POINTER(RegResult)]),
+    ("kicp_register_points_sharded", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_dp, c_dp,
+                                               C.c_double, C.POINTER(RegParams), c_dp, C.POINTER(RegResult)]),
     ("kicp_register_scan_sharded_async", C.c_int, [_P, _P, c_dp, c_dp, C.c_double, C.POINTER(RegParams),
                                                    C.POINTER(RegResult)]),
 ]
@@ -160,6 +166,20 @@ def as_points(a):
     if a.ndim != 2 or a.shape[1] != 3:
         raise ValueError("expected an (N, 3) array of points")
     return a
+
+
+def as_cloud(a):
+    """(array, dtype code) for an (N, 3) float32 or float64 cloud: float32 stays float32 (half the PCIe bytes)."""
+    a = np.asarray(a)
+    if a.dtype == np.float32:
+        a = np.ascontiguousarray(a)
+        code = KICP_DTYPE_F32
+    else:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        code = KICP_DTYPE_F64
+    if a.ndim != 2 or a.shape[1] != 3:
+        raise ValueError("expected an (N, 3) array of points")
+    return a, code
 
 
 def as_pose(p):

@@ -31,6 +31,16 @@ for lo, hi in sorted(set(loops)):
     # (__syncwarp() compiles to WARPSYNC.ALL, or to BRA.DIV -> a warpsync stub when the compiler expects convergence)
     if any(("WARPSYNC.ALL" in t) or ("BRA.DIV" in t) or t.startswith("BAR.SYNC") or (" BAR.SYNC" in t) for a, t in body):
         continue
+    # the same holds for a loop whose body executes a full-warp collective unconditionally (SHFL / VOTE / REDUX / MATCH with
+    # all 32 lanes named: the hardware holds every lane at the instruction until all have arrived), which is how the pooled
+    # registration kernel is written — ptxas proves those loops convergent and drops the explicit WARPSYNC
+    def collective(t):
+        if t.startswith("@"):
+            return False  # predicated: not executed by every lane
+        op = t.split()[0]
+        return op.startswith(("SHFL.", "VOTE.", "VOTEU.", "REDUX", "CREDUX", "MATCH."))
+    if any(collective(t) for a, t in body):
+        continue
     defs = set()
     for a, t in body: defs |= writes(t)
     later = set()

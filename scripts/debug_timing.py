@@ -1,20 +1,30 @@
-import sys, ctypes as C
+"""Per-pass device timings (CTA 0, %globaltimer) and work counters of the registration kernel on one workload.
+usage: python scripts/debug_timing.py <cfg 1..4> [ctas_per_sm]"""
+import sys
 sys.path.insert(0, "."); sys.path.insert(0, "kinematic-icp_b200/python")
 import numpy as np
 import kinematic_icp_b200 as kb
-from kinematic_icp_b200 import _capi
 from oracle import workloads as W
 cfg = int(sys.argv[1])
 w = W.Workload(cfg)
 ctx = kb.Context(0)
+if len(sys.argv) > 2:
+    ctx.set_option("ctas_per_sm", int(sys.argv[2]))
 gm = kb.VoxelHashMap(ctx, w.voxel_size, w.max_range, w.max_points_per_voxel)
 gm.load_voxels(*w.map.export_voxels())
 reg = kb.KinematicRegistration()
-L = _capi.lib()
-L.kicp_debug_last_timing.argtypes = [C.c_void_p, _capi.c_dp]
-for rep in range(3):
-    reg.ComputeRobotMotion(w.scan, gm, w.last_pose, w.rel_odom, w.tau)
-out = np.zeros((64, 4))
-L.kicp_debug_last_timing(ctx.h, _capi.dp(out))
-print("cfg", cfg, "iters", reg.last_result.iterations, "[windows_cta0, -, partial_sum, solve] us per iteration:")
-print(np.round(out[:reg.last_result.iterations] / 1e3, 2))
+scan = kb.Scan(ctx, w.N)
+scan.upload(w.scan)
+res = kb.pinned_result()
+for rep in range(5):
+    reg.enqueue(scan, gm, w.last_pose, w.rel_odom, w.tau, res)
+ctx.synchronize()
+out = ctx.last_timing()
+it = res.iterations
+print("cfg", cfg, "N", w.N, "iters", it, "[windows(cta0), barrier wait, reduce(+exchange), solve] us per pass:")
+print(np.round(out[:it] / 1e3, 2))
+print("sum per pass us:", np.round(out[:it].sum(1) / 1e3, 2), "total us", round(out[:it].sum() / 1e3, 1))
+ctx.set_option("stats", 1)
+reg.enqueue(scan, gm, w.last_pose, w.rel_odom, w.tau, res)
+probes, cands, lines, _ = ctx.last_stats()
+print("per point per pass: probes %.2f candidates %.2f lines %.2f" % (probes / it / w.N, cands / it / w.N, lines / it / w.N))

@@ -135,28 +135,39 @@ def test_registration_vs_reference_golden(oracle, gpu_ctx, name):
 
 @pytest.mark.parametrize("cfg", [1, 2, 3, 4])
 def test_registration_configs_vs_oracle(oracle, gpu_ctx, workload, cfg):
-    """BASELINE.json configs 1-4 at full size: pose, iteration count, per-iteration N and sums — for both kernel
-    variants (pruned thread-per-point, staged-through-shared-memory) and with the binning sort on and off."""
+    """BASELINE.json configs 1-4 at full size: pose, iteration count, per-iteration N and sums — for every launch shape
+    of the registration kernel."""
     import kinematic_icp_b200 as kb
     ko = oracle
     w = workload(cfg)
     gm = gpu_map_from_oracle(kb, gpu_ctx, w.map)
     try:
-        gpu_ctx.set_option("group4_below", 0)  # the matrix names its kernel explicitly; the default choice is checked last
-        for variant, sort_bits, persistent in ((3, 0, 1), (3, 0, 0), (3, 30, 1), (2, 0, 1), (2, 0, 0), (2, 30, 1), (1, 0, 1), (1, 0, 0), (0, 30, 0), (1, 30, 1), (1, 12, 0)):
-            gpu_ctx.set_option("assoc_variant", variant)
-            gpu_ctx.set_option("sort_bits", sort_bits)
+        # launch shapes of the one registration kernel: persistent cooperative launch (default) / one launch per iteration,
+        # grid capped at 1 CTA per SM / occupancy limit; the work counters on
+        for persistent, ctas, stats in ((1, 0, 0), (0, 0, 0), (1, 1, 1), (0, 1, 0)):
             gpu_ctx.set_option("persistent", persistent)
+            gpu_ctx.set_option("ctas_per_sm", ctas)
+            gpu_ctx.set_option("stats", stats)
             pose, dt, ang = check_registration(ko, kb, gpu_ctx, w.map, gm, w.scan, w.last_pose, w.rel_odom, w.tau)
-            print("cfg%d variant=%d sort_bits=%d persistent=%d N=%d M=%d pose delta %.3e m %.3e rad" %
-                  (cfg, variant, sort_bits, persistent, w.N, w.map.num_points(), dt, ang))
+            print("cfg%d persistent=%d ctas_per_sm=%d N=%d M=%d pose delta %.3e m %.3e rad" %
+                  (cfg, persistent, ctas, w.N, w.map.num_points(), dt, ang))
+            if stats:
+                probes, cands, lines = gpu_ctx.last_stats()[:3]
+                assert probes >= w.N and cands > 0 and lines > 0
     finally:
-        gpu_ctx.set_option("assoc_variant", 1)
-        gpu_ctx.set_option("sort_bits", 0)
         gpu_ctx.set_option("persistent", 1)
-        gpu_ctx.set_option("group4_below", 49152)
+        gpu_ctx.set_option("ctas_per_sm", 0)
+        gpu_ctx.set_option("stats", 0)
     pose, dt, ang = check_registration(ko, kb, gpu_ctx, w.map, gm, w.scan, w.last_pose, w.rel_odom, w.tau)
-    print("cfg%d defaults (kernel chosen by scan size) pose delta %.3e m %.3e rad" % (cfg, dt, ang))
+    print("cfg%d defaults pose delta %.3e m %.3e rad" % (cfg, dt, ang))
+    # float32 ingest (the reference's callers hold float32 PointCloud2 fields, RosUtils.cpp:30-39): the workload's scan is
+    # float32-representable, so the float32 upload must give the very same result
+    scan32 = w.scan.astype(np.float32)
+    assert np.array_equal(scan32.astype(np.float64), w.scan)
+    reg = kb.KinematicRegistration()
+    pose32 = reg.ComputeRobotMotion(scan32, gm, w.last_pose, w.rel_odom, w.tau)
+    dt32, ang32 = ko.pose_delta(pose32, pose)
+    assert dt32 <= 1e-12 and ang32 <= 1e-12, (dt32, ang32)
     gm.close()
 
 
