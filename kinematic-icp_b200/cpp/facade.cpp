@@ -85,18 +85,18 @@ void CorrespondenceThreshold::UpdateOdometryError(const Sophus::SE3d &odometry_e
 namespace pipeline {
 // pipeline/KinematicICP.hpp:73-79
 KinematicICP::KinematicICP(const Config &config)
-    : solver_(config.max_num_iterations, config.convergence_criterion, config.max_num_threads,
+    : registration_(config.max_num_iterations, config.convergence_criterion, config.max_num_threads,
                     config.use_adaptive_odometry_regularization, config.fixed_regularization),
-      threshold_(config.map_resolution(), config.max_range, config.use_adaptive_threshold, config.fixed_threshold),
-      settings_(config),
-      front_end_(config.max_range, config.min_range, config.deskew, config.max_num_threads),
-      map_(config.voxel_size, config.max_range, config.max_points_per_voxel) {}
+      correspondence_threshold_(config.map_resolution(), config.max_range, config.use_adaptive_threshold, config.fixed_threshold),
+      config_(config),
+      preprocessor_(config.max_range, config.min_range, config.deskew, config.max_num_threads),
+      local_map_(config.voxel_size, config.max_range, config.max_points_per_voxel) {}
 
 // pipeline/KinematicICP.hpp:85-89
 void KinematicICP::SetPose(const Sophus::SE3d &pose) {
     last_pose_ = pose;
-    map_.Clear();
-    threshold_.Reset();
+    local_map_.Clear();
+    correspondence_threshold_.Reset();
 }
 
 // pipeline/KinematicICP.cpp:48-85: one kicp_register_frame call does the per-point work (ingest, de-skew, range filter,
@@ -112,15 +112,15 @@ KinematicICP::Vector3dVectorTuple KinematicICP::RegisterFrame(const kicp_frame_i
     kicp::to_pose7(last_pose_, last);
     kicp::to_pose7(relative_odometry, odom);
     kicp_frame_params fp;
-    fp.max_range = front_end_.max_range_, fp.min_range = front_end_.min_range_, fp.deskew = front_end_.deskew_ ? 1 : 0;
-    fp.voxel_size = settings_.voxel_size;
-    fp.reg.max_num_iterations = solver_.max_num_iterations_;
-    fp.reg.use_adaptive_odometry_regularization = solver_.use_adaptive_odometry_regularization_ ? 1 : 0;
-    fp.reg.convergence_criterion = solver_.convergence_criterion_;
-    fp.reg.fixed_regularization = solver_.fixed_regularization_;
-    const double tau = threshold_.ComputeThreshold();
+    fp.max_range = preprocessor_.max_range_, fp.min_range = preprocessor_.min_range_, fp.deskew = preprocessor_.deskew_ ? 1 : 0;
+    fp.voxel_size = config_.voxel_size;
+    fp.reg.max_num_iterations = registration_.max_num_iterations_;
+    fp.reg.use_adaptive_odometry_regularization = registration_.use_adaptive_odometry_regularization_ ? 1 : 0;
+    fp.reg.convergence_criterion = registration_.convergence_criterion_;
+    fp.reg.fixed_regularization = registration_.fixed_regularization_;
+    const double tau = correspondence_threshold_.ComputeThreshold();
     fp.stage_clouds = 1;  // the two returned clouds are built below, in one pass each, from the library's pinned staging
-    kicp::check(kicp_register_frame(map_.handle_, &input, motion, l2b, last, odom, tau, &fp, out, nullptr, 0, nullptr, nullptr, 0,
+    kicp::check(kicp_register_frame(local_map_.handle_, &input, motion, l2b, last, odom, tau, &fp, out, nullptr, 0, nullptr, nullptr, 0,
                                     nullptr, nullptr),
                 "kicp_register_frame");
     const double *frame_xyz = nullptr, *source_xyz = nullptr;
@@ -131,7 +131,7 @@ KinematicICP::Vector3dVectorTuple KinematicICP::RegisterFrame(const kicp_frame_i
     Vector3dVector in_base(fb, fb + n_frame), source(sb, sb + n_source);
     const Sophus::SE3d new_pose = kicp::from_pose7(out);
     const Sophus::SE3d odometry_error = (last_pose_ * relative_odometry).inverse() * new_pose;
-    threshold_.UpdateOdometryError(odometry_error);
+    correspondence_threshold_.UpdateOdometryError(odometry_error);
     last_pose_ = new_pose;
     return {std::move(in_base), std::move(source)};
 }

@@ -42,13 +42,25 @@ using namespace kicp_dev;
 #define KR_WARPS 8                    // warps per CTA
 #define KR_THREADS (KR_WARPS * 32)
 #ifndef KR_MINB
-#define KR_MINB 2                     // resident CTAs per SM the kernel is compiled for
+#define KR_MINB 4                     // resident CTAs per SM the kernel is compiled for (64 registers per thread)
 #endif
-#define KR_LCAP 160                   // line-map entries per chunk (32 tasks x 5 lines at 20 points per voxel)
+#define KR_LCAP 96                    // lines per chunk (a batch of 32 tasks has at most 160 at 20 points per voxel: 1-2 chunks)
 #ifndef KR_G
 #define KR_G 4                        // line-rounds (of 8 lines = 32 points) in flight together
 #endif
 #define KR_DBLMAX_BITS 0x7FEFFFFFFFFFFFFFull
+// Development aid (-DKR_PROFILE): per-phase cycle accounting of the window loop (lane 0 of every warp, clock64 deltas).
+#ifdef KR_PROFILE
+#define KR_PROF_DECL long long prof_t[12] = {0}; long long prof_last = clock64();
+#define KR_PROF(i) { const long long t__ = clock64(); prof_t[i] += t__ - prof_last; prof_last = t__; }
+#define KR_PROF_COUNT(i) { prof_t[i] += 1; }
+#define KR_PROF_FLUSH if (lane == 0) { for (int k__ = 0; k__ < 12; ++k__) atomicAdd(&st->prof[k__], (unsigned long long)prof_t[k__]); }
+#else
+#define KR_PROF_DECL
+#define KR_PROF(i)
+#define KR_PROF_COUNT(i)
+#define KR_PROF_FLUSH
+#endif
 
 // Pose + solver state of one registration.  The persistent kernel keeps one replica per CTA in shared memory; the
 // multi-launch (NCCL) path keeps it in RegState.
@@ -67,10 +79,12 @@ struct RegState {
     unsigned int arrive;            // grid-barrier arrivals so far (monotonic inside a registration)
     unsigned int exit_ctr;          // CTAs that have left the kernel; the last one zeroes the three counters
     unsigned int ticket;            // multi-launch path: last-CTA detection
+    unsigned int heavy_n;           // windows pass 0 found expensive (they are handed out first in the later passes)
     int abort;                      // a device-side wait gave up (status code); every CTA leaves after the current pass
     int *iters_out;                 // optional: where to publish the iteration count (profiling)
     double acc[8];                  // multi-launch path: JTJ00 JTJ01 JTJ11 JTr0 JTr1 N sum|r|^2 (unused)
     unsigned long long stats[4];    // optional work counters: probes, candidate points evaluated, lines, windows
+    unsigned long long prof[16];    // -DKR_PROFILE builds only: SM cycles per phase of the window loop, summed over warps
     double dbg[KICP_MAX_ITERATIONS][4];  // per pass, ns (CTA 0): windows phase, barrier wait, partial sum (+ exchange), solve
     kicp_reg_result result;
 };
@@ -185,6 +199,9 @@ struct KernelArgs {
     RegArgs init;
     int pow2_voxel;
     int collect_stats;
+    unsigned int *heavy_list;      // [windows] scheduling hint written by pass 0 (order only, never results)
+    unsigned char *heavy_flag;     // [windows]
+    int heavy_tasks;               // a window with more hash probes than this is "heavy"
     unsigned long long timeout_ns;  // device-side waits (upload flags, peers) give up after this long
 };
 
@@ -246,7 +263,7 @@ __global__ void k_reg_init(RegState *st, RegArgs a) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     pose_init(&st->pose, a);
     result_init(&st->result, &st->pose);
-    st->ticket = 0, st->win_ctr = 0, st->arrive = 0, st->exit_ctr = 0, st->abort = 0;
+    st->ticket = 0, st->win_ctr = 0, st->arrive = 0, st->exit_ctr = 0, st->abort = 0, st->heavy_n = 0;
     st->iters_out = a.iters_out;
     if (a.iters_out) *a.iters_out = 0;
     for (int k = 0; k < 8; ++k) st->acc[k] = 0.0;
@@ -315,16 +332,29 @@ __global__ void k_solve(RegState *st) {
 }
 
 // ------------------------------------------------------------------------------------------- per-warp shared state
+#define KR_TCAP 640  // tasks of one stage: 32 owners x (6 faces | 20 edges + corners)
+struct __align__(16) LineMin {   // minimum over the (valid) points of one 128-byte line of a voxel's run
+    double d2;
+    unsigned gline;              // global index of the line's first point
+    unsigned nvalid;             // points of the line that exist (1..4)
+};
 struct __align__(16) WarpSm {
     double2 qxy[32];                 // owner's query point (map frame)
     double qz[32];
-    unsigned long long best[32];     // bit pattern of the smallest d^2 found so far (atomicMin)
-    unsigned long long kg[32];       // (visiting-order key << 32) | global point index of the FIRST such minimum (atomicMin)
+    LineMin line[KR_LCAP];           // line minima of the current chunk, in visiting order
     int vx[32], vy[32], vz[32];      // owner's voxel
-    unsigned int tend[32];           // inclusive prefix sum of the owners' surviving-neighbour counts
-    unsigned int nmask[32];          // owner's surviving neighbour shifts, bit k <-> voxel_shifts[k]
+    double acc[7][32];               // per-lane running sums of the pass (kept here, not in registers)
+    double px[32], py[32];           // owner's scan point (for the Jacobian)
+    unsigned short task[KR_TCAP];    // task stream of the current stage: owner << 5 | shift index
     unsigned short lmap[KR_LCAP];    // line -> (task lane, line index inside the voxel)
+    unsigned short lbeg[32], lend[32];  // owner's line range [lbeg, lend) in the current batch
 };
+
+// |c - q|^2 with a pinned operation order (the owner re-evaluates the winning line: both evaluations must agree bit for bit)
+__device__ __forceinline__ double dist2(double cx, double cy, double cz, double qx, double qy, double qz) {
+    const double dx = cx - qx, dy = cy - qy, dz = cz - qz;
+    return __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
+}
 
 __device__ __forceinline__ void load_scan_point(const ScanView &sv, int i, double &x, double &y, double &z) {
     const unsigned char *p = sv.base + (size_t)i * (size_t)sv.stride;
@@ -350,6 +380,33 @@ __device__ __forceinline__ void stats_flush(RegState *st, unsigned long long pro
     if ((threadIdx.x & 31) == 0) atomicAdd(&st->stats[0], probes), atomicAdd(&st->stats[1], cands), atomicAdd(&st->stats[2], lines);
 }
 
+// The shifts of one search stage that survive the exact bound (bit k <-> voxel_shifts[k]).  Stage 0: the own voxel;
+// stage 1: the 6 faces; stage 2: the 12 edges and 8 corners, pruned with the best the faces left behind.
+__device__ __forceinline__ unsigned stage_mask(int stage, bool valid, double bound, double qx, double qy, double qz, int vx, int vy,
+                                               int vz, double vs) {
+    if (!valid) return 0u;
+    if (stage == 0) return 1u;
+    double t;
+    t = (double)(vx + 1) * vs - qx; const double gxp = t * t;
+    t = qx - (double)vx * vs;       const double gxm = t * t;
+    t = (double)(vy + 1) * vs - qy; const double gyp = t * t;
+    t = qy - (double)vy * vs;       const double gym = t * t;
+    t = (double)(vz + 1) * vs - qz; const double gzp = t * t;
+    t = qz - (double)vz * vs;       const double gzm = t * t;
+    unsigned mask = (kX0 | (gxp <= bound ? kXP : 0u) | (gxm <= bound ? kXM : 0u)) &
+                    (kY0 | (gyp <= bound ? kYP : 0u) | (gym <= bound ? kYM : 0u)) &
+                    (kZ0 | (gzp <= bound ? kZP : 0u) | (gzm <= bound ? kZM : 0u));
+    if (stage == 1) return mask & 0x0000007Eu;
+    mask &= 0x07FFFF80u;
+#pragma unroll
+    for (int kk = 7; kk < 27; ++kk) {  // edges and corners: the summed gap decides
+        const double lb2 = (shift_x(kk) > 0 ? gxp : (shift_x(kk) < 0 ? gxm : 0.0)) + (shift_y(kk) > 0 ? gyp : (shift_y(kk) < 0 ? gym : 0.0)) +
+                           (shift_z(kk) > 0 ? gzp : (shift_z(kk) < 0 ? gzm : 0.0));
+        if (lb2 > bound) mask &= ~(1u << kk);
+    }
+    return mask;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // k_register.  PERSISTENT = true: cooperative launch, every CTA resident, all IRLS iterations inside the launch
 // (single GPU, and the sharded path with the exchange over NVLink peer memory fused into the barrier).
@@ -357,20 +414,17 @@ __device__ __forceinline__ void stats_flush(RegState *st, unsigned long long pro
 // ---------------------------------------------------------------------------------------------------------------
 template <bool PERSISTENT>
 __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelArgs a) {
-    __shared__ WarpSm s_warp[KR_WARPS];
+    extern __shared__ __align__(16) unsigned char s_dyn[];  // KR_WARPS x WarpSm (more than the 48 KB static limit)
     __shared__ PoseState s_ps;
     __shared__ double s_part[KR_WARPS][8];
     __shared__ double s_sum[8];
-    __shared__ MapView s_map[32];
     __shared__ int s_flag[2];
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int quad = lane >> 2, sub = lane & 3;
     const unsigned FULL = 0xFFFFFFFFu;
-    WarpSm &sm = s_warp[wid];
+    WarpSm &sm = reinterpret_cast<WarpSm *>(s_dyn)[wid];
     RegState *const st = a.st;
-    const MapRegs mr = map_regs(a.map, s_map);  // per-thread copy of the map view (divergence safety, kicp_device.cuh)
-    const double vs = a.map.voxel_size, inv_vs = 1.0 / a.map.voxel_size;
     const int n = a.scan.d_n ? min(__ldg(a.scan.d_n), a.scan.n) : a.scan.n;
     const int num_windows = (n + 31) >> 5;
     const unsigned total_warps = gridDim.x * KR_WARPS;
@@ -390,207 +444,92 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
     if (!PERSISTENT && s_ps.done) return;
 
     unsigned long long n_probe = 0, n_cand = 0, n_line = 0;
+    KR_PROF_DECL
 
     for (unsigned it = 0; !s_ps.done; ++it) {
-        double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0, cntN = 0, ssq = 0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) sm.acc[k][lane] = 0.0;
         const unsigned long long t_iter0 = gtime_ns();
-        const unsigned ticket_base = PERSISTENT ? it * ((unsigned)num_windows + total_warps) : 0u;
-        const double tau = s_ps.tau;
+        // Window tickets.  Pass 0 hands the windows out in index order and records the expensive ones (many hash probes: points
+        // with little or no map around them); the later passes hand those out FIRST, so that the longest windows overlap the
+        // bulk instead of forming the tail of the pass.  Only the order changes, never a result.
+        const bool sched = PERSISTENT && a.heavy_list != nullptr;
+        const unsigned nheavy = (sched && it > 0u) ? __ldcg(&st->heavy_n) : 0u;
+        const unsigned t0span = (unsigned)num_windows + total_warps;
+        const unsigned ticket_base = !PERSISTENT ? 0u : (it == 0u ? 0u : t0span + (it - 1u) * (t0span + nheavy));
+        const unsigned tlimit = nheavy + (unsigned)num_windows;  // tickets at or beyond: nothing left
 
-        // dynamic window fetch (windows differ in cost); the next ticket is requested before the current window is
-        // processed so that the atomic's round trip is off the critical path
+        // the next ticket is requested before the current window is processed: the atomic's round trip is off the critical path
         unsigned tk = 0;
         if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);
-        int w = (int)(__shfl_sync(FULL, tk, 0) - ticket_base);
+        int w;
+        for (;;) {  // ticket -> window (warp-uniform)
+            const unsigned t = __shfl_sync(FULL, tk, 0) - ticket_base;
+            if (t >= tlimit) { w = num_windows; break; }
+            if (t < nheavy) { w = (int)__ldcg(&a.heavy_list[t]); break; }
+            w = (int)(t - nheavy);
+            if (nheavy == 0u || !__ldcg(&a.heavy_flag[w])) break;
+            if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);  // a heavy window reached through its regular ticket: already done
+        }
+        KR_PROF(11)
         while (w < num_windows) {
             if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);
+            int wtasks = 0;
+            KR_PROF_COUNT(8)
             if (PERSISTENT && a.up.flags != nullptr && it == 0u) {
                 // first pass over a frame that is still being uploaded: wait until this window's chunk has landed
-                if (lane == 0) {
-                    const uint32_t *f = a.up.flags + min(w / a.up.windows_per_chunk, KICP_UPLOAD_CHUNKS - 1);
-                    const unsigned long long deadline = gtime_ns() + a.timeout_ns;
-                    const uint32_t want = a.up.seq;
-                    while (ld_acquire_sys_u32(f) != want) {
-                        if (gtime_ns() > deadline) {  // the copy never arrived
-                            atomicExch(&st->abort, KICP_ERR_CUDA);
-                            break;
+                const uint32_t *f = a.up.flags + min(w / a.up.windows_per_chunk, KICP_UPLOAD_CHUNKS - 1);
+                const unsigned long long deadline = gtime_ns() + a.timeout_ns;
+                bool pend = true;
+                while (__any_sync(FULL, pend)) {  // warp-uniform: every lane polls the same word (one transaction)
+                    if (pend) {
+                        if (ld_acquire_sys_u32(f) == a.up.seq) {
+                            pend = false;
+                        } else if (gtime_ns() > deadline) {  // the copy never arrived
+                            if (lane == 0) atomicExch(&st->abort, KICP_ERR_CUDA);
+                            pend = false;
                         }
                     }
                 }
-                __syncwarp();
             }
-            // ---------------------------------------------------------------- owners: q = T p, voxel, face gaps
-            const int i = w * 32 + lane;
-            const bool valid = i < n;
-            double px = 0, py = 0, pz = 0;
-            if (valid) load_scan_point(a.scan, i, px, py, pz);
-            const double qx = s_ps.R[0] * px + s_ps.R[1] * py + s_ps.R[2] * pz + s_ps.t[0];
-            const double qy = s_ps.R[3] * px + s_ps.R[4] * py + s_ps.R[5] * pz + s_ps.t[1];
-            const double qz = s_ps.R[6] * px + s_ps.R[7] * py + s_ps.R[8] * pz + s_ps.t[2];
-            // PointToVoxel: floor(q / voxel_size); for a power-of-two voxel size the product with the (exact) reciprocal
-            // is the same double as the quotient, so the cheaper form is used
-            int vx, vy, vz;
-            if (a.pow2_voxel) {
-                vx = (int)floor(qx * inv_vs), vy = (int)floor(qy * inv_vs), vz = (int)floor(qz * inv_vs);
-            } else {
-                vx = voxel_coord(qx, vs), vy = voxel_coord(qy, vs), vz = voxel_coord(qz, vs);
+            // ---------------------------------------------------------------- owners: q = T p and its voxel
+            const bool valid = w * 32 + lane < n;
+            {
+                double px = 0, py = 0, pz = 0;
+                if (valid) load_scan_point(a.scan, w * 32 + lane, px, py, pz);
+                const double qx = s_ps.R[0] * px + s_ps.R[1] * py + s_ps.R[2] * pz + s_ps.t[0];
+                const double qy = s_ps.R[3] * px + s_ps.R[4] * py + s_ps.R[5] * pz + s_ps.t[1];
+                const double qz = s_ps.R[6] * px + s_ps.R[7] * py + s_ps.R[8] * pz + s_ps.t[2];
+                // PointToVoxel: floor(q / voxel_size); for a power-of-two voxel size the product with the (exact)
+                // reciprocal is the same double as the quotient, so the cheaper form is used
+                int vx, vy, vz;
+                if (a.pow2_voxel) {
+                    const double inv_vs = 1.0 / a.map.voxel_size;
+                    vx = (int)floor(qx * inv_vs), vy = (int)floor(qy * inv_vs), vz = (int)floor(qz * inv_vs);
+                } else {
+                    vx = voxel_coord(qx, a.map.voxel_size), vy = voxel_coord(qy, a.map.voxel_size), vz = voxel_coord(qz, a.map.voxel_size);
+                }
+                sm.qxy[lane] = make_double2(qx, qy), sm.qz[lane] = qz;
+                sm.vx[lane] = vx, sm.vy[lane] = vy, sm.vz[lane] = vz;
+                sm.px[lane] = px, sm.py[lane] = py;
             }
-            sm.qxy[lane] = make_double2(qx, qy), sm.qz[lane] = qz;
-            sm.vx[lane] = vx, sm.vy[lane] = vy, sm.vz[lane] = vz;
-            sm.best[lane] = KR_DBLMAX_BITS, sm.kg[lane] = ~0ull;
-            unsigned long long seen = KR_DBLMAX_BITS;  // sm.best[lane] as this lane last saw it
-            unsigned total = 0;                        // neighbour tasks of the window
-            int nbatch = 0;
+            // the owner's running minimum lives in its lane's registers: d^2, the line that holds it, how many points that line has
+            double best = DBL_MAX;
+            unsigned bline = 0xFFFFFFFFu, bvalid = 0u;
             __syncwarp();
+            KR_PROF(0)
 
-            for (int b = -1; b < nbatch; ++b) {
-                // ------------------------------------------------------------ this lane's task: (owner o, shift k)
-                int o = lane, k = 0;
-                bool act = valid;
-                if (b >= 0) {
-                    const unsigned s = (unsigned)b * 32u + (unsigned)lane;
-                    act = s < total;
-                    int lo = 0;  // owner = number of owners whose tasks end at or before s
-#pragma unroll
-                    for (int step = 16; step > 0; step >>= 1)
-                        if (sm.tend[lo + step - 1] <= s) lo += step;
-                    o = lo;
-                    const unsigned before = o ? sm.tend[o - 1] : 0u;
-                    const unsigned mk = sm.nmask[o];
-                    k = act ? (int)__fns(mk, 0u, (int)(s - before) + 1) : 0;
-                }
-                // ------------------------------------------------------------ hash probe (warp-uniform loop)
-                uint32_t meta = KICP_SLOT_EMPTY;
+            for (int stage = 0; stage < 3; ++stage) {
+                // ------------------------------------------------------------ task stream of the stage (owner-major, KISS order)
+                int total;
                 {
-                    int kx = 0, ky = 0, kz = 0;
-                    uint32_t h = 0;
-                    if (act) {
-                        kx = sm.vx[o] + shift_x(k), ky = sm.vy[o] + shift_y(k), kz = sm.vz[o] + shift_z(k);
-                        h = voxel_hash(kx, ky, kz) & mr.mask;
-                    }
-                    bool pend = act;
-                    while (__any_sync(FULL, pend)) {
-                        if (pend) {
-                            const int4 sl = __ldg(&mr.slots[h]);
-                            if ((uint32_t)sl.w == KICP_SLOT_EMPTY) {
-                                pend = false;
-                            } else if (sl.x == kx && sl.y == ky && sl.z == kz) {
-                                meta = (uint32_t)sl.w, pend = false;
-                            } else {
-                                h = (h + 1) & mr.mask;
-                            }
-                        }
-                        __syncwarp();
-                    }
-                }
-                // ------------------------------------------------------------ number the 128-byte lines of the batch
-                const int cnt = meta == KICP_SLOT_EMPTY ? 0 : (int)(meta & 0xFFu);
-                const int nl = (cnt + 3) >> 2;
-                int incl = nl;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int y = __shfl_up_sync(FULL, incl, d);
-                    if (lane >= d) incl += y;
-                }
-                const int loff = incl - nl;
-                const int ltot = __shfl_sync(FULL, incl, 31);
-                const int maxnl = __reduce_max_sync(FULL, nl);
-                const unsigned okpack = ((unsigned)o << 5) | (unsigned)k;
-                if (a.collect_stats) n_probe += act ? 1 : 0, n_cand += cnt, n_line += nl;
-
-                for (int lbase = 0; lbase < ltot; lbase += KR_LCAP) {
-                    // line map of this chunk: entry = task lane | (line inside the voxel << 5)
-                    for (int li = 0; li < maxnl; ++li) {
-                        const int pos = loff + li - lbase;
-                        if (li < nl && pos >= 0 && pos < KR_LCAP) sm.lmap[pos] = (unsigned short)(lane | (li << 5));
-                    }
-                    __syncwarp();
-                    const int nr = min(KR_LCAP, ltot - lbase);
-                    for (int r0 = 0; r0 < nr; r0 += 8 * KR_G) {
-                        double d2[KR_G];
-                        unsigned long long kgv[KR_G];
-                        int own[KR_G];
-                        unsigned hasm = 0;
-#pragma unroll
-                        for (int g = 0; g < KR_G; ++g) {
-                            const int line = r0 + g * 8 + quad;
-                            const bool lv = line < nr;
-                            const unsigned e = lv ? (unsigned)sm.lmap[line] : 0u;
-                            const int t = (int)(e & 31u), li = (int)(e >> 5);
-                            const uint32_t m = __shfl_sync(FULL, meta, t);
-                            const unsigned ok = __shfl_sync(FULL, okpack, t);
-                            const int j = li * 4 + sub;
-                            const bool has = lv && j < (int)(m & 0xFFu);
-                            const unsigned gidx = (m >> 8) * (unsigned)mr.cap + (unsigned)j;
-                            const int oo = (int)(ok >> 5);
-                            own[g] = oo;
-                            kgv[g] = ((unsigned long long)(((ok & 31u) << 8) | (unsigned)j) << 32) | (unsigned long long)gidx;
-                            d2[g] = DBL_MAX;
-                            if (has) {
-                                const Point4 c = ld_point(mr.pts + (size_t)gidx * KICP_PSTRIDE);
-                                const double2 qq = sm.qxy[oo];
-                                const double dx = c.x - qq.x, dy = c.y - qq.y, dz = c.z - sm.qz[oo];
-                                d2[g] = dx * dx + dy * dy + dz * dz;
-                                hasm |= 1u << g;
-                            }
-                        }
-                        // phase 1: lower the owners' best; remember who could still be (or tie with) the minimum
-                        unsigned lem = 0;
-#pragma unroll
-                        for (int g = 0; g < KR_G; ++g) {
-                            if (hasm & (1u << g)) {
-                                const unsigned long long mine = (unsigned long long)__double_as_longlong(d2[g]);
-                                const unsigned long long br = sm.best[own[g]];
-                                if (mine <= br) {
-                                    lem |= 1u << g;
-                                    if (mine < br) atomicMin(&sm.best[own[g]], mine);
-                                }
-                            }
-                        }
-                        if (__any_sync(FULL, lem != 0u)) {
-                            __syncwarp();
-                            // every lane, as an owner: a strictly smaller best invalidates the recorded first minimum
-                            const unsigned long long cur = sm.best[lane];
-                            if (cur != seen) sm.kg[lane] = ~0ull, seen = cur;
-                            __syncwarp();
-                            // phase 2: among the candidates AT the minimum, the first in visiting order wins
-#pragma unroll
-                            for (int g = 0; g < KR_G; ++g) {
-                                if (lem & (1u << g)) {
-                                    if ((unsigned long long)__double_as_longlong(d2[g]) == sm.best[own[g]])
-                                        atomicMin(&sm.kg[own[g]], kgv[g]);
-                                }
-                            }
-                        }
-                        __syncwarp();
-                    }
-                    __syncwarp();
-                }
-
-                if (b < 0) {
-                    // ------------------------------------------------------------ exact pruning of the 26 neighbours
-                    __syncwarp();
-                    const double best = __longlong_as_double((long long)sm.best[lane]);
-                    const double bound = best * (1.0 + 1e-6) + 1e-10;
-                    double t;
-                    t = (double)(vx + 1) * vs - qx; const double gxp = t * t;
-                    t = qx - (double)vx * vs;       const double gxm = t * t;
-                    t = (double)(vy + 1) * vs - qy; const double gyp = t * t;
-                    t = qy - (double)vy * vs;       const double gym = t * t;
-                    t = (double)(vz + 1) * vs - qz; const double gzp = t * t;
-                    t = qz - (double)vz * vs;       const double gzm = t * t;
-                    unsigned mask = valid ? 0x07FFFFFEu : 0u;
-                    mask &= (kX0 | (gxp <= bound ? kXP : 0u) | (gxm <= bound ? kXM : 0u)) &
-                            (kY0 | (gyp <= bound ? kYP : 0u) | (gym <= bound ? kYM : 0u)) &
-                            (kZ0 | (gzp <= bound ? kZP : 0u) | (gzm <= bound ? kZM : 0u));
-                    // edges and corners: the summed gap decides
-#pragma unroll
-                    for (int kk = 7; kk < 27; ++kk) {
-                        const double lb2 = (shift_x(kk) > 0 ? gxp : (shift_x(kk) < 0 ? gxm : 0.0)) +
-                                           (shift_y(kk) > 0 ? gyp : (shift_y(kk) < 0 ? gym : 0.0)) +
-                                           (shift_z(kk) > 0 ? gzp : (shift_z(kk) < 0 ? gzm : 0.0));
-                        if (lb2 > bound) mask &= ~(1u << kk);
-                    }
+                    const double2 qq = sm.qxy[lane];
+                    // exact pruning bound: the best squared distance found so far, and never more than the gate — a neighbour at
+                    // tau or beyond is rejected anyway (Registration.cpp:75), so voxels that can only hold such points are skipped
+                    const double tau2 = s_ps.tau * s_ps.tau;
+                    const double bsq = fmin(tau2, best);
+                    unsigned mask = stage_mask(stage, valid, bsq * (1.0 + 1e-6) + 1e-10, qq.x, qq.y, sm.qz[lane], sm.vx[lane], sm.vy[lane],
+                                               sm.vz[lane], a.map.voxel_size);
                     const int no = __popc(mask);
                     int tin = no;
 #pragma unroll
@@ -598,41 +537,213 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                         const int y = __shfl_up_sync(FULL, tin, d);
                         if (lane >= d) tin += y;
                     }
-                    sm.tend[lane] = (unsigned)tin, sm.nmask[lane] = mask;
-                    total = (unsigned)__shfl_sync(FULL, tin, 31);
-                    nbatch = (int)((total + 31u) >> 5);
+                    total = __shfl_sync(FULL, tin, 31);
+                    wtasks += total;
+                    int pos = tin - no;
+                    const int maxno = __reduce_max_sync(FULL, no);
+                    for (int i = 0; i < maxno; ++i) {  // warp-uniform trip count, the store predicated per lane
+                        if (mask) {
+                            const int k = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            sm.task[pos++] = (unsigned short)((lane << 5) | k);
+                        }
+                    }
                     __syncwarp();
                 }
+                KR_PROF(1)
+                for (int base = 0; base < total; base += 32) {
+                    KR_PROF_COUNT(9)
+                    // -------------------------------------------------------- this lane's task and its hash probe
+                    const bool act = base + lane < total;
+                    const unsigned okpack = act ? (unsigned)sm.task[base + lane] : 0u;
+                    uint32_t meta = KICP_SLOT_EMPTY;
+                    {
+                        const int o = (int)(okpack >> 5), k = (int)(okpack & 31u);
+                        const int kx = sm.vx[o] + shift_x(k), ky = sm.vy[o] + shift_y(k), kz = sm.vz[o] + shift_z(k);
+                        uint32_t h = voxel_hash(kx, ky, kz) & a.map.mask;
+                        // the home slot and the next one travel together: with a load factor <= 0.25 a longer chain is rare
+                        const int4 s0 = __ldg(&a.map.slots[h]);
+                        const int4 s1 = __ldg(&a.map.slots[(h + 1) & a.map.mask]);
+                        bool pend = false;
+                        if (act && (uint32_t)s0.w != KICP_SLOT_EMPTY) {
+                            if (s0.x == kx && s0.y == ky && s0.z == kz) {
+                                meta = (uint32_t)s0.w;
+                            } else if ((uint32_t)s1.w != KICP_SLOT_EMPTY) {
+                                if (s1.x == kx && s1.y == ky && s1.z == kz) {
+                                    meta = (uint32_t)s1.w;
+                                } else {
+                                    pend = true, h = (h + 2) & a.map.mask;
+                                }
+                            }
+                        }
+                        while (__any_sync(FULL, pend)) {  // warp-uniform loop
+                            if (pend) {
+                                const int4 sl = __ldg(&a.map.slots[h]);
+                                if ((uint32_t)sl.w == KICP_SLOT_EMPTY) {
+                                    pend = false;
+                                } else if (sl.x == kx && sl.y == ky && sl.z == kz) {
+                                    meta = (uint32_t)sl.w, pend = false;
+                                } else {
+                                    h = (h + 1) & a.map.mask;
+                                }
+                            }
+                        }
+                    }
+                    KR_PROF(2)
+                    // -------------------------------------------------------- number the 128-byte lines of the batch
+                    const int cnt = meta == KICP_SLOT_EMPTY ? 0 : (int)(meta & 0xFFu);
+                    const int nl = (cnt + 3) >> 2;
+                    int incl = nl;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int y = __shfl_up_sync(FULL, incl, d);
+                        if (lane >= d) incl += y;
+                    }
+                    const int loff = incl - nl;
+                    const int ltot = __shfl_sync(FULL, incl, 31);
+                    const int maxnl = __reduce_max_sync(FULL, nl);
+                    if (a.collect_stats) n_probe += act ? 1 : 0, n_cand += cnt, n_line += nl;
+                    // the lines of an owner are contiguous (tasks are owner-major): publish every owner's range of this batch
+                    {
+                        const unsigned oprev = __shfl_up_sync(FULL, okpack >> 5, 1), onext = __shfl_down_sync(FULL, okpack >> 5, 1);
+                        const bool anext = __shfl_down_sync(FULL, act ? 1 : 0, 1) != 0;
+                        sm.lbeg[lane] = 0, sm.lend[lane] = 0;
+                        __syncwarp();
+                        if (act && (lane == 0 || oprev != (okpack >> 5))) sm.lbeg[okpack >> 5] = (unsigned short)loff;
+                        if (act && (lane == 31 || !anext || onext != (okpack >> 5))) sm.lend[okpack >> 5] = (unsigned short)(loff + nl);
+                    }
+
+                    for (int lbase = 0; lbase < ltot; lbase += KR_LCAP) {
+                        // line map of this chunk: entry = task lane | (line inside the voxel << 5)
+                        for (int li = 0; li < maxnl; ++li) {
+                            const int pos = loff + li - lbase;
+                            if (li < nl && pos >= 0 && pos < KR_LCAP) sm.lmap[pos] = (unsigned short)(lane | (li << 5));
+                        }
+                        __syncwarp();
+                        KR_PROF(3)
+                        const int nr = min(KR_LCAP, ltot - lbase);
+                        for (int r0 = 0; r0 < nr; r0 += 8 * KR_G) {
+                            // a quad takes a line, a lane ONE point of it; KR_G independent 256-bit loads per lane in flight
+                            unsigned own[KR_G], gix[KR_G], nval[KR_G];
+                            unsigned hasm = 0, lvm = 0;
+#pragma unroll
+                            for (int g = 0; g < KR_G; ++g) {
+                                const int line = r0 + g * 8 + quad;
+                                const bool lv = line < nr;
+                                const unsigned e = lv ? (unsigned)sm.lmap[line] : 0u;
+                                const int t = (int)(e & 31u), li = (int)(e >> 5);
+                                const uint32_t m = __shfl_sync(FULL, meta, t);
+                                own[g] = __shfl_sync(FULL, okpack, t) >> 5;
+                                const int left = (int)(m & 0xFFu) - li * 4;  // points of the voxel from this line on
+                                const bool has = lv && sub < left;
+                                nval[g] = (unsigned)min(left, 4);
+                                gix[g] = lv ? (m >> 8) * (unsigned)a.map.cap + (unsigned)(li * 4) : 0u;
+                                hasm |= has ? (1u << g) : 0u, lvm |= lv ? (1u << g) : 0u;
+                            }
+                            Point4 c[KR_G];
+#pragma unroll
+                            for (int g = 0; g < KR_G; ++g)
+                                c[g] = ld_point(a.map.pts + (size_t)(gix[g] + ((hasm >> g) & 1u ? (unsigned)sub : 0u)) * KICP_PSTRIDE);
+                            KR_PROF_COUNT(10)
+                            KR_PROF(4)
+#pragma unroll
+                            for (int g = 0; g < KR_G; ++g) {
+                                const double2 qq = sm.qxy[own[g]];
+                                double d2 = (hasm >> g) & 1u ? dist2(c[g].x, c[g].y, c[g].z, qq.x, qq.y, sm.qz[own[g]]) : DBL_MAX;
+                                // the line's minimum (a NaN distance never wins, as in the reference's comparisons)
+                                d2 = fmin(d2, __shfl_xor_sync(FULL, d2, 1));
+                                d2 = fmin(d2, __shfl_xor_sync(FULL, d2, 2));
+                                if (sub == 0 && ((lvm >> g) & 1u)) {
+                                    LineMin lm;
+                                    lm.d2 = d2, lm.gline = gix[g], lm.nvalid = nval[g];
+                                    sm.line[r0 + g * 8 + quad] = lm;
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        // every lane, as an owner: first strict minimum over its lines of this chunk, in visiting order
+                        {
+                            const int lb = max((int)sm.lbeg[lane] - lbase, 0), le = min((int)sm.lend[lane] - lbase, nr);
+                            const int maxlen = __reduce_max_sync(FULL, max(le - lb, 0));
+                            for (int u = 0; u < maxlen; ++u) {  // warp-uniform trip count
+                                if (lb + u < le) {
+                                    const LineMin lm = sm.line[lb + u];
+                                    // The reference compares NORMS with a strict < (first minimum wins).  sqrt is monotone, so d^2 decides —
+                                    // except when two squares within an ulp or two round to the same norm: then the earlier point stays.
+                                    if (lm.d2 < best && !(lm.d2 >= best * (1.0 - 4e-16) && sqrt(lm.d2) == sqrt(best)))
+                                        best = lm.d2, bline = lm.gline, bvalid = lm.nvalid;
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        KR_PROF(5)
+                    }
+                    KR_PROF(3)
+                }
+                __syncwarp();
             }
-            __syncwarp();
+            KR_PROF(1)
             // ---------------------------------------------------------------- gate, residual, Jacobian, sums
-            const unsigned long long bb = sm.best[lane];
-            const unsigned gwin = (unsigned)(sm.kg[lane] & 0xFFFFFFFFull);
-            if (valid && bb != KR_DBLMAX_BITS) {
-                const Point4 c = ld_point(mr.pts + (size_t)gwin * KICP_PSTRIDE);
-                const double rx = qx - c.x, ry = qy - c.y, rz = qz - c.z;  // r = T p - n
+            {
+                // the winning line is re-evaluated by its owner (same pinned arithmetic): the first of its points at the minimum is
+                // the neighbour the reference returns
+                const bool have = valid && bline != 0xFFFFFFFFu;
+                const unsigned g0 = have ? bline : 0u;
+                Point4 cc[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cc[j] = ld_point(a.map.pts + (size_t)(g0 + (j < (int)bvalid ? j : 0)) * KICP_PSTRIDE);
+                Point4 c = cc[0];
+                {
+                    const double2 q0 = sm.qxy[lane];
+                    double bd = dist2(cc[0].x, cc[0].y, cc[0].z, q0.x, q0.y, sm.qz[lane]);
+#pragma unroll
+                    for (int j = 1; j < 4; ++j) {
+                        const double dj = dist2(cc[j].x, cc[j].y, cc[j].z, q0.x, q0.y, sm.qz[lane]);
+                        if (j < (int)bvalid && dj < bd && !(dj >= bd * (1.0 - 4e-16) && sqrt(dj) == sqrt(bd))) bd = dj, c = cc[j];
+                    }
+                }
+                const double2 qq = sm.qxy[lane];
+                const double rx = qq.x - c.x, ry = qq.y - c.y, rz = sm.qz[lane] - c.z;  // r = T p - n
                 const double rr = rx * rx + ry * ry + rz * rz;
-                if (sqrt(rr) < tau) {  // distance < max_correspondance_distance   (Registration.cpp:75)
+                if (have && sqrt(rr) < s_ps.tau) {  // distance < max_correspondance_distance   (Registration.cpp:75)
                     // J = [R e_x | R (-p_y, p_x, 0)]      (Registration.cpp:89-91)
+                    const double px = sm.px[lane], py = sm.py[lane];
                     const double c0x = s_ps.R[0], c0y = s_ps.R[3], c0z = s_ps.R[6];
                     const double c1x = s_ps.R[1] * px - s_ps.R[0] * py, c1y = s_ps.R[4] * px - s_ps.R[3] * py,
                                  c1z = s_ps.R[7] * px - s_ps.R[6] * py;
-                    a00 += c0x * c0x + c0y * c0y + c0z * c0z;
-                    a01 += c0x * c1x + c0y * c1y + c0z * c1z;
-                    a11 += c1x * c1x + c1y * c1y + c1z * c1z;
-                    b0 += c0x * rx + c0y * ry + c0z * rz;
-                    b1 += c1x * rx + c1y * ry + c1z * rz;
-                    cntN += 1.0;
-                    ssq += rr;
+                    sm.acc[0][lane] += c0x * c0x + c0y * c0y + c0z * c0z;
+                    sm.acc[1][lane] += c0x * c1x + c0y * c1y + c0z * c1z;
+                    sm.acc[2][lane] += c1x * c1x + c1y * c1y + c1z * c1z;
+                    sm.acc[3][lane] += c0x * rx + c0y * ry + c0z * rz;
+                    sm.acc[4][lane] += c1x * rx + c1y * ry + c1z * rz;
+                    sm.acc[5][lane] += 1.0;
+                    sm.acc[6][lane] += rr;
                 }
             }
             __syncwarp();
-            w = (int)(__shfl_sync(FULL, tk, 0) - ticket_base);
+            KR_PROF(6)
+            if (sched && it == 0u && lane == 0) {  // scheduling hint for the later passes
+                const bool heavy = wtasks > a.heavy_tasks;
+                a.heavy_flag[w] = heavy ? 1 : 0;
+                if (heavy) a.heavy_list[atomicAdd(&st->heavy_n, 1u)] = (unsigned)w;
+            }
+            for (;;) {  // next ticket -> window
+                const unsigned t = __shfl_sync(FULL, tk, 0) - ticket_base;
+                if (t >= tlimit) { w = num_windows; break; }
+                if (t < nheavy) { w = (int)__ldcg(&a.heavy_list[t]); break; }
+                w = (int)(t - nheavy);
+                if (nheavy == 0u || !__ldcg(&a.heavy_flag[w])) break;
+                if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);
+            }
+            KR_PROF(7)
         }
+        KR_PROF(11)
 
         const unsigned long long t_win = gtime_ns();
         // ---------------------------------------------------------------- warp -> CTA partial (plain stores, fixed order)
-        double v[7] = {a00, a01, a11, b0, b1, cntN, ssq};
+        double v[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) v[k] = sm.acc[k][lane];
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
 #pragma unroll
@@ -682,6 +793,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                 const unsigned target = (it + 1u) * gridDim.x;
                 const unsigned long long deadline = t_win + a.timeout_ns;  // per-thread register: no uniform read inside the spin
                 while (ld_acquire_gpu_u32(&st->arrive) < target) {
+                    __nanosleep(40);  // the spinning thread shares its scheduler with warps that are still working
                     if (gtime_ns() > deadline) {  // a CTA of this grid never arrived: give up instead of hanging
                         atomicExch(&st->abort, KICP_ERR_CUDA);
                         break;
@@ -780,13 +892,14 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
 
     if (PERSISTENT) {
         if (a.collect_stats) stats_flush(st, n_probe, n_cand, n_line);
+        KR_PROF_FLUSH
         // the last CTA to leave zeroes the counters for the next registration on this stream
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
             const unsigned left = atomicAdd(&st->exit_ctr, 1u);
             if (left == gridDim.x - 1) {
-                st->win_ctr = 0, st->arrive = 0, st->abort = 0;
+                st->win_ctr = 0, st->arrive = 0, st->abort = 0, st->heavy_n = 0;
                 __threadfence();
                 st->exit_ctr = 0;
             }
@@ -813,6 +926,9 @@ extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value)
     } else if (!strcmp(name, "spin_timeout_ms")) {
         if (value < 1) return KICP_ERR_INVALID;
         c->spin_timeout_ms = value;
+    } else if (!strcmp(name, "heavy_tasks")) {
+        if (value < 0) return KICP_ERR_INVALID;
+        c->heavy_tasks = value;
     } else if (!strcmp(name, "overlap_upload")) {
         if (value != 0 && value != 1) return KICP_ERR_INVALID;
         c->overlap_upload = value;
@@ -823,14 +939,18 @@ extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value)
     return KICP_OK;
 }
 
+static const size_t KR_SMEM_BYTES = (size_t)KR_WARPS * sizeof(WarpSm);
+
 static int reg_reserve(kicp_ctx *c) {
     if (c->d_state) return KICP_OK;
     KICP_CUDA(cudaMalloc(&c->d_state, sizeof(RegState)));
     KICP_CUDA(cudaMemset(c->d_state, 0, sizeof(RegState)));
     int per_sm = 0;
-    KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_register<true>, KR_THREADS, 0));
+    KICP_CUDA(cudaFuncSetAttribute(k_register<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KR_SMEM_BYTES));
+    KICP_CUDA(cudaFuncSetAttribute(k_register<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KR_SMEM_BYTES));
+    KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_register<true>, KR_THREADS, KR_SMEM_BYTES));
     c->persistent_ctas_per_sm = std::max(per_sm, 1);
-    KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_register<false>, KR_THREADS, 0));
+    KICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_register<false>, KR_THREADS, KR_SMEM_BYTES));
     c->pruned_ctas_per_sm = std::max(per_sm, 1);
     const int max_grid = c->sm_count * std::max(c->persistent_ctas_per_sm, c->pruned_ctas_per_sm);
     KICP_CUDA(cudaMalloc(&c->d_partials, (size_t)2 * max_grid * 8 * sizeof(double)));
@@ -911,6 +1031,20 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
         ka.pow2_voxel = std::frexp(m->voxel_size, &e) == 0.5 ? 1 : 0;
     }
     ka.collect_stats = c->collect_stats;
+    ka.heavy_list = nullptr, ka.heavy_flag = nullptr, ka.heavy_tasks = c->heavy_tasks;
+    if (c->heavy_tasks > 0 && scan->n > 0) {
+        const int64_t windows = (scan->n + 31) / 32;
+        if (windows > c->heavy_cap) {
+            KICP_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(c->d_heavy_list), cudaFree(c->d_heavy_flag);
+            c->d_heavy_list = nullptr, c->d_heavy_flag = nullptr, c->heavy_cap = 0;
+            const int64_t cap = windows + windows / 4 + 64;
+            KICP_CUDA(cudaMalloc(&c->d_heavy_list, (size_t)cap * sizeof(unsigned int)));
+            KICP_CUDA(cudaMalloc(&c->d_heavy_flag, (size_t)cap));
+            c->heavy_cap = cap;
+        }
+        ka.heavy_list = c->d_heavy_list, ka.heavy_flag = c->d_heavy_flag;
+    }
     ka.timeout_ns = (unsigned long long)c->spin_timeout_ms * 1000000ull;
     const int n = (int)scan->n;
     const bool p2p = sharded && c->p2p_ready;
@@ -927,7 +1061,8 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
         KICP_CUDA(cudaEventRecord(pr->prep0, c->stream));
     }
     if (c->collect_stats)
-        KICP_CUDA(cudaMemsetAsync((char *)c->d_state + offsetof(RegState, stats), 0, sizeof(((RegState *)0)->stats), c->stream));
+        KICP_CUDA(cudaMemsetAsync((char *)c->d_state + offsetof(RegState, stats), 0,
+                                  sizeof(((RegState *)0)->stats) + sizeof(((RegState *)0)->prof), c->stream));
 
     const bool dbg = getenv("KICP_DEBUG_SYNC") != nullptr;
     if (ka.init.max_iter <= 0 || !persistent) {
@@ -966,7 +1101,7 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
                 KICP_CUDA(cudaEventRecord(e0, c->stream));
             }
             void *args[] = {&ka};
-            KICP_CUDA(cudaLaunchCooperativeKernel((const void *)k_register<true>, dim3(grid), dim3(KR_THREADS), args, 0, c->stream));
+            KICP_CUDA(cudaLaunchCooperativeKernel((const void *)k_register<true>, dim3(grid), dim3(KR_THREADS), args, KR_SMEM_BYTES, c->stream));
             c->launches++;
             if (pr) KICP_CUDA(cudaEventRecord(e1, c->stream));
             if (dbg) {
@@ -982,7 +1117,7 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
                     pr->it.push_back(e0), pr->it.push_back(e1);
                     KICP_CUDA(cudaEventRecord(e0, c->stream));
                 }
-                k_register<false><<<grid, KR_THREADS, 0, c->stream>>>(ka);
+                k_register<false><<<grid, KR_THREADS, KR_SMEM_BYTES, c->stream>>>(ka);
                 KICP_CHECK_LAUNCH(c);
                 if (pr) KICP_CUDA(cudaEventRecord(e1, c->stream));
                 if (sharded) KICP_TRY(kicp_comm_allreduce8(c, c->d_state->acc));
@@ -1012,6 +1147,12 @@ extern "C" int kicp_debug_last_stats(kicp_ctx *c, uint64_t out[4] /* probes, can
     if (!c || !c->d_state || !out) return KICP_ERR_INVALID;
     KICP_CUDA(cudaStreamSynchronize(c->stream));
     KICP_CUDA(cudaMemcpy(out, (const char *)c->d_state + offsetof(RegState, stats), sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost));
+    return KICP_OK;
+}
+extern "C" int kicp_debug_last_prof(kicp_ctx *c, uint64_t out[16] /* -DKR_PROFILE builds: cycles per phase, counts */) {
+    if (!c || !c->d_state || !out) return KICP_ERR_INVALID;
+    KICP_CUDA(cudaStreamSynchronize(c->stream));
+    KICP_CUDA(cudaMemcpy(out, (const char *)c->d_state + offsetof(RegState, prof), sizeof(uint64_t) * 16, cudaMemcpyDeviceToHost));
     return KICP_OK;
 }
 

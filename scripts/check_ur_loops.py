@@ -41,6 +41,17 @@ for lo, hi in sorted(set(loops)):
         return op.startswith(("SHFL.", "VOTE.", "VOTEU.", "REDUX", "CREDUX", "MATCH."))
     if any(collective(t) for a, t in body):
         continue
+    # a counted loop whose trip count is a uniform register (back-edge predicate = ISETP counter, URx): every lane runs the
+    # same number of iterations, nobody leaves early
+    back = ins[addr[hi]][1]
+    mb = re.match(r"@(!?)(P\d+)\s+BRA", back)
+    if mb:
+        setter = None
+        for a, t in body:
+            ms = re.match(r"(?:@!?U?P\d+\s+)?ISETP\S*\s+(P\d+),", t)
+            if ms and ms.group(1) == mb.group(2): setter = t
+        if setter is not None and re.search(r",\s*UR\d+,", setter):
+            continue
     defs = set()
     for a, t in body: defs |= writes(t)
     later = set()
