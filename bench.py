@@ -7,8 +7,10 @@ OS1-128-shape synthetic scan (~262 k points) against the 1 M-point voxel map (BA
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 1..4] [--mode sharded|replicas]
 
 N > 1 is launched by torchrun, one rank per GPU.  In `sharded` mode (default, the north-star layout) the scan's
-points are split by contiguous index range, the map is replicated, and every IRLS iteration ends with one NCCL
-sum-allreduce of 8 doubles: total work is fixed, so "scaling" is "strong".  Rank 0 prints ONE JSON line.
+points are split by contiguous index range, the map is replicated, and every IRLS iteration ends with one exchange of
+8 doubles (fused into the persistent kernel over NVLink peer memory, or NCCL with --comm nccl): total work is fixed, so
+"scaling" is "strong".  The same invocation then also runs BASELINE.json configs[4]'s layout — N independent registrations,
+one per GPU — and reports it under "replicas".  Rank 0 prints ONE JSON line.
 """
 import argparse
 import json
@@ -179,26 +181,47 @@ class NvmlSampler:
 
 
 # -------------------------------------------------------------------------------------------------- CPU baseline
-def cpu_registration_runner(w):
-    """Returns (callable running one full registration on the host cores, kind, cores)."""
+def physical_cores():
+    """Physical cores of the host (one worker per core: SMT siblings share the units the FP64 search saturates)."""
+    seen = set()
+    try:
+        base = "/sys/devices/system/cpu"
+        for d in os.listdir(base):
+            path = os.path.join(base, d, "topology", "thread_siblings_list")
+            if d.startswith("cpu") and d[3:].isdigit() and os.path.exists(path):
+                seen.add(open(path).read().strip())
+    except OSError:
+        pass
+    n = len(seen) if seen else (os.cpu_count() or 1)
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    return max(n, 1)
+
+
+def cpu_registration_runner(w, threads):
+    """Returns (callable running one full registration on `threads` host threads, kind)."""
     from oracle import kicp_oracle_py as ko
-    cores = os.cpu_count() or 1
     if ko.ref_available():
         _, _, pts = w.map.export_voxels()
         rm = ko.RefMap(w.voxel_size, w.max_range, w.max_points_per_voxel)
         rm.add_points(pts)
 
         def run():
-            return rm.register(w.scan, w.last_pose, w.rel_odom, w.tau, threads=cores)
-        return run, "reference", cores
+            return rm.register(w.scan, w.last_pose, w.rel_odom, w.tau, threads=threads)
+        return run, "reference"
 
     def run():
-        return w.map.register(w.scan, w.last_pose, w.rel_odom, w.tau, threads=cores)[0]
-    return run, "port", cores
+        return w.map.register(w.scan, w.last_pose, w.rel_odom, w.tau, threads=threads)[0]
+    return run, "port"
 
 
-def time_cpu(w, steps, warmup):
-    run, kind, cores = cpu_registration_runner(w)
+def time_cpu(w, steps, warmup, single_thread_steps=0):
+    """The reference's own Registration.cpp (oracle/_ref) on the box's physical cores: a persistent worker pool (oracle/shim/tbb),
+    median over `steps` registrations; optionally also T = 1, the reference's online default (pipeline/KinematicICP.hpp:54)."""
+    cores = physical_cores()
+    run, kind = cpu_registration_runner(w, cores)
     for _ in range(warmup):
         run()
     ts = []
@@ -206,12 +229,22 @@ def time_cpu(w, steps, warmup):
         t = time.perf_counter()
         run()
         ts.append(time.perf_counter() - t)
-    total = sum(ts)
-    return {"value": steps / total, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": "%d full registrations of the same workload (all %d scan points, all iterations), %s, "
-                      "%d host threads, %.1f s of CPU work" %
-                      (steps, w.N, "the reference's own Registration.cpp compiled against header shims (oracle/_ref)"
-                       if kind == "reference" else "CPU oracle port", cores, total)}, total / steps
+    med = statistics.median(ts)
+    out = {"value": 1.0 / med, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": "%d full registrations of the same workload (all %d scan points, all iterations), %s, %d host threads "
+                     "(one per physical core, persistent pool), median of %.1f s of CPU work" %
+                     (steps, w.N, "the reference's own Registration.cpp compiled against header shims (oracle/_ref)"
+                      if kind == "reference" else "CPU oracle port", cores, sum(ts)),
+           "min_max_ms": [1e3 * min(ts), 1e3 * max(ts)]}
+    if single_thread_steps > 0:
+        run1, _ = cpu_registration_runner(w, 1)
+        t1 = []
+        for _ in range(single_thread_steps):
+            t = time.perf_counter()
+            run1()
+            t1.append(time.perf_counter() - t)
+        out["value_1_thread"] = 1.0 / statistics.median(t1)
+    return out, med
 
 
 def run_reference_arm(args):
@@ -222,7 +255,7 @@ def run_reference_arm(args):
     from oracle import workloads as W
     ko.build()
     w = W.Workload(args.workload)
-    cb, sec_per_step = time_cpu(w, args.steps, args.warmup)
+    cb, sec_per_step = time_cpu(w, args.steps, max(args.warmup, 1), single_thread_steps=1)
     line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sec_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
@@ -233,11 +266,39 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------------ GPU arm
+def sha256_file(path):
+    import hashlib
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        h.update(f.read())
+    return h.hexdigest()
+
+
+def measure_l2_bandwidth(torch, dev):
+    """Read bandwidth of an L2-resident buffer on this GPU (the ceiling of a path whose working set lives in L2):
+    a 32 MiB float32 buffer summed repeatedly, CUDA events, best of 5."""
+    x = torch.ones(8 << 20, dtype=torch.float32, device=dev)
+    for _ in range(3):
+        x.sum()
+    best = 0.0
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            x.sum()
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, 20 * x.numel() * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    return best
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
         return
+
+    import ctypes as C
 
     import numpy as np
     import torch
@@ -256,6 +317,7 @@ def main():
         args.gpus = world
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -273,26 +335,19 @@ def main():
     gm.load_voxels(*w.map.export_voxels())  # replicated on every GPU
     reg = kb.KinematicRegistration()  # reference defaults: 10 iterations, 1e-3, adaptive regularisation
 
-    sharded = world > 1 and args.mode == "sharded"
     if world > 1:
-        if rank == 0:
-            uid = torch.tensor(list(kb.comm_unique_id()), dtype=torch.uint8, device=dev)
-        else:
-            uid = torch.empty(_capi.KICP_UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
-        dist.broadcast(uid, 0)
         if args.comm == "nccl":
+            if rank == 0:
+                uid = torch.tensor(list(kb.comm_unique_id()), dtype=torch.uint8, device=dev)
+            else:
+                uid = torch.empty(_capi.KICP_UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
+            dist.broadcast(uid, 0)
             ctx.comm_init(bytes(uid.cpu().tolist()), world, rank)
         else:  # fused exchange over NVLink peer memory: all-gather the CUDA-IPC handles of the mailboxes
             mine = torch.tensor(list(ctx.p2p_handle()), dtype=torch.uint8, device=dev)
             allh = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(allh, mine)
             ctx.p2p_init([bytes(h.cpu().tolist()) for h in allh], world, rank)
-    lo, hi = kb.shard_range(w.N, world, rank) if sharded else (0, w.N)
-    shard = np.ascontiguousarray(w.scan[lo:hi])
-    scan = kb.Scan(ctx, len(shard))
-    scan.upload(shard)
-    h_shard = kb.pinned_empty(shard.shape)
-    h_shard[:] = shard
 
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     flush_buf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
@@ -314,7 +369,6 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    results = [kb.pinned_result() for _ in range(args.steps + args.warmup)]
     try:
         gpu_uuid = torch.cuda.get_device_properties(dev).uuid
     except Exception:
@@ -325,7 +379,7 @@ def main():
 
     def timed_loop(enqueue, steps, warmup, profile=False):
         """W untimed warm-up steps, then K steps each bracketed by CUDA events on the launching stream, with an
-        (untimed) L2 flush before every step.  Returns (sum of step ms as max over ranks, kernel profile)."""
+        (untimed) L2 flush before every step.  Returns (sum of step ms as max over ranks, kernel profile, step ms)."""
         for i in range(warmup):
             flush_l2(i)
             enqueue(i)
@@ -347,117 +401,210 @@ def main():
         step_ms = [a.elapsed_time(b) for a, b in ev]
         return max_over_ranks(sum(step_ms)), prof, step_ms
 
-    # ---- value: inputs already resident in HBM --------------------------------------------------------------
-    def enqueue_resident(i):
-        reg.enqueue(scan, gm, w.last_pose, w.rel_odom, w.tau, results[i], sharded=sharded)
-
-    launches0 = ctx.launch_count
-    total_ms, prof, step_ms = timed_loop(enqueue_resident, args.steps, args.warmup, profile=True)
-    gpu_launches = ctx.launch_count - launches0
-    # warm-up launches are included in launch_count; subtract them proportionally
-    gpu_launches = int(round(gpu_launches * args.steps / float(args.steps + args.warmup)))
-    jobs = world if (world > 1 and not sharded) else 1  # replicas: every rank finishes its own registrations
-    value = jobs * args.steps / (total_ms * 1e-3)
-    iters = results[args.warmup].iterations
-
-    # ---- e2e: host buffers through the public synchronous call, copies inside the timed region ------------------
-    out_pose = np.empty(7)
-    res_host = kb.RegResult()
     params = reg._params()
-    import ctypes as C
-    fn = _capi.lib().kicp_register_sharded if sharded else _capi.lib().kicp_register
+    last7, odom7 = _capi.as_pose(w.last_pose), _capi.as_pose(w.rel_odom)
 
-    def e2e_call(i):
-        st = fn(gm.h, _capi.dp(h_shard), len(h_shard), _capi.dp(_capi.as_pose(w.last_pose)),
-                _capi.dp(_capi.as_pose(w.rel_odom)), float(w.tau), C.byref(params), _capi.dp(out_pose), C.byref(res_host))
-        assert st == 0, st
+    def run_mode(sharded):
+        """One layout (whole scan per rank / contiguous index range per rank): HBM-resident `value`, then the e2e variants
+        through the synchronous host-pointer calls.  Returns a dict."""
+        lo, hi = kb.shard_range(w.N, world, rank) if sharded else (0, w.N)
+        shard = np.ascontiguousarray(w.scan[lo:hi])
+        scan = kb.Scan(ctx, len(shard))
+        scan.upload(shard)
+        results = [kb.pinned_result() for _ in range(args.steps + args.warmup)]
 
-    e2e_ms, _, _ = timed_loop(e2e_call, args.steps, args.warmup)
+        def enqueue_resident(i):
+            reg.enqueue(scan, gm, w.last_pose, w.rel_odom, w.tau, results[i], sharded=sharded)
+
+        launches0 = ctx.launch_count
+        total_ms, prof, _ = timed_loop(enqueue_resident, args.steps, args.warmup, profile=True)
+        launches = int(round((ctx.launch_count - launches0) * args.steps / float(args.steps + args.warmup)))
+        timing = ctx.last_timing()  # CTA 0 of this rank, last registration: [pass][windows, barrier wait, reduce(+exchange), solve] ns
+        jobs = world if (world > 1 and not sharded) else 1  # replicas: every rank finishes its own registrations
+        out = {"value": jobs * args.steps / (total_ms * 1e-3), "ms_per_step": total_ms / args.steps, "prof": prof,
+               "launches": launches, "result": results[args.warmup], "n_local": hi - lo, "timing": timing}
+
+        # e2e: host buffers through the public synchronous call, copies inside the timed region
+        out_pose = np.empty(7)
+        res_host = kb.RegResult()
+        L = _capi.lib()
+
+        def make_call(buf, dtype):
+            fn = (L.kicp_register_points_sharded if sharded else L.kicp_register_points)
+
+            def call(i):
+                st = fn(gm.h, buf.ctypes.data, len(buf), dtype, 0, 0, 0, 0, _capi.dp(last7), _capi.dp(odom7), float(w.tau),
+                        C.byref(params), _capi.dp(out_pose), C.byref(res_host))
+                assert st == 0, (st, L.kicp_last_error())
+            return call
+
+        variants = {}
+        shard32 = shard.astype(np.float32)
+        for name, src, dtype in (("pinned_f64", shard, _capi.KICP_DTYPE_F64), ("pageable_f64", shard, _capi.KICP_DTYPE_F64),
+                                 ("pinned_f32", shard32, _capi.KICP_DTYPE_F32), ("pageable_f32", shard32, _capi.KICP_DTYPE_F32)):
+            if name.startswith("pinned"):
+                buf = kb.pinned_empty(src.shape, src.dtype)
+                buf[:] = src
+            else:
+                buf = np.array(src, copy=True)  # ordinary (pageable) numpy storage, like std::vector
+            ms, _, _ = timed_loop(make_call(buf, dtype), args.steps, args.warmup)
+            variants[name] = {"value": jobs * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
+                              "h2d_bytes_per_step": int(buf.nbytes) * (world if sharded else jobs)}
+            out["e2e_pose_" + name] = out_pose.copy()
+        out["e2e"] = variants
+        out["d2h_bytes_per_step"] = int(C.sizeof(kb.RegResult)) * world
+        scan.close()
+        return out
+
+    primary_sharded = world > 1 and args.mode == "sharded"
+    main_run = run_mode(primary_sharded)
+    replicas_run = run_mode(False) if (world > 1 and primary_sharded) else None
     clocks = sampler.stop() if rank == 0 else None
-    e2e_value = jobs * args.steps / (e2e_ms * 1e-3)
+
+    # ---- cross-rank identity of what the sharded run produced (every rank must hold the same pose and the same sums) ----
+    cross_rank_identical = None
+    if world > 1 and primary_sharded:
+        r = main_run["result"]
+        mine = torch.from_numpy(np.concatenate([r.pose_np(), np.ctypeslib.as_array(r.sums).ravel(),
+                                                [float(r.iterations)]])).to(dev)
+        allv = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        same = all(torch.equal(allv[0].view(torch.int64), v.view(torch.int64)) for v in allv)
+        cross_rank_identical = bool(same)
+        assert same, "ranks disagree on the sharded registration result"
+
+    # ---- work counters and per-pass device timings of one extra (untimed) registration --------------------------------
+    lo, hi = kb.shard_range(w.N, world, rank) if primary_sharded else (0, w.N)
+    scan = kb.Scan(ctx, hi - lo)
+    scan.upload(np.ascontiguousarray(w.scan[lo:hi]))
+    ctx.set_option("stats", 1)
+    res_stats = kb.pinned_result()
+    reg.enqueue(scan, gm, w.last_pose, w.rel_odom, w.tau, res_stats, sharded=primary_sharded)
+    probes, cands, lines, _ = ctx.last_stats()
+    ctx.set_option("stats", 0)
+    scan.close()
+    # per-rank pass anatomy (max over ranks of each column, median over the passes of the last timed registration)
+    tim = main_run["timing"][: max(int(main_run["result"].iterations), 1)] / 1e3  # us
+    anatomy = [float(np.median(tim[:, k])) for k in range(4)]
+    if world > 1:
+        t = torch.tensor(anatomy, dtype=torch.float64, device=dev)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tmin = t.clone()
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        anatomy_max, anatomy_min = tmax.tolist(), tmin.tolist()
+    else:
+        anatomy_max = anatomy_min = anatomy
 
     # ---- parity of what was just timed ------------------------------------------------------------------------
-    pose_ref = pose_delta = None
-    cpu_baseline = None
     if rank == 0:
-        pose_ref, st_ref = w.map.register(w.scan, w.last_pose, w.rel_odom, w.tau, threads=os.cpu_count() or 1)
-        dt, ang = ko.pose_delta(results[args.warmup].pose_np(), pose_ref)
-        dt2, ang2 = ko.pose_delta(out_pose, pose_ref)
-        pose_delta = {"translation_m": max(dt, dt2), "rotation_rad": max(ang, ang2), "iterations_gpu": int(iters),
-                      "iterations_cpu": int(st_ref.iterations),
-                      "tolerance": "1e-6 m / 1e-7 rad vs the CPU oracle (sequential-order FP64 restatement)"}
+        iters = int(main_run["result"].iterations)
+        pose_ref, st_ref = w.map.register(w.scan, w.last_pose, w.rel_odom, w.tau, threads=physical_cores())
+        deltas = [ko.pose_delta(main_run["result"].pose_np(), pose_ref)]
+        deltas += [ko.pose_delta(main_run["e2e_pose_" + k], pose_ref) for k in main_run["e2e"]]
+        if replicas_run is not None:
+            deltas.append(ko.pose_delta(replicas_run["result"].pose_np(), pose_ref))
+        pose_delta = {"translation_m": max(d[0] for d in deltas), "rotation_rad": max(d[1] for d in deltas),
+                      "iterations_gpu": iters, "iterations_cpu": int(st_ref.iterations),
+                      "tolerance": "1e-6 m / 1e-7 rad vs the CPU oracle (sequential-order FP64 restatement); float32 uploads "
+                                   "included (the workload's coordinates are float32-representable)"}
+        assert pose_delta["translation_m"] <= 1e-6 and pose_delta["rotation_rad"] <= 1e-7, pose_delta
+        cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu_baseline, _ = time_cpu(w, 5, 1)
+            cpu_baseline, _ = time_cpu(w, 5, 1, single_thread_steps=1)
 
-    if rank == 0:
-        # roofline of the association kernel: algorithmic bytes per point per launch
+        # ---- roofline of the registration kernel ---------------------------------------------------------------
         cbar, kbar = w.map.neighbourhood_stats(w.scan, w.prior)
-        a_pt = 16.0 + 27.0 * 16.0 + cbar * 16.0
-        n_local = hi - lo
+        a_pt = 16.0 + 27.0 * 16.0 + cbar * 16.0  # SURVEY.md 8(d): logical gather bytes per point per pass
+        n_local = main_run["n_local"]
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        prof = main_run["prof"]
         roofline = None
         if prof is not None and prof.assoc_launches > 0:
-            # one launch of the association kernel = all IRLS iterations of one registration (persistent kernel) or one
-            # iteration (multi-launch paths); algorithmic bytes per launch = passes per launch x N x A_pt
             passes_per_launch = prof.assoc_iterations / float(prof.assoc_launches)
             t_launch = prof.assoc_ms / prof.assoc_launches * 1e-3
             bytes_per_launch = passes_per_launch * n_local * a_pt
             achieved = bytes_per_launch / t_launch / 1e9
-            traffic, traffic_note = None, None
+            # what the kernel really moves from L2/HBM into the SMs, from its own counters: two 16-byte hash slots per probe,
+            # 128 bytes per line of candidate points, the scan point and the winner's line once per point and pass
+            touched_per_pass = (probes * 32.0 + lines * 128.0) / max(iters, 1) + n_local * (24.0 + 128.0)
+            l2_peak = measure_l2_bandwidth(torch, dev)
+            t_pass = t_launch / max(passes_per_launch, 1e-9)
+            touched_gbs = touched_per_pass / t_pass / 1e9
+            traffic, traffic_note = None, "no ncu capture of this build of kicp_register.cu under profiles/ (profiles/ncu_traffic.json)"
             ncu_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            src_sha = sha256_file(os.path.join(ROOT, "kinematic-icp_b200", "csrc", "kicp_register.cu"))
             if os.path.exists(ncu_path) and args.workload == 4 and world == 1:
                 tj = json.load(open(ncu_path))
-                traffic = tj.get("dram_bytes_per_launch")
-                traffic_note = "dram__bytes_read+write per launch from %s" % tj.get("source")
-            kernel_name = "k_register"
+                if tj.get("kernel_source_sha256") == src_sha:
+                    traffic = tj.get("dram_bytes_per_launch")
+                    traffic_note = "dram__bytes_read+write per launch, ncu --set full capture of this very source (%s)" % tj.get("source")
+                else:
+                    traffic_note = "profiles/ncu_traffic.json was captured for another build of kicp_register.cu: not reported"
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": traffic, "traffic_note": traffic_note, "kernel": kernel_name,
-                        "launch_us": t_launch * 1e6, "passes_per_launch": passes_per_launch,
-                        "kernel_us": t_launch * 1e6 / max(passes_per_launch, 1e-9),
+                        "traffic": traffic, "traffic_note": traffic_note, "kernel": "k_register<true>",
+                        "launch_us": t_launch * 1e6, "passes_per_launch": passes_per_launch, "kernel_us": t_pass * 1e6,
                         "launches_timed": int(prof.assoc_launches), "iterations_timed": int(prof.assoc_iterations),
-                        "algorithmic_bytes_per_launch": bytes_per_launch,
-                        "algorithmic_bytes_per_point": a_pt, "mean_candidates_per_point": cbar,
-                        "mean_occupied_voxels_of_27": kbar, "peak_source": peak_src,
-                        "note": "achieved = LOGICAL gather bytes (SURVEY.md 8(d): 16 + 27*16 + c*16 per point per pass) / "
-                                "CUDA-event duration of the launch. The kernel prunes the 27-voxel neighbourhood exactly "
-                                "(about 26 of the %.0f candidates per point are evaluated) and the map (%.0f MB) is served "
-                                "from L2 after the first touch, so the logical figure exceeds what HBM carries: ncu "
-                                "dram bytes per launch are in `traffic`. The kernel is latency/issue-bound, not "
-                                "bandwidth-bound (profiles/)." %
-                                (cbar, w.map.num_voxels() * w.max_points_per_voxel * 32 / 1e6)}
-        ms_per_step = total_ms / args.steps
+                        "algorithmic_bytes_per_launch": bytes_per_launch, "algorithmic_bytes_per_point": a_pt,
+                        "mean_candidates_per_point": cbar, "mean_occupied_voxels_of_27": kbar, "peak_source": peak_src,
+                        "touched": {"bytes_per_pass": touched_per_pass, "achieved_gbs": touched_gbs, "l2_read_peak_gbs": l2_peak,
+                                    "frac_of_l2_peak": touched_gbs / l2_peak, "probes_per_point_per_pass": probes / max(iters, 1) / n_local,
+                                    "candidates_per_point_per_pass": cands / max(iters, 1) / n_local,
+                                    "lines_per_point_per_pass": lines / max(iters, 1) / n_local,
+                                    "note": "bytes the kernel itself requests from L2 per pass, from its device-side counters (option "
+                                            "'stats': 32 B per hash probe, 128 B per line of candidate points, the scan point and the "
+                                            "winner's line per point), against the L2 read bandwidth measured on this GPU in this run — "
+                                            "the physical counterpart of the logical figure above"},
+                        "note": "achieved/frac = LOGICAL gather bytes of SURVEY.md 8(d) (16 + 27*16 + c*16 per point and pass, c = all "
+                                "%.0f points of the 27 voxels) / CUDA-event duration, against the measured HBM copy peak: the kernel prunes "
+                                "the neighbourhood exactly (%.1f of those candidates per point are evaluated) and the map is served from "
+                                "L2, so this is not a physical HBM fraction — see `touched` and `traffic` for what moves" %
+                                (cbar, cands / max(iters, 1) / n_local)}
+        e2e_main = main_run["e2e"]["pinned_f64"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong" if (world == 1 or sharded) else "weak",
+            "metric": METRIC, "value": main_run["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": main_run["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong" if (world == 1 or primary_sharded) else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(w, {
                 "parallelism": ("1 GPU" if world == 1 else ("scan sharded by index range over %d GPUs, map replicated, "
                                 "per-iteration exchange of 8 doubles: %s" % (world, "fused into the persistent kernel over NVLink peer memory"
-                                if args.comm == "p2p" else "NCCL allreduce") if sharded else
+                                if args.comm == "p2p" else "NCCL allreduce") if primary_sharded else
                                 "%d independent replicas" % world)),
                 "l2": "flushed before every timed step (%d MiB write, untimed)" % (L2_FLUSH_BYTES >> 20)
                       if not args.no_flush else "NOT flushed (diagnostic run)",
-                "iterations_per_registration": int(iters)}),
-            "ms_per_iter": ms_per_step / max(int(iters), 1),
+                "iterations_per_registration": iters}),
+            "ms_per_iter": main_run["ms_per_step"] / max(iters, 1),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_shard.nbytes) * (world if sharded else jobs),
-                    "d2h_bytes_per_step": int(C.sizeof(kb.RegResult)) * world, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": gpu_launches,
+            "e2e": {"value": e2e_main["value"], "unit": UNIT, "h2d_bytes_per_step": e2e_main["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": main_run["d2h_bytes_per_step"], "ms_per_step": e2e_main["ms_per_step"],
+                    "host_memory": "pinned, float64 xyz (std::vector<Eigen::Vector3d> layout) through kicp_register_points",
+                    "variants": {k: {"value": v["value"], "ms_per_step": v["ms_per_step"], "h2d_bytes_per_step": v["h2d_bytes_per_step"]}
+                                 for k, v in main_run["e2e"].items()}},
+            "gpu_launches": main_run["launches"],
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "pose_delta_vs_cpu": pose_delta,
+            "pass_anatomy_us": {"columns": ["windows phase (CTA 0)", "barrier wait", "reduce (+ exchange)", "solve"],
+                                "median_over_passes_max_over_ranks": anatomy_max, "min_over_ranks": anatomy_min,
+                                "note": "device %globaltimer probes on CTA 0 of every rank, last timed registration"},
             "kernel_time_split_ms_per_step": None if prof is None else {
-                "binning(init+keys+sort+gather)": prof.prep_ms / max(prof.registrations, 1),
-                "association(active launches)": prof.assoc_ms / max(prof.registrations, 1),
+                "setup launches": prof.prep_ms / max(prof.registrations, 1),
+                "registration kernel": prof.assoc_ms / max(prof.registrations, 1),
                 "launches_after_convergence": prof.idle_ms / max(prof.registrations, 1)},
         }
+        if cross_rank_identical is not None:
+            line["cross_rank_identical"] = cross_rank_identical
+        if replicas_run is not None:
+            rv = replicas_run["e2e"]["pinned_f64"]
+            line["replicas"] = {"value": replicas_run["value"], "unit": UNIT, "e2e": rv["value"], "scaling": "weak",
+                                "note": "BASELINE.json configs[4] layout: %d independent registrations, one per GPU, no communication; "
+                                        "aggregate scans/s (HBM-resident / pinned-host e2e)" % world}
         print(json.dumps(line), flush=True)
-    scan.close()
     gm.close()
     ctx.close()
     if world > 1:

@@ -56,10 +56,11 @@ struct kicp_ctx {
     int persistent = 1;     // 1 = all IRLS iterations inside one cooperative launch, 0 = one launch per iteration
     int collect_stats = 0;  // option "stats": count probes / candidate points / lines on the device
     int spin_timeout_ms = 20000;  // bound of every device-side wait (upload flags, peers of the fused exchange)
-    unsigned int *d_heavy_list = nullptr;   // scheduling hint of the persistent kernel: windows pass 0 found expensive
-    unsigned char *d_heavy_flag = nullptr;
-    int64_t heavy_cap = 0;                  // windows the two arrays hold
-    int heavy_tasks = 160;                  // option "heavy_tasks": hash probes per window above which it is "heavy" (0 = no hint)
+    // nearest-neighbour cache of the persistent kernel (one entry per scan point, carried from pass to pass)
+    unsigned int *d_nn_g = nullptr, *d_todo = nullptr;
+    float *d_nn_l = nullptr, *d_nn_seed = nullptr;
+    int64_t nn_cap = 0;
+    int nn_cache = 1;  // option "nn_cache"
     kicp_scan *upload_scan = nullptr;  // staging scan used by the host-pointer entry points
     // chunked upload overlapped with the first IRLS iteration (host-pointer entry points, persistent kernel)
     cudaStream_t copy_stream = nullptr;

@@ -165,8 +165,10 @@ extern "C" int kicp_ctx_destroy(kicp_ctx *ctx) {
     if (ctx->upload_scan) kicp_scan_destroy(ctx->upload_scan);
     cudaFree(ctx->d_state);
     cudaFree(ctx->d_partials);
-    cudaFree(ctx->d_heavy_list);
-    cudaFree(ctx->d_heavy_flag);
+    cudaFree(ctx->d_nn_g);
+    cudaFree(ctx->d_nn_l);
+    cudaFree(ctx->d_nn_seed);
+    cudaFree(ctx->d_todo);
     cudaFree(ctx->d_prof_iters);
     cudaFreeHost(ctx->h_result);
     cudaFreeHost(ctx->h_chunk_tags);

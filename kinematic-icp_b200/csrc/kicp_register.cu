@@ -42,7 +42,7 @@ using namespace kicp_dev;
 #define KR_WARPS 8                    // warps per CTA
 #define KR_THREADS (KR_WARPS * 32)
 #ifndef KR_MINB
-#define KR_MINB 4                     // resident CTAs per SM the kernel is compiled for (64 registers per thread)
+#define KR_MINB 2                     // resident CTAs per SM the kernel is compiled for (measured: the larger L1 beats more warps)
 #endif
 #define KR_LCAP 96                    // lines per chunk (a batch of 32 tasks has at most 160 at 20 points per voxel: 1-2 chunks)
 #ifndef KR_G
@@ -68,6 +68,7 @@ struct PoseState {
     double q[4];  // current estimate: unit quaternion (x, y, z, w) ...
     double t[3];  // ... translation ...
     double R[9];  // ... and the rotation matrix of q, row-major
+    double Rp[9], tp[3];  // R, t of the previous pass (the nearest-neighbour certificates compare the two)
     double tau, conv, fixed_reg, beta;
     int adaptive, max_iter;
     int iter, done, status;
@@ -79,7 +80,8 @@ struct RegState {
     unsigned int arrive;            // grid-barrier arrivals so far (monotonic inside a registration)
     unsigned int exit_ctr;          // CTAs that have left the kernel; the last one zeroes the three counters
     unsigned int ticket;            // multi-launch path: last-CTA detection
-    unsigned int heavy_n;           // windows pass 0 found expensive (they are handed out first in the later passes)
+    unsigned int a_arrive;          // warps that finished the certificate phase of a pass (monotonic inside a registration)
+    unsigned int todo_n[KICP_MAX_ITERATIONS];  // per pass: points whose neighbour has to be searched again
     int abort;                      // a device-side wait gave up (status code); every CTA leaves after the current pass
     int *iters_out;                 // optional: where to publish the iteration count (profiling)
     double acc[8];                  // multi-launch path: JTJ00 JTJ01 JTJ11 JTr0 JTr1 N sum|r|^2 (unused)
@@ -199,9 +201,11 @@ struct KernelArgs {
     RegArgs init;
     int pow2_voxel;
     int collect_stats;
-    unsigned int *heavy_list;      // [windows] scheduling hint written by pass 0 (order only, never results)
-    unsigned char *heavy_flag;     // [windows]
-    int heavy_tasks;               // a window with more hash probes than this is "heavy"
+    // nearest-neighbour cache carried from pass to pass (persistent kernel, option "nn_cache"), one entry per scan point
+    unsigned int *nn_g;            // the neighbour found by the last search (global point index, 0xFFFFFFFF = none)
+    float *nn_l;                   // certified lower bound on the distance to every OTHER candidate of the neighbourhood
+    float *nn_seed;                // distance to the old neighbour from the new position (pruning bound of the repeated search)
+    unsigned int *todo;            // points of the current pass that need the search
     unsigned long long timeout_ns;  // device-side waits (upload flags, peers) give up after this long
 };
 
@@ -232,6 +236,9 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
 struct __align__(32) Point4 {
     double x, y, z, w;
 };
+// Software pipelining without registers: the addresses a later step will load are known early (the task stream of a stage, the
+// runs of a batch), so they are requested into L1 ahead of time and the dependent loads find them there.
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ Point4 ld_point(const double *p) {
     Point4 r;
     asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
@@ -247,7 +254,8 @@ __device__ void pose_init(PoseState *ps, const RegArgs &a) {
     quat_to_matrix(q, R);
     for (int k = 0; k < 4; ++k) ps->q[k] = q[k];
     for (int k = 0; k < 3; ++k) ps->t[k] = t[k];
-    for (int k = 0; k < 9; ++k) ps->R[k] = R[k];
+    for (int k = 0; k < 9; ++k) ps->R[k] = R[k], ps->Rp[k] = R[k];
+    for (int k = 0; k < 3; ++k) ps->tp[k] = t[k];
     ps->tau = a.tau, ps->conv = a.conv, ps->fixed_reg = a.fixed_reg, ps->beta = 0.0;
     ps->adaptive = a.adaptive, ps->max_iter = a.max_iter;
     ps->iter = 0, ps->done = a.max_iter <= 0 ? 1 : 0, ps->status = KICP_OK;
@@ -263,7 +271,8 @@ __global__ void k_reg_init(RegState *st, RegArgs a) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     pose_init(&st->pose, a);
     result_init(&st->result, &st->pose);
-    st->ticket = 0, st->win_ctr = 0, st->arrive = 0, st->exit_ctr = 0, st->abort = 0, st->heavy_n = 0;
+    st->ticket = 0, st->win_ctr = 0, st->arrive = 0, st->exit_ctr = 0, st->abort = 0, st->a_arrive = 0;
+    for (int k = 0; k < KICP_MAX_ITERATIONS; ++k) st->todo_n[k] = 0;
     st->iters_out = a.iters_out;
     if (a.iters_out) *a.iters_out = 0;
     for (int k = 0; k < 8; ++k) st->acc[k] = 0.0;
@@ -299,6 +308,8 @@ __device__ void solve_and_update(PoseState *ps, const double *s, kicp_reg_result
     se3_exp_planar(ux, uy, dx1, dq, dt);
     se3_compose(cq, ct, dq, dt, nq, nt);  // current_estimate = current_estimate * delta_motion  (:182)
     quat_to_matrix(nq, nR);
+    for (int k = 0; k < 9; ++k) ps->Rp[k] = ps->R[k];
+    for (int k = 0; k < 3; ++k) ps->tp[k] = ps->t[k];
     for (int k = 0; k < 4; ++k) ps->q[k] = nq[k];
     for (int k = 0; k < 3; ++k) ps->t[k] = nt[k];
     for (int k = 0; k < 9; ++k) ps->R[k] = nR[k];
@@ -350,6 +361,15 @@ struct __align__(16) WarpSm {
     unsigned short lbeg[32], lend[32];  // owner's line range [lbeg, lend) in the current batch
 };
 
+// The reference compares NORMS with a strict < (first minimum wins).  sqrt is monotone, so the squares decide — except when two
+// squares within an ulp or two round to the same norm: then the earlier point stays.  Kept out of line: it is needed about never.
+__device__ __noinline__ bool same_norm(double a, double b) { return sqrt(a) == sqrt(b); }
+__device__ __forceinline__ bool closer(double d2, double best) {  // "norm(d2) < norm(best)" as the reference would evaluate it
+    if (!(d2 < best)) return false;
+    if (d2 >= best * (1.0 - 4e-16)) return !same_norm(d2, best);
+    return true;
+}
+
 // |c - q|^2 with a pinned operation order (the owner re-evaluates the winning line: both evaluations must agree bit for bit)
 __device__ __forceinline__ double dist2(double cx, double cy, double cz, double qx, double qy, double qz) {
     const double dx = cx - qx, dy = cy - qy, dz = cz - qz;
@@ -383,7 +403,7 @@ __device__ __forceinline__ void stats_flush(RegState *st, unsigned long long pro
 // The shifts of one search stage that survive the exact bound (bit k <-> voxel_shifts[k]).  Stage 0: the own voxel;
 // stage 1: the 6 faces; stage 2: the 12 edges and 8 corners, pruned with the best the faces left behind.
 __device__ __forceinline__ unsigned stage_mask(int stage, bool valid, double bound, double qx, double qy, double qz, int vx, int vy,
-                                               int vz, double vs) {
+                                               int vz, double vs, double &minpruned) {
     if (!valid) return 0u;
     if (stage == 0) return 1u;
     double t;
@@ -393,18 +413,49 @@ __device__ __forceinline__ unsigned stage_mask(int stage, bool valid, double bou
     t = qy - (double)vy * vs;       const double gym = t * t;
     t = (double)(vz + 1) * vs - qz; const double gzp = t * t;
     t = qz - (double)vz * vs;       const double gzm = t * t;
-    unsigned mask = (kX0 | (gxp <= bound ? kXP : 0u) | (gxm <= bound ? kXM : 0u)) &
-                    (kY0 | (gyp <= bound ? kYP : 0u) | (gym <= bound ? kYM : 0u)) &
-                    (kZ0 | (gzp <= bound ? kZP : 0u) | (gzm <= bound ? kZM : 0u));
-    if (stage == 1) return mask & 0x0000007Eu;
-    mask &= 0x07FFFF80u;
+    if (stage == 1) {  // the six faces are decided here for good: remember how close a skipped one can be
+        unsigned mask = 0u;
+        if (gxp <= bound) mask |= 1u << 1; else minpruned = fmin(minpruned, gxp);
+        if (gxm <= bound) mask |= 1u << 2; else minpruned = fmin(minpruned, gxm);
+        if (gyp <= bound) mask |= 1u << 3; else minpruned = fmin(minpruned, gyp);
+        if (gym <= bound) mask |= 1u << 4; else minpruned = fmin(minpruned, gym);
+        if (gzp <= bound) mask |= 1u << 5; else minpruned = fmin(minpruned, gzp);
+        if (gzm <= bound) mask |= 1u << 6; else minpruned = fmin(minpruned, gzm);
+        return mask;
+    }
+    unsigned mask = 0u;
 #pragma unroll
     for (int kk = 7; kk < 27; ++kk) {  // edges and corners: the summed gap decides
         const double lb2 = (shift_x(kk) > 0 ? gxp : (shift_x(kk) < 0 ? gxm : 0.0)) + (shift_y(kk) > 0 ? gyp : (shift_y(kk) < 0 ? gym : 0.0)) +
                            (shift_z(kk) > 0 ? gzp : (shift_z(kk) < 0 ? gzm : 0.0));
-        if (lb2 > bound) mask &= ~(1u << kk);
+        if (lb2 <= bound) mask |= 1u << kk; else minpruned = fmin(minpruned, lb2);
     }
     return mask;
+}
+
+// gate, residual, Jacobian and the seven sums of one correspondence (Registration.cpp:75, 86-93, 110-118)
+__device__ __forceinline__ void accumulate(WarpSm &sm, int lane, const PoseState &ps, double nx, double ny, double nz, double qx, double qy,
+                                           double qz, double px, double py) {
+    const double rx = qx - nx, ry = qy - ny, rz = qz - nz;  // r = T p - n
+    const double rr = rx * rx + ry * ry + rz * rz;
+    if (sqrt(rr) < ps.tau) {  // distance < max_correspondance_distance   (Registration.cpp:75)
+        // J = [R e_x | R (-p_y, p_x, 0)]      (Registration.cpp:89-91)
+        const double c0x = ps.R[0], c0y = ps.R[3], c0z = ps.R[6];
+        const double c1x = ps.R[1] * px - ps.R[0] * py, c1y = ps.R[4] * px - ps.R[3] * py, c1z = ps.R[7] * px - ps.R[6] * py;
+        sm.acc[0][lane] += c0x * c0x + c0y * c0y + c0z * c0z;
+        sm.acc[1][lane] += c0x * c1x + c0y * c1y + c0z * c1z;
+        sm.acc[2][lane] += c1x * c1x + c1y * c1y + c1z * c1z;
+        sm.acc[3][lane] += c0x * rx + c0y * ry + c0z * rz;
+        sm.acc[4][lane] += c1x * rx + c1y * ry + c1z * rz;
+        sm.acc[5][lane] += 1.0;
+        sm.acc[6][lane] += rr;
+    }
+}
+
+__device__ __forceinline__ int voxel_of(double x, double vs, double inv_vs, int pow2) {
+    // PointToVoxel: floor(x / voxel_size); for a power-of-two voxel size the product with the (exact) reciprocal is the same
+    // double as the quotient, so the cheaper form is used
+    return pow2 ? (int)floor(x * inv_vs) : voxel_coord(x, vs);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -444,37 +495,109 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
     if (!PERSISTENT && s_ps.done) return;
 
     unsigned long long n_probe = 0, n_cand = 0, n_line = 0;
+    unsigned tbase = 0;  // first ticket of the current phase (identical in every warp of the grid)
     KR_PROF_DECL
 
     for (unsigned it = 0; !s_ps.done; ++it) {
 #pragma unroll
         for (int k = 0; k < 7; ++k) sm.acc[k][lane] = 0.0;
         const unsigned long long t_iter0 = gtime_ns();
-        // Window tickets.  Pass 0 hands the windows out in index order and records the expensive ones (many hash probes: points
-        // with little or no map around them); the later passes hand those out FIRST, so that the longest windows overlap the
-        // bulk instead of forming the tail of the pass.  Only the order changes, never a result.
-        const bool sched = PERSISTENT && a.heavy_list != nullptr;
-        const unsigned nheavy = (sched && it > 0u) ? __ldcg(&st->heavy_n) : 0u;
-        const unsigned t0span = (unsigned)num_windows + total_warps;
-        const unsigned ticket_base = !PERSISTENT ? 0u : (it == 0u ? 0u : t0span + (it - 1u) * (t0span + nheavy));
-        const unsigned tlimit = nheavy + (unsigned)num_windows;  // tickets at or beyond: nothing left
+        const double inv_vs = 1.0 / a.map.voxel_size;
+        const bool cache = PERSISTENT && a.nn_g != nullptr;
+        // Window tickets come from one monotonic counter; every phase owns a contiguous range of it (each warp draws exactly one
+        // ticket beyond the range of a phase, so a phase of W windows consumes W + total_warps tickets).
+        unsigned tk = 0;  // lane 0: the ticket drawn ahead of time (the atomic's round trip is off the critical path)
+        int nsearch = num_windows;  // windows of the search phase of this pass
 
-        // the next ticket is requested before the current window is processed: the atomic's round trip is off the critical path
-        unsigned tk = 0;
-        if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);
-        int w;
-        for (;;) {  // ticket -> window (warp-uniform)
-            const unsigned t = __shfl_sync(FULL, tk, 0) - ticket_base;
-            if (t >= tlimit) { w = num_windows; break; }
-            if (t < nheavy) { w = (int)__ldcg(&a.heavy_list[t]); break; }
-            w = (int)(t - nheavy);
-            if (nheavy == 0u || !__ldcg(&a.heavy_flag[w])) break;
-            if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);  // a heavy window reached through its regular ticket: already done
-        }
-        KR_PROF(11)
-        while (w < num_windows) {
+        if (cache && it > 0u) {
+            // ------------------------------------------------------------------------------------------------------------
+            // Phase A: CERTIFICATES.  Between two IRLS passes the pose moves by millimetres to centimetres.  The last search
+            // left, per point, its neighbour g and a lower bound l on the distance to every other candidate of the 27-voxel
+            // neighbourhood (evaluated points and the cubes of pruned voxels alike).  If the query stays in its voxel (same
+            // candidate set) and moved by delta, every other candidate is still at least l - delta away; so when
+            // |q' - g| < l - delta, g is still THE strict nearest neighbour and the search is skipped (and when nothing was within
+            // reach and l - delta > tau, nothing can be accepted now).  Everything else goes to the list of the search phase,
+            // with |q' - g| as an exact pruning bound when g still lies in the new neighbourhood.
+            // ------------------------------------------------------------------------------------------------------------
             if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);
-            int wtasks = 0;
+            int w = (int)min(__shfl_sync(FULL, tk, 0) - tbase, (unsigned)num_windows);
+            while (w < num_windows) {
+                if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);
+                const int i = w * 32 + lane;
+                const bool valid = i < n;
+                double px = 0, py = 0, pz = 0;
+                if (valid) load_scan_point(a.scan, i, px, py, pz);
+                const unsigned g = valid ? __ldcg(&a.nn_g[i]) : 0xFFFFFFFFu;
+                const double l = valid ? (double)__ldcg(&a.nn_l[i]) : 0.0;
+                const bool haveg = g != 0xFFFFFFFFu;
+                const Point4 c = ld_point(a.map.pts + (size_t)(haveg ? g : 0u) * KICP_PSTRIDE);
+                const double qx = s_ps.R[0] * px + s_ps.R[1] * py + s_ps.R[2] * pz + s_ps.t[0];
+                const double qy = s_ps.R[3] * px + s_ps.R[4] * py + s_ps.R[5] * pz + s_ps.t[1];
+                const double qz = s_ps.R[6] * px + s_ps.R[7] * py + s_ps.R[8] * pz + s_ps.t[2];
+                const double ox = s_ps.Rp[0] * px + s_ps.Rp[1] * py + s_ps.Rp[2] * pz + s_ps.tp[0];
+                const double oy = s_ps.Rp[3] * px + s_ps.Rp[4] * py + s_ps.Rp[5] * pz + s_ps.tp[1];
+                const double oz = s_ps.Rp[6] * px + s_ps.Rp[7] * py + s_ps.Rp[8] * pz + s_ps.tp[2];
+                const double vs = a.map.voxel_size;
+                const int vx = voxel_of(qx, vs, inv_vs, a.pow2_voxel), vy = voxel_of(qy, vs, inv_vs, a.pow2_voxel),
+                          vz = voxel_of(qz, vs, inv_vs, a.pow2_voxel);
+                const bool same = vx == voxel_of(ox, vs, inv_vs, a.pow2_voxel) && vy == voxel_of(oy, vs, inv_vs, a.pow2_voxel) &&
+                                  vz == voxel_of(oz, vs, inv_vs, a.pow2_voxel);
+                const double mx = qx - ox, my = qy - oy, mz = qz - oz;
+                const double delta = sqrt(mx * mx + my * my + mz * mz) * (1.0 + 1e-9) + 1e-12;
+                const double dn = sqrt(dist2(c.x, c.y, c.z, qx, qy, qz));
+                const double room = l - delta;  // every other candidate is at least this far from the new position
+                const bool cert = valid && same && (haveg ? (dn * (1.0 + 1e-9) + 1e-12 < room) : (room > s_ps.tau * (1.0 + 1e-9)));
+                if (cert) {
+                    a.nn_l[i] = __double2float_rz(room * (1.0 - 1e-7));
+                    if (haveg) accumulate(sm, lane, s_ps, c.x, c.y, c.z, qx, qy, qz, px, py);
+                }
+                const unsigned need = __ballot_sync(FULL, valid && !cert);
+                if (need) {
+                    unsigned pos = 0;
+                    if (lane == 0) pos = atomicAdd(&st->todo_n[it], (unsigned)__popc(need));
+                    pos = __shfl_sync(FULL, pos, 0) + (unsigned)__popc(need & ((1u << lane) - 1u));
+                    if (valid && !cert) {
+                        a.todo[pos] = (unsigned)i;
+                        // the old neighbour bounds the repeated search if it is one of the new 27 voxels' points
+                        float seed = 3.0e38f;
+                        if (haveg && abs(voxel_of(c.x, vs, inv_vs, a.pow2_voxel) - vx) <= 1 && abs(voxel_of(c.y, vs, inv_vs, a.pow2_voxel) - vy) <= 1 &&
+                            abs(voxel_of(c.z, vs, inv_vs, a.pow2_voxel) - vz) <= 1)
+                            seed = __double2float_ru(dn * (1.0 + 1e-7));
+                        a.nn_seed[i] = seed;
+                    }
+                }
+                w = (int)min(__shfl_sync(FULL, tk, 0) - tbase, (unsigned)num_windows);
+            }
+            tbase += (unsigned)num_windows + total_warps;
+            // every warp of the grid has to be through phase A before the list is complete
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                atomicAdd(&st->a_arrive, 1u);
+                const unsigned target = it * total_warps;
+                const unsigned long long deadline = gtime_ns() + a.timeout_ns;
+                while (ld_acquire_gpu_u32(&st->a_arrive) < target) {
+                    __nanosleep(40);
+                    if (gtime_ns() > deadline) {
+                        atomicExch(&st->abort, KICP_ERR_CUDA);
+                        break;
+                    }
+                }
+            }
+            __syncwarp();
+            nsearch = (int)((__ldcg(&st->todo_n[it]) + 31u) >> 5);
+        }
+        const int ncount = (cache && it > 0u) ? (int)__ldcg(&st->todo_n[it]) : n;  // points of the search phase
+        const bool indirect = cache && it > 0u;
+
+        // ------------------------------------------------------------------------------------------------------------------
+        // Phase B: THE SEARCH (all points in pass 0; the uncertified ones, compacted, afterwards)
+        // ------------------------------------------------------------------------------------------------------------------
+        if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);
+        int w = (int)min(__shfl_sync(FULL, tk, 0) - tbase, (unsigned)nsearch);
+        KR_PROF(11)
+        while (w < nsearch) {
+            if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);
             KR_PROF_COUNT(8)
             if (PERSISTENT && a.up.flags != nullptr && it == 0u) {
                 // first pass over a frame that is still being uploaded: wait until this window's chunk has landed
@@ -493,28 +616,28 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                 }
             }
             // ---------------------------------------------------------------- owners: q = T p and its voxel
-            const bool valid = w * 32 + lane < n;
+            const bool valid = w * 32 + lane < ncount;
+            const int pi = valid ? (indirect ? (int)__ldcg(&a.todo[w * 32 + lane]) : w * 32 + lane) : 0;  // the owner's scan point
+            double seed2 = DBL_MAX;  // squared distance to the previous neighbour (an exact pruning bound), if it applies
             {
                 double px = 0, py = 0, pz = 0;
-                if (valid) load_scan_point(a.scan, w * 32 + lane, px, py, pz);
+                if (valid) load_scan_point(a.scan, pi, px, py, pz);
+                if (indirect && valid) {
+                    const double sd = (double)__ldcg(&a.nn_seed[pi]);
+                    if (sd < 1.0e38) seed2 = sd * sd * (1.0 + 1e-6);
+                }
                 const double qx = s_ps.R[0] * px + s_ps.R[1] * py + s_ps.R[2] * pz + s_ps.t[0];
                 const double qy = s_ps.R[3] * px + s_ps.R[4] * py + s_ps.R[5] * pz + s_ps.t[1];
                 const double qz = s_ps.R[6] * px + s_ps.R[7] * py + s_ps.R[8] * pz + s_ps.t[2];
-                // PointToVoxel: floor(q / voxel_size); for a power-of-two voxel size the product with the (exact)
-                // reciprocal is the same double as the quotient, so the cheaper form is used
-                int vx, vy, vz;
-                if (a.pow2_voxel) {
-                    const double inv_vs = 1.0 / a.map.voxel_size;
-                    vx = (int)floor(qx * inv_vs), vy = (int)floor(qy * inv_vs), vz = (int)floor(qz * inv_vs);
-                } else {
-                    vx = voxel_coord(qx, a.map.voxel_size), vy = voxel_coord(qy, a.map.voxel_size), vz = voxel_coord(qz, a.map.voxel_size);
-                }
                 sm.qxy[lane] = make_double2(qx, qy), sm.qz[lane] = qz;
-                sm.vx[lane] = vx, sm.vy[lane] = vy, sm.vz[lane] = vz;
+                sm.vx[lane] = voxel_of(qx, a.map.voxel_size, inv_vs, a.pow2_voxel);
+                sm.vy[lane] = voxel_of(qy, a.map.voxel_size, inv_vs, a.pow2_voxel);
+                sm.vz[lane] = voxel_of(qz, a.map.voxel_size, inv_vs, a.pow2_voxel);
                 sm.px[lane] = px, sm.py[lane] = py;
             }
-            // the owner's running minimum lives in its lane's registers: d^2, the line that holds it, how many points that line has
-            double best = DBL_MAX;
+            // the owner's running minimum lives in its lane's registers: d^2, the line that holds it, how many points that line has;
+            // `second` bounds every evaluated point that is not the winner, `minpruned` the cubes of the voxels that were skipped
+            double best = DBL_MAX, second = DBL_MAX, minpruned = DBL_MAX;
             unsigned bline = 0xFFFFFFFFu, bvalid = 0u;
             __syncwarp();
             KR_PROF(0)
@@ -527,9 +650,9 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                     // exact pruning bound: the best squared distance found so far, and never more than the gate — a neighbour at
                     // tau or beyond is rejected anyway (Registration.cpp:75), so voxels that can only hold such points are skipped
                     const double tau2 = s_ps.tau * s_ps.tau;
-                    const double bsq = fmin(tau2, best);
+                    const double bsq = fmin(fmin(tau2, best), seed2);
                     unsigned mask = stage_mask(stage, valid, bsq * (1.0 + 1e-6) + 1e-10, qq.x, qq.y, sm.qz[lane], sm.vx[lane], sm.vy[lane],
-                                               sm.vz[lane], a.map.voxel_size);
+                                               sm.vz[lane], a.map.voxel_size, minpruned);
                     const int no = __popc(mask);
                     int tin = no;
 #pragma unroll
@@ -538,7 +661,6 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                         if (lane >= d) tin += y;
                     }
                     total = __shfl_sync(FULL, tin, 31);
-                    wtasks += total;
                     int pos = tin - no;
                     const int maxno = __reduce_max_sync(FULL, no);
                     for (int i = 0; i < maxno; ++i) {  // warp-uniform trip count, the store predicated per lane
@@ -549,6 +671,16 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                         }
                     }
                     __syncwarp();
+                }
+                // request the home slots of every task of the stage now: the probes below then hit L1
+                for (int tb = 0; tb < total; tb += 32) {  // warp-uniform trip count
+                    if (tb + lane < total) {
+                        const unsigned tko = (unsigned)sm.task[tb + lane];
+                        const int o = (int)(tko >> 5), k = (int)(tko & 31u);
+                        const uint32_t h = voxel_hash(sm.vx[o] + shift_x(k), sm.vy[o] + shift_y(k), sm.vz[o] + shift_z(k)) & a.map.mask;
+                        prefetch_l1(&a.map.slots[h]);
+                        if ((h & 7u) == 7u) prefetch_l1(&a.map.slots[(h + 1) & a.map.mask]);  // the pair straddles two 128-byte lines
+                    }
                 }
                 KR_PROF(1)
                 for (int base = 0; base < total; base += 32) {
@@ -603,6 +735,9 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                     const int ltot = __shfl_sync(FULL, incl, 31);
                     const int maxnl = __reduce_max_sync(FULL, nl);
                     if (a.collect_stats) n_probe += act ? 1 : 0, n_cand += cnt, n_line += nl;
+                    // request every line of the found runs now: they travel while the lines are being numbered
+                    for (int li = 0; __any_sync(FULL, li < nl); ++li)  // warp-uniform loop
+                        if (li < nl) prefetch_l1(a.map.pts + ((size_t)(meta >> 8) * a.map.cap + (size_t)(li * 4)) * KICP_PSTRIDE);
                     // the lines of an owner are contiguous (tasks are owner-major): publish every owner's range of this batch
                     {
                         const unsigned oprev = __shfl_up_sync(FULL, okpack >> 5, 1), onext = __shfl_down_sync(FULL, okpack >> 5, 1);
@@ -668,10 +803,12 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                             for (int u = 0; u < maxlen; ++u) {  // warp-uniform trip count
                                 if (lb + u < le) {
                                     const LineMin lm = sm.line[lb + u];
-                                    // The reference compares NORMS with a strict < (first minimum wins).  sqrt is monotone, so d^2 decides —
-                                    // except when two squares within an ulp or two round to the same norm: then the earlier point stays.
-                                    if (lm.d2 < best && !(lm.d2 >= best * (1.0 - 4e-16) && sqrt(lm.d2) == sqrt(best)))
+                                    if (closer(lm.d2, best)) {
+                                        second = fmin(second, best);
                                         best = lm.d2, bline = lm.gline, bvalid = lm.nvalid;
+                                    } else {
+                                        second = fmin(second, lm.d2);
+                                    }
                                 }
                             }
                         }
@@ -692,51 +829,36 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                 Point4 cc[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) cc[j] = ld_point(a.map.pts + (size_t)(g0 + (j < (int)bvalid ? j : 0)) * KICP_PSTRIDE);
-                Point4 c = cc[0];
-                {
-                    const double2 q0 = sm.qxy[lane];
-                    double bd = dist2(cc[0].x, cc[0].y, cc[0].z, q0.x, q0.y, sm.qz[lane]);
+                const double2 q0 = sm.qxy[lane];
+                const double q0z = sm.qz[lane];
+                double dj[4];
 #pragma unroll
-                    for (int j = 1; j < 4; ++j) {
-                        const double dj = dist2(cc[j].x, cc[j].y, cc[j].z, q0.x, q0.y, sm.qz[lane]);
-                        if (j < (int)bvalid && dj < bd && !(dj >= bd * (1.0 - 4e-16) && sqrt(dj) == sqrt(bd))) bd = dj, c = cc[j];
-                    }
-                }
-                const double2 qq = sm.qxy[lane];
-                const double rx = qq.x - c.x, ry = qq.y - c.y, rz = sm.qz[lane] - c.z;  // r = T p - n
-                const double rr = rx * rx + ry * ry + rz * rz;
-                if (have && sqrt(rr) < s_ps.tau) {  // distance < max_correspondance_distance   (Registration.cpp:75)
-                    // J = [R e_x | R (-p_y, p_x, 0)]      (Registration.cpp:89-91)
-                    const double px = sm.px[lane], py = sm.py[lane];
-                    const double c0x = s_ps.R[0], c0y = s_ps.R[3], c0z = s_ps.R[6];
-                    const double c1x = s_ps.R[1] * px - s_ps.R[0] * py, c1y = s_ps.R[4] * px - s_ps.R[3] * py,
-                                 c1z = s_ps.R[7] * px - s_ps.R[6] * py;
-                    sm.acc[0][lane] += c0x * c0x + c0y * c0y + c0z * c0z;
-                    sm.acc[1][lane] += c0x * c1x + c0y * c1y + c0z * c1z;
-                    sm.acc[2][lane] += c1x * c1x + c1y * c1y + c1z * c1z;
-                    sm.acc[3][lane] += c0x * rx + c0y * ry + c0z * rz;
-                    sm.acc[4][lane] += c1x * rx + c1y * ry + c1z * rz;
-                    sm.acc[5][lane] += 1.0;
-                    sm.acc[6][lane] += rr;
+                for (int j = 0; j < 4; ++j) dj[j] = dist2(cc[j].x, cc[j].y, cc[j].z, q0.x, q0.y, q0z);
+                int jw = 0;
+#pragma unroll
+                for (int j = 1; j < 4; ++j)
+                    if (j < (int)bvalid && closer(dj[j], dj[jw])) jw = j;
+                Point4 c = cc[0];
+#pragma unroll
+                for (int j = 1; j < 4; ++j)
+                    if (jw == j) c = cc[j];
+                if (have) accumulate(sm, lane, s_ps, c.x, c.y, c.z, q0.x, q0.y, q0z, sm.px[lane], sm.py[lane]);
+                if (cache && valid) {
+                    // what the next pass may rely on: the neighbour, and how far every other candidate is at least
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (have && j < (int)bvalid && j != jw) second = fmin(second, dj[j]);
+                    const double lo2 = fmin(second, minpruned);
+                    a.nn_g[pi] = have ? g0 + (unsigned)jw : 0xFFFFFFFFu;
+                    a.nn_l[pi] = lo2 >= 1.0e60 ? 1.0e30f : __double2float_rz(sqrt(lo2) * (1.0 - 1e-7));
                 }
             }
             __syncwarp();
             KR_PROF(6)
-            if (sched && it == 0u && lane == 0) {  // scheduling hint for the later passes
-                const bool heavy = wtasks > a.heavy_tasks;
-                a.heavy_flag[w] = heavy ? 1 : 0;
-                if (heavy) a.heavy_list[atomicAdd(&st->heavy_n, 1u)] = (unsigned)w;
-            }
-            for (;;) {  // next ticket -> window
-                const unsigned t = __shfl_sync(FULL, tk, 0) - ticket_base;
-                if (t >= tlimit) { w = num_windows; break; }
-                if (t < nheavy) { w = (int)__ldcg(&a.heavy_list[t]); break; }
-                w = (int)(t - nheavy);
-                if (nheavy == 0u || !__ldcg(&a.heavy_flag[w])) break;
-                if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);
-            }
+            w = (int)min(__shfl_sync(FULL, tk, 0) - tbase, (unsigned)nsearch);
             KR_PROF(7)
         }
+        tbase += (unsigned)nsearch + total_warps;
         KR_PROF(11)
 
         const unsigned long long t_win = gtime_ns();
@@ -899,7 +1021,8 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             __threadfence();
             const unsigned left = atomicAdd(&st->exit_ctr, 1u);
             if (left == gridDim.x - 1) {
-                st->win_ctr = 0, st->arrive = 0, st->abort = 0, st->heavy_n = 0;
+                st->win_ctr = 0, st->arrive = 0, st->abort = 0, st->a_arrive = 0;
+                for (int k = 0; k < KICP_MAX_ITERATIONS; ++k) st->todo_n[k] = 0;
                 __threadfence();
                 st->exit_ctr = 0;
             }
@@ -910,8 +1033,8 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
 // ------------------------------------------------------------------------------------------------------- host
 // Per-context options (kicp_ctx_set_option): "persistent" 1 = one cooperative launch per registration (default), 0 = one
 // launch per IRLS iteration; "stats" 1 = count probes / candidate points / lines on the device (kicp_debug_last_stats);
-// "ctas_per_sm" caps the resident CTAs per SM the grid is sized for (0 = occupancy limit); "spin_timeout_ms" bounds every
-// device-side wait (upload flags, peers of the fused exchange).
+// "ctas_per_sm" caps the resident CTAs per SM the grid is sized for (0 = occupancy limit); "nn_cache" 1 = carry every point's
+// neighbour and its certificate from pass to pass (default); "spin_timeout_ms" bounds every device-side wait.
 extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value) {
     if (!c || !name) return KICP_ERR_INVALID;
     if (!strcmp(name, "persistent")) {
@@ -926,9 +1049,9 @@ extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value)
     } else if (!strcmp(name, "spin_timeout_ms")) {
         if (value < 1) return KICP_ERR_INVALID;
         c->spin_timeout_ms = value;
-    } else if (!strcmp(name, "heavy_tasks")) {
-        if (value < 0) return KICP_ERR_INVALID;
-        c->heavy_tasks = value;
+    } else if (!strcmp(name, "nn_cache")) {
+        if (value != 0 && value != 1) return KICP_ERR_INVALID;
+        c->nn_cache = value;
     } else if (!strcmp(name, "overlap_upload")) {
         if (value != 0 && value != 1) return KICP_ERR_INVALID;
         c->overlap_upload = value;
@@ -1031,19 +1154,20 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
         ka.pow2_voxel = std::frexp(m->voxel_size, &e) == 0.5 ? 1 : 0;
     }
     ka.collect_stats = c->collect_stats;
-    ka.heavy_list = nullptr, ka.heavy_flag = nullptr, ka.heavy_tasks = c->heavy_tasks;
-    if (c->heavy_tasks > 0 && scan->n > 0) {
-        const int64_t windows = (scan->n + 31) / 32;
-        if (windows > c->heavy_cap) {
+    ka.nn_g = nullptr, ka.nn_l = nullptr, ka.nn_seed = nullptr, ka.todo = nullptr;
+    if (c->nn_cache && scan->n > 0) {
+        if (scan->n > c->nn_cap) {
             KICP_CUDA(cudaStreamSynchronize(c->stream));
-            cudaFree(c->d_heavy_list), cudaFree(c->d_heavy_flag);
-            c->d_heavy_list = nullptr, c->d_heavy_flag = nullptr, c->heavy_cap = 0;
-            const int64_t cap = windows + windows / 4 + 64;
-            KICP_CUDA(cudaMalloc(&c->d_heavy_list, (size_t)cap * sizeof(unsigned int)));
-            KICP_CUDA(cudaMalloc(&c->d_heavy_flag, (size_t)cap));
-            c->heavy_cap = cap;
+            cudaFree(c->d_nn_g), cudaFree(c->d_nn_l), cudaFree(c->d_nn_seed), cudaFree(c->d_todo);
+            c->d_nn_g = nullptr, c->d_nn_l = nullptr, c->d_nn_seed = nullptr, c->d_todo = nullptr, c->nn_cap = 0;
+            const int64_t cap = scan->n + scan->n / 4 + 1024;
+            KICP_CUDA(cudaMalloc(&c->d_nn_g, (size_t)cap * sizeof(unsigned int)));
+            KICP_CUDA(cudaMalloc(&c->d_nn_l, (size_t)cap * sizeof(float)));
+            KICP_CUDA(cudaMalloc(&c->d_nn_seed, (size_t)cap * sizeof(float)));
+            KICP_CUDA(cudaMalloc(&c->d_todo, (size_t)cap * sizeof(unsigned int)));
+            c->nn_cap = cap;
         }
-        ka.heavy_list = c->d_heavy_list, ka.heavy_flag = c->d_heavy_flag;
+        ka.nn_g = c->d_nn_g, ka.nn_l = c->d_nn_l, ka.nn_seed = c->d_nn_seed, ka.todo = c->d_todo;
     }
     ka.timeout_ns = (unsigned long long)c->spin_timeout_ms * 1000000ull;
     const int n = (int)scan->n;

@@ -1,12 +1,16 @@
 // TEST INFRASTRUCTURE — NOT PRODUCT CODE.
 // Stand-in for the oneTBB subset the reference's Registration.cpp uses (includes at
 // cpp/kinematic_icp/registration/Registration.cpp:25-31), so that file can be compiled in place for oracle/_ref
-// (oneTBB is not installed offline).  std::thread workers over a static contiguous partition; the worker count is
-// the process-wide tbb::global_control value, like the reference's function-local static cap (:147-148).
+// (oneTBB is not installed offline).  A PERSISTENT pool of std::thread workers (created once, parked on a condition
+// variable between jobs — like TBB's arena, no thread creation per parallel_for) over a static contiguous partition;
+// the worker count is the process-wide tbb::global_control value, like the reference's function-local static cap
+// (:147-148).
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstddef>
+#include <functional>
 #include <iterator>
 #include <memory>
 #include <mutex>
@@ -26,6 +30,69 @@ inline size_t workers() {
     if (v == 0) v = std::max(1u, std::thread::hardware_concurrency());
     return v;
 }
+
+// Fork-join pool: run(T, f) executes f(0) .. f(T-1), f(0) on the calling thread, the rest on parked workers.
+class Pool {
+public:
+    static Pool &instance() {
+        static Pool p;
+        return p;
+    }
+    void run(size_t T, const std::function<void(size_t)> &f) {
+        if (T <= 1) {
+            f(0);
+            return;
+        }
+        std::unique_lock<std::mutex> outer(run_mutex_);  // one job at a time (callers are single-threaded anyway)
+        {
+            std::unique_lock<std::mutex> g(m_);
+            while (threads_.size() + 1 < T) {
+                const size_t idx = threads_.size();
+                threads_.emplace_back([this, idx] { worker(idx); });
+            }
+            job_ = &f, job_T_ = T, remaining_ = T - 1, ++generation_;
+        }
+        cv_job_.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> g(m_);
+        cv_done_.wait(g, [this] { return remaining_ == 0; });
+        job_ = nullptr;
+    }
+    ~Pool() {
+        {
+            std::unique_lock<std::mutex> g(m_);
+            stop_ = true;
+        }
+        cv_job_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+
+private:
+    void worker(size_t idx) {
+        size_t seen = 0;
+        for (;;) {
+            const std::function<void(size_t)> *f = nullptr;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_job_.wait(g, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+                if (idx + 1 < job_T_) f = job_;
+            }
+            if (f) {
+                (*f)(idx + 1);
+                std::unique_lock<std::mutex> g(m_);
+                if (--remaining_ == 0) cv_done_.notify_one();
+            }
+        }
+    }
+    std::mutex m_, run_mutex_;
+    std::condition_variable cv_job_, cv_done_;
+    std::vector<std::thread> threads_;
+    const std::function<void(size_t)> *job_ = nullptr;
+    size_t job_T_ = 0, remaining_ = 0, generation_ = 0;
+    bool stop_ = false;
+};
 }  // namespace detail_shim
 
 class global_control {
@@ -62,11 +129,7 @@ void parallel_for(const Range &range, const Body &body) {
         body(range);
         return;
     }
-    std::vector<std::thread> th;
-    th.reserve(T);
-    for (size_t t = 0; t < T; ++t)
-        th.emplace_back([&, t]() { body(Range(range.begin() + n * t / T, range.begin() + n * (t + 1) / T)); });
-    for (auto &x : th) x.join();
+    detail_shim::Pool::instance().run(T, [&](size_t t) { body(Range(range.begin() + n * t / T, range.begin() + n * (t + 1) / T)); });
 }
 
 template <typename Range, typename Value, typename Func, typename Reduction>
@@ -75,12 +138,8 @@ Value parallel_reduce(const Range &range, const Value &identity, const Func &fun
     const size_t T = std::min(detail_shim::workers(), std::max<size_t>(n, 1));
     if (T <= 1 || n == 0) return func(range, identity);
     std::vector<Value> parts(T, identity);
-    std::vector<std::thread> th;
-    th.reserve(T);
-    for (size_t t = 0; t < T; ++t)
-        th.emplace_back(
-            [&, t]() { parts[t] = func(Range(range.begin() + n * t / T, range.begin() + n * (t + 1) / T), identity); });
-    for (auto &x : th) x.join();
+    detail_shim::Pool::instance().run(
+        T, [&](size_t t) { parts[t] = func(Range(range.begin() + n * t / T, range.begin() + n * (t + 1) / T), identity); });
     Value acc = parts[0];
     for (size_t t = 1; t < T; ++t) acc = reduction(acc, parts[t]);
     return acc;

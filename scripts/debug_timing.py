@@ -28,3 +28,11 @@ ctx.set_option("stats", 1)
 reg.enqueue(scan, gm, w.last_pose, w.rel_odom, w.tau, res)
 probes, cands, lines, _ = ctx.last_stats()
 print("per point per pass: probes %.2f candidates %.2f lines %.2f" % (probes / it / w.N, cands / it / w.N, lines / it / w.N))
+# the same with the neighbour cache off (every point searched in every pass)
+ctx.set_option("stats", 0)
+ctx.set_option("nn_cache", 0)
+for rep in range(3):
+    reg.enqueue(scan, gm, w.last_pose, w.rel_odom, w.tau, res)
+ctx.synchronize()
+out = ctx.last_timing()
+print("nn_cache=0: sum per pass us:", np.round(out[:it].sum(1) / 1e3, 2), "total us", round(out[:it].sum() / 1e3, 1))
