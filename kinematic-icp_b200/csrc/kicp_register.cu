@@ -344,21 +344,20 @@ __global__ void k_solve(RegState *st) {
 
 // ------------------------------------------------------------------------------------------- per-warp shared state
 #define KR_TCAP 640  // tasks of one stage: 32 owners x (6 faces | 20 edges + corners)
-struct __align__(16) LineMin {   // minimum over the (valid) points of one 128-byte line of a voxel's run
-    double d2;
+struct __align__(8) LineDesc {   // one 128-byte line of a found voxel's run, as the task lane that probed it describes it
     unsigned gline;              // global index of the line's first point
-    unsigned nvalid;             // points of the line that exist (1..4)
+    unsigned short owner;        // the scan point (lane of the window) this line is a candidate set for
+    unsigned short nvalid;       // points of the line that exist (1..4)
 };
 struct __align__(16) WarpSm {
     double2 qxy[32];                 // owner's query point (map frame)
     double qz[32];
-    LineMin line[KR_LCAP];           // line minima of the current chunk, in visiting order
+    double lmin[KR_LCAP];            // minimum squared distance over each line of the current chunk, in visiting order
+    LineDesc ldesc[KR_LCAP];         // the lines of the current chunk
     int vx[32], vy[32], vz[32];      // owner's voxel
     double acc[7][32];               // per-lane running sums of the pass (kept here, not in registers)
     double px[32], py[32];           // owner's scan point (for the Jacobian)
     unsigned short task[KR_TCAP];    // task stream of the current stage: owner << 5 | shift index
-    unsigned short lmap[KR_LCAP];    // line -> (task lane, line index inside the voxel)
-    unsigned short lbeg[32], lend[32];  // owner's line range [lbeg, lend) in the current batch
 };
 
 // The reference compares NORMS with a strict < (first minimum wins).  sqrt is monotone, so the squares decide — except when two
@@ -479,6 +478,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
     const int n = a.scan.d_n ? min(__ldg(a.scan.d_n), a.scan.n) : a.scan.n;
     const int num_windows = (n + 31) >> 5;
     const unsigned total_warps = gridDim.x * KR_WARPS;
+    const unsigned gwarp = blockIdx.x * KR_WARPS + (threadIdx.x >> 5);  // this warp's index in the grid
 
     if (threadIdx.x == 0) {
         if (PERSISTENT) {
@@ -519,10 +519,8 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             // reach and l - delta > tau, nothing can be accepted now).  Everything else goes to the list of the search phase,
             // with |q' - g| as an exact pruning bound when g still lies in the new neighbourhood.
             // ------------------------------------------------------------------------------------------------------------
-            if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);
-            int w = (int)min(__shfl_sync(FULL, tk, 0) - tbase, (unsigned)num_windows);
-            while (w < num_windows) {
-                if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);
+            // the certificate of a point costs the same everywhere: the windows are dealt out statically (no ticket traffic)
+            for (int w = (int)gwarp; w < num_windows; w += (int)total_warps) {
                 const int i = w * 32 + lane;
                 const bool valid = i < n;
                 double px = 0, py = 0, pz = 0;
@@ -566,25 +564,23 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                         a.nn_seed[i] = seed;
                     }
                 }
-                w = (int)min(__shfl_sync(FULL, tk, 0) - tbase, (unsigned)num_windows);
             }
-            tbase += (unsigned)num_windows + total_warps;
-            // every warp of the grid has to be through phase A before the list is complete
-            __syncwarp();
-            if (lane == 0) {
+            // every CTA of the grid has to be through phase A before the list is complete
+            __syncthreads();
+            if (threadIdx.x == 0) {
                 __threadfence();
                 atomicAdd(&st->a_arrive, 1u);
-                const unsigned target = it * total_warps;
+                const unsigned target = it * gridDim.x;
                 const unsigned long long deadline = gtime_ns() + a.timeout_ns;
                 while (ld_acquire_gpu_u32(&st->a_arrive) < target) {
-                    __nanosleep(40);
+                    __nanosleep(20);
                     if (gtime_ns() > deadline) {
                         atomicExch(&st->abort, KICP_ERR_CUDA);
                         break;
                     }
                 }
             }
-            __syncwarp();
+            __syncthreads();
             nsearch = (int)((__ldcg(&st->todo_n[it]) + 31u) >> 5);
         }
         const int ncount = (cache && it > 0u) ? (int)__ldcg(&st->todo_n[it]) : n;  // points of the search phase
@@ -593,8 +589,10 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
         // ------------------------------------------------------------------------------------------------------------------
         // Phase B: THE SEARCH (all points in pass 0; the uncertified ones, compacted, afterwards)
         // ------------------------------------------------------------------------------------------------------------------
-        if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);
-        int w = (int)min(__shfl_sync(FULL, tk, 0) - tbase, (unsigned)nsearch);
+        // the first window of every warp is its own index (no burst of atomics on one word when a phase starts); the remaining
+        // windows [total_warps, nsearch) are handed out dynamically, because windows differ in cost
+        int w = min((int)gwarp, nsearch);
+        const unsigned dyn = (unsigned)max(nsearch - (int)total_warps, 0);  // windows behind tickets
         KR_PROF(11)
         while (w < nsearch) {
             if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);
@@ -644,7 +642,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
 
             for (int stage = 0; stage < 3; ++stage) {
                 // ------------------------------------------------------------ task stream of the stage (owner-major, KISS order)
-                int total;
+                int total, tfirst, tcount;  // tasks of the stage; this owner's range [tfirst, tfirst + tcount) of the stream
                 {
                     const double2 qq = sm.qxy[lane];
                     // exact pruning bound: the best squared distance found so far, and never more than the gate — a neighbour at
@@ -662,6 +660,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                     }
                     total = __shfl_sync(FULL, tin, 31);
                     int pos = tin - no;
+                    tfirst = pos, tcount = no;
                     const int maxno = __reduce_max_sync(FULL, no);
                     for (int i = 0; i < maxno; ++i) {  // warp-uniform trip count, the store predicated per lane
                         if (mask) {
@@ -671,16 +670,6 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                         }
                     }
                     __syncwarp();
-                }
-                // request the home slots of every task of the stage now: the probes below then hit L1
-                for (int tb = 0; tb < total; tb += 32) {  // warp-uniform trip count
-                    if (tb + lane < total) {
-                        const unsigned tko = (unsigned)sm.task[tb + lane];
-                        const int o = (int)(tko >> 5), k = (int)(tko & 31u);
-                        const uint32_t h = voxel_hash(sm.vx[o] + shift_x(k), sm.vy[o] + shift_y(k), sm.vz[o] + shift_z(k)) & a.map.mask;
-                        prefetch_l1(&a.map.slots[h]);
-                        if ((h & 7u) == 7u) prefetch_l1(&a.map.slots[(h + 1) & a.map.mask]);  // the pair straddles two 128-byte lines
-                    }
                 }
                 KR_PROF(1)
                 for (int base = 0; base < total; base += 32) {
@@ -735,50 +724,48 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                     const int ltot = __shfl_sync(FULL, incl, 31);
                     const int maxnl = __reduce_max_sync(FULL, nl);
                     if (a.collect_stats) n_probe += act ? 1 : 0, n_cand += cnt, n_line += nl;
-                    // request every line of the found runs now: they travel while the lines are being numbered
-                    for (int li = 0; __any_sync(FULL, li < nl); ++li)  // warp-uniform loop
-                        if (li < nl) prefetch_l1(a.map.pts + ((size_t)(meta >> 8) * a.map.cap + (size_t)(li * 4)) * KICP_PSTRIDE);
-                    // the lines of an owner are contiguous (tasks are owner-major): publish every owner's range of this batch
+                    // the lines of an owner are contiguous (tasks are owner-major): this lane's, as an owner, are those of the task
+                    // lanes [t0, t1) of the batch
+                    int olb = 0, ole = 0;
                     {
-                        const unsigned oprev = __shfl_up_sync(FULL, okpack >> 5, 1), onext = __shfl_down_sync(FULL, okpack >> 5, 1);
-                        const bool anext = __shfl_down_sync(FULL, act ? 1 : 0, 1) != 0;
-                        sm.lbeg[lane] = 0, sm.lend[lane] = 0;
-                        __syncwarp();
-                        if (act && (lane == 0 || oprev != (okpack >> 5))) sm.lbeg[okpack >> 5] = (unsigned short)loff;
-                        if (act && (lane == 31 || !anext || onext != (okpack >> 5))) sm.lend[okpack >> 5] = (unsigned short)(loff + nl);
+                        const int t0 = max(tfirst - base, 0), t1 = min(tfirst + tcount - base, 32);
+                        const int b0 = __shfl_sync(FULL, loff, t0 & 31), e1 = __shfl_sync(FULL, incl, (t1 - 1) & 31);
+                        if (t1 > t0) olb = b0, ole = e1;
                     }
 
                     for (int lbase = 0; lbase < ltot; lbase += KR_LCAP) {
-                        // line map of this chunk: entry = task lane | (line inside the voxel << 5)
+                        // describe the lines of this chunk (every task lane its own run)
                         for (int li = 0; li < maxnl; ++li) {
                             const int pos = loff + li - lbase;
-                            if (li < nl && pos >= 0 && pos < KR_LCAP) sm.lmap[pos] = (unsigned short)(lane | (li << 5));
+                            if (li < nl && pos >= 0 && pos < KR_LCAP) {
+                                LineDesc ld;
+                                ld.gline = (meta >> 8) * (unsigned)a.map.cap + (unsigned)(li * 4);
+                                ld.owner = (unsigned short)(okpack >> 5);
+                                ld.nvalid = (unsigned short)min(cnt - li * 4, 4);
+                                sm.ldesc[pos] = ld;
+                            }
                         }
                         __syncwarp();
                         KR_PROF(3)
                         const int nr = min(KR_LCAP, ltot - lbase);
                         for (int r0 = 0; r0 < nr; r0 += 8 * KR_G) {
                             // a quad takes a line, a lane ONE point of it; KR_G independent 256-bit loads per lane in flight
-                            unsigned own[KR_G], gix[KR_G], nval[KR_G];
-                            unsigned hasm = 0, lvm = 0;
+                            unsigned own[KR_G], gix[KR_G];
+                            unsigned hasm = 0;
 #pragma unroll
                             for (int g = 0; g < KR_G; ++g) {
                                 const int line = r0 + g * 8 + quad;
-                                const bool lv = line < nr;
-                                const unsigned e = lv ? (unsigned)sm.lmap[line] : 0u;
-                                const int t = (int)(e & 31u), li = (int)(e >> 5);
-                                const uint32_t m = __shfl_sync(FULL, meta, t);
-                                own[g] = __shfl_sync(FULL, okpack, t) >> 5;
-                                const int left = (int)(m & 0xFFu) - li * 4;  // points of the voxel from this line on
-                                const bool has = lv && sub < left;
-                                nval[g] = (unsigned)min(left, 4);
-                                gix[g] = lv ? (m >> 8) * (unsigned)a.map.cap + (unsigned)(li * 4) : 0u;
-                                hasm |= has ? (1u << g) : 0u, lvm |= lv ? (1u << g) : 0u;
+                                LineDesc ld;
+                                ld.gline = 0u, ld.owner = 0, ld.nvalid = 0;
+                                if (line < nr) ld = sm.ldesc[line];
+                                const bool has = sub < (int)ld.nvalid;
+                                own[g] = ld.owner;
+                                gix[g] = ld.gline + (has ? (unsigned)sub : 0u);
+                                hasm |= has ? (1u << g) : 0u;
                             }
                             Point4 c[KR_G];
 #pragma unroll
-                            for (int g = 0; g < KR_G; ++g)
-                                c[g] = ld_point(a.map.pts + (size_t)(gix[g] + ((hasm >> g) & 1u ? (unsigned)sub : 0u)) * KICP_PSTRIDE);
+                            for (int g = 0; g < KR_G; ++g) c[g] = ld_point(a.map.pts + (size_t)gix[g] * KICP_PSTRIDE);
                             KR_PROF_COUNT(10)
                             KR_PROF(4)
 #pragma unroll
@@ -788,26 +775,23 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                                 // the line's minimum (a NaN distance never wins, as in the reference's comparisons)
                                 d2 = fmin(d2, __shfl_xor_sync(FULL, d2, 1));
                                 d2 = fmin(d2, __shfl_xor_sync(FULL, d2, 2));
-                                if (sub == 0 && ((lvm >> g) & 1u)) {
-                                    LineMin lm;
-                                    lm.d2 = d2, lm.gline = gix[g], lm.nvalid = nval[g];
-                                    sm.line[r0 + g * 8 + quad] = lm;
-                                }
+                                if (sub == 0 && r0 + g * 8 + quad < nr) sm.lmin[r0 + g * 8 + quad] = d2;
                             }
                         }
                         __syncwarp();
                         // every lane, as an owner: first strict minimum over its lines of this chunk, in visiting order
                         {
-                            const int lb = max((int)sm.lbeg[lane] - lbase, 0), le = min((int)sm.lend[lane] - lbase, nr);
+                            const int lb = max(olb - lbase, 0), le = min(ole - lbase, nr);
                             const int maxlen = __reduce_max_sync(FULL, max(le - lb, 0));
                             for (int u = 0; u < maxlen; ++u) {  // warp-uniform trip count
                                 if (lb + u < le) {
-                                    const LineMin lm = sm.line[lb + u];
-                                    if (closer(lm.d2, best)) {
+                                    const double dl = sm.lmin[lb + u];
+                                    if (closer(dl, best)) {
+                                        const LineDesc ld = sm.ldesc[lb + u];
                                         second = fmin(second, best);
-                                        best = lm.d2, bline = lm.gline, bvalid = lm.nvalid;
+                                        best = dl, bline = ld.gline, bvalid = ld.nvalid;
                                     } else {
-                                        second = fmin(second, lm.d2);
+                                        second = fmin(second, dl);
                                     }
                                 }
                             }
@@ -855,10 +839,11 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             }
             __syncwarp();
             KR_PROF(6)
-            w = (int)min(__shfl_sync(FULL, tk, 0) - tbase, (unsigned)nsearch);
+            w = (int)(total_warps + min(__shfl_sync(FULL, tk, 0) - tbase, dyn));  // >= nsearch once the tickets are used up
             KR_PROF(7)
         }
-        tbase += (unsigned)nsearch + total_warps;
+        // every processed window drew exactly one ticket (its warp's request for the next one), so the phase consumed `nsearch`
+        tbase += (unsigned)nsearch;
         KR_PROF(11)
 
         const unsigned long long t_win = gtime_ns();
