@@ -274,22 +274,16 @@ def sha256_file(path):
     return h.hexdigest()
 
 
-def measure_l2_bandwidth(torch, dev):
-    """Read bandwidth of an L2-resident buffer on this GPU (the ceiling of a path whose working set lives in L2):
-    a 32 MiB float32 buffer summed repeatedly, CUDA events, best of 5."""
-    x = torch.ones(8 << 20, dtype=torch.float32, device=dev)
-    for _ in range(3):
-        x.sum()
-    best = 0.0
-    for _ in range(5):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(20):
-            x.sum()
-        e1.record()
-        torch.cuda.synchronize()
-        best = max(best, 20 * x.numel() * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9)
-    return best
+def measure_l2_bandwidth(ctx):
+    """Read bandwidth of an L2-resident buffer on this GPU (the ceiling of a path whose working set lives in L2): 48 MiB read
+    40 times by one grid-stride launch with 128-bit loads (kicp_debug_l2_read_bandwidth), CUDA events, best of 3."""
+    import ctypes as C
+    from kinematic_icp_b200 import _capi
+    L = _capi.lib()
+    L.kicp_debug_l2_read_bandwidth.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]
+    out = C.c_double()
+    st = L.kicp_debug_l2_read_bandwidth(ctx.h, 48 << 20, 40, C.byref(out))
+    return float(out.value) if st == 0 else None
 
 
 def main():
@@ -532,7 +526,7 @@ def main():
             # what the kernel really moves from L2/HBM into the SMs, from its own counters: two 16-byte hash slots per probe,
             # 128 bytes per line of candidate points, the scan point and the winner's line once per point and pass
             touched_per_pass = (probes * 32.0 + lines * 128.0) / max(iters, 1) + n_local * (24.0 + 128.0)
-            l2_peak = measure_l2_bandwidth(torch, dev)
+            l2_peak = measure_l2_bandwidth(ctx)
             t_pass = t_launch / max(passes_per_launch, 1e-9)
             touched_gbs = touched_per_pass / t_pass / 1e9
             traffic, traffic_note = None, "no ncu capture of this build of kicp_register.cu under profiles/ (profiles/ncu_traffic.json)"
@@ -552,7 +546,7 @@ def main():
                         "algorithmic_bytes_per_launch": bytes_per_launch, "algorithmic_bytes_per_point": a_pt,
                         "mean_candidates_per_point": cbar, "mean_occupied_voxels_of_27": kbar, "peak_source": peak_src,
                         "touched": {"bytes_per_pass": touched_per_pass, "achieved_gbs": touched_gbs, "l2_read_peak_gbs": l2_peak,
-                                    "frac_of_l2_peak": touched_gbs / l2_peak, "probes_per_point_per_pass": probes / max(iters, 1) / n_local,
+                                    "frac_of_l2_peak": (touched_gbs / l2_peak) if l2_peak else None, "probes_per_point_per_pass": probes / max(iters, 1) / n_local,
                                     "candidates_per_point_per_pass": cands / max(iters, 1) / n_local,
                                     "lines_per_point_per_pass": lines / max(iters, 1) / n_local,
                                     "note": "bytes the kernel itself requests from L2 per pass, from its device-side counters (option "
@@ -564,7 +558,7 @@ def main():
                                 "the neighbourhood exactly (%.1f of those candidates per point are evaluated) and the map is served from "
                                 "L2, so this is not a physical HBM fraction — see `touched` and `traffic` for what moves" %
                                 (cbar, cands / max(iters, 1) / n_local)}
-        e2e_main = main_run["e2e"]["pinned_f64"]
+        e2e_main = main_run["e2e"]["pinned_f32"]
         line = {
             "metric": METRIC, "value": main_run["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": main_run["ms_per_step"], "higher_is_better": True,
@@ -582,7 +576,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_main["value"], "unit": UNIT, "h2d_bytes_per_step": e2e_main["h2d_bytes_per_step"],
                     "d2h_bytes_per_step": main_run["d2h_bytes_per_step"], "ms_per_step": e2e_main["ms_per_step"],
-                    "host_memory": "pinned, float64 xyz (std::vector<Eigen::Vector3d> layout) through kicp_register_points",
+                    "host_memory": "pinned float32 xyz — what the reference's callers hold (PointCloud2 FLOAT32 fields, widened to double by "
+                                   "RosUtils.cpp:30-39) — through kicp_register_points; the float64 / pageable variants are alongside",
                     "variants": {k: {"value": v["value"], "ms_per_step": v["ms_per_step"], "h2d_bytes_per_step": v["h2d_bytes_per_step"]}
                                  for k, v in main_run["e2e"].items()}},
             "gpu_launches": main_run["launches"],
@@ -600,7 +595,7 @@ def main():
         if cross_rank_identical is not None:
             line["cross_rank_identical"] = cross_rank_identical
         if replicas_run is not None:
-            rv = replicas_run["e2e"]["pinned_f64"]
+            rv = replicas_run["e2e"]["pinned_f32"]
             line["replicas"] = {"value": replicas_run["value"], "unit": UNIT, "e2e": rv["value"], "scaling": "weak",
                                 "note": "BASELINE.json configs[4] layout: %d independent registrations, one per GPU, no communication; "
                                         "aggregate scans/s (HBM-resident / pinned-host e2e)" % world}

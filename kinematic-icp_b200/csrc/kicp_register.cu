@@ -44,7 +44,7 @@ using namespace kicp_dev;
 #ifndef KR_MINB
 #define KR_MINB 2                     // resident CTAs per SM the kernel is compiled for (measured: the larger L1 beats more warps)
 #endif
-#define KR_LCAP 96                    // lines per chunk (a batch of 32 tasks has at most 160 at 20 points per voxel: 1-2 chunks)
+#define KR_LCAP 192                   // lines the per-warp buffer holds (a batch of 32 tasks adds at most 160 at 20 points per voxel)
 #ifndef KR_G
 #define KR_G 4                        // line-rounds (of 8 lines = 32 points) in flight together
 #endif
@@ -503,6 +503,8 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
         for (int k = 0; k < 7; ++k) sm.acc[k][lane] = 0.0;
         const unsigned long long t_iter0 = gtime_ns();
         const double inv_vs = 1.0 / a.map.voxel_size;
+        // tasks per batch: a batch's lines must fit the line buffer even if every voxel is full
+        const int tpb = max(1, min(32, KR_LCAP / ((a.map.cap + 3) >> 2)));
         const bool cache = PERSISTENT && a.nn_g != nullptr;
         // Window tickets come from one monotonic counter; every phase owns a contiguous range of it (each warp draws exactly one
         // ticket beyond the range of a phase, so a phase of W windows consumes W + total_warps tickets).
@@ -672,13 +674,19 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                     __syncwarp();
                 }
                 KR_PROF(1)
-                for (int base = 0; base < total; base += 32) {
-                    KR_PROF_COUNT(9)
+                // The lines of the stage's found runs are collected in a buffer of KR_LCAP lines (stage-global numbering, visiting
+                // order) and evaluated whenever it would overflow and at the end of the stage — full rounds of 8 lines x KR_G.
+                int fill = 0, lbase = 0;           // lines in the buffer; stage-global index of its first line
+                int olb = 0, ole = 0;              // this lane's, as an owner: its lines so far are [olb, ole) (stage-global)
+                bool ohas = false;
+                for (int base = 0;; base += tpb) {
+                    const bool more = base < total;
                     // -------------------------------------------------------- this lane's task and its hash probe
-                    const bool act = base + lane < total;
+                    const bool act = more && lane < tpb && base + lane < total;
                     const unsigned okpack = act ? (unsigned)sm.task[base + lane] : 0u;
                     uint32_t meta = KICP_SLOT_EMPTY;
-                    {
+                    if (more) {
+                        KR_PROF_COUNT(9)
                         const int o = (int)(okpack >> 5), k = (int)(okpack & 31u);
                         const int kx = sm.vx[o] + shift_x(k), ky = sm.vy[o] + shift_y(k), kz = sm.vz[o] + shift_z(k);
                         uint32_t h = voxel_hash(kx, ky, kz) & a.map.mask;
@@ -720,35 +728,13 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                         const int y = __shfl_up_sync(FULL, incl, d);
                         if (lane >= d) incl += y;
                     }
-                    const int loff = incl - nl;
                     const int ltot = __shfl_sync(FULL, incl, 31);
-                    const int maxnl = __reduce_max_sync(FULL, nl);
                     if (a.collect_stats) n_probe += act ? 1 : 0, n_cand += cnt, n_line += nl;
-                    // the lines of an owner are contiguous (tasks are owner-major): this lane's, as an owner, are those of the task
-                    // lanes [t0, t1) of the batch
-                    int olb = 0, ole = 0;
-                    {
-                        const int t0 = max(tfirst - base, 0), t1 = min(tfirst + tcount - base, 32);
-                        const int b0 = __shfl_sync(FULL, loff, t0 & 31), e1 = __shfl_sync(FULL, incl, (t1 - 1) & 31);
-                        if (t1 > t0) olb = b0, ole = e1;
-                    }
 
-                    for (int lbase = 0; lbase < ltot; lbase += KR_LCAP) {
-                        // describe the lines of this chunk (every task lane its own run)
-                        for (int li = 0; li < maxnl; ++li) {
-                            const int pos = loff + li - lbase;
-                            if (li < nl && pos >= 0 && pos < KR_LCAP) {
-                                LineDesc ld;
-                                ld.gline = (meta >> 8) * (unsigned)a.map.cap + (unsigned)(li * 4);
-                                ld.owner = (unsigned short)(okpack >> 5);
-                                ld.nvalid = (unsigned short)min(cnt - li * 4, 4);
-                                sm.ldesc[pos] = ld;
-                            }
-                        }
-                        __syncwarp();
+                    if ((!more || fill + ltot > KR_LCAP) && fill > 0) {
+                        // ---------------------------------------------------- evaluate the buffered lines
                         KR_PROF(3)
-                        const int nr = min(KR_LCAP, ltot - lbase);
-                        for (int r0 = 0; r0 < nr; r0 += 8 * KR_G) {
+                        for (int r0 = 0; r0 < fill; r0 += 8 * KR_G) {
                             // a quad takes a line, a lane ONE point of it; KR_G independent 256-bit loads per lane in flight
                             unsigned own[KR_G], gix[KR_G];
                             unsigned hasm = 0;
@@ -757,7 +743,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                                 const int line = r0 + g * 8 + quad;
                                 LineDesc ld;
                                 ld.gline = 0u, ld.owner = 0, ld.nvalid = 0;
-                                if (line < nr) ld = sm.ldesc[line];
+                                if (line < fill) ld = sm.ldesc[line];
                                 const bool has = sub < (int)ld.nvalid;
                                 own[g] = ld.owner;
                                 gix[g] = ld.gline + (has ? (unsigned)sub : 0u);
@@ -775,13 +761,13 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                                 // the line's minimum (a NaN distance never wins, as in the reference's comparisons)
                                 d2 = fmin(d2, __shfl_xor_sync(FULL, d2, 1));
                                 d2 = fmin(d2, __shfl_xor_sync(FULL, d2, 2));
-                                if (sub == 0 && r0 + g * 8 + quad < nr) sm.lmin[r0 + g * 8 + quad] = d2;
+                                if (sub == 0 && r0 + g * 8 + quad < fill) sm.lmin[r0 + g * 8 + quad] = d2;
                             }
                         }
                         __syncwarp();
-                        // every lane, as an owner: first strict minimum over its lines of this chunk, in visiting order
+                        // every lane, as an owner: first strict minimum over its lines in the buffer, in visiting order
                         {
-                            const int lb = max(olb - lbase, 0), le = min(ole - lbase, nr);
+                            const int lb = ohas ? max(olb - lbase, 0) : 0, le = ohas ? min(ole - lbase, fill) : 0;
                             const int maxlen = __reduce_max_sync(FULL, max(le - lb, 0));
                             for (int u = 0; u < maxlen; ++u) {  // warp-uniform trip count
                                 if (lb + u < le) {
@@ -797,8 +783,34 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                             }
                         }
                         __syncwarp();
+                        lbase += fill, fill = 0;
                         KR_PROF(5)
                     }
+                    if (!more) break;
+                    // -------------------------------------------------------- describe the batch's lines in the buffer
+                    {
+                        const int gl = lbase + fill + (incl - nl);  // stage-global index of this task's first line
+                        // the lines of an owner are contiguous (tasks are owner-major): this lane's, as an owner, are those of the
+                        // task lanes [t0, t1) of the batch
+                        const int t0 = max(tfirst - base, 0), t1 = min(tfirst + tcount - base, tpb);
+                        const int b0 = __shfl_sync(FULL, gl, t0 & 31), e1 = __shfl_sync(FULL, gl + nl, (t1 - 1) & 31);
+                        if (t1 > t0) {
+                            if (!ohas) olb = b0, ohas = true;
+                            ole = e1;
+                        }
+                        const int maxnl = __reduce_max_sync(FULL, nl);
+                        for (int li = 0; li < maxnl; ++li) {  // warp-uniform trip count
+                            if (li < nl) {
+                                LineDesc ld;
+                                ld.gline = (meta >> 8) * (unsigned)a.map.cap + (unsigned)(li * 4);
+                                ld.owner = (unsigned short)(okpack >> 5);
+                                ld.nvalid = (unsigned short)min(cnt - li * 4, 4);
+                                sm.ldesc[gl - lbase + li] = ld;
+                            }
+                        }
+                        fill += ltot;
+                    }
+                    __syncwarp();
                     KR_PROF(3)
                 }
                 __syncwarp();
@@ -1256,6 +1268,44 @@ extern "C" int kicp_debug_last_stats(kicp_ctx *c, uint64_t out[4] /* probes, can
     if (!c || !c->d_state || !out) return KICP_ERR_INVALID;
     KICP_CUDA(cudaStreamSynchronize(c->stream));
     KICP_CUDA(cudaMemcpy(out, (const char *)c->d_state + offsetof(RegState, stats), sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost));
+    return KICP_OK;
+}
+// Read bandwidth of an L2-resident buffer on this GPU: the physical ceiling of a path whose working set lives in L2 (bench.py
+// reports the registration kernel's touched bytes against it).  `bytes` (<= 64 MiB) are read `reps` times by one launch of a
+// grid-stride kernel with 128-bit loads; returns GB/s of the best of 3 launches.
+__global__ void k_l2_read(const uint4 *__restrict__ p, size_t n, int reps, unsigned *sink) {
+    unsigned acc = 0;
+    for (int r = 0; r < reps; ++r)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+            const uint4 v = __ldcg(p + i);
+            acc += v.x ^ v.y ^ v.z ^ v.w;
+        }
+    if (acc == 0x12345678u) *sink = acc;  // keeps the loads alive
+}
+extern "C" int kicp_debug_l2_read_bandwidth(kicp_ctx *c, uint64_t bytes, int32_t reps, double *gbps) {
+    if (!c || !gbps || bytes < 4096 || bytes > (64ull << 20) || reps < 1) return KICP_ERR_INVALID;
+    KICP_CUDA(cudaSetDevice(c->device));
+    uint4 *buf = nullptr;
+    unsigned *sink = nullptr;
+    KICP_CUDA(cudaMalloc(&buf, bytes));
+    KICP_CUDA(cudaMalloc(&sink, sizeof(unsigned)));
+    KICP_CUDA(cudaMemsetAsync(buf, 1, bytes, c->stream));
+    cudaEvent_t e0, e1;
+    KICP_CUDA(cudaEventCreate(&e0));
+    KICP_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int k = 0; k < 4; ++k) {  // the first launch warms L2
+        KICP_CUDA(cudaEventRecord(e0, c->stream));
+        k_l2_read<<<c->sm_count * 8, 256, 0, c->stream>>>(buf, (size_t)(bytes / 16), reps, sink);
+        KICP_CUDA(cudaEventRecord(e1, c->stream));
+        KICP_CUDA(cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        KICP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (k > 0) best = std::max(best, (double)bytes * reps / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    cudaFree(buf), cudaFree(sink);
+    *gbps = best;
     return KICP_OK;
 }
 extern "C" int kicp_debug_last_prof(kicp_ctx *c, uint64_t out[16] /* -DKR_PROFILE builds: cycles per phase, counts */) {
