@@ -479,7 +479,7 @@ def main():
     scan.close()
     # per-rank pass anatomy (max over ranks of each column, median over the passes of the last timed registration)
     tim = main_run["timing"][: max(int(main_run["result"].iterations), 1)] / 1e3  # us
-    anatomy = [float(np.median(tim[:, k])) for k in range(4)]
+    anatomy = [float(np.median(tim[:, k])) for k in range(6)]
     if world > 1:
         t = torch.tensor(anatomy, dtype=torch.float64, device=dev)
         tmax = t.clone()
@@ -584,7 +584,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "pose_delta_vs_cpu": pose_delta,
-            "pass_anatomy_us": {"columns": ["windows phase (CTA 0)", "barrier wait", "reduce (+ exchange)", "solve"],
+            "pass_anatomy_us": {"columns": ["certificate phase", "its grid barrier", "search phase (CTA 0)", "barrier wait", "reduce (+ exchange)", "solve"],
                                 "median_over_passes_max_over_ranks": anatomy_max, "min_over_ranks": anatomy_min,
                                 "note": "device %globaltimer probes on CTA 0 of every rank, last timed registration"},
             "kernel_time_split_ms_per_step": None if prof is None else {

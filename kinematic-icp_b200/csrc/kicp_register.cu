@@ -51,14 +51,16 @@ using namespace kicp_dev;
 #define KR_DBLMAX_BITS 0x7FEFFFFFFFFFFFFFull
 // Development aid (-DKR_PROFILE): per-phase cycle accounting of the window loop (lane 0 of every warp, clock64 deltas).
 #ifdef KR_PROFILE
-#define KR_PROF_DECL long long prof_t[12] = {0}; long long prof_last = clock64();
-#define KR_PROF(i) { const long long t__ = clock64(); prof_t[i] += t__ - prof_last; prof_last = t__; }
-#define KR_PROF_COUNT(i) { prof_t[i] += 1; }
-#define KR_PROF_FLUSH if (lane == 0) { for (int k__ = 0; k__ < 12; ++k__) atomicAdd(&st->prof[k__], (unsigned long long)prof_t[k__]); }
+#define KR_PROF_DECL long long prof_t[24] = {0}; long long prof_last = clock64(); int prof_o = 0;
+#define KR_PROF(i) { const long long t__ = clock64(); prof_t[prof_o + (i)] += t__ - prof_last; prof_last = t__; }
+#define KR_PROF_COUNT(i) { prof_t[prof_o + (i)] += 1; }
+#define KR_PROF_PASS(it) { prof_o = (it) ? 12 : 0; }
+#define KR_PROF_FLUSH if (lane == 0) { for (int k__ = 0; k__ < 24; ++k__) atomicAdd(&st->prof[k__], (unsigned long long)prof_t[k__]); }
 #else
 #define KR_PROF_DECL
 #define KR_PROF(i)
 #define KR_PROF_COUNT(i)
+#define KR_PROF_PASS(it)
 #define KR_PROF_FLUSH
 #endif
 
@@ -86,8 +88,8 @@ struct RegState {
     int *iters_out;                 // optional: where to publish the iteration count (profiling)
     double acc[8];                  // multi-launch path: JTJ00 JTJ01 JTJ11 JTr0 JTr1 N sum|r|^2 (unused)
     unsigned long long stats[4];    // optional work counters: probes, candidate points evaluated, lines, windows
-    unsigned long long prof[16];    // -DKR_PROFILE builds only: SM cycles per phase of the window loop, summed over warps
-    double dbg[KICP_MAX_ITERATIONS][4];  // per pass, ns (CTA 0): windows phase, barrier wait, partial sum (+ exchange), solve
+    unsigned long long prof[24];    // -DKR_PROFILE builds only: SM cycles per phase of the window loop, summed over warps
+    double dbg[KICP_MAX_ITERATIONS][6];  // per pass, ns (CTA 0): certificate phase, its barrier, search phase, barrier wait, partial sum (+ exchange), solve
     kicp_reg_result result;
 };
 
@@ -502,6 +504,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
 #pragma unroll
         for (int k = 0; k < 7; ++k) sm.acc[k][lane] = 0.0;
         const unsigned long long t_iter0 = gtime_ns();
+        KR_PROF_PASS(it)
         const double inv_vs = 1.0 / a.map.voxel_size;
         // tasks per batch: a batch's lines must fit the line buffer even if every voxel is full
         const int tpb = max(1, min(32, KR_LCAP / ((a.map.cap + 3) >> 2)));
@@ -510,6 +513,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
         // ticket beyond the range of a phase, so a phase of W windows consumes W + total_warps tickets).
         unsigned tk = 0;  // lane 0: the ticket drawn ahead of time (the atomic's round trip is off the critical path)
         int nsearch = num_windows;  // windows of the search phase of this pass
+        unsigned long long t_a1 = t_iter0, t_a2 = t_iter0;  // end of the certificate phase / of its barrier (thread 0)
 
         if (cache && it > 0u) {
             // ------------------------------------------------------------------------------------------------------------
@@ -570,6 +574,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             // every CTA of the grid has to be through phase A before the list is complete
             __syncthreads();
             if (threadIdx.x == 0) {
+                t_a1 = gtime_ns();
                 __threadfence();
                 atomicAdd(&st->a_arrive, 1u);
                 const unsigned target = it * gridDim.x;
@@ -581,6 +586,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                         break;
                     }
                 }
+                t_a2 = gtime_ns();
             }
             __syncthreads();
             nsearch = (int)((__ldcg(&st->todo_n[it]) + 31u) >> 5);
@@ -642,8 +648,13 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             __syncwarp();
             KR_PROF(0)
 
+            // A point that comes with the distance to its previous neighbour (search phase of a later pass) already has a tight
+            // pruning bound: its few surviving neighbour voxels join the own voxel in ONE stage instead of three.
+            unsigned donem = 0u;    // shifts of this owner that have been scheduled already
+            bool merged = false;
             for (int stage = 0; stage < 3; ++stage) {
                 // ------------------------------------------------------------ task stream of the stage (owner-major, KISS order)
+                if (stage == 1 && !__any_sync(FULL, valid && !merged)) break;  // every owner of the window took the short way
                 int total, tfirst, tcount;  // tasks of the stage; this owner's range [tfirst, tfirst + tcount) of the stream
                 {
                     const double2 qq = sm.qxy[lane];
@@ -651,8 +662,19 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                     // tau or beyond is rejected anyway (Registration.cpp:75), so voxels that can only hold such points are skipped
                     const double tau2 = s_ps.tau * s_ps.tau;
                     const double bsq = fmin(fmin(tau2, best), seed2);
-                    unsigned mask = stage_mask(stage, valid, bsq * (1.0 + 1e-6) + 1e-10, qq.x, qq.y, sm.qz[lane], sm.vx[lane], sm.vy[lane],
-                                               sm.vz[lane], a.map.voxel_size, minpruned);
+                    const double bound = bsq * (1.0 + 1e-6) + 1e-10;
+                    unsigned mask = stage_mask(stage, valid, bound, qq.x, qq.y, sm.qz[lane], sm.vx[lane], sm.vy[lane], sm.vz[lane],
+                                               a.map.voxel_size, minpruned);
+                    if (stage == 0 && valid && seed2 < DBL_MAX) {
+                        double mp = minpruned;
+                        const unsigned near = stage_mask(1, true, bound, qq.x, qq.y, sm.qz[lane], sm.vx[lane], sm.vy[lane], sm.vz[lane],
+                                                         a.map.voxel_size, mp) |
+                                              stage_mask(2, true, bound, qq.x, qq.y, sm.qz[lane], sm.vx[lane], sm.vy[lane], sm.vz[lane],
+                                                         a.map.voxel_size, mp);
+                        if (__popc(near) <= 8) mask |= near, minpruned = mp, merged = true;  // (a loose bound keeps the staged way)
+                    }
+                    mask &= ~donem;
+                    donem |= mask;
                     const int no = __popc(mask);
                     int tin = no;
 #pragma unroll
@@ -1002,8 +1024,8 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                 solve_and_update(&s_ps, s, blockIdx.x == 0 ? &st->result : nullptr, blockIdx.x == 0 ? a.init.iters_out : nullptr);
             }
             if (blockIdx.x == 0 && it < KICP_MAX_ITERATIONS) {
-                st->dbg[it][0] = (double)(t_win - t_iter0), st->dbg[it][1] = (double)(t_arr - t_win);
-                st->dbg[it][2] = (double)(t_red - t_arr), st->dbg[it][3] = (double)(gtime_ns() - t_red);
+                st->dbg[it][0] = (double)(t_a1 - t_iter0), st->dbg[it][1] = (double)(t_a2 - t_a1), st->dbg[it][2] = (double)(t_win - t_a2);
+                st->dbg[it][3] = (double)(t_arr - t_win), st->dbg[it][4] = (double)(t_red - t_arr), st->dbg[it][5] = (double)(gtime_ns() - t_red);
             }
         }
         __syncthreads();
@@ -1257,10 +1279,10 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
 }
 
 // debugging aids (not part of the public header): per-pass device timings and work counters of the last registration
-extern "C" int kicp_debug_last_timing(kicp_ctx *c, double *out /* [KICP_MAX_ITERATIONS][4] */) {
+extern "C" int kicp_debug_last_timing(kicp_ctx *c, double *out /* [KICP_MAX_ITERATIONS][6] */) {
     if (!c || !c->d_state || !out) return KICP_ERR_INVALID;
     KICP_CUDA(cudaStreamSynchronize(c->stream));
-    KICP_CUDA(cudaMemcpy(out, (const char *)c->d_state + offsetof(RegState, dbg), sizeof(double) * KICP_MAX_ITERATIONS * 4,
+    KICP_CUDA(cudaMemcpy(out, (const char *)c->d_state + offsetof(RegState, dbg), sizeof(double) * KICP_MAX_ITERATIONS * 6,
                          cudaMemcpyDeviceToHost));
     return KICP_OK;
 }
@@ -1308,10 +1330,10 @@ extern "C" int kicp_debug_l2_read_bandwidth(kicp_ctx *c, uint64_t bytes, int32_t
     *gbps = best;
     return KICP_OK;
 }
-extern "C" int kicp_debug_last_prof(kicp_ctx *c, uint64_t out[16] /* -DKR_PROFILE builds: cycles per phase, counts */) {
+extern "C" int kicp_debug_last_prof(kicp_ctx *c, uint64_t out[24] /* -DKR_PROFILE builds: cycles per phase, counts */) {
     if (!c || !c->d_state || !out) return KICP_ERR_INVALID;
     KICP_CUDA(cudaStreamSynchronize(c->stream));
-    KICP_CUDA(cudaMemcpy(out, (const char *)c->d_state + offsetof(RegState, prof), sizeof(uint64_t) * 16, cudaMemcpyDeviceToHost));
+    KICP_CUDA(cudaMemcpy(out, (const char *)c->d_state + offsetof(RegState, prof), sizeof(uint64_t) * 24, cudaMemcpyDeviceToHost));
     return KICP_OK;
 }
 

@@ -43,11 +43,12 @@ class Context:
         check(lib().kicp_ctx_set_option(self.h, name.encode(), int(value)), "kicp_ctx_set_option")
 
     def last_timing(self):
-        """Per-pass device timings of the last registration, ns: [pass][windows phase, barrier wait, reduce(+exchange), solve]
+        """Per-pass device timings of the last registration, ns: [pass][certificate phase, its barrier, search phase, barrier
+        wait, reduce(+exchange), solve]
         measured on CTA 0 with %globaltimer (kicp_debug_last_timing; synchronises the stream)."""
         L = lib()
         L.kicp_debug_last_timing.argtypes = [C.c_void_p, _capi.c_dp]
-        out = np.zeros((_capi.KICP_MAX_ITERATIONS, 4))
+        out = np.zeros((_capi.KICP_MAX_ITERATIONS, 6))
         check(L.kicp_debug_last_timing(self.h, dp(out)), "kicp_debug_last_timing")
         return out
 

@@ -20,15 +20,17 @@ reg.enqueue(scan, gm, w.last_pose, w.rel_odom, w.tau, res)
 ctx.synchronize()
 L = _capi.lib()
 L.kicp_debug_last_prof.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
-out = (C.c_uint64 * 16)()
+out = (C.c_uint64 * 24)()
 L.kicp_debug_last_prof(ctx.h, out)
-p = [int(x) for x in out]
-names = ["setup", "tasklist", "probe", "linemap", "decode+load+math", "reduction", "final", "next-ticket"]
-nwin, nbatch, ngroup = p[8], p[9], p[10]
-tot = sum(p[:8])
-print("cfg", cfg, "iters", res.iterations, "windows", nwin, "batches/window %.2f groups/window %.2f" % (nbatch / max(nwin, 1), ngroup / max(nwin, 1)))
-print("cycles per window: total %.0f (%.1f us at 1.965 GHz)" % (tot / max(nwin, 1), tot / max(nwin, 1) / 1965.0))
-for k in range(8):
-    print("  %-18s %8.0f cyc/window  %5.1f%%" % (names[k], p[k] / max(nwin, 1), 100.0 * p[k] / max(tot, 1)))
-print("  per batch: probe %.0f, linemap %.0f; per group: load+math %.0f, reduction %.0f" % (p[2] / max(nbatch, 1), p[3] / max(nbatch, 1), p[4] / max(ngroup, 1), p[5] / max(ngroup, 1)))
-print("  outside windows (barrier etc.) per warp-pass: %.0f cyc" % (p[11] / max(1, res.iterations)))
+allp = [int(x) for x in out]
+names = ["setup", "tasklist", "probe", "linemap", "decode+load", "math+reduce", "final", "next-ticket"]
+print("cfg", cfg, "iters", res.iterations)
+for label, p in (("pass 0 (every point searched)", allp[:12]), ("later passes (search of the uncertified points)", allp[12:])):
+    nwin, nbatch, ngroup = p[8], p[9], p[10]
+    tot = sum(p[:8])
+    print(label, ": windows", nwin, "batches/window %.2f groups/window %.2f" % (nbatch / max(nwin, 1), ngroup / max(nwin, 1)))
+    print("  cycles per window: total %.0f (%.1f us at 1.965 GHz)" % (tot / max(nwin, 1), tot / max(nwin, 1) / 1965.0))
+    for k in range(8):
+        print("    %-14s %8.0f cyc/window  %5.1f%%" % (names[k], p[k] / max(nwin, 1), 100.0 * p[k] / max(tot, 1)))
+    print("    per batch: probe %.0f, linemap %.0f; per group: decode+load %.0f, math+reduce %.0f; outside windows per warp-pass %.0f cyc" %
+          (p[2] / max(nbatch, 1), p[3] / max(nbatch, 1), p[4] / max(ngroup, 1), p[5] / max(ngroup, 1), p[11] / max(1, res.iterations)))

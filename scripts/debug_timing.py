@@ -21,7 +21,7 @@ for rep in range(5):
 ctx.synchronize()
 out = ctx.last_timing()
 it = res.iterations
-print("cfg", cfg, "N", w.N, "iters", it, "[windows(cta0), barrier wait, reduce(+exchange), solve] us per pass:")
+print("cfg", cfg, "N", w.N, "iters", it, "[certificates, their barrier, search, barrier wait, reduce(+exchange), solve] us per pass (CTA 0):")
 print(np.round(out[:it] / 1e3, 2))
 print("sum per pass us:", np.round(out[:it].sum(1) / 1e3, 2), "total us", round(out[:it].sum() / 1e3, 1))
 ctx.set_option("stats", 1)
