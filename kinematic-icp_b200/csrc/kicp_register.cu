@@ -205,7 +205,8 @@ struct KernelArgs {
     int collect_stats;
     // nearest-neighbour cache carried from pass to pass (persistent kernel, option "nn_cache"), one entry per scan point
     unsigned int *nn_g;            // the neighbour found by the last search (global point index, 0xFFFFFFFF = none)
-    float *nn_l;                   // certified lower bound on the distance to every OTHER candidate of the neighbourhood
+    unsigned int *nn_g2;           // the runner-up of that search (0xFFFFFFFF = none): between passes the two may swap
+    float *nn_l;                   // certified lower bound on the distance to every candidate OTHER than those two
     float *nn_seed;                // distance to the old neighbour from the new position (pruning bound of the repeated search)
     unsigned int *todo;            // points of the current pass that need the search
     unsigned long long timeout_ns;  // device-side waits (upload flags, peers) give up after this long
@@ -531,10 +532,12 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                 const bool valid = i < n;
                 double px = 0, py = 0, pz = 0;
                 if (valid) load_scan_point(a.scan, i, px, py, pz);
-                const unsigned g = valid ? __ldcg(&a.nn_g[i]) : 0xFFFFFFFFu;
+                const unsigned g1 = valid ? __ldcg(&a.nn_g[i]) : 0xFFFFFFFFu;
+                const unsigned g2 = valid ? __ldcg(&a.nn_g2[i]) : 0xFFFFFFFFu;
                 const double l = valid ? (double)__ldcg(&a.nn_l[i]) : 0.0;
-                const bool haveg = g != 0xFFFFFFFFu;
-                const Point4 c = ld_point(a.map.pts + (size_t)(haveg ? g : 0u) * KICP_PSTRIDE);
+                const bool haveg = g1 != 0xFFFFFFFFu, have2 = g2 != 0xFFFFFFFFu;
+                const Point4 c1 = ld_point(a.map.pts + (size_t)(haveg ? g1 : 0u) * KICP_PSTRIDE);
+                const Point4 c2 = ld_point(a.map.pts + (size_t)(have2 ? g2 : 0u) * KICP_PSTRIDE);
                 const double qx = s_ps.R[0] * px + s_ps.R[1] * py + s_ps.R[2] * pz + s_ps.t[0];
                 const double qy = s_ps.R[3] * px + s_ps.R[4] * py + s_ps.R[5] * pz + s_ps.t[1];
                 const double qz = s_ps.R[6] * px + s_ps.R[7] * py + s_ps.R[8] * pz + s_ps.t[2];
@@ -548,11 +551,19 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                                   vz == voxel_of(oz, vs, inv_vs, a.pow2_voxel);
                 const double mx = qx - ox, my = qy - oy, mz = qz - oz;
                 const double delta = sqrt(mx * mx + my * my + mz * mz) * (1.0 + 1e-9) + 1e-12;
-                const double dn = sqrt(dist2(c.x, c.y, c.z, qx, qy, qz));
+                const double d1 = sqrt(dist2(c1.x, c1.y, c1.z, qx, qy, qz));
+                const double d2 = have2 ? sqrt(dist2(c2.x, c2.y, c2.z, qx, qy, qz)) : DBL_MAX;
+                // the two remembered candidates may have swapped; a near-tie between them is left to the search (only it applies the
+                // reference's visiting-order rule)
+                const bool second_wins = d2 < d1;
+                const double dn = second_wins ? d2 : d1;
+                const bool clear = !have2 || fabs(d1 - d2) > 1e-9 * (d1 + d2) + 1e-12;
+                const Point4 c = second_wins ? c2 : c1;
                 const double room = l - delta;  // every other candidate is at least this far from the new position
-                const bool cert = valid && same && (haveg ? (dn * (1.0 + 1e-9) + 1e-12 < room) : (room > s_ps.tau * (1.0 + 1e-9)));
+                const bool cert = valid && same && (haveg ? (clear && dn * (1.0 + 1e-9) + 1e-12 < room) : (room > s_ps.tau * (1.0 + 1e-9)));
                 if (cert) {
                     a.nn_l[i] = __double2float_rz(room * (1.0 - 1e-7));
+                    if (second_wins) a.nn_g[i] = g2, a.nn_g2[i] = g1;
                     if (haveg) accumulate(sm, lane, s_ps, c.x, c.y, c.z, qx, qy, qz, px, py);
                 }
                 const unsigned need = __ballot_sync(FULL, valid && !cert);
@@ -589,9 +600,16 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                 t_a2 = gtime_ns();
             }
             __syncthreads();
-            nsearch = (int)((__ldcg(&st->todo_n[it]) + 31u) >> 5);
         }
         const int ncount = (cache && it > 0u) ? (int)__ldcg(&st->todo_n[it]) : n;  // points of the search phase
+        // Window size of the phase: the points are spread evenly over the whole grid in as few rounds as 32-point windows would
+        // need (a window's latency is what a pass waits for at its end, so 2 x 19 points beats 32 + 6)
+        int wsz = 32;
+        if (PERSISTENT && ncount > 0) {
+            const int rounds = (ncount + 32 * (int)total_warps - 1) / (32 * (int)total_warps);
+            wsz = min(32, (ncount + rounds * (int)total_warps - 1) / (rounds * (int)total_warps));
+        }
+        nsearch = (ncount + wsz - 1) / wsz;
         const bool indirect = cache && it > 0u;
 
         // ------------------------------------------------------------------------------------------------------------------
@@ -607,7 +625,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             KR_PROF_COUNT(8)
             if (PERSISTENT && a.up.flags != nullptr && it == 0u) {
                 // first pass over a frame that is still being uploaded: wait until this window's chunk has landed
-                const uint32_t *f = a.up.flags + min(w / a.up.windows_per_chunk, KICP_UPLOAD_CHUNKS - 1);
+                const uint32_t *f = a.up.flags + min((min((w + 1) * wsz, n) - 1) / 32 / a.up.windows_per_chunk, KICP_UPLOAD_CHUNKS - 1);
                 const unsigned long long deadline = gtime_ns() + a.timeout_ns;
                 bool pend = true;
                 while (__any_sync(FULL, pend)) {  // warp-uniform: every lane polls the same word (one transaction)
@@ -622,8 +640,8 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                 }
             }
             // ---------------------------------------------------------------- owners: q = T p and its voxel
-            const bool valid = w * 32 + lane < ncount;
-            const int pi = valid ? (indirect ? (int)__ldcg(&a.todo[w * 32 + lane]) : w * 32 + lane) : 0;  // the owner's scan point
+            const bool valid = lane < wsz && w * wsz + lane < ncount;
+            const int pi = valid ? (indirect ? (int)__ldcg(&a.todo[w * wsz + lane]) : w * wsz + lane) : 0;  // the owner's scan point
             double seed2 = DBL_MAX;  // squared distance to the previous neighbour (an exact pruning bound), if it applies
             {
                 double px = 0, py = 0, pz = 0;
@@ -642,9 +660,10 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                 sm.px[lane] = px, sm.py[lane] = py;
             }
             // the owner's running minimum lives in its lane's registers: d^2, the line that holds it, how many points that line has;
-            // `second` bounds every evaluated point that is not the winner, `minpruned` the cubes of the voxels that were skipped
-            double best = DBL_MAX, second = DBL_MAX, minpruned = DBL_MAX;
-            unsigned bline = 0xFFFFFFFFu, bvalid = 0u;
+            // the runner-up lines and `minpruned` (the cubes of the voxels that were skipped) feed the certificate of the next pass
+            double best = DBL_MAX, second = DBL_MAX, third = DBL_MAX, minpruned = DBL_MAX;  // three smallest LINE minima (+ skipped cubes)
+            unsigned bline = 0xFFFFFFFFu, bvalid = 0u;   // the line holding `best` ...
+            unsigned sline = 0xFFFFFFFFu, svalid = 0u;   // ... and the one holding `second`
             __syncwarp();
             KR_PROF(0)
 
@@ -796,10 +815,15 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                                     const double dl = sm.lmin[lb + u];
                                     if (closer(dl, best)) {
                                         const LineDesc ld = sm.ldesc[lb + u];
-                                        second = fmin(second, best);
+                                        third = second;
+                                        second = best, sline = bline, svalid = bvalid;
                                         best = dl, bline = ld.gline, bvalid = ld.nvalid;
+                                    } else if (dl < second) {
+                                        const LineDesc ld = sm.ldesc[lb + u];
+                                        third = second;
+                                        second = dl, sline = ld.gline, svalid = ld.nvalid;
                                     } else {
-                                        second = fmin(second, dl);
+                                        third = fmin(third, dl);
                                     }
                                 }
                             }
@@ -862,12 +886,32 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                     if (jw == j) c = cc[j];
                 if (have) accumulate(sm, lane, s_ps, c.x, c.y, c.z, q0.x, q0.y, q0z, sm.px[lane], sm.py[lane]);
                 if (cache && valid) {
-                    // what the next pass may rely on: the neighbour, and how far every other candidate is at least
+                    // What the next pass may rely on: the neighbour g1, the runner-up g2 among the points of the two best lines, and
+                    // l = how far every OTHER candidate is at least (third point of those lines, every other line, skipped cubes).
+                    const bool have2 = have && sline != 0xFFFFFFFFu;
+                    Point4 ce[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (have && j < (int)bvalid && j != jw) second = fmin(second, dj[j]);
-                    const double lo2 = fmin(second, minpruned);
+                    for (int j = 0; j < 4; ++j) ce[j] = ld_point(a.map.pts + (size_t)((have2 ? sline : 0u) + (j < (int)svalid ? j : 0)) * KICP_PSTRIDE);
+                    double ru = DBL_MAX, ru2 = DBL_MAX;  // smallest and second smallest squared distance among the non-winners
+                    unsigned g2 = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (have && j < (int)bvalid && j != jw) {
+                            if (dj[j] < ru) ru2 = ru, ru = dj[j], g2 = g0 + (unsigned)j;
+                            else ru2 = fmin(ru2, dj[j]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double de = dist2(ce[j].x, ce[j].y, ce[j].z, q0.x, q0.y, q0z);
+                        if (have2 && j < (int)svalid) {
+                            if (de < ru) ru2 = ru, ru = de, g2 = sline + (unsigned)j;
+                            else ru2 = fmin(ru2, de);
+                        }
+                    }
+                    const double lo2 = fmin(fmin(ru2, third), minpruned);
                     a.nn_g[pi] = have ? g0 + (unsigned)jw : 0xFFFFFFFFu;
+                    a.nn_g2[pi] = g2;
                     a.nn_l[pi] = lo2 >= 1.0e60 ? 1.0e30f : __double2float_rz(sqrt(lo2) * (1.0 - 1e-7));
                 }
             }
@@ -1173,20 +1217,21 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
         ka.pow2_voxel = std::frexp(m->voxel_size, &e) == 0.5 ? 1 : 0;
     }
     ka.collect_stats = c->collect_stats;
-    ka.nn_g = nullptr, ka.nn_l = nullptr, ka.nn_seed = nullptr, ka.todo = nullptr;
+    ka.nn_g = nullptr, ka.nn_g2 = nullptr, ka.nn_l = nullptr, ka.nn_seed = nullptr, ka.todo = nullptr;
     if (c->nn_cache && scan->n > 0) {
         if (scan->n > c->nn_cap) {
             KICP_CUDA(cudaStreamSynchronize(c->stream));
-            cudaFree(c->d_nn_g), cudaFree(c->d_nn_l), cudaFree(c->d_nn_seed), cudaFree(c->d_todo);
-            c->d_nn_g = nullptr, c->d_nn_l = nullptr, c->d_nn_seed = nullptr, c->d_todo = nullptr, c->nn_cap = 0;
+            cudaFree(c->d_nn_g), cudaFree(c->d_nn_g2), cudaFree(c->d_nn_l), cudaFree(c->d_nn_seed), cudaFree(c->d_todo);
+            c->d_nn_g = nullptr, c->d_nn_g2 = nullptr, c->d_nn_l = nullptr, c->d_nn_seed = nullptr, c->d_todo = nullptr, c->nn_cap = 0;
             const int64_t cap = scan->n + scan->n / 4 + 1024;
             KICP_CUDA(cudaMalloc(&c->d_nn_g, (size_t)cap * sizeof(unsigned int)));
+            KICP_CUDA(cudaMalloc(&c->d_nn_g2, (size_t)cap * sizeof(unsigned int)));
             KICP_CUDA(cudaMalloc(&c->d_nn_l, (size_t)cap * sizeof(float)));
             KICP_CUDA(cudaMalloc(&c->d_nn_seed, (size_t)cap * sizeof(float)));
             KICP_CUDA(cudaMalloc(&c->d_todo, (size_t)cap * sizeof(unsigned int)));
             c->nn_cap = cap;
         }
-        ka.nn_g = c->d_nn_g, ka.nn_l = c->d_nn_l, ka.nn_seed = c->d_nn_seed, ka.todo = c->d_todo;
+        ka.nn_g = c->d_nn_g, ka.nn_g2 = c->d_nn_g2, ka.nn_l = c->d_nn_l, ka.nn_seed = c->d_nn_seed, ka.todo = c->d_todo;
     }
     ka.timeout_ns = (unsigned long long)c->spin_timeout_ms * 1000000ull;
     const int n = (int)scan->n;
@@ -1216,7 +1261,9 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
     if (ka.init.max_iter > 0) {
         // every CTA is resident and pulls 32-point windows from a device-side counter; a small scan is spread one window per
         // CTA over the whole machine (a window is a chain of dependent memory round trips: latency, not throughput)
-        const int num_windows = (n + 31) / 32;
+        // (the persistent kernel sizes its windows so that the points spread evenly over the grid: a small scan runs as many tiny
+        // windows on the whole machine)
+        const int num_windows = persistent ? (n + 7) / 8 : (n + 31) / 32;
         int per_sm = persistent ? c->persistent_ctas_per_sm : c->pruned_ctas_per_sm;
         if (c->ctas_per_sm_cap > 0) per_sm = std::min(per_sm, c->ctas_per_sm_cap);
         const int grid = std::max(1, std::min(num_windows, c->sm_count * per_sm));
