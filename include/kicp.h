@@ -81,10 +81,10 @@ void *kicp_ctx_stream(kicp_ctx *ctx);
 int64_t kicp_ctx_launch_count(kicp_ctx *ctx);
 /* Options: "persistent" 1 = all IRLS iterations of a registration inside ONE cooperative launch (default), 0 = one launch per
  * iteration; "stats" 1 = count hash probes / candidate points / 128-byte lines on the device (bench.py's touched-bytes figure);
- * "ctas_per_sm" = cap of the resident CTAs per SM the grid is sized for (0 = occupancy limit); "nn_cache" 1 = between IRLS
- * passes every point keeps its neighbour together with a certificate (a lower bound on the distance to every other candidate);
- * a pass re-searches only the points whose certificate the pose update broke (default; exact), 0 = search every
- * point in every pass; "overlap_upload" 1 = the
+ * "ctas_per_sm" = cap of the resident CTAs per SM the grid is sized for (0 = occupancy limit); "nn_cache" = between IRLS
+ * passes every point keeps its two nearest candidates together with a certificate (a lower bound on the distance to every other
+ * candidate) and a pass re-searches only the points whose certificate the pose update broke (exact): 1 = for
+ * scans of 49152 points or more (default: smaller scans gain nothing from the extra phase), 2 = always, 0 = never; "overlap_upload" 1 = the
  * host-pointer entry points overlap the frame's upload with the first pass (default); "spin_timeout_ms" = bound of every
  * device-side wait (upload flags, peers of the fused exchange; default 20000).  Unknown names fail with KICP_ERR_INVALID.
  * Every setting computes the same result up to the summation order. */

@@ -83,7 +83,8 @@ struct RegState {
     unsigned int exit_ctr;          // CTAs that have left the kernel; the last one zeroes the three counters
     unsigned int ticket;            // multi-launch path: last-CTA detection
     unsigned int a_arrive;          // warps that finished the certificate phase of a pass (monotonic inside a registration)
-    unsigned int todo_n[KICP_MAX_ITERATIONS];  // per pass: points whose neighbour has to be searched again
+    unsigned int todo_h[KICP_MAX_ITERATIONS];  // per pass: points to search again that have no pruning bound yet (expensive) ...
+    unsigned int todo_l[KICP_MAX_ITERATIONS];  // ... and those that come with the distance to their previous neighbour (cheap)
     int abort;                      // a device-side wait gave up (status code); every CTA leaves after the current pass
     int *iters_out;                 // optional: where to publish the iteration count (profiling)
     double acc[8];                  // multi-launch path: JTJ00 JTJ01 JTJ11 JTr0 JTr1 N sum|r|^2 (unused)
@@ -208,7 +209,8 @@ struct KernelArgs {
     unsigned int *nn_g2;           // the runner-up of that search (0xFFFFFFFF = none): between passes the two may swap
     float *nn_l;                   // certified lower bound on the distance to every candidate OTHER than those two
     float *nn_seed;                // distance to the old neighbour from the new position (pruning bound of the repeated search)
-    unsigned int *todo;            // points of the current pass that need the search
+    unsigned int *todo;            // points of the current pass that need the search: the expensive ones from the front, the cheap
+    unsigned int todo_cap;         // ones from the back (the search phase starts with the expensive ones)
     unsigned long long timeout_ns;  // device-side waits (upload flags, peers) give up after this long
 };
 
@@ -275,7 +277,7 @@ __global__ void k_reg_init(RegState *st, RegArgs a) {
     pose_init(&st->pose, a);
     result_init(&st->result, &st->pose);
     st->ticket = 0, st->win_ctr = 0, st->arrive = 0, st->exit_ctr = 0, st->abort = 0, st->a_arrive = 0;
-    for (int k = 0; k < KICP_MAX_ITERATIONS; ++k) st->todo_n[k] = 0;
+    for (int k = 0; k < KICP_MAX_ITERATIONS; ++k) st->todo_h[k] = 0, st->todo_l[k] = 0;
     st->iters_out = a.iters_out;
     if (a.iters_out) *a.iters_out = 0;
     for (int k = 0; k < 8; ++k) st->acc[k] = 0.0;
@@ -566,20 +568,25 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                     if (second_wins) a.nn_g[i] = g2, a.nn_g2[i] = g1;
                     if (haveg) accumulate(sm, lane, s_ps, c.x, c.y, c.z, qx, qy, qz, px, py);
                 }
-                const unsigned need = __ballot_sync(FULL, valid && !cert);
-                if (need) {
-                    unsigned pos = 0;
-                    if (lane == 0) pos = atomicAdd(&st->todo_n[it], (unsigned)__popc(need));
-                    pos = __shfl_sync(FULL, pos, 0) + (unsigned)__popc(need & ((1u << lane) - 1u));
-                    if (valid && !cert) {
-                        a.todo[pos] = (unsigned)i;
-                        // the old neighbour bounds the repeated search if it is one of the new 27 voxels' points
-                        float seed = 3.0e38f;
-                        if (haveg && abs(voxel_of(c.x, vs, inv_vs, a.pow2_voxel) - vx) <= 1 && abs(voxel_of(c.y, vs, inv_vs, a.pow2_voxel) - vy) <= 1 &&
-                            abs(voxel_of(c.z, vs, inv_vs, a.pow2_voxel) - vz) <= 1)
-                            seed = __double2float_ru(dn * (1.0 + 1e-7));
-                        a.nn_seed[i] = seed;
+                // the old neighbour bounds the repeated search if it is one of the new 27 voxels' points; points without such a bound
+                // (nothing found last time, or the neighbourhood moved away) are the expensive ones and are searched first
+                float seed = 3.0e38f;
+                if (haveg && abs(voxel_of(c.x, vs, inv_vs, a.pow2_voxel) - vx) <= 1 && abs(voxel_of(c.y, vs, inv_vs, a.pow2_voxel) - vy) <= 1 &&
+                    abs(voxel_of(c.z, vs, inv_vs, a.pow2_voxel) - vz) <= 1)
+                    seed = __double2float_ru(dn * (1.0 + 1e-7));
+                const bool heavy = valid && !cert && !(seed < 1.0e38f), light = valid && !cert && seed < 1.0e38f;
+                const unsigned mh = __ballot_sync(FULL, heavy), ml = __ballot_sync(FULL, light);
+                if (mh | ml) {
+                    unsigned ph = 0, pl = 0;
+                    if (lane == 0) {
+                        if (mh) ph = atomicAdd(&st->todo_h[it], (unsigned)__popc(mh));
+                        if (ml) pl = atomicAdd(&st->todo_l[it], (unsigned)__popc(ml));
                     }
+                    ph = __shfl_sync(FULL, ph, 0) + (unsigned)__popc(mh & ((1u << lane) - 1u));
+                    pl = __shfl_sync(FULL, pl, 0) + (unsigned)__popc(ml & ((1u << lane) - 1u));
+                    if (heavy) a.todo[ph] = (unsigned)i;
+                    if (light) a.todo[a.todo_cap - 1u - pl] = (unsigned)i;
+                    if (heavy || light) a.nn_seed[i] = seed;
                 }
             }
             // every CTA of the grid has to be through phase A before the list is complete
@@ -601,7 +608,8 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             }
             __syncthreads();
         }
-        const int ncount = (cache && it > 0u) ? (int)__ldcg(&st->todo_n[it]) : n;  // points of the search phase
+        const int nheavy = (cache && it > 0u) ? (int)__ldcg(&st->todo_h[it]) : 0, nlight = (cache && it > 0u) ? (int)__ldcg(&st->todo_l[it]) : 0;
+        const int ncount = (cache && it > 0u) ? nheavy + nlight : n;  // points of the search phase
         // Window size of the phase: the points are spread evenly over the whole grid in as few rounds as 32-point windows would
         // need (a window's latency is what a pass waits for at its end, so 2 x 19 points beats 32 + 6)
         int wsz = 32;
@@ -609,7 +617,8 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             const int rounds = (ncount + 32 * (int)total_warps - 1) / (32 * (int)total_warps);
             wsz = min(32, (ncount + rounds * (int)total_warps - 1) / (rounds * (int)total_warps));
         }
-        nsearch = (ncount + wsz - 1) / wsz;
+        const int wheavy = (nheavy + wsz - 1) / wsz;  // the expensive windows come first
+        nsearch = (cache && it > 0u) ? wheavy + (nlight + wsz - 1) / wsz : (ncount + wsz - 1) / wsz;
         const bool indirect = cache && it > 0u;
 
         // ------------------------------------------------------------------------------------------------------------------
@@ -640,8 +649,18 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                 }
             }
             // ---------------------------------------------------------------- owners: q = T p and its voxel
-            const bool valid = lane < wsz && w * wsz + lane < ncount;
-            const int pi = valid ? (indirect ? (int)__ldcg(&a.todo[w * wsz + lane]) : w * wsz + lane) : 0;  // the owner's scan point
+            bool valid;
+            int pi = 0;  // the owner's scan point
+            if (!indirect) {
+                valid = lane < wsz && w * wsz + lane < ncount;
+                if (valid) pi = w * wsz + lane;
+            } else if (w < wheavy) {
+                valid = lane < wsz && w * wsz + lane < nheavy;
+                if (valid) pi = (int)__ldcg(&a.todo[w * wsz + lane]);
+            } else {
+                valid = lane < wsz && (w - wheavy) * wsz + lane < nlight;
+                if (valid) pi = (int)__ldcg(&a.todo[a.todo_cap - 1u - (unsigned)((w - wheavy) * wsz + lane)]);
+            }
             double seed2 = DBL_MAX;  // squared distance to the previous neighbour (an exact pruning bound), if it applies
             {
                 double px = 0, py = 0, pz = 0;
@@ -1085,7 +1104,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             const unsigned left = atomicAdd(&st->exit_ctr, 1u);
             if (left == gridDim.x - 1) {
                 st->win_ctr = 0, st->arrive = 0, st->abort = 0, st->a_arrive = 0;
-                for (int k = 0; k < KICP_MAX_ITERATIONS; ++k) st->todo_n[k] = 0;
+                for (int k = 0; k < KICP_MAX_ITERATIONS; ++k) st->todo_h[k] = 0, st->todo_l[k] = 0;
                 __threadfence();
                 st->exit_ctr = 0;
             }
@@ -1096,8 +1115,8 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
 // ------------------------------------------------------------------------------------------------------- host
 // Per-context options (kicp_ctx_set_option): "persistent" 1 = one cooperative launch per registration (default), 0 = one
 // launch per IRLS iteration; "stats" 1 = count probes / candidate points / lines on the device (kicp_debug_last_stats);
-// "ctas_per_sm" caps the resident CTAs per SM the grid is sized for (0 = occupancy limit); "nn_cache" 1 = carry every point's
-// neighbour and its certificate from pass to pass (default); "spin_timeout_ms" bounds every device-side wait.
+// "ctas_per_sm" caps the resident CTAs per SM the grid is sized for (0 = occupancy limit); "nn_cache" 0 / 1 / 2 = never / for scans of
+// 49152 points or more (default) / always carry every point's neighbours and their certificate from pass to pass; "spin_timeout_ms" bounds every device-side wait.
 extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value) {
     if (!c || !name) return KICP_ERR_INVALID;
     if (!strcmp(name, "persistent")) {
@@ -1113,7 +1132,7 @@ extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value)
         if (value < 1) return KICP_ERR_INVALID;
         c->spin_timeout_ms = value;
     } else if (!strcmp(name, "nn_cache")) {
-        if (value != 0 && value != 1) return KICP_ERR_INVALID;
+        if (value < 0 || value > 2) return KICP_ERR_INVALID;
         c->nn_cache = value;
     } else if (!strcmp(name, "overlap_upload")) {
         if (value != 0 && value != 1) return KICP_ERR_INVALID;
@@ -1218,7 +1237,8 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
     }
     ka.collect_stats = c->collect_stats;
     ka.nn_g = nullptr, ka.nn_g2 = nullptr, ka.nn_l = nullptr, ka.nn_seed = nullptr, ka.todo = nullptr;
-    if (c->nn_cache && scan->n > 0) {
+    // (1 = automatic: a small scan is one or two tiny windows per warp and gains nothing from the extra phase and its barrier)
+    if ((c->nn_cache == 2 || (c->nn_cache == 1 && scan->n >= 49152)) && scan->n > 0) {
         if (scan->n > c->nn_cap) {
             KICP_CUDA(cudaStreamSynchronize(c->stream));
             cudaFree(c->d_nn_g), cudaFree(c->d_nn_g2), cudaFree(c->d_nn_l), cudaFree(c->d_nn_seed), cudaFree(c->d_todo);
@@ -1232,6 +1252,7 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
             c->nn_cap = cap;
         }
         ka.nn_g = c->d_nn_g, ka.nn_g2 = c->d_nn_g2, ka.nn_l = c->d_nn_l, ka.nn_seed = c->d_nn_seed, ka.todo = c->d_todo;
+        ka.todo_cap = (unsigned)c->nn_cap;
     }
     ka.timeout_ns = (unsigned long long)c->spin_timeout_ms * 1000000ull;
     const int n = (int)scan->n;

@@ -8,6 +8,7 @@ from oracle import workloads as W
 cfg = int(sys.argv[1])
 w = W.Workload(cfg)
 ctx = kb.Context(0)
+ctx.set_option("nn_cache", 2)
 if len(sys.argv) > 2:
     ctx.set_option("ctas_per_sm", int(sys.argv[2]))
 gm = kb.VoxelHashMap(ctx, w.voxel_size, w.max_range, w.max_points_per_voxel)

@@ -144,11 +144,11 @@ def test_registration_configs_vs_oracle(oracle, gpu_ctx, workload, cfg):
     try:
         # launch shapes of the one registration kernel: persistent cooperative launch (default) / one launch per iteration,
         # grid capped at 1 CTA per SM / occupancy limit; the work counters on
-        for persistent, ctas, stats, cache in ((1, 0, 0, 1), (1, 0, 0, 0), (0, 0, 0, 1), (1, 1, 1, 1), (0, 1, 0, 0)):
+        for persistent, ctas, stats, cache in ((1, 0, 0, 2), (1, 0, 0, 0), (0, 0, 0, 2), (1, 1, 1, 2), (0, 1, 0, 0), (1, 0, 0, 1)):
             gpu_ctx.set_option("persistent", persistent)
             gpu_ctx.set_option("ctas_per_sm", ctas)
             gpu_ctx.set_option("stats", stats)
-            gpu_ctx.set_option("nn_cache", cache)  # neighbour certificates carried between passes / every point searched in every pass
+            gpu_ctx.set_option("nn_cache", cache)  # neighbour certificates carried between passes: 2 = always, 0 = never, 1 = by scan size
             pose, dt, ang = check_registration(ko, kb, gpu_ctx, w.map, gm, w.scan, w.last_pose, w.rel_odom, w.tau)
             print("cfg%d persistent=%d ctas_per_sm=%d nn_cache=%d N=%d M=%d pose delta %.3e m %.3e rad" %
                   (cfg, persistent, ctas, cache, w.N, w.map.num_points(), dt, ang))
