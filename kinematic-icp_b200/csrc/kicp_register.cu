@@ -83,8 +83,7 @@ struct RegState {
     unsigned int exit_ctr;          // CTAs that have left the kernel; the last one zeroes the three counters
     unsigned int ticket;            // multi-launch path: last-CTA detection
     unsigned int a_arrive;          // warps that finished the certificate phase of a pass (monotonic inside a registration)
-    unsigned int todo_h[KICP_MAX_ITERATIONS];  // per pass: points to search again that have no pruning bound yet (expensive) ...
-    unsigned int todo_l[KICP_MAX_ITERATIONS];  // ... and those that come with the distance to their previous neighbour (cheap)
+    unsigned int todo_n[KICP_MAX_ITERATIONS];  // per pass: points whose neighbour has to be searched again
     int abort;                      // a device-side wait gave up (status code); every CTA leaves after the current pass
     int *iters_out;                 // optional: where to publish the iteration count (profiling)
     double acc[8];                  // multi-launch path: JTJ00 JTJ01 JTJ11 JTr0 JTr1 N sum|r|^2 (unused)
@@ -206,11 +205,9 @@ struct KernelArgs {
     int collect_stats;
     // nearest-neighbour cache carried from pass to pass (persistent kernel, option "nn_cache"), one entry per scan point
     unsigned int *nn_g;            // the neighbour found by the last search (global point index, 0xFFFFFFFF = none)
-    unsigned int *nn_g2;           // the runner-up of that search (0xFFFFFFFF = none): between passes the two may swap
-    float *nn_l;                   // certified lower bound on the distance to every candidate OTHER than those two
+    float *nn_l;                   // certified lower bound on the distance to every OTHER candidate of the neighbourhood
     float *nn_seed;                // distance to the old neighbour from the new position (pruning bound of the repeated search)
-    unsigned int *todo;            // points of the current pass that need the search: the expensive ones from the front, the cheap
-    unsigned int todo_cap;         // ones from the back (the search phase starts with the expensive ones)
+    unsigned int *todo;            // points of the current pass that need the search
     unsigned long long timeout_ns;  // device-side waits (upload flags, peers) give up after this long
 };
 
@@ -241,9 +238,6 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
 struct __align__(32) Point4 {
     double x, y, z, w;
 };
-// Software pipelining without registers: the addresses a later step will load are known early (the task stream of a stage, the
-// runs of a batch), so they are requested into L1 ahead of time and the dependent loads find them there.
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ Point4 ld_point(const double *p) {
     Point4 r;
     asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
@@ -277,7 +271,7 @@ __global__ void k_reg_init(RegState *st, RegArgs a) {
     pose_init(&st->pose, a);
     result_init(&st->result, &st->pose);
     st->ticket = 0, st->win_ctr = 0, st->arrive = 0, st->exit_ctr = 0, st->abort = 0, st->a_arrive = 0;
-    for (int k = 0; k < KICP_MAX_ITERATIONS; ++k) st->todo_h[k] = 0, st->todo_l[k] = 0;
+    for (int k = 0; k < KICP_MAX_ITERATIONS; ++k) st->todo_n[k] = 0;
     st->iters_out = a.iters_out;
     if (a.iters_out) *a.iters_out = 0;
     for (int k = 0; k < 8; ++k) st->acc[k] = 0.0;
@@ -534,12 +528,10 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                 const bool valid = i < n;
                 double px = 0, py = 0, pz = 0;
                 if (valid) load_scan_point(a.scan, i, px, py, pz);
-                const unsigned g1 = valid ? __ldcg(&a.nn_g[i]) : 0xFFFFFFFFu;
-                const unsigned g2 = valid ? __ldcg(&a.nn_g2[i]) : 0xFFFFFFFFu;
+                const unsigned g = valid ? __ldcg(&a.nn_g[i]) : 0xFFFFFFFFu;
                 const double l = valid ? (double)__ldcg(&a.nn_l[i]) : 0.0;
-                const bool haveg = g1 != 0xFFFFFFFFu, have2 = g2 != 0xFFFFFFFFu;
-                const Point4 c1 = ld_point(a.map.pts + (size_t)(haveg ? g1 : 0u) * KICP_PSTRIDE);
-                const Point4 c2 = ld_point(a.map.pts + (size_t)(have2 ? g2 : 0u) * KICP_PSTRIDE);
+                const bool haveg = g != 0xFFFFFFFFu;
+                const Point4 c = ld_point(a.map.pts + (size_t)(haveg ? g : 0u) * KICP_PSTRIDE);
                 const double qx = s_ps.R[0] * px + s_ps.R[1] * py + s_ps.R[2] * pz + s_ps.t[0];
                 const double qy = s_ps.R[3] * px + s_ps.R[4] * py + s_ps.R[5] * pz + s_ps.t[1];
                 const double qz = s_ps.R[6] * px + s_ps.R[7] * py + s_ps.R[8] * pz + s_ps.t[2];
@@ -553,40 +545,27 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                                   vz == voxel_of(oz, vs, inv_vs, a.pow2_voxel);
                 const double mx = qx - ox, my = qy - oy, mz = qz - oz;
                 const double delta = sqrt(mx * mx + my * my + mz * mz) * (1.0 + 1e-9) + 1e-12;
-                const double d1 = sqrt(dist2(c1.x, c1.y, c1.z, qx, qy, qz));
-                const double d2 = have2 ? sqrt(dist2(c2.x, c2.y, c2.z, qx, qy, qz)) : DBL_MAX;
-                // the two remembered candidates may have swapped; a near-tie between them is left to the search (only it applies the
-                // reference's visiting-order rule)
-                const bool second_wins = d2 < d1;
-                const double dn = second_wins ? d2 : d1;
-                const bool clear = !have2 || fabs(d1 - d2) > 1e-9 * (d1 + d2) + 1e-12;
-                const Point4 c = second_wins ? c2 : c1;
+                const double dn = sqrt(dist2(c.x, c.y, c.z, qx, qy, qz));
                 const double room = l - delta;  // every other candidate is at least this far from the new position
-                const bool cert = valid && same && (haveg ? (clear && dn * (1.0 + 1e-9) + 1e-12 < room) : (room > s_ps.tau * (1.0 + 1e-9)));
+                const bool cert = valid && same && (haveg ? (dn * (1.0 + 1e-9) + 1e-12 < room) : (room > s_ps.tau * (1.0 + 1e-9)));
                 if (cert) {
                     a.nn_l[i] = __double2float_rz(room * (1.0 - 1e-7));
-                    if (second_wins) a.nn_g[i] = g2, a.nn_g2[i] = g1;
                     if (haveg) accumulate(sm, lane, s_ps, c.x, c.y, c.z, qx, qy, qz, px, py);
                 }
-                // the old neighbour bounds the repeated search if it is one of the new 27 voxels' points; points without such a bound
-                // (nothing found last time, or the neighbourhood moved away) are the expensive ones and are searched first
-                float seed = 3.0e38f;
-                if (haveg && abs(voxel_of(c.x, vs, inv_vs, a.pow2_voxel) - vx) <= 1 && abs(voxel_of(c.y, vs, inv_vs, a.pow2_voxel) - vy) <= 1 &&
-                    abs(voxel_of(c.z, vs, inv_vs, a.pow2_voxel) - vz) <= 1)
-                    seed = __double2float_ru(dn * (1.0 + 1e-7));
-                const bool heavy = valid && !cert && !(seed < 1.0e38f), light = valid && !cert && seed < 1.0e38f;
-                const unsigned mh = __ballot_sync(FULL, heavy), ml = __ballot_sync(FULL, light);
-                if (mh | ml) {
-                    unsigned ph = 0, pl = 0;
-                    if (lane == 0) {
-                        if (mh) ph = atomicAdd(&st->todo_h[it], (unsigned)__popc(mh));
-                        if (ml) pl = atomicAdd(&st->todo_l[it], (unsigned)__popc(ml));
+                const unsigned need = __ballot_sync(FULL, valid && !cert);
+                if (need) {
+                    unsigned pos = 0;
+                    if (lane == 0) pos = atomicAdd(&st->todo_n[it], (unsigned)__popc(need));
+                    pos = __shfl_sync(FULL, pos, 0) + (unsigned)__popc(need & ((1u << lane) - 1u));
+                    if (valid && !cert) {
+                        a.todo[pos] = (unsigned)i;
+                        // the old neighbour bounds the repeated search if it is one of the new 27 voxels' points
+                        float seed = 3.0e38f;
+                        if (haveg && abs(voxel_of(c.x, vs, inv_vs, a.pow2_voxel) - vx) <= 1 && abs(voxel_of(c.y, vs, inv_vs, a.pow2_voxel) - vy) <= 1 &&
+                            abs(voxel_of(c.z, vs, inv_vs, a.pow2_voxel) - vz) <= 1)
+                            seed = __double2float_ru(dn * (1.0 + 1e-7));
+                        a.nn_seed[i] = seed;
                     }
-                    ph = __shfl_sync(FULL, ph, 0) + (unsigned)__popc(mh & ((1u << lane) - 1u));
-                    pl = __shfl_sync(FULL, pl, 0) + (unsigned)__popc(ml & ((1u << lane) - 1u));
-                    if (heavy) a.todo[ph] = (unsigned)i;
-                    if (light) a.todo[a.todo_cap - 1u - pl] = (unsigned)i;
-                    if (heavy || light) a.nn_seed[i] = seed;
                 }
             }
             // every CTA of the grid has to be through phase A before the list is complete
@@ -608,17 +587,13 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             }
             __syncthreads();
         }
-        const int nheavy = (cache && it > 0u) ? (int)__ldcg(&st->todo_h[it]) : 0, nlight = (cache && it > 0u) ? (int)__ldcg(&st->todo_l[it]) : 0;
-        const int ncount = (cache && it > 0u) ? nheavy + nlight : n;  // points of the search phase
-        // Window size of the phase: the points are spread evenly over the whole grid in as few rounds as 32-point windows would
-        // need (a window's latency is what a pass waits for at its end, so 2 x 19 points beats 32 + 6)
+        const int ncount = (cache && it > 0u) ? (int)__ldcg(&st->todo_n[it]) : n;  // points of the search phase
+        // Window size of the phase.  A window costs about the same whether it holds 12 points or 32 (its chain of dependent
+        // steps), so full windows are the efficient unit; but when the whole phase fits ONE round of the grid, the points are spread
+        // evenly over all warps instead (a small scan, the remainder of a later pass): the phase then lasts one light window.
         int wsz = 32;
-        if (PERSISTENT && ncount > 0) {
-            const int rounds = (ncount + 32 * (int)total_warps - 1) / (32 * (int)total_warps);
-            wsz = min(32, (ncount + rounds * (int)total_warps - 1) / (rounds * (int)total_warps));
-        }
-        const int wheavy = (nheavy + wsz - 1) / wsz;  // the expensive windows come first
-        nsearch = (cache && it > 0u) ? wheavy + (nlight + wsz - 1) / wsz : (ncount + wsz - 1) / wsz;
+        if (PERSISTENT && ncount > 0 && ncount <= 32 * (int)total_warps) wsz = max(1, (ncount + (int)total_warps - 1) / (int)total_warps);
+        nsearch = (ncount + wsz - 1) / wsz;
         const bool indirect = cache && it > 0u;
 
         // ------------------------------------------------------------------------------------------------------------------
@@ -649,18 +624,8 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                 }
             }
             // ---------------------------------------------------------------- owners: q = T p and its voxel
-            bool valid;
-            int pi = 0;  // the owner's scan point
-            if (!indirect) {
-                valid = lane < wsz && w * wsz + lane < ncount;
-                if (valid) pi = w * wsz + lane;
-            } else if (w < wheavy) {
-                valid = lane < wsz && w * wsz + lane < nheavy;
-                if (valid) pi = (int)__ldcg(&a.todo[w * wsz + lane]);
-            } else {
-                valid = lane < wsz && (w - wheavy) * wsz + lane < nlight;
-                if (valid) pi = (int)__ldcg(&a.todo[a.todo_cap - 1u - (unsigned)((w - wheavy) * wsz + lane)]);
-            }
+            const bool valid = lane < wsz && w * wsz + lane < ncount;
+            const int pi = valid ? (indirect ? (int)__ldcg(&a.todo[w * wsz + lane]) : w * wsz + lane) : 0;  // the owner's scan point
             double seed2 = DBL_MAX;  // squared distance to the previous neighbour (an exact pruning bound), if it applies
             {
                 double px = 0, py = 0, pz = 0;
@@ -679,10 +644,9 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                 sm.px[lane] = px, sm.py[lane] = py;
             }
             // the owner's running minimum lives in its lane's registers: d^2, the line that holds it, how many points that line has;
-            // the runner-up lines and `minpruned` (the cubes of the voxels that were skipped) feed the certificate of the next pass
-            double best = DBL_MAX, second = DBL_MAX, third = DBL_MAX, minpruned = DBL_MAX;  // three smallest LINE minima (+ skipped cubes)
-            unsigned bline = 0xFFFFFFFFu, bvalid = 0u;   // the line holding `best` ...
-            unsigned sline = 0xFFFFFFFFu, svalid = 0u;   // ... and the one holding `second`
+            // `second` bounds every evaluated point that is not the winner, `minpruned` the cubes of the voxels that were skipped
+            double best = DBL_MAX, second = DBL_MAX, minpruned = DBL_MAX;
+            unsigned bline = 0xFFFFFFFFu, bvalid = 0u;
             __syncwarp();
             KR_PROF(0)
 
@@ -834,15 +798,10 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                                     const double dl = sm.lmin[lb + u];
                                     if (closer(dl, best)) {
                                         const LineDesc ld = sm.ldesc[lb + u];
-                                        third = second;
-                                        second = best, sline = bline, svalid = bvalid;
+                                        second = fmin(second, best);
                                         best = dl, bline = ld.gline, bvalid = ld.nvalid;
-                                    } else if (dl < second) {
-                                        const LineDesc ld = sm.ldesc[lb + u];
-                                        third = second;
-                                        second = dl, sline = ld.gline, svalid = ld.nvalid;
                                     } else {
-                                        third = fmin(third, dl);
+                                        second = fmin(second, dl);
                                     }
                                 }
                             }
@@ -905,32 +864,12 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                     if (jw == j) c = cc[j];
                 if (have) accumulate(sm, lane, s_ps, c.x, c.y, c.z, q0.x, q0.y, q0z, sm.px[lane], sm.py[lane]);
                 if (cache && valid) {
-                    // What the next pass may rely on: the neighbour g1, the runner-up g2 among the points of the two best lines, and
-                    // l = how far every OTHER candidate is at least (third point of those lines, every other line, skipped cubes).
-                    const bool have2 = have && sline != 0xFFFFFFFFu;
-                    Point4 ce[4];
+                    // what the next pass may rely on: the neighbour, and how far every other candidate is at least
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) ce[j] = ld_point(a.map.pts + (size_t)((have2 ? sline : 0u) + (j < (int)svalid ? j : 0)) * KICP_PSTRIDE);
-                    double ru = DBL_MAX, ru2 = DBL_MAX;  // smallest and second smallest squared distance among the non-winners
-                    unsigned g2 = 0xFFFFFFFFu;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (have && j < (int)bvalid && j != jw) {
-                            if (dj[j] < ru) ru2 = ru, ru = dj[j], g2 = g0 + (unsigned)j;
-                            else ru2 = fmin(ru2, dj[j]);
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const double de = dist2(ce[j].x, ce[j].y, ce[j].z, q0.x, q0.y, q0z);
-                        if (have2 && j < (int)svalid) {
-                            if (de < ru) ru2 = ru, ru = de, g2 = sline + (unsigned)j;
-                            else ru2 = fmin(ru2, de);
-                        }
-                    }
-                    const double lo2 = fmin(fmin(ru2, third), minpruned);
+                    for (int j = 0; j < 4; ++j)
+                        if (have && j < (int)bvalid && j != jw) second = fmin(second, dj[j]);
+                    const double lo2 = fmin(second, minpruned);
                     a.nn_g[pi] = have ? g0 + (unsigned)jw : 0xFFFFFFFFu;
-                    a.nn_g2[pi] = g2;
                     a.nn_l[pi] = lo2 >= 1.0e60 ? 1.0e30f : __double2float_rz(sqrt(lo2) * (1.0 - 1e-7));
                 }
             }
@@ -1040,6 +979,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                     const uint32_t half = (lane & 1) ? (uint32_t)(bits >> 32) : (uint32_t)bits;
                     const unsigned long long word = ((unsigned long long)tag << 32) | half;
                     // lanes 16..31 repeat the stores of lanes 0..15 (same address, same value): no divergent section
+#pragma unroll 1
                     for (int r = 0; r < a.px.nranks; ++r) {
                         st_relaxed_sys_u64(&a.px.peer[r]->ll[a.px.parity][it][a.px.rank][lane & 15], word);
                         __syncwarp();
@@ -1104,7 +1044,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             const unsigned left = atomicAdd(&st->exit_ctr, 1u);
             if (left == gridDim.x - 1) {
                 st->win_ctr = 0, st->arrive = 0, st->abort = 0, st->a_arrive = 0;
-                for (int k = 0; k < KICP_MAX_ITERATIONS; ++k) st->todo_h[k] = 0, st->todo_l[k] = 0;
+                for (int k = 0; k < KICP_MAX_ITERATIONS; ++k) st->todo_n[k] = 0;
                 __threadfence();
                 st->exit_ctr = 0;
             }
@@ -1116,7 +1056,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
 // Per-context options (kicp_ctx_set_option): "persistent" 1 = one cooperative launch per registration (default), 0 = one
 // launch per IRLS iteration; "stats" 1 = count probes / candidate points / lines on the device (kicp_debug_last_stats);
 // "ctas_per_sm" caps the resident CTAs per SM the grid is sized for (0 = occupancy limit); "nn_cache" 0 / 1 / 2 = never / for scans of
-// 49152 points or more (default) / always carry every point's neighbours and their certificate from pass to pass; "spin_timeout_ms" bounds every device-side wait.
+// 49152 points or more (default) / always carry every point's neighbour and its certificate from pass to pass; "spin_timeout_ms" bounds every device-side wait.
 extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value) {
     if (!c || !name) return KICP_ERR_INVALID;
     if (!strcmp(name, "persistent")) {
@@ -1236,23 +1176,21 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
         ka.pow2_voxel = std::frexp(m->voxel_size, &e) == 0.5 ? 1 : 0;
     }
     ka.collect_stats = c->collect_stats;
-    ka.nn_g = nullptr, ka.nn_g2 = nullptr, ka.nn_l = nullptr, ka.nn_seed = nullptr, ka.todo = nullptr;
-    // (1 = automatic: a small scan is one or two tiny windows per warp and gains nothing from the extra phase and its barrier)
+    ka.nn_g = nullptr, ka.nn_l = nullptr, ka.nn_seed = nullptr, ka.todo = nullptr;
+    // (1 = automatic: a small scan is one tiny window per warp and gains nothing from the extra phase and its barrier)
     if ((c->nn_cache == 2 || (c->nn_cache == 1 && scan->n >= 49152)) && scan->n > 0) {
         if (scan->n > c->nn_cap) {
             KICP_CUDA(cudaStreamSynchronize(c->stream));
-            cudaFree(c->d_nn_g), cudaFree(c->d_nn_g2), cudaFree(c->d_nn_l), cudaFree(c->d_nn_seed), cudaFree(c->d_todo);
-            c->d_nn_g = nullptr, c->d_nn_g2 = nullptr, c->d_nn_l = nullptr, c->d_nn_seed = nullptr, c->d_todo = nullptr, c->nn_cap = 0;
+            cudaFree(c->d_nn_g), cudaFree(c->d_nn_l), cudaFree(c->d_nn_seed), cudaFree(c->d_todo);
+            c->d_nn_g = nullptr, c->d_nn_l = nullptr, c->d_nn_seed = nullptr, c->d_todo = nullptr, c->nn_cap = 0;
             const int64_t cap = scan->n + scan->n / 4 + 1024;
             KICP_CUDA(cudaMalloc(&c->d_nn_g, (size_t)cap * sizeof(unsigned int)));
-            KICP_CUDA(cudaMalloc(&c->d_nn_g2, (size_t)cap * sizeof(unsigned int)));
             KICP_CUDA(cudaMalloc(&c->d_nn_l, (size_t)cap * sizeof(float)));
             KICP_CUDA(cudaMalloc(&c->d_nn_seed, (size_t)cap * sizeof(float)));
             KICP_CUDA(cudaMalloc(&c->d_todo, (size_t)cap * sizeof(unsigned int)));
             c->nn_cap = cap;
         }
-        ka.nn_g = c->d_nn_g, ka.nn_g2 = c->d_nn_g2, ka.nn_l = c->d_nn_l, ka.nn_seed = c->d_nn_seed, ka.todo = c->d_todo;
-        ka.todo_cap = (unsigned)c->nn_cap;
+        ka.nn_g = c->d_nn_g, ka.nn_l = c->d_nn_l, ka.nn_seed = c->d_nn_seed, ka.todo = c->d_todo;
     }
     ka.timeout_ns = (unsigned long long)c->spin_timeout_ms * 1000000ull;
     const int n = (int)scan->n;
@@ -1282,8 +1220,8 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
     if (ka.init.max_iter > 0) {
         // every CTA is resident and pulls 32-point windows from a device-side counter; a small scan is spread one window per
         // CTA over the whole machine (a window is a chain of dependent memory round trips: latency, not throughput)
-        // (the persistent kernel sizes its windows so that the points spread evenly over the grid: a small scan runs as many tiny
-        // windows on the whole machine)
+        // (the persistent kernel sizes its windows so that a phase that fits one round spreads evenly over the grid: a small scan
+        // runs as many tiny windows on the whole machine)
         const int num_windows = persistent ? (n + 7) / 8 : (n + 31) / 32;
         int per_sm = persistent ? c->persistent_ctas_per_sm : c->pruned_ctas_per_sm;
         if (c->ctas_per_sm_cap > 0) per_sm = std::min(per_sm, c->ctas_per_sm_cap);
