@@ -166,6 +166,7 @@ extern "C" int kicp_ctx_destroy(kicp_ctx *ctx) {
     cudaFree(ctx->d_state);
     cudaFree(ctx->d_partials);
     cudaFree(ctx->d_nn_g);
+    cudaFree(ctx->d_nn_g2);
     cudaFree(ctx->d_nn_l);
     cudaFree(ctx->d_nn_seed);
     cudaFree(ctx->d_todo);

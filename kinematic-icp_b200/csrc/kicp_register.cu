@@ -45,14 +45,16 @@
 
 using namespace kicp_dev;
 
-#define KR_WARPS 8                    // warps per CTA
+#ifndef KR_WARPS
+#define KR_WARPS 10                   // warps per CTA (measured: 2 x 10 warps per SM beat 2 x 8 and 3 x 8)
+#endif
 #define KR_THREADS (KR_WARPS * 32)
 #ifndef KR_MINB
 #define KR_MINB 2                     // resident CTAs per SM the kernel is compiled for (measured: the larger L1 beats more warps)
 #endif
 #define KR_LCAP 192                   // lines the per-warp buffer holds (a batch of 32 tasks adds at most 160 at 20 points per voxel)
 #ifndef KR_G
-#define KR_G 4                        // line-rounds (of 8 lines = 32 points) in flight together
+#define KR_G 2                        // line-rounds (of 8 lines = 32 points) in flight together (96 registers at 2 x 320 threads)
 #endif
 #define KR_DBLMAX_BITS 0x7FEFFFFFFFFFFFFFull
 // Development aid (-DKR_PROFILE): per-phase cycle accounting of the window loop (lane 0 of every warp, clock64 deltas).
@@ -484,10 +486,12 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                 const bool valid = i < n;
                 double px = 0, py = 0, pz = 0;
                 if (valid) load_scan_point(a.scan, i, px, py, pz);
-                const unsigned g = valid ? __ldcg(&a.nn_g[i]) : 0xFFFFFFFFu;
+                const unsigned g1 = valid ? __ldcg(&a.nn_g[i]) : 0xFFFFFFFFu;
+                const unsigned g2 = valid ? __ldcg(&a.nn_g2[i]) : 0xFFFFFFFFu;
                 const double l = valid ? (double)__ldcg(&a.nn_l[i]) : 0.0;
-                const bool haveg = g != 0xFFFFFFFFu;
-                const Point4 c = ld_point(a.map.pts + (size_t)(haveg ? g : 0u) * KICP_PSTRIDE);
+                const bool haveg = g1 != 0xFFFFFFFFu, have2 = g2 != 0xFFFFFFFFu;
+                const Point4 c1 = ld_point(a.map.pts + (size_t)(haveg ? g1 : 0u) * KICP_PSTRIDE);
+                const Point4 c2 = ld_point(a.map.pts + (size_t)(have2 ? g2 : 0u) * KICP_PSTRIDE);
                 const double qx = s_ps.R[0] * px + s_ps.R[1] * py + s_ps.R[2] * pz + s_ps.t[0];
                 const double qy = s_ps.R[3] * px + s_ps.R[4] * py + s_ps.R[5] * pz + s_ps.t[1];
                 const double qz = s_ps.R[6] * px + s_ps.R[7] * py + s_ps.R[8] * pz + s_ps.t[2];
@@ -501,11 +505,19 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                                   vz == voxel_of(oz, vs, inv_vs, a.pow2_voxel);
                 const double mx = qx - ox, my = qy - oy, mz = qz - oz;
                 const double delta = sqrt(mx * mx + my * my + mz * mz) * (1.0 + 1e-9) + 1e-12;
-                const double dn = sqrt(dist2(c.x, c.y, c.z, qx, qy, qz));
+                const double d1 = sqrt(dist2(c1.x, c1.y, c1.z, qx, qy, qz));
+                const double d2 = have2 ? sqrt(dist2(c2.x, c2.y, c2.z, qx, qy, qz)) : DBL_MAX;
+                // the two remembered candidates may have swapped; a near-tie between them is left to the search (only it applies the
+                // reference's visiting-order rule)
+                const bool second_wins = d2 < d1;
+                const double dn = second_wins ? d2 : d1;
+                const bool clear = !have2 || fabs(d1 - d2) > 1e-9 * (d1 + d2) + 1e-12;
+                const Point4 c = second_wins ? c2 : c1;
                 const double room = l - delta;  // every other candidate is at least this far from the new position
-                const bool cert = valid && same && (haveg ? (dn * (1.0 + 1e-9) + 1e-12 < room) : (room > s_ps.tau * (1.0 + 1e-9)));
+                const bool cert = valid && same && (haveg ? (clear && dn * (1.0 + 1e-9) + 1e-12 < room) : (room > s_ps.tau * (1.0 + 1e-9)));
                 if (cert) {
                     a.nn_l[i] = __double2float_rz(room * (1.0 - 1e-7));
+                    if (second_wins) a.nn_g[i] = g2, a.nn_g2[i] = g1;
                     if (haveg) accumulate(sm, lane, s_ps, c.x, c.y, c.z, qx, qy, qz, px, py);
                 }
                 const unsigned need = __ballot_sync(FULL, valid && !cert);
@@ -543,13 +555,22 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             }
             __syncthreads();
         }
+        const bool indirect_phase = cache && it > 0u;
         const int ncount = (cache && it > 0u) ? (int)__ldcg(&st->todo_n[it]) : n;  // points of the search phase
         // Window size of the phase.  A window costs about the same whether it holds 12 points or 32 (its chain of dependent
         // steps), so full windows are the efficient unit; but when the whole phase fits ONE round of the grid, the points are spread
         // evenly over all warps instead (a small scan, the remainder of a later pass): the phase then lasts one light window.
         int wsz = 32;
         if (PERSISTENT && ncount > 0 && ncount <= 32 * (int)total_warps) wsz = max(1, (ncount + (int)total_warps - 1) / (int)total_warps);
-        nsearch = (ncount + wsz - 1) / wsz;
+        // pass 0: the frame in KICP_UPLOAD_CHUNKS segments of `segpts` points (the host uploads it in exactly these pieces)
+        const int segpts = max(32, ((((n + 31) >> 5) + KICP_UPLOAD_CHUNKS - 1) / KICP_UPLOAD_CHUNKS) * 32);
+        const int segwin = (segpts + wsz - 1) / wsz;  // windows per (full) segment
+        if (indirect_phase) {
+            nsearch = (ncount + wsz - 1) / wsz;
+        } else {
+            const int nseg = min(KICP_UPLOAD_CHUNKS, (n + segpts - 1) / segpts), lastn = n - (nseg - 1) * segpts;
+            nsearch = n > 0 ? (nseg - 1) * segwin + (lastn + wsz - 1) / wsz : 0;
+        }
         const bool indirect = cache && it > 0u;
 
         // ------------------------------------------------------------------------------------------------------------------
@@ -563,9 +584,26 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
         while (w < nsearch) {
             if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);
             KR_PROF_COUNT(8)
+            // ---------------------------------------------------------------- owners: q = T p and its voxel
+            // The points of a phase are DEALT to its windows like cards (owner `lane` of window w = entry lane * windows + w): points
+            // that are expensive to search (little or no map around them) sit next to each other in the scan and in the list, and a
+            // window made of them alone would outlast the phase.  Pass 0 deals inside each of the KICP_UPLOAD_CHUNKS segments the
+            // frame is uploaded in, so that a window still needs only its own chunk.
+            int slot, limit, seg_of_w = 0;
+            if (indirect) {
+                slot = lane * nsearch + w, limit = ncount;
+            } else {
+                const int sgi = min(w / segwin, KICP_UPLOAD_CHUNKS - 1), lw = w - sgi * segwin;
+                const int sbase = sgi * segpts, sn = min(segpts, n - sbase);  // this segment's points
+                const int sw = (sn + wsz - 1) / wsz;                          // ... and windows
+                slot = sbase + lane * sw + lw, limit = lw < sw ? sbase + min(sn, (lane + 1) * sw) : 0;
+                seg_of_w = sgi;
+            }
+            const bool valid = lane < wsz && slot < limit;
+            const int pi = valid ? (indirect ? (int)__ldcg(&a.todo[slot]) : slot) : 0;  // the owner's scan point
             if (PERSISTENT && a.up.flags != nullptr && it == 0u) {
                 // first pass over a frame that is still being uploaded: wait until this window's chunk has landed
-                const uint32_t *f = a.up.flags + min((min((w + 1) * wsz, n) - 1) / 32 / a.up.windows_per_chunk, KICP_UPLOAD_CHUNKS - 1);
+                const uint32_t *f = a.up.flags + seg_of_w;
                 const unsigned long long deadline = gtime_ns() + a.timeout_ns;
                 bool pend = true;
                 while (__any_sync(FULL, pend)) {  // warp-uniform: every lane polls the same word (one transaction)
@@ -579,9 +617,6 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                     }
                 }
             }
-            // ---------------------------------------------------------------- owners: q = T p and its voxel
-            const bool valid = lane < wsz && w * wsz + lane < ncount;
-            const int pi = valid ? (indirect ? (int)__ldcg(&a.todo[w * wsz + lane]) : w * wsz + lane) : 0;  // the owner's scan point
             double seed2 = DBL_MAX;  // squared distance to the previous neighbour (an exact pruning bound), if it applies
             {
                 double px = 0, py = 0, pz = 0;
@@ -600,9 +635,10 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                 sm.px[lane] = px, sm.py[lane] = py;
             }
             // the owner's running minimum lives in its lane's registers: d^2, the line that holds it, how many points that line has;
-            // `second` bounds every evaluated point that is not the winner, `minpruned` the cubes of the voxels that were skipped
-            double best = DBL_MAX, second = DBL_MAX, minpruned = DBL_MAX;
-            unsigned bline = 0xFFFFFFFFu, bvalid = 0u;
+            // the runner-up lines and `minpruned` (the cubes of the voxels that were skipped) feed the certificate of the next pass
+            double best = DBL_MAX, second = DBL_MAX, third = DBL_MAX, minpruned = DBL_MAX;  // three smallest LINE minima (+ skipped cubes)
+            unsigned bline = 0xFFFFFFFFu, bvalid = 0u;   // the line holding `best` ...
+            unsigned sline = 0xFFFFFFFFu, svalid = 0u;   // ... and the one holding `second`
             __syncwarp();
             KR_PROF(0)
 
@@ -754,10 +790,15 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                                     const double dl = sm.lmin[lb + u];
                                     if (closer(dl, best)) {
                                         const LineDesc ld = sm.ldesc[lb + u];
-                                        second = fmin(second, best);
+                                        third = second;
+                                        second = best, sline = bline, svalid = bvalid;
                                         best = dl, bline = ld.gline, bvalid = ld.nvalid;
+                                    } else if (dl < second) {
+                                        const LineDesc ld = sm.ldesc[lb + u];
+                                        third = second;
+                                        second = dl, sline = ld.gline, svalid = ld.nvalid;
                                     } else {
-                                        second = fmin(second, dl);
+                                        third = fmin(third, dl);
                                     }
                                 }
                             }
@@ -820,12 +861,32 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                     if (jw == j) c = cc[j];
                 if (have) accumulate(sm, lane, s_ps, c.x, c.y, c.z, q0.x, q0.y, q0z, sm.px[lane], sm.py[lane]);
                 if (cache && valid) {
-                    // what the next pass may rely on: the neighbour, and how far every other candidate is at least
+                    // What the next pass may rely on: the neighbour g1, the runner-up g2 among the points of the two best lines, and
+                    // l = how far every OTHER candidate is at least (third point of those lines, every other line, skipped cubes).
+                    const bool have2 = have && sline != 0xFFFFFFFFu;
+                    Point4 ce[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (have && j < (int)bvalid && j != jw) second = fmin(second, dj[j]);
-                    const double lo2 = fmin(second, minpruned);
+                    for (int j = 0; j < 4; ++j) ce[j] = ld_point(a.map.pts + (size_t)((have2 ? sline : 0u) + (j < (int)svalid ? j : 0)) * KICP_PSTRIDE);
+                    double ru = DBL_MAX, ru2 = DBL_MAX;  // smallest and second smallest squared distance among the non-winners
+                    unsigned g2 = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (have && j < (int)bvalid && j != jw) {
+                            if (dj[j] < ru) ru2 = ru, ru = dj[j], g2 = g0 + (unsigned)j;
+                            else ru2 = fmin(ru2, dj[j]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double de = dist2(ce[j].x, ce[j].y, ce[j].z, q0.x, q0.y, q0z);
+                        if (have2 && j < (int)svalid) {
+                            if (de < ru) ru2 = ru, ru = de, g2 = sline + (unsigned)j;
+                            else ru2 = fmin(ru2, de);
+                        }
+                    }
+                    const double lo2 = fmin(fmin(ru2, third), minpruned);
                     a.nn_g[pi] = have ? g0 + (unsigned)jw : 0xFFFFFFFFu;
+                    a.nn_g2[pi] = g2;
                     a.nn_l[pi] = lo2 >= 1.0e60 ? 1.0e30f : __double2float_rz(sqrt(lo2) * (1.0 - 1e-7));
                 }
             }

@@ -49,7 +49,8 @@ struct KernelArgs {
     int collect_stats;
     // nearest-neighbour cache carried from pass to pass (persistent kernel, option "nn_cache"), one entry per scan point
     unsigned int *nn_g;            // the neighbour found by the last search (global point index, 0xFFFFFFFF = none)
-    float *nn_l;                   // certified lower bound on the distance to every OTHER candidate of the neighbourhood
+    unsigned int *nn_g2;           // the runner-up of that search (0xFFFFFFFF = none): between passes the two may swap
+    float *nn_l;                   // certified lower bound on the distance to every candidate OTHER than those two
     float *nn_seed;                // distance to the old neighbour from the new position (pruning bound of the repeated search)
     unsigned int *todo;            // points of the current pass that need the search
     unsigned long long timeout_ns;  // device-side waits (upload flags, peers) give up after this long
