@@ -262,7 +262,7 @@ def run_reference_arm(args):
             "config": workload_config(w), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------ GPU arm
@@ -286,8 +286,31 @@ def measure_l2_bandwidth(ctx):
     return float(out.value) if st == 0 else None
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE line (the JSON): anything a library prints there meanwhile (NCCL's version banner under
+    NCCL_DEBUG=VERSION, compiler chatter) is sent to stderr by pointing fd 1 at fd 2 until emit() restores it."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+    if _REAL_STDOUT is not None:
+        os.dup2(2, 1)
+
+
 def main():
     args = parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -599,7 +622,7 @@ def main():
             line["replicas"] = {"value": replicas_run["value"], "unit": UNIT, "e2e": rv["value"], "scaling": "weak",
                                 "note": "BASELINE.json configs[4] layout: %d independent registrations, one per GPU, no communication; "
                                         "aggregate scans/s (HBM-resident / pinned-host e2e)" % world}
-        print(json.dumps(line), flush=True)
+        emit(line)
     gm.close()
     ctx.close()
     if world > 1:

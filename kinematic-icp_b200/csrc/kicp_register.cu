@@ -64,7 +64,19 @@ using namespace kicp_dev;
 #define KR_PROF_COUNT(i) { prof_t[prof_o + (i)] += 1; }
 #define KR_PROF_PASS(it) { prof_o = (it) ? 12 : 0; }
 #define KR_PROF_FLUSH if (lane == 0) { for (int k__ = 0; k__ < 24; ++k__) atomicAdd(&st->prof[k__], (unsigned long long)prof_t[k__]); }
+// ... and a timeline: one record per window / per warp and certificate phase {start ns, end ns, kind|pass|SM|warp, a|b}
+#define KR_WLOG_CAP 65536
+__device__ unsigned long long g_wlog[KR_WLOG_CAP][4];
+__device__ unsigned int g_wlog_n;
+__device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+#define KR_WLOG(kind, t0, t1, a_, b_) if (lane == 0) { const unsigned i__ = atomicAdd(&g_wlog_n, 1u); if (i__ < KR_WLOG_CAP) { \
+    g_wlog[i__][0] = (t0), g_wlog[i__][1] = (t1); \
+    g_wlog[i__][2] = ((unsigned long long)(kind) << 56) | ((unsigned long long)it << 48) | ((unsigned long long)smid() << 32) | gwarp; \
+    g_wlog[i__][3] = ((unsigned long long)(unsigned)(a_) << 32) | (unsigned)(b_); } }
+#define KR_WLOG_DO(x) x
 #else
+#define KR_WLOG(kind, t0, t1, a_, b_)
+#define KR_WLOG_DO(x)
 #define KR_PROF_DECL
 #define KR_PROF(i)
 #define KR_PROF_COUNT(i)
@@ -536,6 +548,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                     }
                 }
             }
+            KR_WLOG(1, t_iter0, gtime_ns(), 0, 0)
             // every CTA of the grid has to be through phase A before the list is complete
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -584,6 +597,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
         while (w < nsearch) {
             if (lane == 0) tk = atomicAdd(&st->win_ctr, 1u);
             KR_PROF_COUNT(8)
+            KR_WLOG_DO(const unsigned long long wl_t0 = gtime_ns(); unsigned wl_tasks = 0; unsigned wl_lines = 0;)
             // ---------------------------------------------------------------- owners: q = T p and its voxel
             // The points of a phase are DEALT to its windows like cards (owner `lane` of window w = entry lane * windows + w): points
             // that are expensive to search (little or no map around them) sit next to each other in the scan and in the list, and a
@@ -692,6 +706,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                 KR_PROF(1)
                 // The lines of the stage's found runs are collected in a buffer of KR_LCAP lines (stage-global numbering, visiting
                 // order) and evaluated whenever it would overflow and at the end of the stage — full rounds of 8 lines x KR_G.
+                KR_WLOG_DO(wl_tasks += (unsigned)total;)
                 int fill = 0, lbase = 0;           // lines in the buffer; stage-global index of its first line
                 int olb = 0, ole = 0;              // this lane's, as an owner: its lines so far are [olb, ole) (stage-global)
                 bool ohas = false;
@@ -804,6 +819,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                             }
                         }
                         __syncwarp();
+                        KR_WLOG_DO(wl_lines += (unsigned)fill;)
                         lbase += fill, fill = 0;
                         KR_PROF(5)
                     }
@@ -892,6 +908,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             }
             __syncwarp();
             KR_PROF(6)
+            KR_WLOG(0, wl_t0, gtime_ns(), (wl_tasks << 8) | (unsigned)__popc(__ballot_sync(FULL, valid)), wl_lines)
             w = (int)(total_warps + min(__shfl_sync(FULL, tk, 0) - tbase, dyn));  // >= nsearch once the tickets are used up
             KR_PROF(7)
         }
@@ -1106,7 +1123,27 @@ cudaError_t kr_launch_solve(RegState *st, cudaStream_t stream) {
     k_solve<<<1, 32, 0, stream>>>(st);
     return cudaGetLastError();
 }
+cudaError_t kr_window_log(unsigned long long *out, size_t cap_entries, size_t *n) {  // -DKR_PROFILE builds: the last launch's timeline
+    *n = 0;
+#ifdef KR_PROFILE
+    unsigned cnt = 0;
+    cudaError_t e = cudaMemcpyFromSymbol(&cnt, g_wlog_n, sizeof(cnt));
+    if (e != cudaSuccess) return e;
+    *n = std::min<size_t>(std::min<size_t>(cnt, KR_WLOG_CAP), cap_entries);
+    return cudaMemcpyFromSymbol(out, g_wlog, *n * 4 * sizeof(unsigned long long));
+#else
+    (void)out, (void)cap_entries;
+    return cudaSuccess;
+#endif
+}
 cudaError_t kr_launch_register(bool persistent, int grid, KernelArgs &ka, cudaStream_t stream) {
+#ifdef KR_PROFILE
+    {
+        void *p = nullptr;
+        cudaGetSymbolAddress(&p, g_wlog_n);
+        cudaMemsetAsync(p, 0, sizeof(unsigned), stream);
+    }
+#endif
     if (persistent) {  // cooperative: every CTA resident (the grid barrier inside the kernel relies on it)
         void *args[] = {&ka};
         return cudaLaunchCooperativeKernel((const void *)k_register<true>, dim3(grid), dim3(KR_THREADS), args, kr_smem_bytes(), stream);

@@ -71,5 +71,6 @@ size_t kr_smem_bytes();     // dynamic shared memory of k_register
 cudaError_t kr_prepare(int *persistent_ctas_per_sm, int *multilaunch_ctas_per_sm);  // opt-in shared memory + occupancy
 cudaError_t kr_launch_init(RegState *st, const RegArgs &a, cudaStream_t stream);
 cudaError_t kr_launch_solve(RegState *st, cudaStream_t stream);
+cudaError_t kr_window_log(unsigned long long *out, size_t cap_entries, size_t *n);
 cudaError_t kr_launch_register(bool persistent, int grid, KernelArgs &ka, cudaStream_t stream);
 cudaError_t kr_launch_l2_read(const void *buf, size_t bytes, int reps, unsigned *sink, int grid, cudaStream_t stream);

@@ -285,6 +285,17 @@ extern "C" int kicp_debug_last_prof(kicp_ctx *c, uint64_t out[24] /* -DKR_PROFIL
     return KICP_OK;
 }
 
+// -DKR_PROFILE builds: the timeline of the last registration launch, 4 uint64 per record (0 records otherwise)
+extern "C" int kicp_debug_window_log(kicp_ctx *c, uint64_t *out, int64_t cap_entries, int64_t *n) {
+    if (!c || !out || !n || cap_entries < 0) return KICP_ERR_INVALID;
+    KICP_CUDA(cudaSetDevice(c->device));
+    KICP_CUDA(cudaStreamSynchronize(c->stream));
+    size_t got = 0;
+    KICP_CUDA(kr_window_log(reinterpret_cast<unsigned long long *>(out), (size_t)cap_entries, &got));
+    *n = (int64_t)got;
+    return KICP_OK;
+}
+
 extern "C" int kicp_ctx_profile_begin(kicp_ctx *c) {
     if (!c) return KICP_ERR_INVALID;
     KICP_CUDA(cudaSetDevice(c->device));
