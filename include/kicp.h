@@ -86,7 +86,9 @@ int64_t kicp_ctx_launch_count(kicp_ctx *ctx);
  * candidate) and a pass re-searches only the points whose certificate the pose update broke (exact): 1 = for
  * scans of 49152 points or more (default: smaller scans gain nothing from the extra phase), 2 = always, 0 = never; "overlap_upload" 1 = the
  * host-pointer entry points overlap the frame's upload with the first pass (default); "spin_timeout_ms" = bound of every
- * device-side wait (upload flags, peers of the fused exchange; default 20000).  Unknown names fail with KICP_ERR_INVALID.
+ * device-side wait (upload flags, peers of the fused exchange; default 20000); "frame_sync" 1 = kicp_register_frame reads the
+ * survivor counts back in the middle of a frame (legacy order; default 0 = ONE host synchronisation per frame, at its end).
+ * Unknown names fail with KICP_ERR_INVALID.
  * Every setting computes the same result up to the summation order. */
 int kicp_ctx_set_option(kicp_ctx *ctx, const char *name, int32_t value);
 /* Per-kernel device timing with CUDA events recorded on the context stream around (a) the set-up of each registration
@@ -188,7 +190,10 @@ int kicp_preprocess(kicp_ctx *ctx, const double *xyz, int64_t n, const double *s
  *      stays with the caller (tau in, pose out).  out_frame / out_source receive the two clouds RegisterFrame returns
  *      (preprocessed frame in base, registration source); either may be NULL to skip its download.  On zero
  *      correspondences the pose is NaN like the reference's, KICP_WARN_NO_CORRESPONDENCES is returned and the map is
- *      left untouched. ------------------------------------------------------------------------------------------- */
+ *      left untouched.  The host synchronises with the device ONCE per frame, at its end: the survivor counts of the
+ *      filters, the pose and the map's bookkeeping all stay on the device in between (with out_frame / out_source buffers
+ *      smaller than in->n points, or option "frame_sync", the counts are read back mid-frame instead, so that
+ *      KICP_ERR_CAPACITY can be reported before the map changes). ------------------------------------------------- */
 typedef struct kicp_frame_input {
     const void *data;   /* host pointer: n points */
     int64_t n;

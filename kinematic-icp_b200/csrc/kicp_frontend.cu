@@ -169,6 +169,9 @@ struct Scratch {
     unsigned char *raw = nullptr;
     size_t raw_cap = 0;
     int *h_count = nullptr;  // pinned, 4 ints
+    uint32_t *h_mapctr = nullptr;  // pinned, 8 words: the map's counters after an asynchronous update
+    cudaEvent_t ev_front = nullptr;  // front end finished (the copy stream waits for it before staging the clouds)
+    int64_t last_source = 0;       // registration-source points of the previous frame (sizes this frame's grid and staging copy)
     P3 *h_frame = nullptr, *h_source = nullptr;  // pinned staging of the two clouds RegisterFrame returns (cap points each)
     int64_t staged_frame = 0, staged_source = 0;
     double timing[8] = {0};  // host-side stage times of the last kicp_register_frame, milliseconds (debug export)
@@ -183,7 +186,8 @@ struct Scratch {
 void release(Scratch &s) {
     cudaFree(s.in), cudaFree(s.mid), cudaFree(s.out), cudaFree(s.out2), cudaFree(s.out3), cudaFree(s.stamps), cudaFree(s.flags);
     cudaFree(s.first_idx), cudaFree(s.slot_of), cudaFree(s.slots), cudaFree(s.tmp), cudaFree(s.d_count), cudaFree(s.d_mm);
-    cudaFree(s.raw), cudaFreeHost(s.h_count), cudaFreeHost(s.h_frame), cudaFreeHost(s.h_source);
+    cudaFree(s.raw), cudaFreeHost(s.h_count), cudaFreeHost(s.h_frame), cudaFreeHost(s.h_source), cudaFreeHost(s.h_mapctr);
+    if (s.ev_front) cudaEventDestroy(s.ev_front);
     s = Scratch();
 }
 void free_scratch(kicp_ctx *c) {
@@ -217,6 +221,8 @@ int reserve(kicp_ctx *c, Scratch &s, int64_t n) {
     KICP_CUDA(cudaMalloc(&s.out3, cap * sizeof(P3)));
     KICP_CUDA(cudaMalloc(&s.d_mm, 2 * sizeof(double)));
     KICP_CUDA(cudaMallocHost(&s.h_count, 4 * sizeof(int)));
+    KICP_CUDA(cudaMallocHost(&s.h_mapctr, 8 * sizeof(uint32_t)));
+    KICP_CUDA(cudaEventCreateWithFlags(&s.ev_front, cudaEventDisableTiming));
     KICP_CUDA(cudaMallocHost(&s.h_frame, cap * sizeof(P3)));
     KICP_CUDA(cudaMallocHost(&s.h_source, cap * sizeof(P3)));
     KICP_CUDA(cudaMalloc(&s.stamps, cap * sizeof(double)));
@@ -407,9 +413,61 @@ extern "C" int kicp_register_frame(kicp_map *map, const kicp_frame_input *in, co
                                     fp->deskew, s.out, s.d_count));
         KICP_TRY(enqueue_downsample(c, s, s.out, (int)n, s.d_count, fp->voxel_size * 0.5, s.out2, s.d_count + 1));
         KICP_TRY(enqueue_downsample(c, s, s.out2, (int)n, s.d_count + 1, fp->voxel_size * 1.5, s.out3, s.d_count + 2));
+        // A frame is ONE host synchronisation (at its end): every later stage reads the survivor counts and the pose from device
+        // memory.  The legacy order (read the counts back, size everything exactly) remains for callers whose output buffers
+        // might be too small for the worst case — they are owed KICP_ERR_CAPACITY before the map changes — and as option
+        // "frame_sync" for A/B measurements.
+        const bool async_frame = !c->frame_sync && (!out_frame || cap_frame >= n) && (!out_source || cap_source >= n);
+        if (async_frame) {
+            s.timing[0] = ms_since();  // upload + front end enqueued
+            const bool stage = fp->stage_clouds || out_frame || out_source;
+            if (stage) KICP_CUDA(cudaEventRecord(s.ev_front, c->stream));
+            // registration of the source against the local map; the grid is sized from the previous frame's source
+            c->reg_n_hint = s.last_source > 0 ? s.last_source + s.last_source / 4 + 256 : 0;
+            KICP_TRY(kicp_enqueue_registration_device(map, reinterpret_cast<const double *>(s.out3), n, s.d_count + 2, last_pose,
+                                                      relative_odometry, tau, &fp->reg));
+            s.timing[1] = ms_since();  // + registration enqueued
+            // the two clouds go to pinned staging on the copy stream while the registration runs (sizes: upper bounds)
+            s.staged_frame = s.staged_source = 0;
+            const int64_t src_copy = std::min<int64_t>(n, std::max<int64_t>(2 * s.last_source, 32768));
+            if (stage) {
+                KICP_CUDA(cudaStreamWaitEvent(c->copy_stream, s.ev_front, 0));
+                KICP_CUDA(cudaMemcpyAsync(s.h_frame, s.out, (size_t)n * sizeof(P3), cudaMemcpyDeviceToHost, c->copy_stream));
+                KICP_CUDA(cudaMemcpyAsync(s.h_source, s.out3, (size_t)src_copy * sizeof(P3), cudaMemcpyDeviceToHost, c->copy_stream));
+            }
+            // local_map_.Update(frame_downsample, new_pose) (KinematicICP.cpp:79), pose and count still on the device; a NaN pose
+            // (zero correspondences, which the reference does not defend against) leaves the map untouched
+            KICP_TRY(kicp_map_update_pose_async(map, reinterpret_cast<const double *>(s.out2), n, s.d_count + 1, kicp_device_result(c),
+                                                s.h_mapctr));
+            KICP_CUDA(cudaMemcpyAsync(s.h_count, s.d_count, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            KICP_CUDA(cudaStreamSynchronize(c->stream));  // THE synchronisation of the frame
+            s.timing[2] = s.timing[3] = ms_since();      // + registration and map update finished
+            for (int k = 0; k < 3; ++k) counts[k] = s.h_count[k];
+            s.last_source = counts[2];
+            const kicp_reg_result &r = *c->h_result;
+            for (int k = 0; k < 7; ++k) out_pose[k] = r.pose[k];
+            if (result) *result = r;
+            int status = r.status;
+            const int mst = kicp_map_finish_update(map, s.h_mapctr);
+            if (mst != KICP_OK) status = mst;
+            if (n_frame) *n_frame = counts[0];
+            if (n_source) *n_source = counts[2];
+            if (stage) {
+                if (counts[2] > src_copy)  // the source outgrew the previous frame's twofold: fetch the rest
+                    KICP_CUDA(cudaMemcpyAsync(s.h_source + src_copy, s.out3 + src_copy, (size_t)(counts[2] - src_copy) * sizeof(P3),
+                                              cudaMemcpyDeviceToHost, c->copy_stream));
+                KICP_CUDA(cudaStreamSynchronize(c->copy_stream));
+                s.staged_frame = counts[0], s.staged_source = counts[2];
+                if (out_frame && counts[0]) memcpy(out_frame, s.h_frame, (size_t)counts[0] * sizeof(P3));
+                if (out_source && counts[2]) memcpy(out_source, s.h_source, (size_t)counts[2] * sizeof(P3));
+            }
+            s.timing[4] = ms_since();  // + clouds delivered
+            return status;
+        }
         KICP_CUDA(cudaMemcpyAsync(s.h_count, s.d_count, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        KICP_CUDA(cudaStreamSynchronize(c->stream));  // the one mid-frame round trip: 12 bytes, sizes the registration grid
+        KICP_CUDA(cudaStreamSynchronize(c->stream));  // legacy order: 12 bytes back, sizes the registration grid exactly
         for (int k = 0; k < 3; ++k) counts[k] = s.h_count[k];
+        s.last_source = counts[2];
     }
     s.timing[0] = ms_since();  // upload + front end (ingest, de-skew, filter, transform, both down-samples)
     if (n_frame) *n_frame = counts[0];

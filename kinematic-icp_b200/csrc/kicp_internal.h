@@ -61,6 +61,10 @@ struct kicp_ctx {
     float *d_nn_l = nullptr, *d_nn_seed = nullptr;
     int64_t nn_cap = 0;
     int nn_cache = 1;  // option "nn_cache"
+    int even_rounds = 0;      // option "even_rounds"
+    int deal_shift = 0;       // option "deal_group": log2 of the run of consecutive points dealt to a search window as one card
+    int frame_sync = 0;       // option "frame_sync": 1 = kicp_register_frame reads the survivor counts back mid-frame (legacy order)
+    int64_t reg_n_hint = 0;   // expected point count of the next registration whose exact count lives on the device (0 = none)
     kicp_scan *upload_scan = nullptr;  // staging scan used by the host-pointer entry points
     // chunked upload overlapped with the first IRLS iteration (host-pointer entry points, persistent kernel)
     cudaStream_t copy_stream = nullptr;
@@ -163,6 +167,12 @@ int kicp_scan_reserve_bytes(kicp_scan *scan, int64_t bytes);
 int kicp_scan_set_layout(kicp_scan *scan, int32_t dtype, int32_t point_step, int32_t ox, int32_t oy, int32_t oz);
 // VoxelHashMap::Update(points, pose) with `d_xyz` already resident in HBM (packed xyz doubles): used by kicp_register_frame
 int kicp_map_update_pose_device(kicp_map *m, const double *d_xyz, int64_t n, const double pose[7]);
+// the same with the point count and the pose still on the device (no read-back; kicp_map.cu)
+int kicp_map_update_pose_async(kicp_map *m, const double *d_xyz, int64_t n_max, const int *d_n, const kicp_reg_result *d_res,
+                               uint32_t *h_counters);
+int kicp_map_finish_update(kicp_map *m, const uint32_t *h_counters);
+// device address of the result block the last enqueued registration on this context writes (kicp_register_api.cu)
+const kicp_reg_result *kicp_device_result(kicp_ctx *c);
 // defined in kicp_register.cu: enqueue one registration of n device-resident points on the context stream; the result
 // lands in ctx->h_result (pinned) once the stream has drained
 // (`d_n`, optional: device-resident point count written earlier on the same stream; n_max is then the upper bound)

@@ -66,6 +66,8 @@ extern "C" int kicp_ctx_create(int device, kicp_ctx **out) {
     if (const char *e = getenv("KICP_PERSISTENT")) c->persistent = atoi(e) ? 1 : 0;
     if (const char *e = getenv("KICP_CTAS_PER_SM")) c->ctas_per_sm_cap = std::min(16, std::max(0, atoi(e)));
     if (const char *e = getenv("KICP_SPIN_TIMEOUT_MS")) c->spin_timeout_ms = std::max(1, atoi(e));
+    if (const char *e = getenv("KICP_FRAME_SYNC")) c->frame_sync = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("KICP_DEAL_GROUP")) c->deal_shift = std::min(5, std::max(0, atoi(e)));
     *out = c;
     return KICP_OK;
 }
@@ -205,10 +207,12 @@ __device__ __forceinline__ void table_insert_unique(int4 *slots, uint32_t mask, 
     }
 }
 
-__global__ void k_table_rebuild(int4 *slots, uint32_t mask_in, const int4 *blk, uint32_t num_blocks) {
+// `ctr` (optional): the block count lives on the device — blocks after the last AddPoints minus the ones just evicted
+__global__ void k_table_rebuild(int4 *slots, uint32_t mask_in, const int4 *blk, uint32_t num_blocks, const uint32_t *ctr = nullptr) {
     __shared__ uint32_t s_mask[32];
     const uint32_t mask = lane_private(mask_in, s_mask);  // divergence safety, see kicp_device.cuh
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ctr) num_blocks = min(num_blocks, ctr[0] - ctr[4]);
     if (b >= num_blocks) return;
     const int4 h = blk[b];
     table_insert_unique(slots, mask, h.x, h.y, h.z, (b << 8) | (uint32_t)h.w);
@@ -216,12 +220,20 @@ __global__ void k_table_rebuild(int4 *slots, uint32_t mask_in, const int4 *blk, 
 
 // AddPoints, phase 1: per input point, (optionally) transform by the pose, find or create its voxel, and push the
 // point's index on that voxel's pending list.
+// Asynchronous frames (kicp_register_frame): the point count (`d_n`, n is then its upper bound) and the pose (`d_res`, the result
+// block of the registration that precedes this launch on the stream) are read from device memory; a registration that did not
+// end with KICP_OK (NaN pose) leaves the map untouched.
 __global__ void k_add_find_or_create(MapRW m, const double *__restrict__ xyz, int64_t n, int has_pose, Pose pose,
                                      double *__restrict__ xyz_t, int32_t *__restrict__ pend_next, uint32_t *counters,
-                                     int32_t *__restrict__ touched) {
+                                     int32_t *__restrict__ touched, const int *d_n = nullptr, const kicp_reg_result *d_res = nullptr) {
     __shared__ uint32_t s_mask[32];
     const uint32_t tmask = lane_private(m.mask, s_mask);  // divergence safety, see kicp_device.cuh
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d_n) n = min((int64_t)*d_n, n);
+    if (d_res) {
+        if (d_res->status != KICP_OK) return;
+        pose = Pose{d_res->pose[0], d_res->pose[1], d_res->pose[2], d_res->pose[3], d_res->pose[4], d_res->pose[5], d_res->pose[6]};
+    }
     if (i >= n) return;
     double px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
     if (has_pose) {
@@ -281,12 +293,34 @@ __global__ void k_add_commit(MapRW m, const double *__restrict__ xyz_t, const in
     const int cnt0 = cnt;
     double *vp = m.pts + (size_t)b * m.cap * KICP_PSTRIDE;
     const int32_t head = m.pend_head[b];
+    // the pending list is in arrival order (a stack of atomic pushes); the reference replays input order.  Short lists — the rule
+    // in a pipeline, where the 0.5-voxel down-sample leaves at most 8 points per map voxel — are sorted in a local array; a longer
+    // one (a dense raw cloud through kicp_map_add_points) falls back to repeated selection of the next index.
+    constexpr int KMAX = 48;
+    int32_t idx[KMAX];
+    int k = 0;
+    bool longlist = false;
+    for (int32_t i = head; i != -1; i = pend_next[i]) {
+        if (k == KMAX) {
+            longlist = true;
+            break;
+        }
+        int j = k++;
+        for (; j > 0 && idx[j - 1] > i; --j) idx[j] = idx[j - 1];  // insertion sort, ascending
+        idx[j] = i;
+    }
     int32_t last = -1;
+    int next_sorted = 0;
     while (cnt < m.cap) {
         int32_t best = 0x7FFFFFFF;
-        for (int32_t i = head; i != -1; i = pend_next[i])
-            if (i > last && i < best) best = i;
-        if (best == 0x7FFFFFFF) break;
+        if (!longlist) {
+            if (next_sorted == k) break;
+            best = idx[next_sorted++];
+        } else {
+            for (int32_t i = head; i != -1; i = pend_next[i])
+                if (i > last && i < best) best = i;
+            if (best == 0x7FFFFFFF) break;
+        }
         last = best;
         const double px = xyz_t[3 * (size_t)best], py = xyz_t[3 * (size_t)best + 1], pz = xyz_t[3 * (size_t)best + 2];
         bool too_close = false;
@@ -318,23 +352,35 @@ __global__ void k_add_commit(MapRW m, const double *__restrict__ xyz_t, const in
 }
 
 // RemovePointsFarFromLocation: a voxel dies when its FIRST point is >= max_distance from the origin.
+// `d_res` (asynchronous frames): the block count is counters[0] (num_blocks is its upper bound: the flags beyond it are
+// cleared for the scan that follows), the origin is the translation of the registration result, removed points are counted in
+// counters[5], and nothing dies after a registration that did not end with KICP_OK.
 __global__ void k_mark_far(const int4 *blk, const double *pts, int cap, uint32_t num_blocks, double ox, double oy, double oz,
-                           double max_distance2, uint32_t *keep, uint32_t *counters) {
+                           double max_distance2, uint32_t *keep, uint32_t *counters, const kicp_reg_result *d_res = nullptr) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= num_blocks) return;
+    bool alive_only = false;
+    if (d_res) {
+        if (b >= counters[0]) {
+            keep[b] = 0u;
+            return;
+        }
+        ox = d_res->pose[4], oy = d_res->pose[5], oz = d_res->pose[6];
+        alive_only = d_res->status != KICP_OK;
+    }
     const double *p = pts + (size_t)b * cap * KICP_PSTRIDE;
     const double dx = p[0] - ox, dy = p[1] - oy, dz = p[2] - oz;
-    const bool dead = (dx * dx + dy * dy + dz * dz) >= max_distance2;
+    const bool dead = !alive_only && (dx * dx + dy * dy + dz * dz) >= max_distance2;
     keep[b] = dead ? 0u : 1u;
     if (dead) {
         atomicAdd(&counters[4], 1u);
-        atomicAdd(&counters[3], (uint32_t)blk[b].w);  // points removed
+        atomicAdd(&counters[d_res ? 5 : 3], (uint32_t)blk[b].w);  // points removed
     }
 }
 
 __global__ void k_compact_blocks(const int4 *blk, const double *pts, int cap, uint32_t num_blocks, const uint32_t *keep,
                                  const uint32_t *new_id, int4 *blk_out, double *pts_out) {
-    // one warp per block: header by lane 0, points copied cooperatively
+    // one warp per block: header by lane 0, points copied cooperatively (blocks beyond the live count carry keep = 0)
     const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (b >= num_blocks || !keep[b]) return;
@@ -649,14 +695,93 @@ int kicp_map_update_pose_device(kicp_map *m, const double *d_xyz, int64_t n, con
     return kicp_map_remove_far(m, pose + 4);
 }
 
-static int map_download(kicp_map *m, std::vector<int4> &hdr, std::vector<double> &pts) {
+// local_map_.Update(frame, pose) (KinematicICP.cpp:79) for a frame whose point count (`d_n` <= n_max) and pose (`d_res`) are
+// still being computed on the stream: everything is enqueued, nothing is read back.  The eviction always compacts (into the spare
+// arrays, then the arrays swap) — a moving sensor evicts voxels on practically every frame anyway, and the host cannot know.
+// The counters are copied to `h_counters` (pinned, 8 words); after the caller's end-of-frame synchronisation,
+// kicp_map_finish_update() brings the host mirrors up to date.
+int kicp_map_update_pose_async(kicp_map *m, const double *d_xyz, int64_t n_max, const int *d_n, const kicp_reg_result *d_res,
+                               uint32_t *h_counters) {
+    if (!m || n_max <= 0 || !d_xyz || !d_n || !d_res || !h_counters) return KICP_ERR_INVALID;
     kicp_ctx *c = m->ctx;
     KICP_CUDA(cudaSetDevice(c->device));
-    hdr.resize(m->num_blocks);
-    pts.resize((size_t)m->num_blocks * m->cap * KICP_PSTRIDE);
-    if (m->num_blocks) {
-        KICP_CUDA(cudaMemcpyAsync(hdr.data(), m->blk, hdr.size() * sizeof(int4), cudaMemcpyDeviceToHost, c->stream));
-        KICP_CUDA(cudaMemcpyAsync(pts.data(), m->pts, pts.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    KICP_TRY(map_reserve_input(m, n_max));
+    KICP_TRY(map_reserve(m, (uint64_t)n_max));  // worst case: every point opens a new voxel (grows — and synchronises — rarely)
+    const uint32_t init[8] = {m->num_blocks, 0, 0, 0, 0, 0, 0, 0};
+    KICP_CUDA(cudaMemcpyAsync(m->d_counters, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    MapRW rw{m->slots, m->nslots - 1, m->blk, m->pts, m->pend_head, m->blocks_cap, (int)m->cap, m->voxel_size};
+    const int threads = 256;
+    const unsigned pgrid = (unsigned)((n_max + threads - 1) / threads);
+    k_add_find_or_create<<<pgrid, threads, 0, c->stream>>>(rw, d_xyz, n_max, 1, Pose{0, 0, 0, 1, 0, 0, 0}, m->d_xyz_t, m->d_next, m->d_counters,
+                                                        m->d_touched, d_n, d_res);
+    KICP_CHECK_LAUNCH(c);
+    const double map_resolution = std::sqrt(m->voxel_size * m->voxel_size / (double)m->cap);
+    k_add_commit<<<pgrid, threads, 0, c->stream>>>(rw, m->d_xyz_t, m->d_next, m->d_counters, m->d_touched, map_resolution);
+    KICP_CHECK_LAUNCH(c);
+    // RemovePointsFarFromLocation(pose.translation()) over the blocks that exist now: at most ub
+    const uint32_t ub = (uint32_t)std::min<uint64_t>((uint64_t)m->num_blocks + (uint64_t)n_max, m->blocks_cap);
+    k_mark_far<<<(ub + 255) / 256, 256, 0, c->stream>>>(m->blk, m->pts, (int)m->cap, ub, 0.0, 0.0, 0.0, m->max_distance * m->max_distance,
+                                                     m->d_keep, m->d_counters, d_res);
+    KICP_CHECK_LAUNCH(c);
+    size_t scan_bytes = m->scan_tmp_bytes;
+    KICP_CUDA(cub::DeviceScan::ExclusiveSum(m->d_scan_tmp, scan_bytes, m->d_keep, m->d_new_id, (int)ub, c->stream));
+    c->launches += 2;  // CUB's scan passes (library kernels)
+    k_compact_blocks<<<(unsigned)(((uint64_t)ub * 32 + 255) / 256), 256, 0, c->stream>>>(m->blk, m->pts, (int)m->cap, ub, m->d_keep,
+                                                                                       m->d_new_id, m->blk_spare, m->pts_spare);
+    KICP_CHECK_LAUNCH(c);
+    std::swap(m->blk, m->blk_spare);
+    std::swap(m->pts, m->pts_spare);
+    KICP_CUDA(cudaMemsetAsync(m->slots, 0xFF, (size_t)m->nslots * sizeof(int4), c->stream));
+    k_table_rebuild<<<(ub + 255) / 256, 256, 0, c->stream>>>(m->slots, m->nslots - 1, m->blk, ub, m->d_counters);
+    KICP_CHECK_LAUNCH(c);
+    KICP_CUDA(cudaMemcpyAsync(h_counters, m->d_counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    return KICP_OK;
+}
+// after the stream has drained: host mirrors from the counters of kicp_map_update_pose_async
+int kicp_map_finish_update(kicp_map *m, const uint32_t *h_counters) {
+    if (!m || !h_counters) return KICP_ERR_INVALID;
+    m->num_blocks = h_counters[0] - h_counters[4];
+    m->num_points += (int64_t)h_counters[3] - (int64_t)h_counters[5];
+    if (h_counters[2]) {
+        kicp_set_error("voxel map: block storage overflow during AddPoints");
+        return KICP_ERR_CAPACITY;
+    }
+    return KICP_OK;
+}
+
+// Pointcloud / export: the stored points are packed ON THE DEVICE (block order, insertion order inside a block — the order the
+// host loop used to produce) and exactly num_points * 24 bytes cross PCIe, instead of the padded block array (20 slots of 32
+// bytes per voxel whatever it holds).  The spare point array is the scratch: it holds nothing between two evictions.
+__global__ void k_block_counts(const int4 *blk, uint32_t num_blocks, uint32_t *cnt) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < num_blocks) cnt[b] = (uint32_t)blk[b].w;
+}
+__global__ void k_pack_points(const int4 *blk, const double *pts, int cap, uint32_t num_blocks, const uint32_t *first, double *out) {
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per block
+    const int lane = threadIdx.x & 31;
+    if (b >= num_blocks) return;
+    const int cnt = blk[b].w;
+    const double *src = pts + (size_t)b * cap * KICP_PSTRIDE;
+    double *dst = out + (size_t)first[b] * 3;
+    for (int i = lane; i < cnt * 3; i += 32) dst[i] = src[(i / 3) * KICP_PSTRIDE + (i % 3)];
+}
+// packed xyz of every stored point -> host `out_xyz` (num_points * 3 doubles); headers -> `hdr` when asked for
+static int map_download_packed(kicp_map *m, double *out_xyz, std::vector<int4> *hdr) {
+    kicp_ctx *c = m->ctx;
+    KICP_CUDA(cudaSetDevice(c->device));
+    if (m->num_blocks == 0) return KICP_OK;
+    k_block_counts<<<(m->num_blocks + 255) / 256, 256, 0, c->stream>>>(m->blk, m->num_blocks, m->d_keep);
+    KICP_CHECK_LAUNCH(c);
+    size_t scan_bytes = m->scan_tmp_bytes;
+    KICP_CUDA(cub::DeviceScan::ExclusiveSum(m->d_scan_tmp, scan_bytes, m->d_keep, m->d_new_id, (int)m->num_blocks, c->stream));
+    c->launches += 2;  // CUB's scan passes (library kernels)
+    k_pack_points<<<(unsigned)(((uint64_t)m->num_blocks * 32 + 255) / 256), 256, 0, c->stream>>>(m->blk, m->pts, (int)m->cap, m->num_blocks,
+                                                                                                m->d_new_id, m->pts_spare);
+    KICP_CHECK_LAUNCH(c);
+    KICP_CUDA(cudaMemcpyAsync(out_xyz, m->pts_spare, (size_t)m->num_points * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (hdr) {
+        hdr->resize(m->num_blocks);
+        KICP_CUDA(cudaMemcpyAsync(hdr->data(), m->blk, hdr->size() * sizeof(int4), cudaMemcpyDeviceToHost, c->stream));
     }
     KICP_CUDA(cudaStreamSynchronize(c->stream));
     return KICP_OK;
@@ -668,16 +793,7 @@ extern "C" int kicp_map_pointcloud(kicp_map *m, double *out_xyz, int64_t cap, in
     if (m->num_points > cap) return KICP_ERR_CAPACITY;
     if (m->num_points == 0) return KICP_OK;
     if (!out_xyz) return KICP_ERR_INVALID;
-    std::vector<int4> hdr;
-    std::vector<double> pts;
-    KICP_TRY(map_download(m, hdr, pts));
-    int64_t w = 0;
-    for (uint32_t b = 0; b < m->num_blocks; ++b) {
-        const double *src = pts.data() + (size_t)b * m->cap * KICP_PSTRIDE;
-        for (int j = 0; j < hdr[b].w; ++j, ++w)
-            out_xyz[3 * w] = src[KICP_PSTRIDE * j], out_xyz[3 * w + 1] = src[KICP_PSTRIDE * j + 1], out_xyz[3 * w + 2] = src[KICP_PSTRIDE * j + 2];
-    }
-    return KICP_OK;
+    return map_download_packed(m, out_xyz, nullptr);
 }
 
 extern "C" int kicp_map_export_voxels(kicp_map *m, int32_t *keys, int32_t *counts, double *points, int64_t cap_voxels,
@@ -688,15 +804,10 @@ extern "C" int kicp_map_export_voxels(kicp_map *m, int32_t *keys, int32_t *count
     if (m->num_blocks == 0) return KICP_OK;
     if (!keys || !counts || !points) return KICP_ERR_INVALID;
     std::vector<int4> hdr;
-    std::vector<double> pts;
-    KICP_TRY(map_download(m, hdr, pts));
-    int64_t w = 0;
+    KICP_TRY(map_download_packed(m, points, &hdr));
     for (uint32_t b = 0; b < m->num_blocks; ++b) {
         keys[3 * b] = hdr[b].x, keys[3 * b + 1] = hdr[b].y, keys[3 * b + 2] = hdr[b].z;
         counts[b] = hdr[b].w;
-        const double *src = pts.data() + (size_t)b * m->cap * KICP_PSTRIDE;
-        for (int j = 0; j < hdr[b].w; ++j, ++w)
-            points[3 * w] = src[KICP_PSTRIDE * j], points[3 * w + 1] = src[KICP_PSTRIDE * j + 1], points[3 * w + 2] = src[KICP_PSTRIDE * j + 2];
     }
     return KICP_OK;
 }

@@ -52,7 +52,9 @@ using namespace kicp_dev;
 #ifndef KR_MINB
 #define KR_MINB 2                     // resident CTAs per SM the kernel is compiled for (measured: the larger L1 beats more warps)
 #endif
+#ifndef KR_LCAP
 #define KR_LCAP 192                   // lines the per-warp buffer holds (a batch of 32 tasks adds at most 160 at 20 points per voxel)
+#endif
 #ifndef KR_G
 #define KR_G 2                        // line-rounds (of 8 lines = 32 points) in flight together (96 registers at 2 x 320 threads)
 #endif
@@ -492,59 +494,85 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             // reach and l - delta > tau, nothing can be accepted now).  Everything else goes to the list of the search phase,
             // with |q' - g| as an exact pruning bound when g still lies in the new neighbourhood.
             // ------------------------------------------------------------------------------------------------------------
-            // the certificate of a point costs the same everywhere: the windows are dealt out statically (no ticket traffic)
-            for (int w = (int)gwarp; w < num_windows; w += (int)total_warps) {
-                const int i = w * 32 + lane;
-                const bool valid = i < n;
-                double px = 0, py = 0, pz = 0;
-                if (valid) load_scan_point(a.scan, i, px, py, pz);
-                const unsigned g1 = valid ? __ldcg(&a.nn_g[i]) : 0xFFFFFFFFu;
-                const unsigned g2 = valid ? __ldcg(&a.nn_g2[i]) : 0xFFFFFFFFu;
-                const double l = valid ? (double)__ldcg(&a.nn_l[i]) : 0.0;
-                const bool haveg = g1 != 0xFFFFFFFFu, have2 = g2 != 0xFFFFFFFFu;
-                const Point4 c1 = ld_point(a.map.pts + (size_t)(haveg ? g1 : 0u) * KICP_PSTRIDE);
-                const Point4 c2 = ld_point(a.map.pts + (size_t)(have2 ? g2 : 0u) * KICP_PSTRIDE);
-                const double qx = s_ps.R[0] * px + s_ps.R[1] * py + s_ps.R[2] * pz + s_ps.t[0];
-                const double qy = s_ps.R[3] * px + s_ps.R[4] * py + s_ps.R[5] * pz + s_ps.t[1];
-                const double qz = s_ps.R[6] * px + s_ps.R[7] * py + s_ps.R[8] * pz + s_ps.t[2];
-                const double ox = s_ps.Rp[0] * px + s_ps.Rp[1] * py + s_ps.Rp[2] * pz + s_ps.tp[0];
-                const double oy = s_ps.Rp[3] * px + s_ps.Rp[4] * py + s_ps.Rp[5] * pz + s_ps.tp[1];
-                const double oz = s_ps.Rp[6] * px + s_ps.Rp[7] * py + s_ps.Rp[8] * pz + s_ps.tp[2];
-                const double vs = a.map.voxel_size;
-                const int vx = voxel_of(qx, vs, inv_vs, a.pow2_voxel), vy = voxel_of(qy, vs, inv_vs, a.pow2_voxel),
-                          vz = voxel_of(qz, vs, inv_vs, a.pow2_voxel);
-                const bool same = vx == voxel_of(ox, vs, inv_vs, a.pow2_voxel) && vy == voxel_of(oy, vs, inv_vs, a.pow2_voxel) &&
-                                  vz == voxel_of(oz, vs, inv_vs, a.pow2_voxel);
-                const double mx = qx - ox, my = qy - oy, mz = qz - oz;
-                const double delta = sqrt(mx * mx + my * my + mz * mz) * (1.0 + 1e-9) + 1e-12;
-                const double d1 = sqrt(dist2(c1.x, c1.y, c1.z, qx, qy, qz));
-                const double d2 = have2 ? sqrt(dist2(c2.x, c2.y, c2.z, qx, qy, qz)) : DBL_MAX;
-                // the two remembered candidates may have swapped; a near-tie between them is left to the search (only it applies the
-                // reference's visiting-order rule)
-                const bool second_wins = d2 < d1;
-                const double dn = second_wins ? d2 : d1;
-                const bool clear = !have2 || fabs(d1 - d2) > 1e-9 * (d1 + d2) + 1e-12;
-                const Point4 c = second_wins ? c2 : c1;
-                const double room = l - delta;  // every other candidate is at least this far from the new position
-                const bool cert = valid && same && (haveg ? (clear && dn * (1.0 + 1e-9) + 1e-12 < room) : (room > s_ps.tau * (1.0 + 1e-9)));
-                if (cert) {
-                    a.nn_l[i] = __double2float_rz(room * (1.0 - 1e-7));
-                    if (second_wins) a.nn_g[i] = g2, a.nn_g2[i] = g1;
-                    if (haveg) accumulate(sm, lane, s_ps, c.x, c.y, c.z, qx, qy, qz, px, py);
+            // the certificate of a point costs the same everywhere: the windows are dealt out statically (no ticket traffic), two
+            // at a time — their loads, the dependent gathers of the remembered candidates and the one atomic that reserves list
+            // space for both are each issued together (a window alone is a chain of three memory round trips)
+            for (int w0 = (int)gwarp; w0 < num_windows; w0 += 2 * (int)total_warps) {
+                int pidx[2];
+                bool valid[2];
+                double px[2], py[2], pz[2], lb[2];
+                unsigned g1[2], g2[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int w = w0 + k * (int)total_warps;
+                    pidx[k] = w * 32 + lane;
+                    valid[k] = w < num_windows && pidx[k] < n;
+                    px[k] = 0, py[k] = 0, pz[k] = 0;
+                    if (valid[k]) load_scan_point(a.scan, pidx[k], px[k], py[k], pz[k]);
+                    g1[k] = valid[k] ? __ldcg(&a.nn_g[pidx[k]]) : 0xFFFFFFFFu;
+                    g2[k] = valid[k] ? __ldcg(&a.nn_g2[pidx[k]]) : 0xFFFFFFFFu;
+                    lb[k] = valid[k] ? (double)__ldcg(&a.nn_l[pidx[k]]) : 0.0;
                 }
-                const unsigned need = __ballot_sync(FULL, valid && !cert);
-                if (need) {
+                Point4 c1[2], c2[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    c1[k] = ld_point(a.map.pts + (size_t)(g1[k] != 0xFFFFFFFFu ? g1[k] : 0u) * KICP_PSTRIDE);
+                    c2[k] = ld_point(a.map.pts + (size_t)(g2[k] != 0xFFFFFFFFu ? g2[k] : 0u) * KICP_PSTRIDE);
+                }
+                unsigned need[2];
+                bool again[2];
+                float seedv[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const bool haveg = g1[k] != 0xFFFFFFFFu, have2 = g2[k] != 0xFFFFFFFFu;
+                    const double qx = s_ps.R[0] * px[k] + s_ps.R[1] * py[k] + s_ps.R[2] * pz[k] + s_ps.t[0];
+                    const double qy = s_ps.R[3] * px[k] + s_ps.R[4] * py[k] + s_ps.R[5] * pz[k] + s_ps.t[1];
+                    const double qz = s_ps.R[6] * px[k] + s_ps.R[7] * py[k] + s_ps.R[8] * pz[k] + s_ps.t[2];
+                    const double ox = s_ps.Rp[0] * px[k] + s_ps.Rp[1] * py[k] + s_ps.Rp[2] * pz[k] + s_ps.tp[0];
+                    const double oy = s_ps.Rp[3] * px[k] + s_ps.Rp[4] * py[k] + s_ps.Rp[5] * pz[k] + s_ps.tp[1];
+                    const double oz = s_ps.Rp[6] * px[k] + s_ps.Rp[7] * py[k] + s_ps.Rp[8] * pz[k] + s_ps.tp[2];
+                    const double vs = a.map.voxel_size;
+                    const int vx = voxel_of(qx, vs, inv_vs, a.pow2_voxel), vy = voxel_of(qy, vs, inv_vs, a.pow2_voxel),
+                              vz = voxel_of(qz, vs, inv_vs, a.pow2_voxel);
+                    const bool same = vx == voxel_of(ox, vs, inv_vs, a.pow2_voxel) && vy == voxel_of(oy, vs, inv_vs, a.pow2_voxel) &&
+                                      vz == voxel_of(oz, vs, inv_vs, a.pow2_voxel);
+                    const double mx = qx - ox, my = qy - oy, mz = qz - oz;
+                    const double delta = sqrt(mx * mx + my * my + mz * mz) * (1.0 + 1e-9) + 1e-12;
+                    const double d1 = sqrt(dist2(c1[k].x, c1[k].y, c1[k].z, qx, qy, qz));
+                    const double d2 = have2 ? sqrt(dist2(c2[k].x, c2[k].y, c2[k].z, qx, qy, qz)) : DBL_MAX;
+                    // the two remembered candidates may have swapped; a near-tie between them is left to the search (only it applies
+                    // the reference's visiting-order rule)
+                    const bool second_wins = d2 < d1;
+                    const double dn = second_wins ? d2 : d1;
+                    const bool clear = !have2 || fabs(d1 - d2) > 1e-9 * (d1 + d2) + 1e-12;
+                    const double cx = second_wins ? c2[k].x : c1[k].x, cy = second_wins ? c2[k].y : c1[k].y, cz = second_wins ? c2[k].z : c1[k].z;
+                    const double room = lb[k] - delta;  // every other candidate is at least this far from the new position
+                    const bool cert = valid[k] && same &&
+                                      (haveg ? (clear && dn * (1.0 + 1e-9) + 1e-12 < room) : (room > s_ps.tau * (1.0 + 1e-9)));
+                    if (cert) {
+                        a.nn_l[pidx[k]] = __double2float_rz(room * (1.0 - 1e-7));
+                        if (second_wins) a.nn_g[pidx[k]] = g2[k], a.nn_g2[pidx[k]] = g1[k];
+                        if (haveg) accumulate(sm, lane, s_ps, cx, cy, cz, qx, qy, qz, px[k], py[k]);
+                    }
+                    again[k] = valid[k] && !cert;
+                    // the old neighbour bounds the repeated search if it is one of the new 27 voxels' points
+                    seedv[k] = 3.0e38f;
+                    if (haveg && abs(voxel_of(cx, vs, inv_vs, a.pow2_voxel) - vx) <= 1 && abs(voxel_of(cy, vs, inv_vs, a.pow2_voxel) - vy) <= 1 &&
+                        abs(voxel_of(cz, vs, inv_vs, a.pow2_voxel) - vz) <= 1)
+                        seedv[k] = __double2float_ru(dn * (1.0 + 1e-7));
+                    need[k] = __ballot_sync(FULL, again[k]);
+                }
+                const unsigned n0 = (unsigned)__popc(need[0]), n1 = (unsigned)__popc(need[1]);
+                if (n0 + n1) {  // warp-uniform
                     unsigned pos = 0;
-                    if (lane == 0) pos = atomicAdd(&st->todo_n[it], (unsigned)__popc(need));
-                    pos = __shfl_sync(FULL, pos, 0) + (unsigned)__popc(need & ((1u << lane) - 1u));
-                    if (valid && !cert) {
-                        a.todo[pos] = (unsigned)i;
-                        // the old neighbour bounds the repeated search if it is one of the new 27 voxels' points
-                        float seed = 3.0e38f;
-                        if (haveg && abs(voxel_of(c.x, vs, inv_vs, a.pow2_voxel) - vx) <= 1 && abs(voxel_of(c.y, vs, inv_vs, a.pow2_voxel) - vy) <= 1 &&
-                            abs(voxel_of(c.z, vs, inv_vs, a.pow2_voxel) - vz) <= 1)
-                            seed = __double2float_ru(dn * (1.0 + 1e-7));
-                        a.nn_seed[i] = seed;
+                    if (lane == 0) pos = atomicAdd(&st->todo_n[it], n0 + n1);
+                    pos = __shfl_sync(FULL, pos, 0);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        if (again[k]) {
+                            a.todo[pos + (k ? n0 : 0u) + (unsigned)__popc(need[k] & ((1u << lane) - 1u))] = (unsigned)pidx[k];
+                            a.nn_seed[pidx[k]] = seedv[k];
+                        }
                     }
                 }
             }
@@ -574,7 +602,25 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
         // steps), so full windows are the efficient unit; but when the whole phase fits ONE round of the grid, the points are spread
         // evenly over all warps instead (a small scan, the remainder of a later pass): the phase then lasts one light window.
         int wsz = 32;
-        if (PERSISTENT && ncount > 0 && ncount <= 32 * (int)total_warps) wsz = max(1, (ncount + (int)total_warps - 1) / (int)total_warps);
+        int gs = a.deal_shift;  // log2 of the run of consecutive points that is dealt as one card (see below)
+        if (PERSISTENT && ncount > 0 && ncount <= 32 * (int)total_warps) {
+            wsz = max(1, (ncount + (int)total_warps - 1) / (int)total_warps);
+            if (gs > 0) {  // whole cards only
+                if (wsz >= 24) {
+                    wsz = 32;
+                } else {
+                    gs = min(gs, 31 - __clz(wsz));  // the largest card that is not larger than the window
+                    wsz = ((wsz + (1 << gs) - 1) >> gs) << gs;
+                }
+            }
+        } else if (PERSISTENT && a.even_rounds && ncount > 0) {
+            // a phase of k rounds: windows sized so that every warp gets k of them (instead of a last round that only part of
+            // the grid takes part in)
+            const int rounds = (ncount + 32 * (int)total_warps - 1) / (32 * (int)total_warps);
+            wsz = min(32, (ncount + rounds * (int)total_warps - 1) / (rounds * (int)total_warps));
+            if (gs > 0) wsz = min(32, ((wsz + (1 << gs) - 1) >> gs) << gs);
+        }
+        const int gsm = (1 << gs) - 1;
         // pass 0: the frame in KICP_UPLOAD_CHUNKS segments of `segpts` points (the host uploads it in exactly these pieces)
         const int segpts = max(32, ((((n + 31) >> 5) + KICP_UPLOAD_CHUNKS - 1) / KICP_UPLOAD_CHUNKS) * 32);
         const int segwin = (segpts + wsz - 1) / wsz;  // windows per (full) segment
@@ -604,13 +650,15 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             // window made of them alone would outlast the phase.  Pass 0 deals inside each of the KICP_UPLOAD_CHUNKS segments the
             // frame is uploaded in, so that a window still needs only its own chunk.
             int slot, limit, seg_of_w = 0;
+            // A card is a run of 2^gs consecutive entries (option "deal_group"): neighbours in the scan share voxels and lines, so a
+            // run keeps that locality inside the window while the window as a whole still samples 32 / 2^gs distant places.
             if (indirect) {
-                slot = lane * nsearch + w, limit = ncount;
+                slot = ((((lane >> gs) * nsearch) + w) << gs) | (lane & gsm), limit = ncount;
             } else {
                 const int sgi = min(w / segwin, KICP_UPLOAD_CHUNKS - 1), lw = w - sgi * segwin;
                 const int sbase = sgi * segpts, sn = min(segpts, n - sbase);  // this segment's points
                 const int sw = (sn + wsz - 1) / wsz;                          // ... and windows
-                slot = sbase + lane * sw + lw, limit = lw < sw ? sbase + min(sn, (lane + 1) * sw) : 0;
+                slot = sbase + (((((lane >> gs) * sw) + lw) << gs) | (lane & gsm)), limit = lw < sw ? sbase + sn : 0;
                 seg_of_w = sgi;
             }
             const bool valid = lane < wsz && slot < limit;
@@ -908,7 +956,8 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             }
             __syncwarp();
             KR_PROF(6)
-            KR_WLOG(0, wl_t0, gtime_ns(), (wl_tasks << 8) | (unsigned)__popc(__ballot_sync(FULL, valid)), wl_lines)
+            KR_WLOG_DO(const unsigned wl_pts = (unsigned)__popc(__ballot_sync(FULL, valid));)
+            KR_WLOG(0, wl_t0, gtime_ns(), (wl_tasks << 8) | wl_pts, wl_lines)
             w = (int)(total_warps + min(__shfl_sync(FULL, tk, 0) - tbase, dyn));  // >= nsearch once the tickets are used up
             KR_PROF(7)
         }

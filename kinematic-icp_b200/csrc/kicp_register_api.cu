@@ -36,6 +36,15 @@ extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value)
     } else if (!strcmp(name, "overlap_upload")) {
         if (value != 0 && value != 1) return KICP_ERR_INVALID;
         c->overlap_upload = value;
+    } else if (!strcmp(name, "even_rounds")) {
+        if (value != 0 && value != 1) return KICP_ERR_INVALID;
+        c->even_rounds = value;
+    } else if (!strcmp(name, "deal_group")) {
+        if (value < 0 || value > 5) return KICP_ERR_INVALID;
+        c->deal_shift = value;
+    } else if (!strcmp(name, "frame_sync")) {
+        if (value != 0 && value != 1) return KICP_ERR_INVALID;
+        c->frame_sync = value;
     } else {
         kicp_set_error(std::string("kicp_ctx_set_option: unknown option ") + name);
         return KICP_ERR_INVALID;
@@ -132,7 +141,10 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
     ka.collect_stats = c->collect_stats;
     ka.nn_g = nullptr, ka.nn_g2 = nullptr, ka.nn_l = nullptr, ka.nn_seed = nullptr, ka.todo = nullptr;
     // (1 = automatic: a small scan is one tiny window per warp and gains nothing from the extra phase and its barrier)
-    if ((c->nn_cache == 2 || (c->nn_cache == 1 && scan->n >= 49152)) && scan->n > 0) {
+    // a frame whose exact count is still on the device is planned (grid, certificates) for the count its producer expects
+    const int64_t n_plan = (scan->d_n && c->reg_n_hint > 0) ? std::min<int64_t>(c->reg_n_hint, scan->n) : scan->n;
+    c->reg_n_hint = 0;
+    if ((c->nn_cache == 2 || (c->nn_cache == 1 && n_plan >= 49152)) && scan->n > 0) {
         if (scan->n > c->nn_cap) {
             KICP_CUDA(cudaStreamSynchronize(c->stream));
             cudaFree(c->d_nn_g), cudaFree(c->d_nn_g2), cudaFree(c->d_nn_l), cudaFree(c->d_nn_seed), cudaFree(c->d_todo);
@@ -148,6 +160,7 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
         ka.nn_g = c->d_nn_g, ka.nn_g2 = c->d_nn_g2, ka.nn_l = c->d_nn_l, ka.nn_seed = c->d_nn_seed, ka.todo = c->d_todo;
     }
     ka.timeout_ns = (unsigned long long)c->spin_timeout_ms * 1000000ull;
+    ka.deal_shift = c->deal_shift, ka.even_rounds = c->even_rounds;
     const int n = (int)scan->n;
     const bool p2p = sharded && c->p2p_ready;
     const bool persistent = c->persistent && (!sharded || p2p);
@@ -176,7 +189,7 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
         // CTA over the whole machine (a window is a chain of dependent memory round trips: latency, not throughput)
         // (the persistent kernel sizes its windows so that a phase that fits one round spreads evenly over the grid: a small scan
         // runs as many tiny windows on the whole machine)
-        const int num_windows = persistent ? (n + 7) / 8 : (n + 31) / 32;
+        const int num_windows = persistent ? (int)((n_plan + 7) / 8) : (n + 31) / 32;
         int per_sm = persistent ? c->persistent_ctas_per_sm : c->pruned_ctas_per_sm;
         if (c->ctas_per_sm_cap > 0) per_sm = std::min(per_sm, c->ctas_per_sm_cap);
         const int grid = std::max(1, std::min(num_windows, c->sm_count * per_sm));
@@ -236,6 +249,10 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
         KICP_CUDA(cudaMemcpyAsync(result, (const char *)c->d_state + kr_offset_result(), sizeof(kicp_reg_result), cudaMemcpyDeviceToHost,
                                   c->stream));
     return KICP_OK;
+}
+
+const kicp_reg_result *kicp_device_result(kicp_ctx *c) {
+    return c && c->d_state ? reinterpret_cast<const kicp_reg_result *>((const char *)c->d_state + kr_offset_result()) : nullptr;
 }
 
 // debugging aids (not part of the public header): per-pass device timings and work counters of the last registration
