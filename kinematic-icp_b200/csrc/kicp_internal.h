@@ -61,8 +61,6 @@ struct kicp_ctx {
     float *d_nn_l = nullptr, *d_nn_seed = nullptr;
     int64_t nn_cap = 0;
     int nn_cache = 1;  // option "nn_cache"
-    int even_rounds = 0;      // option "even_rounds"
-    int deal_shift = 0;       // option "deal_group": log2 of the run of consecutive points dealt to a search window as one card
     int frame_sync = 0;       // option "frame_sync": 1 = kicp_register_frame reads the survivor counts back mid-frame (legacy order)
     int64_t reg_n_hint = 0;   // expected point count of the next registration whose exact count lives on the device (0 = none)
     kicp_scan *upload_scan = nullptr;  // staging scan used by the host-pointer entry points

@@ -28,11 +28,14 @@
 // coordinates by 9 orders of magnitude); bound = min(best so far, tau^2) — a neighbour at tau or beyond is rejected by the
 // gate anyway.  Everything that could tie or win is still evaluated, so the chosen neighbour is the reference's.
 //
-// CERTIFICATES (passes after the first, option "nn_cache").  Each search leaves, per point, its neighbour g and a lower bound
-// l on the distance to every OTHER candidate of the 27-voxel neighbourhood (evaluated points and skipped cubes alike).  The
-// next pass first checks every point (phase A): if it stayed in its voxel and moved by delta, all other candidates are still
-// at least l - delta away, so |q' - g| < l - delta proves g is still THE strict nearest neighbour and the search is skipped.
-// The remaining points are compacted and searched (phase B), with |q' - g| as an exact pruning bound.
+// CERTIFICATES (passes after the first, option "nn_cache").  Each search leaves, per point, its neighbour g1, the runner-up g2 and
+// a lower bound l on the distance to every OTHER candidate of the 27-voxel neighbourhood (evaluated points and skipped cubes alike).
+// The next pass first checks every point (phase A): if it moved by delta, all other candidates are still at least l - delta away
+// (a step into a neighbouring voxel brings one layer of voxels in: those lie beyond the far face of the new own voxel), so
+// min(|q' - g1|, |q' - g2|) < l - delta proves the nearer of the two is still THE strict nearest neighbour and the search is skipped.
+// The remaining points are compacted and searched (phase B) with |q' - g| as an exact pruning bound: the usual ones — few voxels
+// inside that bound — in ONE merged stage (front of the list, ordinary windows), the stragglers staged, in small windows of their
+// own (back of the list), so that no ordinary window walks through three stages for the sake of one lane.
 #include <cfloat>
 #include <cmath>
 #include <cstddef>
@@ -42,6 +45,7 @@
 #include <algorithm>
 
 #include "kicp_register.cuh"
+#include "kicp_solve.cuh"
 
 using namespace kicp_dev;
 
@@ -57,6 +61,12 @@ using namespace kicp_dev;
 #endif
 #ifndef KR_G
 #define KR_G 2                        // line-rounds (of 8 lines = 32 points) in flight together (96 registers at 2 x 320 threads)
+#endif
+#ifndef KR_MERGE_MAX
+#define KR_MERGE_MAX 19               // neighbour voxels a seeded point may bring into its single merged stage (20 tasks x 32 owners = KR_TCAP)
+#endif
+#ifndef KR_SLOWWIN
+#define KR_SLOWWIN 8                  // points per window of the staged stragglers of a later pass
 #endif
 #define KR_DBLMAX_BITS 0x7FEFFFFFFFFFFFFFull
 // Development aid (-DKR_PROFILE): per-phase cycle accounting of the window loop (lane 0 of every warp, clock64 deltas).
@@ -86,18 +96,6 @@ __device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %
 #define KR_PROF_FLUSH
 #endif
 
-// Pose + solver state of one registration.  The persistent kernel keeps one replica per CTA in shared memory; the
-// multi-launch (NCCL) path keeps it in RegState.
-struct PoseState {
-    double q[4];  // current estimate: unit quaternion (x, y, z, w) ...
-    double t[3];  // ... translation ...
-    double R[9];  // ... and the rotation matrix of q, row-major
-    double Rp[9], tp[3];  // R, t of the previous pass (the nearest-neighbour certificates compare the two)
-    double tau, conv, fixed_reg, beta;
-    int adaptive, max_iter;
-    int iter, done, status;
-};
-
 struct RegState {
     PoseState pose;                 // multi-launch path only
     unsigned int win_ctr;           // window tickets handed out so far (monotonic inside a registration)
@@ -105,7 +103,8 @@ struct RegState {
     unsigned int exit_ctr;          // CTAs that have left the kernel; the last one zeroes the three counters
     unsigned int ticket;            // multi-launch path: last-CTA detection
     unsigned int a_arrive;          // warps that finished the certificate phase of a pass (monotonic inside a registration)
-    unsigned int todo_n[KICP_MAX_ITERATIONS];  // per pass: points whose neighbour has to be searched again
+    unsigned int todo_n[KICP_MAX_ITERATIONS];  // per pass: points whose neighbour has to be searched again (front of the list) ...
+    unsigned int slow_n[KICP_MAX_ITERATIONS];  // ... and those among them that need the staged search (back of the list)
     int abort;                      // a device-side wait gave up (status code); every CTA leaves after the current pass
     int *iters_out;                 // optional: where to publish the iteration count (profiling)
     double acc[8];                  // multi-launch path: JTJ00 JTJ01 JTJ11 JTr0 JTr1 N sum|r|^2 (unused)
@@ -114,74 +113,6 @@ struct RegState {
     double dbg[KICP_MAX_ITERATIONS][6];  // per pass, ns (CTA 0): certificate phase, its barrier, search phase, barrier wait, partial sum (+ exchange), solve
     kicp_reg_result result;
 };
-
-// ------------------------------------------------------------------------------------------ SE3 helpers (Sophus)
-__device__ void quat_to_matrix(const double q[4], double R[9]) {  // Eigen::Quaternion::toRotationMatrix
-    const double x = q[0], y = q[1], z = q[2], w = q[3];
-    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
-    const double twx = tx * w, twy = ty * w, twz = tz * w;
-    const double txx = tx * x, txy = ty * x, txz = tz * x;
-    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
-    R[0] = 1 - (tyy + tzz), R[1] = txy - twz, R[2] = txz + twy;
-    R[3] = txy + twz, R[4] = 1 - (txx + tzz), R[5] = tyz - twx;
-    R[6] = txz - twy, R[7] = tyz + twx, R[8] = 1 - (txx + tyy);
-}
-
-// Sophus SE3 product: q = normalize(a.q * b.q) (the SO3(quaternion) ctor normalises), t = a.t + a.q * b.t
-__device__ void se3_compose(const double aq[4], const double at[3], const double bq[4], const double bt[3], double oq[4],
-                            double ot[3]) {
-    const double ax = aq[0], ay = aq[1], az = aq[2], aw = aq[3];
-    const double bx = bq[0], by = bq[1], bz = bq[2], bw = bq[3];
-    double w = aw * bw - ax * bx - ay * by - az * bz;
-    double x = aw * bx + ax * bw + ay * bz - az * by;
-    double y = aw * by + ay * bw + az * bx - ax * bz;
-    double z = aw * bz + az * bw + ax * by - ay * bx;
-    const double len = sqrt(x * x + y * y + z * z + w * w);
-    x /= len, y /= len, z /= len, w /= len;
-    double rx, ry, rz;
-    quat_rotate(ax, ay, az, aw, bt[0], bt[1], bt[2], rx, ry, rz);
-    oq[0] = x, oq[1] = y, oq[2] = z, oq[3] = w;
-    ot[0] = at[0] + rx, ot[1] = at[1] + ry, ot[2] = at[2] + rz;
-}
-
-// Sophus SE3::exp for the tangent the motion model produces: (ux, uy, 0, 0, 0, theta)
-__device__ void se3_exp_planar(double ux, double uy, double theta_in, double oq[4], double ot[3]) {
-    const double eps = 1e-10;  // Sophus::Constants<double>::epsilon()
-    const double wx = 0.0, wy = 0.0, wz = theta_in;
-    const double theta_sq = wx * wx + wy * wy + wz * wz;
-    double theta, imag, real;
-    if (theta_sq < eps * eps) {
-        theta = 0.0;
-        const double theta_po4 = theta_sq * theta_sq;
-        imag = 0.5 - (1.0 / 48.0) * theta_sq + (1.0 / 3840.0) * theta_po4;
-        real = 1.0 - (1.0 / 8.0) * theta_sq + (1.0 / 384.0) * theta_po4;
-    } else {
-        theta = sqrt(theta_sq);
-        const double half_theta = 0.5 * theta;
-        double sh, ch;
-        sincos(half_theta, &sh, &ch);
-        imag = sh / theta;
-        real = ch;
-    }
-    oq[0] = imag * wx, oq[1] = imag * wy, oq[2] = imag * wz, oq[3] = real;
-    // V = I + (1-cos)/th^2 W + (th - sin)/th^3 W^2, or V = R when theta < eps;  W = hat(0, 0, wz)
-    double V[9];
-    if (theta < eps) {
-        quat_to_matrix(oq, V);
-    } else {
-        double st_, ct_;
-        sincos(theta, &st_, &ct_);
-        const double c1 = (1.0 - ct_) / (theta * theta);
-        const double c2 = (theta - st_) / (theta * theta * theta);
-        const double w2 = wz * wz;
-        V[0] = 1.0 + c2 * (-w2), V[1] = c1 * (-wz), V[2] = 0.0;
-        V[3] = c1 * wz, V[4] = 1.0 + c2 * (-w2), V[5] = 0.0;
-        V[6] = 0.0, V[7] = 0.0, V[8] = 1.0;
-    }
-    ot[0] = V[0] * ux + V[1] * uy;
-    ot[1] = V[3] * ux + V[4] * uy;
-    ot[2] = V[6] * ux + V[7] * uy;
-}
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
     unsigned long long t;
@@ -216,91 +147,16 @@ __device__ __forceinline__ Point4 ld_point(const double *p) {
     return r;
 }
 
-// current_estimate = last_robot_pose * relative_wheel_odometry   (Registration.cpp:156)
-__device__ void pose_init(PoseState *ps, const RegArgs &a) {
-    const double lq[4] = {a.last.qx, a.last.qy, a.last.qz, a.last.qw}, lt[3] = {a.last.tx, a.last.ty, a.last.tz};
-    const double oq[4] = {a.odom.qx, a.odom.qy, a.odom.qz, a.odom.qw}, ot[3] = {a.odom.tx, a.odom.ty, a.odom.tz};
-    double q[4], t[3], R[9];
-    se3_compose(lq, lt, oq, ot, q, t);
-    quat_to_matrix(q, R);
-    for (int k = 0; k < 4; ++k) ps->q[k] = q[k];
-    for (int k = 0; k < 3; ++k) ps->t[k] = t[k];
-    for (int k = 0; k < 9; ++k) ps->R[k] = R[k], ps->Rp[k] = R[k];
-    for (int k = 0; k < 3; ++k) ps->tp[k] = t[k];
-    ps->tau = a.tau, ps->conv = a.conv, ps->fixed_reg = a.fixed_reg, ps->beta = 0.0;
-    ps->adaptive = a.adaptive, ps->max_iter = a.max_iter;
-    ps->iter = 0, ps->done = a.max_iter <= 0 ? 1 : 0, ps->status = KICP_OK;
-}
-__device__ void result_init(kicp_reg_result *r, const PoseState *ps) {
-    for (int k = 0; k < 4; ++k) r->pose[k] = ps->q[k];
-    for (int k = 0; k < 3; ++k) r->pose[4 + k] = ps->t[k];
-    r->beta = 0.0, r->last_dx_norm = 0.0, r->iterations = 0, r->status = ps->status;
-}
-
 // Multi-launch path and the "nothing to do" case (empty map / max_iter <= 0): state in global memory.
 __global__ void k_reg_init(RegState *st, RegArgs a) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     pose_init(&st->pose, a);
     result_init(&st->result, &st->pose);
     st->ticket = 0, st->win_ctr = 0, st->arrive = 0, st->exit_ctr = 0, st->abort = 0, st->a_arrive = 0;
-    for (int k = 0; k < KICP_MAX_ITERATIONS; ++k) st->todo_n[k] = 0;
+    for (int k = 0; k < KICP_MAX_ITERATIONS; ++k) st->todo_n[k] = 0, st->slow_n[k] = 0;
     st->iters_out = a.iters_out;
     if (a.iters_out) *a.iters_out = 0;
     for (int k = 0; k < 8; ++k) st->acc[k] = 0.0;
-}
-
-// ComputePerturbation's tail + motion model + pose update + convergence test (one thread).  `s` holds the (all-reduced)
-// sums of this iteration; `res` (optional) receives the public result fields.
-__device__ void solve_and_update(PoseState *ps, const double *s, kicp_reg_result *res, int *iters_out) {
-    const int j = ps->iter;
-    if (res && j < KICP_MAX_ITERATIONS)
-        for (int k = 0; k < 8; ++k) res->sums[j][k] = k < 7 ? s[k] : 0.0;
-    const double N = s[5];
-    if (j == 0) {
-        // ComputeOdometryRegularization (Registration.cpp:48-60): beta = 1 / (mean |T0 p - n|^2 + DBL_MIN), computed
-        // once from the first association; the fixed value otherwise (:171-177)
-        ps->beta = ps->adaptive ? 1.0 / (s[6] / N + DBL_MIN) : ps->fixed_reg;
-        if (res) res->beta = ps->beta;
-    }
-    // JTJ /= N; JTr /= N; JTJ += diag(beta, 0); dx = -(JTJ^-1 JTr)     (Registration.cpp:119-125)
-    const double a = s[0] / N + ps->beta, b = s[1] / N, d = s[2] / N + 0.0;
-    const double r0 = s[3] / N, r1 = s[4] / N;
-    const double invdet = 1.0 / (a * d - b * b);
-    const double i00 = d * invdet, i01 = -b * invdet, i10 = -b * invdet, i11 = a * invdet;
-    const double dx0 = -(i00 * r0 + i01 * r1), dx1 = -(i10 * r0 + i11 * r1);
-    // motion_model (Registration.cpp:159-167), epsilon = DBL_MIN
-    double sn, cs;
-    sincos(dx1, &sn, &cs);
-    const double ux = dx0 * sn / (dx1 + DBL_MIN);
-    const double uy = dx0 * (1.0 - cs) / (dx1 + DBL_MIN);
-    double dq[4], dt[3], nq[4], nt[3], cq[4], ct[3], nR[9];
-    for (int k = 0; k < 4; ++k) cq[k] = ps->q[k];
-    for (int k = 0; k < 3; ++k) ct[k] = ps->t[k];
-    se3_exp_planar(ux, uy, dx1, dq, dt);
-    se3_compose(cq, ct, dq, dt, nq, nt);  // current_estimate = current_estimate * delta_motion  (:182)
-    quat_to_matrix(nq, nR);
-    for (int k = 0; k < 9; ++k) ps->Rp[k] = ps->R[k];
-    for (int k = 0; k < 3; ++k) ps->tp[k] = ps->t[k];
-    for (int k = 0; k < 4; ++k) ps->q[k] = nq[k];
-    for (int k = 0; k < 3; ++k) ps->t[k] = nt[k];
-    for (int k = 0; k < 9; ++k) ps->R[k] = nR[k];
-    const double dxn = sqrt(dx0 * dx0 + dx1 * dx1);
-    ps->iter = j + 1;
-    int done = (dxn < ps->conv) || (j + 1 >= ps->max_iter);  // break BEFORE re-association (:184)
-    if (!(N > 0.0)) {  // the reference has no guard: the pose is NaN from here on; stop early and say so
-        ps->status = KICP_WARN_NO_CORRESPONDENCES;
-        done = 1;
-    }
-    ps->done = done;
-    if (res) {
-        if (j < KICP_MAX_ITERATIONS) res->dx[j][0] = dx0, res->dx[j][1] = dx1;
-        res->last_dx_norm = dxn;
-        res->iterations = j + 1;
-        for (int k = 0; k < 4; ++k) res->pose[k] = nq[k];
-        for (int k = 0; k < 3; ++k) res->pose[4 + k] = nt[k];
-        res->status = ps->status;
-    }
-    if (iters_out) *iters_out = j + 1;
 }
 
 // Multi-launch path: the solve between the NCCL allreduce and the next association launch.
@@ -403,6 +259,16 @@ __device__ __forceinline__ unsigned stage_mask(int stage, bool valid, double bou
     return mask;
 }
 
+// A point that enters a later pass with `sd`, the distance to its previous neighbour at the new position, has an exact pruning bound
+// from the start: the neighbour voxels that survive it.  Evaluated identically by the certificate sweep (which sorts the point into
+// the list of one-stage searches if they are few) and by the search itself.
+__device__ __forceinline__ unsigned seeded_near_mask(double sd, double tau, double qx, double qy, double qz, int vx, int vy, int vz, double vs,
+                                                     double &minpruned) {
+    const double seed2 = sd * sd * (1.0 + 1e-6);
+    const double bound = fmin(tau * tau, seed2) * (1.0 + 1e-6) + 1e-10;
+    return stage_mask(1, true, bound, qx, qy, qz, vx, vy, vz, vs, minpruned) | stage_mask(2, true, bound, qx, qy, qz, vx, vy, vz, vs, minpruned);
+}
+
 // gate, residual, Jacobian and the seven sums of one correspondence (Registration.cpp:75, 86-93, 110-118)
 __device__ __forceinline__ void accumulate(WarpSm &sm, int lane, const PoseState &ps, double nx, double ny, double nz, double qx, double qy,
                                            double qz, double px, double py) {
@@ -494,86 +360,92 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             // reach and l - delta > tau, nothing can be accepted now).  Everything else goes to the list of the search phase,
             // with |q' - g| as an exact pruning bound when g still lies in the new neighbourhood.
             // ------------------------------------------------------------------------------------------------------------
-            // the certificate of a point costs the same everywhere: the windows are dealt out statically (no ticket traffic), two
-            // at a time — their loads, the dependent gathers of the remembered candidates and the one atomic that reserves list
-            // space for both are each issued together (a window alone is a chain of three memory round trips)
-            for (int w0 = (int)gwarp; w0 < num_windows; w0 += 2 * (int)total_warps) {
-                int pidx[2];
-                bool valid[2];
-                double px[2], py[2], pz[2], lb[2];
-                unsigned g1[2], g2[2];
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int w = w0 + k * (int)total_warps;
-                    pidx[k] = w * 32 + lane;
-                    valid[k] = w < num_windows && pidx[k] < n;
-                    px[k] = 0, py[k] = 0, pz[k] = 0;
-                    if (valid[k]) load_scan_point(a.scan, pidx[k], px[k], py[k], pz[k]);
-                    g1[k] = valid[k] ? __ldcg(&a.nn_g[pidx[k]]) : 0xFFFFFFFFu;
-                    g2[k] = valid[k] ? __ldcg(&a.nn_g2[pidx[k]]) : 0xFFFFFFFFu;
-                    lb[k] = valid[k] ? (double)__ldcg(&a.nn_l[pidx[k]]) : 0.0;
+            // the certificate of a point costs the same everywhere: the windows are dealt out statically (no ticket traffic)
+            for (int w = (int)gwarp; w < num_windows; w += (int)total_warps) {
+                const int i = w * 32 + lane;
+                const bool valid = i < n;
+                double px = 0, py = 0, pz = 0;
+                if (valid) load_scan_point(a.scan, i, px, py, pz);
+                const unsigned g1 = valid ? __ldcg(&a.nn_g[i]) : 0xFFFFFFFFu;
+                const unsigned g2 = valid ? __ldcg(&a.nn_g2[i]) : 0xFFFFFFFFu;
+                const double l = valid ? (double)__ldcg(&a.nn_l[i]) : 0.0;
+                const bool haveg = g1 != 0xFFFFFFFFu, have2 = g2 != 0xFFFFFFFFu;
+                const Point4 c1 = ld_point(a.map.pts + (size_t)(haveg ? g1 : 0u) * KICP_PSTRIDE);
+                const Point4 c2 = ld_point(a.map.pts + (size_t)(have2 ? g2 : 0u) * KICP_PSTRIDE);
+                const double qx = s_ps.R[0] * px + s_ps.R[1] * py + s_ps.R[2] * pz + s_ps.t[0];
+                const double qy = s_ps.R[3] * px + s_ps.R[4] * py + s_ps.R[5] * pz + s_ps.t[1];
+                const double qz = s_ps.R[6] * px + s_ps.R[7] * py + s_ps.R[8] * pz + s_ps.t[2];
+                const double ox = s_ps.Rp[0] * px + s_ps.Rp[1] * py + s_ps.Rp[2] * pz + s_ps.tp[0];
+                const double oy = s_ps.Rp[3] * px + s_ps.Rp[4] * py + s_ps.Rp[5] * pz + s_ps.tp[1];
+                const double oz = s_ps.Rp[6] * px + s_ps.Rp[7] * py + s_ps.Rp[8] * pz + s_ps.tp[2];
+                const double vs = a.map.voxel_size;
+                const int vx = voxel_of(qx, vs, inv_vs, a.pow2_voxel), vy = voxel_of(qy, vs, inv_vs, a.pow2_voxel),
+                          vz = voxel_of(qz, vs, inv_vs, a.pow2_voxel);
+                const int ovx = voxel_of(ox, vs, inv_vs, a.pow2_voxel), ovy = voxel_of(oy, vs, inv_vs, a.pow2_voxel),
+                          ovz = voxel_of(oz, vs, inv_vs, a.pow2_voxel);
+                const double mx = qx - ox, my = qy - oy, mz = qz - oz;
+                const double delta = sqrt(mx * mx + my * my + mz * mz) * (1.0 + 1e-9) + 1e-12;
+                const double d1 = sqrt(dist2(c1.x, c1.y, c1.z, qx, qy, qz));
+                const double d2 = have2 ? sqrt(dist2(c2.x, c2.y, c2.z, qx, qy, qz)) : DBL_MAX;
+                // the two remembered candidates may have swapped; a near-tie between them is left to the search (only it applies the
+                // reference's visiting-order rule)
+                const bool second_wins = d2 < d1;
+                const double dn = second_wins ? d2 : d1;
+                const bool clear = !have2 || fabs(d1 - d2) > 1e-9 * (d1 + d2) + 1e-12;
+                const Point4 c = second_wins ? c2 : c1;
+                // A step into a NEIGHBOURING voxel shifts the 27-voxel neighbourhood by one layer per changed axis: the layer that
+                // drops out only removes candidates, the layer that comes in lies beyond the far face of the new own voxel along
+                // that axis — `slab` away at least.  Both remembered candidates must still be inside the new neighbourhood.
+                double slab = DBL_MAX;
+                bool reach = true;
+                if (vx != ovx || vy != ovy || vz != ovz) {
+                    reach = abs(vx - ovx) <= 1 && abs(vy - ovy) <= 1 && abs(vz - ovz) <= 1;
+                    if (vx > ovx) slab = fmin(slab, (double)(vx + 1) * vs - qx); else if (vx < ovx) slab = fmin(slab, qx - (double)vx * vs);
+                    if (vy > ovy) slab = fmin(slab, (double)(vy + 1) * vs - qy); else if (vy < ovy) slab = fmin(slab, qy - (double)vy * vs);
+                    if (vz > ovz) slab = fmin(slab, (double)(vz + 1) * vs - qz); else if (vz < ovz) slab = fmin(slab, qz - (double)vz * vs);
+                    if (haveg)
+                        reach = reach && abs(voxel_of(c1.x, vs, inv_vs, a.pow2_voxel) - vx) <= 1 && abs(voxel_of(c1.y, vs, inv_vs, a.pow2_voxel) - vy) <= 1 &&
+                                abs(voxel_of(c1.z, vs, inv_vs, a.pow2_voxel) - vz) <= 1;
+                    if (have2)
+                        reach = reach && abs(voxel_of(c2.x, vs, inv_vs, a.pow2_voxel) - vx) <= 1 && abs(voxel_of(c2.y, vs, inv_vs, a.pow2_voxel) - vy) <= 1 &&
+                                abs(voxel_of(c2.z, vs, inv_vs, a.pow2_voxel) - vz) <= 1;
                 }
-                Point4 c1[2], c2[2];
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    c1[k] = ld_point(a.map.pts + (size_t)(g1[k] != 0xFFFFFFFFu ? g1[k] : 0u) * KICP_PSTRIDE);
-                    c2[k] = ld_point(a.map.pts + (size_t)(g2[k] != 0xFFFFFFFFu ? g2[k] : 0u) * KICP_PSTRIDE);
+                // every other candidate of the (new) neighbourhood is at least this far from the new position
+                const double room = fmin(l - delta, slab * (1.0 - 1e-9) - 1e-12);
+                const bool cert = valid && reach && (haveg ? (clear && dn * (1.0 + 1e-9) + 1e-12 < room) : (room > s_ps.tau * (1.0 + 1e-9)));
+                if (cert) {
+                    a.nn_l[i] = __double2float_rz(room * (1.0 - 1e-7));
+                    if (second_wins) a.nn_g[i] = g2, a.nn_g2[i] = g1;
+                    if (haveg) accumulate(sm, lane, s_ps, c.x, c.y, c.z, qx, qy, qz, px, py);
                 }
-                unsigned need[2];
-                bool again[2];
-                float seedv[2];
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const bool haveg = g1[k] != 0xFFFFFFFFu, have2 = g2[k] != 0xFFFFFFFFu;
-                    const double qx = s_ps.R[0] * px[k] + s_ps.R[1] * py[k] + s_ps.R[2] * pz[k] + s_ps.t[0];
-                    const double qy = s_ps.R[3] * px[k] + s_ps.R[4] * py[k] + s_ps.R[5] * pz[k] + s_ps.t[1];
-                    const double qz = s_ps.R[6] * px[k] + s_ps.R[7] * py[k] + s_ps.R[8] * pz[k] + s_ps.t[2];
-                    const double ox = s_ps.Rp[0] * px[k] + s_ps.Rp[1] * py[k] + s_ps.Rp[2] * pz[k] + s_ps.tp[0];
-                    const double oy = s_ps.Rp[3] * px[k] + s_ps.Rp[4] * py[k] + s_ps.Rp[5] * pz[k] + s_ps.tp[1];
-                    const double oz = s_ps.Rp[6] * px[k] + s_ps.Rp[7] * py[k] + s_ps.Rp[8] * pz[k] + s_ps.tp[2];
-                    const double vs = a.map.voxel_size;
-                    const int vx = voxel_of(qx, vs, inv_vs, a.pow2_voxel), vy = voxel_of(qy, vs, inv_vs, a.pow2_voxel),
-                              vz = voxel_of(qz, vs, inv_vs, a.pow2_voxel);
-                    const bool same = vx == voxel_of(ox, vs, inv_vs, a.pow2_voxel) && vy == voxel_of(oy, vs, inv_vs, a.pow2_voxel) &&
-                                      vz == voxel_of(oz, vs, inv_vs, a.pow2_voxel);
-                    const double mx = qx - ox, my = qy - oy, mz = qz - oz;
-                    const double delta = sqrt(mx * mx + my * my + mz * mz) * (1.0 + 1e-9) + 1e-12;
-                    const double d1 = sqrt(dist2(c1[k].x, c1[k].y, c1[k].z, qx, qy, qz));
-                    const double d2 = have2 ? sqrt(dist2(c2[k].x, c2[k].y, c2[k].z, qx, qy, qz)) : DBL_MAX;
-                    // the two remembered candidates may have swapped; a near-tie between them is left to the search (only it applies
-                    // the reference's visiting-order rule)
-                    const bool second_wins = d2 < d1;
-                    const double dn = second_wins ? d2 : d1;
-                    const bool clear = !have2 || fabs(d1 - d2) > 1e-9 * (d1 + d2) + 1e-12;
-                    const double cx = second_wins ? c2[k].x : c1[k].x, cy = second_wins ? c2[k].y : c1[k].y, cz = second_wins ? c2[k].z : c1[k].z;
-                    const double room = lb[k] - delta;  // every other candidate is at least this far from the new position
-                    const bool cert = valid[k] && same &&
-                                      (haveg ? (clear && dn * (1.0 + 1e-9) + 1e-12 < room) : (room > s_ps.tau * (1.0 + 1e-9)));
-                    if (cert) {
-                        a.nn_l[pidx[k]] = __double2float_rz(room * (1.0 - 1e-7));
-                        if (second_wins) a.nn_g[pidx[k]] = g2[k], a.nn_g2[pidx[k]] = g1[k];
-                        if (haveg) accumulate(sm, lane, s_ps, cx, cy, cz, qx, qy, qz, px[k], py[k]);
+                // Everything else is searched again.  The old neighbour bounds that search if it is one of the new 27 voxels' points; with
+                // few neighbour voxels inside the bound the search is ONE merged stage (front of the list), else it is staged (back).
+                const bool again = valid && !cert;
+                bool slow = false;
+                if (again) {
+                    float seed = 3.0e38f;
+                    if (haveg && abs(voxel_of(c.x, vs, inv_vs, a.pow2_voxel) - vx) <= 1 && abs(voxel_of(c.y, vs, inv_vs, a.pow2_voxel) - vy) <= 1 &&
+                        abs(voxel_of(c.z, vs, inv_vs, a.pow2_voxel) - vz) <= 1)
+                        seed = __double2float_ru(dn * (1.0 + 1e-7));
+                    a.nn_seed[i] = seed;
+                    slow = true;
+                    if (seed < 1.0e38f) {
+                        double mp = DBL_MAX;
+                        slow = __popc(seeded_near_mask((double)seed, s_ps.tau, qx, qy, qz, vx, vy, vz, vs, mp)) > KR_MERGE_MAX;
                     }
-                    again[k] = valid[k] && !cert;
-                    // the old neighbour bounds the repeated search if it is one of the new 27 voxels' points
-                    seedv[k] = 3.0e38f;
-                    if (haveg && abs(voxel_of(cx, vs, inv_vs, a.pow2_voxel) - vx) <= 1 && abs(voxel_of(cy, vs, inv_vs, a.pow2_voxel) - vy) <= 1 &&
-                        abs(voxel_of(cz, vs, inv_vs, a.pow2_voxel) - vz) <= 1)
-                        seedv[k] = __double2float_ru(dn * (1.0 + 1e-7));
-                    need[k] = __ballot_sync(FULL, again[k]);
                 }
-                const unsigned n0 = (unsigned)__popc(need[0]), n1 = (unsigned)__popc(need[1]);
-                if (n0 + n1) {  // warp-uniform
+                const unsigned needf = __ballot_sync(FULL, again && !slow), needs = __ballot_sync(FULL, again && slow);
+                if (needf) {
                     unsigned pos = 0;
-                    if (lane == 0) pos = atomicAdd(&st->todo_n[it], n0 + n1);
-                    pos = __shfl_sync(FULL, pos, 0);
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        if (again[k]) {
-                            a.todo[pos + (k ? n0 : 0u) + (unsigned)__popc(need[k] & ((1u << lane) - 1u))] = (unsigned)pidx[k];
-                            a.nn_seed[pidx[k]] = seedv[k];
-                        }
-                    }
+                    if (lane == 0) pos = atomicAdd(&st->todo_n[it], (unsigned)__popc(needf));
+                    pos = __shfl_sync(FULL, pos, 0) + (unsigned)__popc(needf & ((1u << lane) - 1u));
+                    if (again && !slow) a.todo[pos] = (unsigned)i;
+                }
+                if (needs) {
+                    unsigned pos = 0;
+                    if (lane == 0) pos = atomicAdd(&st->slow_n[it], (unsigned)__popc(needs));
+                    pos = __shfl_sync(FULL, pos, 0) + (unsigned)__popc(needs & ((1u << lane) - 1u));
+                    if (again && slow) a.todo[(unsigned)n - 1u - pos] = (unsigned)i;
                 }
             }
             KR_WLOG(1, t_iter0, gtime_ns(), 0, 0)
@@ -596,41 +468,40 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             }
             __syncthreads();
         }
-        const bool indirect_phase = cache && it > 0u;
-        const int ncount = (cache && it > 0u) ? (int)__ldcg(&st->todo_n[it]) : n;  // points of the search phase
-        // Window size of the phase.  A window costs about the same whether it holds 12 points or 32 (its chain of dependent
-        // steps), so full windows are the efficient unit; but when the whole phase fits ONE round of the grid, the points are spread
-        // evenly over all warps instead (a small scan, the remainder of a later pass): the phase then lasts one light window.
+        const bool indirect = cache && it > 0u;
+        // points of the search phase: in pass 0 the whole frame; afterwards the uncertified ones — at the front of the list those
+        // that get by with ONE merged stage (the usual case), at its back the few that need the staged search
+        const int nfast = indirect ? (int)__ldcg(&st->todo_n[it]) : n;
+        const int nslow = indirect ? (int)__ldcg(&st->slow_n[it]) : 0;
+        // Window size of the phase.  A window is a chain of dependent steps whose length depends little on how many points it holds,
+        // so full windows are the efficient unit; but when the whole phase fits ONE round of the grid, the points are spread evenly
+        // over all warps (a small scan, the remainder of a later pass), and a phase of k rounds sizes its windows so that every warp
+        // gets k of them (no last round that only part of the grid takes part in).  The staged stragglers of a later pass go into
+        // small windows of their own (KR_SLOWWIN points, handed out first): one of them inside an ordinary window would make all
+        // its 32 lanes walk through the three stages.
+        const int P = (int)total_warps;
+        const int nslowwin = (nslow + KR_SLOWWIN - 1) / KR_SLOWWIN;
+        const int Pf = max(P - nslowwin, P / 2);  // warps left for the ordinary windows of a single-round phase
         int wsz = 32;
-        int gs = a.deal_shift;  // log2 of the run of consecutive points that is dealt as one card (see below)
-        if (PERSISTENT && ncount > 0 && ncount <= 32 * (int)total_warps) {
-            wsz = max(1, (ncount + (int)total_warps - 1) / (int)total_warps);
-            if (gs > 0) {  // whole cards only
-                if (wsz >= 24) {
-                    wsz = 32;
-                } else {
-                    gs = min(gs, 31 - __clz(wsz));  // the largest card that is not larger than the window
-                    wsz = ((wsz + (1 << gs) - 1) >> gs) << gs;
-                }
+        if (PERSISTENT && nfast > 0) {
+            if (nfast <= 32 * Pf) {
+                wsz = max(1, (nfast + Pf - 1) / Pf);
+            } else {
+                const int rounds = (nfast + 32 * P - 1) / (32 * P);
+                wsz = min(32, (nfast + rounds * P - 1) / (rounds * P));
             }
-        } else if (PERSISTENT && a.even_rounds && ncount > 0) {
-            // a phase of k rounds: windows sized so that every warp gets k of them (instead of a last round that only part of
-            // the grid takes part in)
-            const int rounds = (ncount + 32 * (int)total_warps - 1) / (32 * (int)total_warps);
-            wsz = min(32, (ncount + rounds * (int)total_warps - 1) / (rounds * (int)total_warps));
-            if (gs > 0) wsz = min(32, ((wsz + (1 << gs) - 1) >> gs) << gs);
         }
-        const int gsm = (1 << gs) - 1;
         // pass 0: the frame in KICP_UPLOAD_CHUNKS segments of `segpts` points (the host uploads it in exactly these pieces)
         const int segpts = max(32, ((((n + 31) >> 5) + KICP_UPLOAD_CHUNKS - 1) / KICP_UPLOAD_CHUNKS) * 32);
         const int segwin = (segpts + wsz - 1) / wsz;  // windows per (full) segment
-        if (indirect_phase) {
-            nsearch = (ncount + wsz - 1) / wsz;
+        int nfastwin;
+        if (indirect) {
+            nfastwin = (nfast + wsz - 1) / wsz;
         } else {
             const int nseg = min(KICP_UPLOAD_CHUNKS, (n + segpts - 1) / segpts), lastn = n - (nseg - 1) * segpts;
-            nsearch = n > 0 ? (nseg - 1) * segwin + (lastn + wsz - 1) / wsz : 0;
+            nfastwin = n > 0 ? (nseg - 1) * segwin + (lastn + wsz - 1) / wsz : 0;
         }
-        const bool indirect = cache && it > 0u;
+        nsearch = nslowwin + nfastwin;
 
         // ------------------------------------------------------------------------------------------------------------------
         // Phase B: THE SEARCH (all points in pass 0; the uncertified ones, compacted, afterwards)
@@ -649,20 +520,23 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             // that are expensive to search (little or no map around them) sit next to each other in the scan and in the list, and a
             // window made of them alone would outlast the phase.  Pass 0 deals inside each of the KICP_UPLOAD_CHUNKS segments the
             // frame is uploaded in, so that a window still needs only its own chunk.
-            int slot, limit, seg_of_w = 0;
-            // A card is a run of 2^gs consecutive entries (option "deal_group"): neighbours in the scan share voxels and lines, so a
-            // run keeps that locality inside the window while the window as a whole still samples 32 / 2^gs distant places.
+            int slot, limit, seg_of_w = 0, wlanes = wsz;
+            bool from_back = false;
             if (indirect) {
-                slot = ((((lane >> gs) * nsearch) + w) << gs) | (lane & gsm), limit = ncount;
+                if (w < nslowwin) {  // a small window of staged stragglers (back of the list)
+                    slot = lane * nslowwin + w, limit = nslow, wlanes = KR_SLOWWIN, from_back = true;
+                } else {
+                    slot = lane * nfastwin + (w - nslowwin), limit = nfast;
+                }
             } else {
                 const int sgi = min(w / segwin, KICP_UPLOAD_CHUNKS - 1), lw = w - sgi * segwin;
                 const int sbase = sgi * segpts, sn = min(segpts, n - sbase);  // this segment's points
                 const int sw = (sn + wsz - 1) / wsz;                          // ... and windows
-                slot = sbase + (((((lane >> gs) * sw) + lw) << gs) | (lane & gsm)), limit = lw < sw ? sbase + sn : 0;
+                slot = sbase + lane * sw + lw, limit = lw < sw ? sbase + sn : 0;
                 seg_of_w = sgi;
             }
-            const bool valid = lane < wsz && slot < limit;
-            const int pi = valid ? (indirect ? (int)__ldcg(&a.todo[slot]) : slot) : 0;  // the owner's scan point
+            const bool valid = lane < wlanes && slot < limit;
+            const int pi = valid ? (indirect ? (int)__ldcg(&a.todo[from_back ? n - 1 - slot : slot]) : slot) : 0;  // the owner's scan point
             if (PERSISTENT && a.up.flags != nullptr && it == 0u) {
                 // first pass over a frame that is still being uploaded: wait until this window's chunk has landed
                 const uint32_t *f = a.up.flags + seg_of_w;
@@ -679,13 +553,13 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                     }
                 }
             }
-            double seed2 = DBL_MAX;  // squared distance to the previous neighbour (an exact pruning bound), if it applies
+            double seed2 = DBL_MAX, seed_d = 3.0e38;  // (squared) distance to the previous neighbour — an exact pruning bound —, if it applies
             {
                 double px = 0, py = 0, pz = 0;
                 if (valid) load_scan_point(a.scan, pi, px, py, pz);
                 if (indirect && valid) {
                     const double sd = (double)__ldcg(&a.nn_seed[pi]);
-                    if (sd < 1.0e38) seed2 = sd * sd * (1.0 + 1e-6);
+                    if (sd < 1.0e38) seed_d = sd, seed2 = sd * sd * (1.0 + 1e-6);
                 }
                 const double qx = s_ps.R[0] * px + s_ps.R[1] * py + s_ps.R[2] * pz + s_ps.t[0];
                 const double qy = s_ps.R[3] * px + s_ps.R[4] * py + s_ps.R[5] * pz + s_ps.t[1];
@@ -721,13 +595,11 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
                     const double bound = bsq * (1.0 + 1e-6) + 1e-10;
                     unsigned mask = stage_mask(stage, valid, bound, qq.x, qq.y, sm.qz[lane], sm.vx[lane], sm.vy[lane], sm.vz[lane],
                                                a.map.voxel_size, minpruned);
-                    if (stage == 0 && valid && seed2 < DBL_MAX) {
+                    if (stage == 0 && valid && seed_d < 1.0e38) {
                         double mp = minpruned;
-                        const unsigned near = stage_mask(1, true, bound, qq.x, qq.y, sm.qz[lane], sm.vx[lane], sm.vy[lane], sm.vz[lane],
-                                                         a.map.voxel_size, mp) |
-                                              stage_mask(2, true, bound, qq.x, qq.y, sm.qz[lane], sm.vx[lane], sm.vy[lane], sm.vz[lane],
-                                                         a.map.voxel_size, mp);
-                        if (__popc(near) <= 8) mask |= near, minpruned = mp, merged = true;  // (a loose bound keeps the staged way)
+                        const unsigned near = seeded_near_mask(seed_d, s_ps.tau, qq.x, qq.y, sm.qz[lane], sm.vx[lane], sm.vy[lane], sm.vz[lane],
+                                                               a.map.voxel_size, mp);
+                        if (__popc(near) <= KR_MERGE_MAX) mask |= near, minpruned = mp, merged = true;  // (a loose bound keeps the staged way)
                     }
                     mask &= ~donem;
                     donem |= mask;
@@ -1127,7 +999,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
             const unsigned left = atomicAdd(&st->exit_ctr, 1u);
             if (left == gridDim.x - 1) {
                 st->win_ctr = 0, st->arrive = 0, st->abort = 0, st->a_arrive = 0;
-                for (int k = 0; k < KICP_MAX_ITERATIONS; ++k) st->todo_n[k] = 0;
+                for (int k = 0; k < KICP_MAX_ITERATIONS; ++k) st->todo_n[k] = 0, st->slow_n[k] = 0;
                 __threadfence();
                 st->exit_ctr = 0;
             }

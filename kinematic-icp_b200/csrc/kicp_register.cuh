@@ -54,8 +54,6 @@ struct KernelArgs {
     float *nn_seed;                // distance to the old neighbour from the new position (pruning bound of the repeated search)
     unsigned int *todo;            // points of the current pass that need the search
     unsigned long long timeout_ns;  // device-side waits (upload flags, peers) give up after this long
-    int even_rounds;                // size the windows of a multi-round phase so that every warp gets the same number of them
-    int deal_shift;                 // log2 of the run of consecutive points dealt to a window as one card (0..5)
 };
 
 

@@ -36,12 +36,6 @@ extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value)
     } else if (!strcmp(name, "overlap_upload")) {
         if (value != 0 && value != 1) return KICP_ERR_INVALID;
         c->overlap_upload = value;
-    } else if (!strcmp(name, "even_rounds")) {
-        if (value != 0 && value != 1) return KICP_ERR_INVALID;
-        c->even_rounds = value;
-    } else if (!strcmp(name, "deal_group")) {
-        if (value < 0 || value > 5) return KICP_ERR_INVALID;
-        c->deal_shift = value;
     } else if (!strcmp(name, "frame_sync")) {
         if (value != 0 && value != 1) return KICP_ERR_INVALID;
         c->frame_sync = value;
@@ -160,7 +154,6 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
         ka.nn_g = c->d_nn_g, ka.nn_g2 = c->d_nn_g2, ka.nn_l = c->d_nn_l, ka.nn_seed = c->d_nn_seed, ka.todo = c->d_todo;
     }
     ka.timeout_ns = (unsigned long long)c->spin_timeout_ms * 1000000ull;
-    ka.deal_shift = c->deal_shift, ka.even_rounds = c->even_rounds;
     const int n = (int)scan->n;
     const bool p2p = sharded && c->p2p_ready;
     const bool persistent = c->persistent && (!sharded || p2p);

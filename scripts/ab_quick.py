@@ -1,6 +1,6 @@
 """Same-process sweep of the registration kernel's scheduling options on one library build (KICP_LIB selects it):
 flushed-L2 timing of the resident path, CUDA events on the library's stream.
-usage: python scripts/ab_quick.py "4,3" "dg,er;dg,er;..."     (dg = deal_group 0..5, er = even_rounds 0/1)"""
+usage: python scripts/ab_quick.py "4,3" "opt=v,opt=v;opt=v;..."     (each ';'-separated entry is one configuration of kicp_ctx_set_option)"""
 import os, sys
 sys.path.insert(0, "."); sys.path.insert(0, "kinematic-icp_b200/python")
 import numpy as np
@@ -8,7 +8,9 @@ import torch
 import kinematic_icp_b200 as kb
 from oracle import workloads as W
 cfgs = [int(x) for x in sys.argv[1].split(",")]
-combos = [tuple(int(v) for v in c.split(",")) for c in sys.argv[2].split(";")]
+combos = [[(kv.split("=")[0], int(kv.split("=")[1])) for kv in c.split(",") if kv] for c in sys.argv[2].split(";")]
+allopts = sorted({k for c in combos for k, _ in c})
+defaults = {k: int(os.environ.get("AB_DEFAULT_" + k.upper(), "0")) for k in allopts}
 steps, warm = 20, 5
 ctx = kb.Context(0)
 stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", 0))
@@ -23,8 +25,10 @@ for cfg in cfgs:
     res = kb.pinned_result()
     ref = None
     for rep in range(2):
-        for dg, er in combos:
-            ctx.set_option("deal_group", dg); ctx.set_option("even_rounds", er)
+        for combo in combos:
+            for k in allopts:
+                ctx.set_option(k, dict(combo).get(k, defaults[k]))
+            label = ",".join("%s=%d" % kv for kv in combo) or "defaults"
             for i in range(warm):
                 with torch.cuda.stream(stream):
                     flush_buf.fill_(i)
@@ -45,7 +49,7 @@ for cfg in cfgs:
             if ref is None:
                 ref = (pose, nsum)
             ok = np.abs(pose - ref[0]).max() < 1e-9 and nsum == ref[1] and res.status == 0
-            print("cfg %d deal_group %d even_rounds %d : %.1f us (min %.1f) = %.0f scans/s | pass0 search+wait %.1f+%.1f  later: cert %.1f search %.1f wait %.1f | %s" %
-                  (cfg, dg, er, us.mean(), us.min(), 1e6 / us.mean(), t[0][2], t[0][3], np.median(t[1:, 0]) if len(t) > 1 else 0,
+            print("cfg %d %-28s : %.1f us (min %.1f) = %.0f scans/s | pass0 search+wait %.1f+%.1f  later: cert %.1f search %.1f wait %.1f | %s" %
+                  (cfg, label, us.mean(), us.min(), 1e6 / us.mean(), t[0][2], t[0][3], np.median(t[1:, 0]) if len(t) > 1 else 0,
                    np.median(t[1:, 2]) if len(t) > 1 else 0, np.median(t[1:, 3]) if len(t) > 1 else 0, "ok" if ok else "MISMATCH"), flush=True)
     gm.close()
