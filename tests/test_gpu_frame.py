@@ -17,11 +17,13 @@ def _oracle_frame(ko, w, om, frame, stamps, deskew_motion, l2b, deskew):
     return in_base, fd, src, pose, stats
 
 
+@pytest.mark.parametrize("frame_sync", [0, 1])  # 0: ONE host synchronisation per frame (default); 1: counts read back mid-frame
 @pytest.mark.parametrize("deskew", [False, True])
-def test_register_frame_matches_oracle_stages(oracle, gpu_ctx, workload, deskew):
+def test_register_frame_matches_oracle_stages(oracle, gpu_ctx, workload, deskew, frame_sync):
     import kinematic_icp_b200 as kb
     ko = oracle
     w = workload(2)
+    gpu_ctx.set_option("frame_sync", frame_sync)
     l2b = ko.se3_exp([0.2, -0.1, 0.3, 0.0, 0.0, 0.05])
     # the workload scan is in the base frame at true_pose: move it to the lidar frame, and add out-of-range clutter
     frame = ko.se3_transform(ko.se3_inverse(l2b), w.scan)
@@ -33,9 +35,19 @@ def test_register_frame_matches_oracle_stages(oracle, gpu_ctx, workload, deskew)
     om.add_points(pts)  # private copy of the workload map (voxel-grouped insertion keeps it identical)
     gm = gpu_map_from_oracle(kb, gpu_ctx, om)
     in_base, fd, src, opose, ostats = _oracle_frame(ko, w, om, frame, stamps, deskew_motion, l2b, deskew)
-    pose, g_frame, g_src, res = kb.RegisterFrame(gm, frame, stamps, deskew_motion, l2b, w.last_pose, w.rel_odom, w.tau, max_range=100.0,
-                                                 min_range=0.5, deskew=deskew, voxel_size=w.voxel_size)
+    try:
+        pose, g_frame, g_src, res = kb.RegisterFrame(gm, frame, stamps, deskew_motion, l2b, w.last_pose, w.rel_odom, w.tau, max_range=100.0,
+                                                     min_range=0.5, deskew=deskew, voxel_size=w.voxel_size)
+        # the same frame against a fresh copy of the same map: this call plans its registration (grid, staging copy) from the first
+        # one's survivor count instead of the worst case, and must land on the same pose
+        gm2 = gpu_map_from_oracle(kb, gpu_ctx, om)
+        pose2, _, g_src2, res2 = kb.RegisterFrame(gm2, frame, stamps, deskew_motion, l2b, w.last_pose, w.rel_odom, w.tau, max_range=100.0,
+                                                  min_range=0.5, deskew=deskew, voxel_size=w.voxel_size)
+    finally:
+        gpu_ctx.set_option("frame_sync", 0)
     assert res.status == 0 and res.iterations == ostats.iterations
+    d2 = ko.pose_delta(pose2, pose)
+    assert res2.status == 0 and res2.iterations == res.iterations and d2[0] < 1e-12 and d2[1] < 1e-12 and np.array_equal(g_src2, g_src)
     if deskew:  # sin/cos of the de-skew differ in the last bits between device and glibc
         assert g_frame.shape == in_base.shape and np.abs(g_frame - in_base).max() < 1e-12
         assert g_src.shape == src.shape and np.abs(g_src - src).max() < 1e-12

@@ -37,13 +37,19 @@ def test_map_addpoints_bit_exact(oracle, gpu_ctx):
     for it in range(6):
         # clustered points: many per voxel, negative coordinates, repeated inserts
         pts = rng.normal(size=(6000, 3)) * [6.0, 6.0, 1.5] + [-2.0, 1.0, 0.0]
+        if it == 4:  # a dense blob: hundreds of candidates per voxel (the long pending lists of k_add_commit)
+            pts = np.concatenate([pts, rng.uniform(-1.0, 1.0, size=(3000, 3)) + [20.0, -7.0, 0.5]])
         om.add_points(pts)
         gm.AddPoints(pts)
         assert gm.num_points() == om.num_points() and gm.num_voxels() == om.num_voxels()
     k1, c1, p1 = sorted_voxels(*gm.export_voxels())
     k0, c0, p0 = om.export_voxels()
     assert np.array_equal(k1, k0) and np.array_equal(c1, c0) and np.array_equal(p1, p0)
-    assert not gm.Empty() and len(gm.Pointcloud()) == om.num_points()
+    # Pointcloud(): every stored point exactly once (packed on the device, block order)
+    cloud = gm.Pointcloud()
+    assert not gm.Empty() and cloud.shape == (om.num_points(), 3)
+    rows = lambda a: a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]
+    assert np.array_equal(rows(cloud), rows(p0))
     gm.Clear()
     assert gm.Empty() and gm.num_points() == 0
 
