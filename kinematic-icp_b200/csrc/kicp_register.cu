@@ -992,8 +992,15 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
     if (PERSISTENT) {
         if (a.collect_stats) stats_flush(st, n_probe, n_cand, n_line);
         KR_PROF_FLUSH
-        // the last CTA to leave zeroes the counters for the next registration on this stream
         __syncthreads();
+        // the result block goes straight to the caller's page-locked host memory (no copy-engine operation after the kernel)
+        if (blockIdx.x == 0 && a.result_host != nullptr) {
+            const double *src = reinterpret_cast<const double *>(&st->result);
+            double *dst = reinterpret_cast<double *>(a.result_host);
+            for (unsigned i = threadIdx.x; i < sizeof(kicp_reg_result) / sizeof(double); i += KR_THREADS) dst[i] = __ldcg(src + i);
+            __threadfence_system();
+        }
+        // the last CTA to leave zeroes the counters for the next registration on this stream
         if (threadIdx.x == 0) {
             __threadfence();
             const unsigned left = atomicAdd(&st->exit_ctr, 1u);

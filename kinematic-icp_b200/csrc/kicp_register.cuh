@@ -53,6 +53,7 @@ struct KernelArgs {
     float *nn_l;                   // certified lower bound on the distance to every candidate OTHER than those two
     float *nn_seed;                // distance to the old neighbour from the new position (pruning bound of the repeated search)
     unsigned int *todo;            // points of the current pass that need the search
+    kicp_reg_result *result_host;   // optional: device-visible alias of the caller's page-locked result block (written by CTA 0 at the end)
     unsigned long long timeout_ns;  // device-side waits (upload flags, peers) give up after this long
 };
 

@@ -154,6 +154,16 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
         ka.nn_g = c->d_nn_g, ka.nn_g2 = c->d_nn_g2, ka.nn_l = c->d_nn_l, ka.nn_seed = c->d_nn_seed, ka.todo = c->d_todo;
     }
     ka.timeout_ns = (unsigned long long)c->spin_timeout_ms * 1000000ull;
+    // A result block in page-locked host memory (kicp_host_alloc, the context's own staging) is written by the persistent kernel
+    // itself; anything else is filled by a copy after the kernel.
+    ka.result_host = nullptr;
+    if (result && c->persistent && (!sharded || c->p2p_ready) && m->num_blocks != 0 && p->max_num_iterations > 0) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, result) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            ka.result_host = static_cast<kicp_reg_result *>(at.devicePointer);
+        else
+            cudaGetLastError();  // (ordinary memory: not an error, just not ours to write)
+    }
     const int n = (int)scan->n;
     const bool p2p = sharded && c->p2p_ready;
     const bool persistent = c->persistent && (!sharded || p2p);
@@ -238,7 +248,7 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
             }
         }
     }
-    if (result)
+    if (result && !ka.result_host)
         KICP_CUDA(cudaMemcpyAsync(result, (const char *)c->d_state + kr_offset_result(), sizeof(kicp_reg_result), cudaMemcpyDeviceToHost,
                                   c->stream));
     return KICP_OK;

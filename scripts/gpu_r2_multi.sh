@@ -3,7 +3,8 @@
 N=${1:-2}
 mkdir -p gpurun_out
 export KICP_SPIN_TIMEOUT_MS=20000
-nvidia-smi -L
+nvidia-smi -L | head -8
+timeout 400 python -m pytest tests/test_multigpu.py -m gpu -x -q 2>&1 | tail -2
 for mode in p2p nccl; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 scripts/sharded_check.py 2 $mode 2>&1 | grep -E "SHARDED|Error|error|Traceback" | head -5
 done
