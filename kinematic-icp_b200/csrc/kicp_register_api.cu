@@ -81,12 +81,18 @@ struct HostUpload {
     int64_t stride;   // bytes per point
 };
 static int issue_chunks(kicp_ctx *c, const HostUpload &hu) {
-    for (int k = 0; k < KICP_UPLOAD_CHUNKS; ++k) {
-        const int64_t lo = std::min<int64_t>(hu.n, k * hu.wpc * 32), hi = std::min<int64_t>(hu.n, (k + 1) * hu.wpc * 32);
+    // The kernel always sees KICP_UPLOAD_CHUNKS segments; the host groups them into copies of at least ~384 KB (a small frame is
+    // ONE copy and one flag copy: every DMA operation costs microseconds, which a 24 KB scan cannot win back by overlapping).
+    const int64_t bytes = hu.n * hu.stride;
+    const int copies = (int)std::max<int64_t>(1, std::min<int64_t>(KICP_UPLOAD_CHUNKS, bytes / (384 << 10)));
+    for (int j = 0; j < copies; ++j) {
+        const int k0 = j * KICP_UPLOAD_CHUNKS / copies, k1 = (j + 1) * KICP_UPLOAD_CHUNKS / copies;  // segments [k0, k1)
+        const int64_t lo = std::min<int64_t>(hu.n, k0 * hu.wpc * 32), hi = std::min<int64_t>(hu.n, k1 * hu.wpc * 32);
         if (hi > lo)
             KICP_CUDA(cudaMemcpyAsync(hu.dst + lo * hu.stride, hu.src + lo * hu.stride, (size_t)((hi - lo) * hu.stride),
                                       cudaMemcpyHostToDevice, c->copy_stream));
-        KICP_CUDA(cudaMemcpyAsync(c->d_chunk_flags + k, c->h_chunk_tags + k, sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
+        KICP_CUDA(cudaMemcpyAsync(c->d_chunk_flags + k0, c->h_chunk_tags + k0, (size_t)(k1 - k0) * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                  c->copy_stream));
     }
     return KICP_OK;
 }
