@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1 sharded mode: fused peer-memory exchange inside the persistent kernel (default) or NCCL allreduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-replay", action="store_true", help="skip the whole-pipeline replay (kicp_replay) reported under `replay`")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between steps")
     return ap.parse_args()
 
@@ -308,6 +309,32 @@ def emit(line):
         os.dup2(2, 1)
 
 
+def run_pipeline_replay(frames=24, beams=64, n_az=2048):
+    """Row (f) of SURVEY.md 8 on the record: a synthetic 64-beam drive (BASELINE.json configs[4] shape, one sequence) written as a
+    .kseq file and replayed by the product's native harness, kinematic-icp_b200/bin/kicp_replay — every frame through
+    kinematic_icp::pipeline::KinematicICP::RegisterFrame of the C++ facade (float32 ingest, de-skew, filters, both down-samples,
+    registration, map update on the device), wall clock over the loop, second of two repetitions.  Not part of the timed steps."""
+    exe = os.path.join(ROOT, "kinematic-icp_b200", "bin", "kicp_replay")
+    if not os.path.exists(exe):
+        return {"unavailable": "kinematic-icp_b200/bin/kicp_replay not built"}
+    from oracle import sequences as S
+    with tempfile.TemporaryDirectory() as d:
+        seq = S.make_sequence(n_frames=frames, beams=beams, n_az=n_az, seed=4242, deskew=True)
+        kseq, tum = os.path.join(d, "drive.kseq"), os.path.join(d, "drive.tum")
+        S.write_kseq(seq, kseq)
+        out = {}
+        for name, extra in (("pinned", []), ("pageable", ["--pageable"])):
+            r = subprocess.run([exe, kseq, tum, "--repeat", "2"] + extra, capture_output=True, text=True, timeout=300)
+            lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            if r.returncode != 0 or not lines:
+                return {"unavailable": "kicp_replay failed: " + r.stderr.strip()[-200:]}
+            out[name] = json.loads(lines[-1])
+    return {"metric": "frames/s through KinematicICP::RegisterFrame (offline replay, 1 sequence)", "value": out["pinned"]["frames_per_s"],
+            "ms_per_frame": out["pinned"]["ms_per_frame"], "pageable_host_buffers": out["pageable"]["frames_per_s"], "frames": frames,
+            "points_per_frame": out["pinned"]["points_per_frame"], "harness": "kinematic-icp_b200/bin/kicp_replay (C++, float32 ingest, de-skew on)",
+            "data": "synthetic %d-beam x %d drive" % (beams, n_az)}
+
+
 def main():
     args = parse_args()
     quiet_stdout()
@@ -530,6 +557,10 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cpu_baseline, _ = time_cpu(w, 5, 1, single_thread_steps=1)
 
+        replay = None
+        if world == 1 and args.workload == 4 and not args.no_cpu_baseline and not args.no_replay:
+            replay = run_pipeline_replay()
+
         # ---- roofline of the registration kernel ---------------------------------------------------------------
         cbar, kbar = w.map.neighbourhood_stats(w.scan, w.prior)
         a_pt = 16.0 + 27.0 * 16.0 + cbar * 16.0  # logical gather bytes per point per pass
@@ -615,6 +646,8 @@ def main():
                 "registration kernel": prof.assoc_ms / max(prof.registrations, 1),
                 "launches_after_convergence": prof.idle_ms / max(prof.registrations, 1)},
         }
+        if replay is not None:
+            line["replay"] = replay
         if cross_rank_identical is not None:
             line["cross_rank_identical"] = cross_rank_identical
         if replicas_run is not None:

@@ -52,3 +52,21 @@ def unpack_sequence(z, deskew):
     frames = [z["seq_frames"][off[i]:off[i + 1]].astype(np.float64) for i in range(len(z["seq_lens"]))]
     stamps = [np.linspace(0.0, 1.0, len(f)) if deskew else np.zeros(0) for f in frames]
     return dict(frames=frames, stamps=stamps, odoms=list(z["seq_odoms"]), lidar_to_base=z["seq_lidar_to_base"], start=z["seq_start"])
+
+
+def write_kseq(seq, path, header_stamps=None):
+    """The sequence as a .kseq file, the input of the product's native replay harness (kinematic-icp_b200/cpp/tools/kicp_replay.cpp
+    documents the layout): float32 points as a PointCloud2 message carries them, per-point stamps, the wheel odometry of every frame."""
+    import struct
+    with open(path, "wb") as f:
+        f.write(b"KSEQ1\0\0\0")
+        f.write(struct.pack("<ii", len(seq["frames"]), 0))
+        f.write(np.asarray(seq["lidar_to_base"], dtype="<f8").tobytes())
+        f.write(np.asarray(seq["start"], dtype="<f8").tobytes())
+        for k, (fr, st, od) in enumerate(zip(seq["frames"], seq["stamps"], seq["odoms"])):
+            has = 1 if len(st) else 0
+            f.write(struct.pack("<iid", len(fr), has, float(header_stamps[k]) if header_stamps is not None else 0.1 * k))
+            f.write(np.asarray(od, dtype="<f8").tobytes())
+            f.write(np.ascontiguousarray(fr, dtype="<f4").tobytes())
+            if has:
+                f.write(np.ascontiguousarray(st, dtype="<f8").tobytes())

@@ -115,3 +115,23 @@ def test_sweep_timing_matches_timestamp_handler():
     # no stamps: the interval is [last processed, header]
     s4, last, be = process([], 7.5, 7.4)
     assert len(s4) == 0 and be.tolist() == [7.4, 7.5] and last == 7.5
+
+
+def test_replay_harness_binary_is_built_and_has_no_cpu_fallback(tmp_path):
+    """kicp_replay (the product's offline_node counterpart) is part of the build; without a CUDA device it refuses to run."""
+    import subprocess
+    import __graft_entry__ as g
+    g.build()
+    exe = os.path.join(ROOT, "kinematic-icp_b200", "bin", "kicp_replay")
+    assert os.path.exists(exe)
+    usage = subprocess.run([exe], capture_output=True, text=True)
+    assert usage.returncode == 2 and "usage:" in usage.stderr
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        (tmp_path / "empty.kseq").write_bytes(b"KSEQ1\0\0\0" + b"\0" * 120)
+        run = subprocess.run([exe, str(tmp_path / "empty.kseq"), str(tmp_path / "o.tum")], capture_output=True, text=True)
+        assert run.returncode == 1 and "CUDA" in run.stderr and not (tmp_path / "o.tum").exists()
