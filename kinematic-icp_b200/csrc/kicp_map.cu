@@ -163,6 +163,7 @@ extern "C" int kicp_ctx_destroy(kicp_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     kicp_comm_destroy(ctx);
     if (ctx->frontend_free) ctx->frontend_free(ctx);
+    if (ctx->sorted_free) ctx->sorted_free(ctx);
     if (ctx->upload_scan) kicp_scan_destroy(ctx->upload_scan);
     cudaFree(ctx->d_state);
     cudaFree(ctx->d_partials);
