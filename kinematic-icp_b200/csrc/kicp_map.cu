@@ -67,6 +67,7 @@ extern "C" int kicp_ctx_create(int device, kicp_ctx **out) {
     if (const char *e = getenv("KICP_CTAS_PER_SM")) c->ctas_per_sm_cap = std::min(16, std::max(0, atoi(e)));
     if (const char *e = getenv("KICP_SPIN_TIMEOUT_MS")) c->spin_timeout_ms = std::max(1, atoi(e));
     if (const char *e = getenv("KICP_FRAME_SYNC")) c->frame_sync = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("KICP_ENGINE")) c->engine = std::min(2, std::max(0, atoi(e)));
     *out = c;
     return KICP_OK;
 }

@@ -108,7 +108,6 @@ static int sorted_reserve(kicp_ctx *c, int64_t n) {
 
 static int reg_reserve(kicp_ctx *c) {
     if (c->d_state) return KICP_OK;
-    if (const char *e = getenv("KICP_ENGINE")) c->engine = std::max(0, std::min(2, atoi(e)));
     KICP_CUDA(cudaMalloc((void **)&c->d_state, kr_state_bytes()));
     KICP_CUDA(cudaMemset(c->d_state, 0, kr_state_bytes()));
     int per_sm_p = 0, per_sm_m = 0;
@@ -237,6 +236,7 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
     // the voxel-sorted engine: single GPU, persistent launch (the sharded exchange and the one-launch-per-pass path stay pooled)
     const bool use_sorted = persistent && !sharded && ka.init.max_iter > 0 && (c->engine == 2 || (c->engine == 1 && n_plan >= 49152));
     if (use_sorted) KICP_TRY(sorted_reserve(c, scan->n));
+    c->last_engine = use_sorted ? 1 : 0;
 
     kicp_ctx::ProfReg *pr = nullptr;
     if (c->profiling && (int64_t)c->prof.size() < c->prof_cap) {
@@ -298,7 +298,9 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
                 sa.stats = reinterpret_cast<unsigned long long *>((char *)c->d_state + kr_offset_stats());
                 sa.scan = ka.scan, sa.map = ka.map, sa.partials = sc->partials, sa.up = ka.up, sa.init = ka.init;
                 sa.pow2_voxel = ka.pow2_voxel, sa.collect_stats = ka.collect_stats;
-                sa.bin_key = sc->bin_key, sa.bin_cnt = sc->bin_cnt, sa.bin_mask = sc->slots - 1u;
+                uint32_t bslots = 1024;  // at least two slots per point of this frame (the allocation covers two per point of capacity)
+                while ((int64_t)bslots < 2 * (int64_t)scan->n && bslots < sc->slots) bslots <<= 1;
+                sa.bin_key = sc->bin_key, sa.bin_cnt = sc->bin_cnt, sa.bin_mask = bslots - 1u;
                 sa.pslot = sc->pslot, sa.sorted = sc->sorted, sa.nn_g = sc->nn_g;
                 sa.result_host = ka.result_host, sa.timeout_ns = ka.timeout_ns;
                 int per_sm_s = sc->ctas_per_sm;
@@ -355,6 +357,7 @@ extern "C" int kicp_debug_last_timing(kicp_ctx *c, double *out /* [KICP_MAX_ITER
                          cudaMemcpyDeviceToHost));
     return KICP_OK;
 }
+extern "C" int kicp_debug_last_engine(kicp_ctx *c) { return c ? c->last_engine : -1; }  // 0 = pooled windows, 1 = voxel-sorted lanes
 extern "C" int kicp_debug_last_stats(kicp_ctx *c, uint64_t out[4] /* probes, candidate points, 128-byte lines, 0 */) {
     if (!c || !c->d_state || !out) return KICP_ERR_INVALID;
     KICP_CUDA(cudaStreamSynchronize(c->stream));

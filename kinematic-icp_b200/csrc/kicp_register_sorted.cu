@@ -45,6 +45,9 @@ using namespace kicp_dev;
 #define KS_MINB 3                     // resident CTAs per SM the kernel is compiled for
 #endif
 #define KS_WARPS (KS_THREADS / 32)
+#ifndef KS_COUNT
+#define KS_COUNT(counter, value)      // tests/emu: warp-level work model (shift-loop steps, candidate-loop steps); nothing on the device
+#endif
 #define KS_NONE 0xFFFFFFFFu
 #define KS_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 
@@ -388,6 +391,8 @@ __global__ void __launch_bounds__(KS_THREADS, KS_MINB) k_register_sorted(const S
                     const bool act = mask != 0u;
                     const int k = act ? __ffs(mask) - 1 : 0;
                     mask &= mask - 1u;
+                    KS_COUNT(0 + (it ? 4 : 0), lane == 0 ? 1 : 0)
+                    KS_COUNT(2 + (it ? 4 : 0), act ? 1 : 0)
                     const int kx = vx + shift_x(k), ky = vy + shift_y(k), kz = vz + shift_z(k);
                     uint32_t h = voxel_hash(kx, ky, kz) & mmask;
                     uint32_t meta = KICP_SLOT_EMPTY;
@@ -417,6 +422,8 @@ __global__ void __launch_bounds__(KS_THREADS, KS_MINB) k_register_sorted(const S
                     const unsigned first = meta == KICP_SLOT_EMPTY ? 0u : (meta >> 8) * (unsigned)mcap;  // the run's first point
                     if (a.collect_stats) n_probe += act ? 1 : 0, n_cand += cnt, n_line += (cnt + 3) >> 2;
                     const int maxcnt = __reduce_max_sync(FULL, cnt);
+                    KS_COUNT(1 + (it ? 4 : 0), lane == 0 ? (maxcnt + 1) / 2 : 0)
+                    KS_COUNT(3 + (it ? 4 : 0), cnt)
                     for (int j = 0; j < maxcnt; j += 2) {  // warp-uniform trip count; two independent 256-bit loads in flight
                         const bool h0 = j < cnt, h1 = j + 1 < cnt;
                         const KsPoint c0 = ks_ld_map_point(mpts + (size_t)(first + (h0 ? (unsigned)j : 0u)) * KICP_PSTRIDE);

@@ -5,6 +5,9 @@
 #include "cuda_emu.hpp"
 
 #define KS_EMU 1
+// warp-level work model: [0] shift-loop steps, [1] candidate-loop steps (2 points each), [2] lane visits, [3] candidate points; +4: passes >= 1
+static unsigned long long ks_emu_counters[8];
+#define KS_COUNT(counter, value) __atomic_fetch_add(&ks_emu_counters[counter], (unsigned long long)(value), __ATOMIC_RELAXED);
 // the few PTX helpers of the kernel file, host versions
 struct KsPoint;
 static inline unsigned long long ks_gtime_ns() {
@@ -33,7 +36,7 @@ static inline P ks_emu_ld_point(const double *p) {
 extern "C" int ks_emu_register(const int32_t *keys, const int32_t *counts, const double *pts, int64_t nvox, int32_t cap, double voxel_size,
                                const void *scan, int64_t n, int32_t f32, const double last[7], const double odom[7], double tau,
                                const kicp_reg_params *params, int32_t grid, kicp_reg_result *result, double *sorted_out /* [n][4] or null */,
-                               uint64_t *stats_out /* [3] probes, candidate points, 128-byte lines; or null */) {
+                               uint64_t *stats_out /* [11] probes, candidate points, 128-byte lines, the 8 work-model counters; or null */) {
     uint32_t nslots = 1024;
     while ((int64_t)nslots < 4 * nvox) nslots <<= 1;
     std::vector<int4> slots(nslots, make_int4(0, 0, 0, (int)KICP_SLOT_EMPTY));
@@ -76,6 +79,7 @@ extern "C" int ks_emu_register(const int32_t *keys, const int32_t *counts, const
     a.nn_g = nn.data();
     a.result_host = nullptr, a.timeout_ns = 600ull * 1000000000ull;
     emu::launch(grid, KS_THREADS, [a]() { k_register_sorted<0>(a); });
+    if (stats_out) for (int k = 0; k < 8; ++k) stats_out[3 + k] = ks_emu_counters[k], ks_emu_counters[k] = 0;
     if (stats_out) stats_out[0] = stats[0], stats_out[1] = stats[1], stats_out[2] = stats[2];
     if (sorted_out) memcpy(sorted_out, sorted.data(), (size_t)n * 4 * sizeof(double));
     // what every launch must leave behind for the next one: an empty table, zero counts, zero counters

@@ -43,7 +43,7 @@ def run_emu(lib, om, scan, last, odom, tau, grid, max_iter=10, conv=1e-3, adapti
     p = _capi.RegParams(max_iter, 1 if adaptive else 0, conv, fixed_reg)
     r = _capi.RegResult()
     so = np.zeros((max(n, 1), 4))
-    stats = (C.c_uint64 * 3)()
+    stats = (C.c_uint64 * 11)()
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
     rc = lib.ks_emu_register(vp(keys), vp(counts), vp(pts), C.c_int64(len(counts)), C.c_int32(om.max_points_per_voxel), C.c_double(om.voxel_size),
                              vp(scan), C.c_int64(n), C.c_int32(1 if f32 else 0), vp(last), vp(odom), C.c_double(tau), C.byref(p), C.c_int32(grid),
