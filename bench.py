@@ -42,9 +42,6 @@ def parse_args():
     ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"])
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1 sharded mode: fused peer-memory exchange inside the persistent kernel (default) or NCCL allreduce")
-    ap.add_argument("--engine", type=int, default=None, choices=[0, 1, 2],
-                    help="registration kernel of single-GPU registrations (kicp_ctx_set_option 'engine'): 0 pooled windows, 1 voxel-sorted "
-                         "lanes for frames of 49152+ points, 2 voxel-sorted lanes always; default: the library's")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-replay", action="store_true", help="skip the whole-pipeline replay (kicp_replay) reported under `replay`")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between steps")
@@ -378,8 +375,6 @@ def main():
         w = W.Workload(args.workload)
 
     ctx = kb.Context(local_rank)
-    if args.engine is not None:
-        ctx.set_option("engine", args.engine)
     gm = kb.VoxelHashMap(ctx, w.voxel_size, w.max_range, w.max_points_per_voxel)
     gm.load_voxels(*w.map.export_voxels())  # replicated on every GPU
     reg = kb.KinematicRegistration()  # reference defaults: 10 iterations, 1e-3, adaptive regularisation
@@ -531,7 +526,6 @@ def main():
     reg.enqueue(scan, gm, w.last_pose, w.rel_odom, w.tau, res_stats, sharded=primary_sharded)
     probes, cands, lines, _ = ctx.last_stats()
     ctx.set_option("stats", 0)
-    sorted_engine = ctx.last_engine() == 1  # which registration kernel the timed path ran (option "engine")
     scan.close()
     # per-rank pass anatomy (max over ranks of each column, median over the passes of the last timed registration)
     tim = main_run["timing"][: max(int(main_run["result"].iterations), 1)] / 1e3  # us
@@ -585,27 +579,22 @@ def main():
             achieved = bytes_per_launch / t_launch / 1e9
             # what the kernel really moves from L2/HBM into the SMs, from its own counters: two 16-byte hash slots per probe,
             # 128 bytes per line of candidate points, the scan point and the winner's line once per point and pass
-            if sorted_engine:  # one 32-byte load per candidate point; the sorted frame point, the previous neighbour (index + point), the winner
-                touched_per_pass = (probes * 32.0 + cands * 32.0) / max(iters, 1) + n_local * (32.0 + 8.0 + 32.0 + 32.0)
-            else:
-                touched_per_pass = (probes * 32.0 + lines * 128.0) / max(iters, 1) + n_local * (24.0 + 128.0)
+            touched_per_pass = (probes * 32.0 + lines * 128.0) / max(iters, 1) + n_local * (24.0 + 128.0)
             l2_peak = measure_l2_bandwidth(ctx)
             t_pass = t_launch / max(passes_per_launch, 1e-9)
             touched_gbs = touched_per_pass / t_pass / 1e9
-            ksrc = "kicp_register_sorted.cu" if sorted_engine else "kicp_register.cu"
-            kjson = "ncu_traffic_sorted.json" if sorted_engine else "ncu_traffic.json"
-            traffic, traffic_note = None, "no ncu capture of this build of %s under profiles/ (profiles/%s)" % (ksrc, kjson)
-            ncu_path = os.path.join(ROOT, "profiles", kjson)
-            src_sha = sha256_file(os.path.join(ROOT, "kinematic-icp_b200", "csrc", ksrc))
+            traffic, traffic_note = None, "no ncu capture of this build of kicp_register.cu under profiles/ (profiles/ncu_traffic.json)"
+            ncu_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            src_sha = sha256_file(os.path.join(ROOT, "kinematic-icp_b200", "csrc", "kicp_register.cu"))
             if os.path.exists(ncu_path) and args.workload == 4 and world == 1:
                 tj = json.load(open(ncu_path))
                 if tj.get("kernel_source_sha256") == src_sha:
                     traffic = tj.get("dram_bytes_per_launch")
                     traffic_note = "dram__bytes_read+write per launch, ncu --set full capture of this very source (%s)" % tj.get("source")
                 else:
-                    traffic_note = "profiles/%s was captured for another build of %s: not reported" % (kjson, ksrc)
+                    traffic_note = "profiles/ncu_traffic.json was captured for another build of kicp_register.cu: not reported"
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": traffic, "traffic_note": traffic_note, "kernel": "k_register_sorted" if sorted_engine else "k_register<true>",
+                        "traffic": traffic, "traffic_note": traffic_note, "kernel": "k_register<true>",
                         "launch_us": t_launch * 1e6, "passes_per_launch": passes_per_launch, "kernel_us": t_pass * 1e6,
                         "launches_timed": int(prof.assoc_launches), "iterations_timed": int(prof.assoc_iterations),
                         "algorithmic_bytes_per_launch": bytes_per_launch, "algorithmic_bytes_per_point": a_pt,
@@ -615,9 +604,8 @@ def main():
                                     "candidates_per_point_per_pass": cands / max(iters, 1) / n_local,
                                     "lines_per_point_per_pass": lines / max(iters, 1) / n_local,
                                     "note": "bytes the kernel itself requests from L2 per pass, from its device-side counters (option "
-                                            "'stats': 32 B per hash probe, " + ("32 B per candidate point, the sorted frame point, the previous "
-                                            "neighbour and the winner per point" if sorted_engine else "128 B per line of candidate points, the scan "
-                                            "point and the winner's line per point") + "), against the L2 read bandwidth measured on this GPU in this run — "
+                                            "'stats': 32 B per hash probe, 128 B per line of candidate points, the scan point and the "
+                                            "winner's line per point), against the L2 read bandwidth measured on this GPU in this run — "
                                             "the physical counterpart of the logical figure above"},
                         "note": "achieved/frac = LOGICAL gather bytes of SURVEY.md 8(d) (16 + 27*16 + c*16 per point and pass, c = all "
                                 "%.0f points of the 27 voxels) / CUDA-event duration, against the measured HBM copy peak: the kernel prunes "
@@ -637,7 +625,6 @@ def main():
                                 "%d independent replicas" % world)),
                 "l2": "flushed before every timed step (%d MiB write, untimed)" % (L2_FLUSH_BYTES >> 20)
                       if not args.no_flush else "NOT flushed (diagnostic run)",
-                "engine": ("voxel-sorted lanes (kicp_register_sorted.cu)" if sorted_engine else "pooled windows (kicp_register.cu)"),
                 "iterations_per_registration": iters}),
             "ms_per_iter": main_run["ms_per_step"] / max(iters, 1),
             "clocks": clocks,
@@ -651,8 +638,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "pose_delta_vs_cpu": pose_delta,
-            "pass_anatomy_us": {"columns": (["sort of the frame (first pass only)", "-", "search (CTA 0)", "barrier wait", "reduce", "solve"] if sorted_engine else
-                                            ["certificate phase", "its grid barrier", "search phase (CTA 0)", "barrier wait", "reduce (+ exchange)", "solve"]),
+            "pass_anatomy_us": {"columns": ["certificate phase", "its grid barrier", "search phase (CTA 0)", "barrier wait", "reduce (+ exchange)", "solve"],
                                 "median_over_passes_max_over_ranks": anatomy_max, "min_over_ranks": anatomy_min,
                                 "note": "device %globaltimer probes on CTA 0 of every rank, last timed registration"},
             "kernel_time_split_ms_per_step": None if prof is None else {

@@ -87,11 +87,7 @@ int64_t kicp_ctx_launch_count(kicp_ctx *ctx);
  * scans of 49152 points or more (default: smaller scans gain nothing from the extra phase), 2 = always, 0 = never; "overlap_upload" 1 = the
  * host-pointer entry points overlap the frame's upload with the first pass (default); "spin_timeout_ms" = bound of every
  * device-side wait (upload flags, peers of the fused exchange; default 20000); "frame_sync" 1 = kicp_register_frame reads the
- * survivor counts back in the middle of a frame (legacy order; default 0 = ONE host synchronisation per frame, at its end);
- * "engine" = which registration kernel a single-GPU persistent registration runs: 0 = pooled warp-cooperative windows
- * (kicp_register.cu), 1 = voxel-sorted lanes (kicp_register_sorted.cu: the frame is grouped by voxel once, then searched one
- * point per lane) for frames of 49152 points or more, 2 = voxel-sorted lanes for every frame; sharded and one-launch-per-pass
- * registrations always use the pooled kernel.  The environment variable KICP_ENGINE gives the initial value.
+ * survivor counts back in the middle of a frame (legacy order; default 0 = ONE host synchronisation per frame, at its end).
  * Unknown names fail with KICP_ERR_INVALID.
  * Every setting computes the same result up to the summation order. */
 int kicp_ctx_set_option(kicp_ctx *ctx, const char *name, int32_t value);

@@ -61,12 +61,6 @@ struct kicp_ctx {
     float *d_nn_l = nullptr, *d_nn_seed = nullptr;
     int64_t nn_cap = 0;
     int nn_cache = 1;  // option "nn_cache"
-    // option "engine": 0 = pooled windows (kicp_register.cu), 1 = voxel-sorted lanes (kicp_register_sorted.cu) for frames of 49152
-    // points or more on a single GPU, 2 = voxel-sorted lanes for every single-GPU persistent registration
-    int engine = 0;
-    int last_engine = 0;                           // engine of the last enqueued registration (0 pooled, 1 voxel-sorted)
-    void *sorted = nullptr;                        // scratch of the voxel-sorted engine (kicp_register_api.cu owns the type)
-    void (*sorted_free)(kicp_ctx *) = nullptr;
     int frame_sync = 0;       // option "frame_sync": 1 = kicp_register_frame reads the survivor counts back mid-frame (legacy order)
     int64_t reg_n_hint = 0;   // expected point count of the next registration whose exact count lives on the device (0 = none)
     kicp_scan *upload_scan = nullptr;  // staging scan used by the host-pointer entry points

@@ -11,14 +11,11 @@
 #include <vector>
 
 #include "kicp_register.cuh"
-#include "kicp_register_sorted.cuh"
 
 // Per-context options (kicp_ctx_set_option): "persistent" 1 = one cooperative launch per registration (default), 0 = one
 // launch per IRLS iteration; "stats" 1 = count probes / candidate points / lines on the device (kicp_debug_last_stats);
 // "ctas_per_sm" caps the resident CTAs per SM the grid is sized for (0 = occupancy limit); "nn_cache" 0 / 1 / 2 = never / for scans of
-// 49152 points or more (default) / always carry every point's neighbour and its certificate from pass to pass; "spin_timeout_ms" bounds every device-side wait;
-// "engine" 0 = pooled windows (default) / 1 = voxel-sorted lanes for single-GPU frames of 49152 points or more / 2 = voxel-sorted lanes always
-// (environment variable KICP_ENGINE sets the initial value).
+// 49152 points or more (default) / always carry every point's neighbour and its certificate from pass to pass; "spin_timeout_ms" bounds every device-side wait.
 extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value) {
     if (!c || !name) return KICP_ERR_INVALID;
     if (!strcmp(name, "persistent")) {
@@ -36,9 +33,6 @@ extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value)
     } else if (!strcmp(name, "nn_cache")) {
         if (value < 0 || value > 2) return KICP_ERR_INVALID;
         c->nn_cache = value;
-    } else if (!strcmp(name, "engine")) {
-        if (value < 0 || value > 2) return KICP_ERR_INVALID;
-        c->engine = value;
     } else if (!strcmp(name, "overlap_upload")) {
         if (value != 0 && value != 1) return KICP_ERR_INVALID;
         c->overlap_upload = value;
@@ -48,60 +42,6 @@ extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value)
     } else {
         kicp_set_error(std::string("kicp_ctx_set_option: unknown option ") + name);
         return KICP_ERR_INVALID;
-    }
-    return KICP_OK;
-}
-
-// Scratch of the voxel-sorted engine (kicp_register_sorted.cu): the sort's table, the frame in voxel order, the neighbours
-// carried from pass to pass.  Sized by the largest frame seen (plus a quarter), freed with the context.
-struct SortedScratch {
-    SortedState *st = nullptr;
-    unsigned long long *bin_key = nullptr;
-    unsigned int *bin_cnt = nullptr;
-    uint32_t slots = 0;
-    uint2 *pslot = nullptr;
-    double *sorted = nullptr;
-    unsigned int *nn_g = nullptr;
-    double *partials = nullptr;
-    int64_t cap = 0;
-    int ctas_per_sm = 0;
-};
-static void sorted_free(kicp_ctx *c) {
-    SortedScratch *sc = static_cast<SortedScratch *>(c->sorted);
-    if (!sc) return;
-    cudaFree(sc->st), cudaFree(sc->bin_key), cudaFree(sc->bin_cnt), cudaFree(sc->pslot), cudaFree(sc->sorted), cudaFree(sc->nn_g),
-        cudaFree(sc->partials);
-    delete sc;
-    c->sorted = nullptr;
-}
-static int sorted_reserve(kicp_ctx *c, int64_t n) {
-    SortedScratch *sc = static_cast<SortedScratch *>(c->sorted);
-    if (!sc) {
-        sc = new SortedScratch();
-        c->sorted = sc, c->sorted_free = sorted_free;
-        KICP_CUDA(cudaMalloc((void **)&sc->st, ks_state_bytes()));
-        KICP_CUDA(cudaMemset(sc->st, 0, ks_state_bytes()));
-        int per_sm = 0;
-        KICP_CUDA(ks_prepare(&per_sm));
-        sc->ctas_per_sm = std::max(per_sm, 1);
-        KICP_CUDA(cudaMalloc(&sc->partials, (size_t)2 * c->sm_count * sc->ctas_per_sm * 8 * sizeof(double)));
-    }
-    if (n > sc->cap || !sc->sorted) {
-        KICP_CUDA(cudaStreamSynchronize(c->stream));
-        cudaFree(sc->bin_key), cudaFree(sc->bin_cnt), cudaFree(sc->pslot), cudaFree(sc->sorted), cudaFree(sc->nn_g);
-        sc->bin_key = nullptr, sc->bin_cnt = nullptr, sc->pslot = nullptr, sc->sorted = nullptr, sc->nn_g = nullptr, sc->cap = 0;
-        const int64_t cap = n + n / 4 + 1024;
-        uint32_t slots = 1024;
-        while ((int64_t)slots < 2 * cap) slots <<= 1;  // at least two slots per point: the table cannot fill up
-        KICP_CUDA(cudaMalloc(&sc->bin_key, (size_t)slots * sizeof(unsigned long long)));
-        KICP_CUDA(cudaMalloc(&sc->bin_cnt, (size_t)slots * sizeof(unsigned int)));
-        KICP_CUDA(cudaMalloc(&sc->pslot, (size_t)cap * sizeof(uint2)));
-        KICP_CUDA(cudaMalloc(&sc->sorted, (size_t)cap * 4 * sizeof(double)));
-        KICP_CUDA(cudaMalloc(&sc->nn_g, (size_t)cap * sizeof(unsigned int)));
-        // every launch leaves the table empty and the counts zero; this is the first state
-        KICP_CUDA(cudaMemset(sc->bin_key, 0xFF, (size_t)slots * sizeof(unsigned long long)));
-        KICP_CUDA(cudaMemset(sc->bin_cnt, 0, (size_t)slots * sizeof(unsigned int)));
-        sc->slots = slots, sc->cap = cap;
     }
     return KICP_OK;
 }
@@ -233,10 +173,6 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
     const int n = (int)scan->n;
     const bool p2p = sharded && c->p2p_ready;
     const bool persistent = c->persistent && (!sharded || p2p);
-    // the voxel-sorted engine: single GPU, persistent launch (the sharded exchange and the one-launch-per-pass path stay pooled)
-    const bool use_sorted = persistent && !sharded && ka.init.max_iter > 0 && (c->engine == 2 || (c->engine == 1 && n_plan >= 49152));
-    if (use_sorted) KICP_TRY(sorted_reserve(c, scan->n));
-    c->last_engine = use_sorted ? 1 : 0;
 
     kicp_ctx::ProfReg *pr = nullptr;
     if (c->profiling && (int64_t)c->prof.size() < c->prof_cap) {
@@ -289,28 +225,7 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
                 pr->persistent = true;
                 KICP_CUDA(cudaEventRecord(e0, c->stream));
             }
-            if (use_sorted) {
-                SortedScratch *sc = static_cast<SortedScratch *>(c->sorted);
-                SortedArgs sa{};
-                sa.st = sc->st;
-                sa.result = reinterpret_cast<kicp_reg_result *>((char *)c->d_state + kr_offset_result());
-                sa.dbg = reinterpret_cast<double *>((char *)c->d_state + kr_offset_dbg());
-                sa.stats = reinterpret_cast<unsigned long long *>((char *)c->d_state + kr_offset_stats());
-                sa.scan = ka.scan, sa.map = ka.map, sa.partials = sc->partials, sa.up = ka.up, sa.init = ka.init;
-                sa.pow2_voxel = ka.pow2_voxel, sa.collect_stats = ka.collect_stats;
-                uint32_t bslots = 1024;  // at least two slots per point of this frame (the allocation covers two per point of capacity)
-                while ((int64_t)bslots < 2 * (int64_t)scan->n && bslots < sc->slots) bslots <<= 1;
-                sa.bin_key = sc->bin_key, sa.bin_cnt = sc->bin_cnt, sa.bin_mask = bslots - 1u;
-                sa.pslot = sc->pslot, sa.sorted = sc->sorted, sa.nn_g = sc->nn_g;
-                sa.result_host = ka.result_host, sa.timeout_ns = ka.timeout_ns;
-                int per_sm_s = sc->ctas_per_sm;
-                if (c->ctas_per_sm_cap > 0) per_sm_s = std::min(per_sm_s, c->ctas_per_sm_cap);
-                const int64_t chunks = (n_plan + 31) / 32, wpc = ks_threads() / 32;  // 32-point chunks; warps per CTA
-                const int grid_s = (int)std::max<int64_t>(1, std::min<int64_t>((chunks + wpc - 1) / wpc, (int64_t)c->sm_count * per_sm_s));
-                KICP_CUDA(ks_launch(grid_s, sa, c->stream));
-            } else {
-                KICP_CUDA(kr_launch_register(true, grid, ka, c->stream));
-            }
+            KICP_CUDA(kr_launch_register(true, grid, ka, c->stream));
             c->launches++;
             if (pr) KICP_CUDA(cudaEventRecord(e1, c->stream));
             if (dbg) {
@@ -357,7 +272,6 @@ extern "C" int kicp_debug_last_timing(kicp_ctx *c, double *out /* [KICP_MAX_ITER
                          cudaMemcpyDeviceToHost));
     return KICP_OK;
 }
-extern "C" int kicp_debug_last_engine(kicp_ctx *c) { return c ? c->last_engine : -1; }  // 0 = pooled windows, 1 = voxel-sorted lanes
 extern "C" int kicp_debug_last_stats(kicp_ctx *c, uint64_t out[4] /* probes, candidate points, 128-byte lines, 0 */) {
     if (!c || !c->d_state || !out) return KICP_ERR_INVALID;
     KICP_CUDA(cudaStreamSynchronize(c->stream));

@@ -52,14 +52,6 @@ class Context:
         check(L.kicp_debug_last_timing(self.h, dp(out)), "kicp_debug_last_timing")
         return out
 
-    def last_engine(self):
-        """Engine that ran the last enqueued registration: 0 = pooled windows (kicp_register.cu), 1 = voxel-sorted lanes
-        (kicp_register_sorted.cu); see option "engine"."""
-        L = lib()
-        L.kicp_debug_last_engine.argtypes = [C.c_void_p]
-        L.kicp_debug_last_engine.restype = C.c_int
-        return int(L.kicp_debug_last_engine(self.h))
-
     def last_stats(self):
         """(hash probes, candidate points evaluated, 128-byte lines loaded, 0) of the last registration run with option
         "stats" = 1 (kicp_debug_last_stats; synchronises the stream)."""

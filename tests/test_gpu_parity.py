@@ -10,7 +10,6 @@ import pytest
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL_T, TOL_R = 1e-6, 1e-7
-DEFAULT_ENGINE = int(os.environ.get("KICP_ENGINE", "0"))  # what the library starts with (kicp_ctx_set_option "engine")
 DBL_MAX = np.finfo(np.float64).max
 
 
@@ -151,19 +150,14 @@ def test_registration_configs_vs_oracle(oracle, gpu_ctx, workload, cfg):
     try:
         # launch shapes of the one registration kernel: persistent cooperative launch (default) / one launch per iteration,
         # grid capped at 1 CTA per SM / occupancy limit; the work counters on
-        # ... and both engines: 0 = pooled windows, 2 = voxel-sorted lanes (always), 1 = voxel-sorted lanes for large frames
-        for persistent, ctas, stats, cache, engine in ((1, 0, 0, 2, 0), (1, 0, 0, 0, 0), (0, 0, 0, 2, 0), (1, 1, 1, 2, 0), (0, 1, 0, 0, 0),
-                                                       (1, 0, 0, 1, 0), (1, 0, 0, 1, 2), (1, 1, 1, 1, 2), (1, 0, 0, 1, 1), (0, 0, 0, 1, 2)):
+        for persistent, ctas, stats, cache in ((1, 0, 0, 2), (1, 0, 0, 0), (0, 0, 0, 2), (1, 1, 1, 2), (0, 1, 0, 0), (1, 0, 0, 1)):
             gpu_ctx.set_option("persistent", persistent)
             gpu_ctx.set_option("ctas_per_sm", ctas)
             gpu_ctx.set_option("stats", stats)
             gpu_ctx.set_option("nn_cache", cache)  # neighbour certificates carried between passes: 2 = always, 0 = never, 1 = by scan size
-            gpu_ctx.set_option("engine", engine)
             pose, dt, ang = check_registration(ko, kb, gpu_ctx, w.map, gm, w.scan, w.last_pose, w.rel_odom, w.tau)
-            ran_sorted = gpu_ctx.last_engine() == 1
-            assert ran_sorted == bool(persistent and (engine == 2 or (engine == 1 and w.N >= 49152)))
-            print("cfg%d persistent=%d ctas_per_sm=%d nn_cache=%d engine=%d N=%d M=%d pose delta %.3e m %.3e rad" %
-                  (cfg, persistent, ctas, cache, engine, w.N, w.map.num_points(), dt, ang))
+            print("cfg%d persistent=%d ctas_per_sm=%d nn_cache=%d N=%d M=%d pose delta %.3e m %.3e rad" %
+                  (cfg, persistent, ctas, cache, w.N, w.map.num_points(), dt, ang))
             if stats:
                 probes, cands, lines = gpu_ctx.last_stats()[:3]
                 assert probes >= w.N and cands > 0 and lines > 0
@@ -172,7 +166,6 @@ def test_registration_configs_vs_oracle(oracle, gpu_ctx, workload, cfg):
         gpu_ctx.set_option("ctas_per_sm", 0)
         gpu_ctx.set_option("stats", 0)
         gpu_ctx.set_option("nn_cache", 1)
-        gpu_ctx.set_option("engine", DEFAULT_ENGINE)
     pose, dt, ang = check_registration(ko, kb, gpu_ctx, w.map, gm, w.scan, w.last_pose, w.rel_odom, w.tau)
     print("cfg%d defaults pose delta %.3e m %.3e rad" % (cfg, dt, ang))
     # float32 ingest (the reference's callers hold float32 PointCloud2 fields, RosUtils.cpp:30-39): the workload's scan is
@@ -186,19 +179,10 @@ def test_registration_configs_vs_oracle(oracle, gpu_ctx, workload, cfg):
     gm.close()
 
 
-@pytest.mark.parametrize("engine", [0, 2])
-def test_registration_edge_cases(oracle, gpu_ctx, workload, engine):
+def test_registration_edge_cases(oracle, gpu_ctx, workload):
     import kinematic_icp_b200 as kb
     ko = oracle
     w = workload(1)
-    gpu_ctx.set_option("engine", engine)
-    try:
-        _edge_cases(ko, kb, gpu_ctx, w)
-    finally:
-        gpu_ctx.set_option("engine", DEFAULT_ENGINE)
-
-
-def _edge_cases(ko, kb, gpu_ctx, w):
     # empty map: the prediction, no iterations (Registration.cpp:157)
     gm = kb.VoxelHashMap(gpu_ctx, 1.0, 100.0, 20)
     reg = kb.KinematicRegistration()
