@@ -114,6 +114,7 @@ struct RegState {
     kicp_reg_result result;
 };
 
+#ifndef KR_EMU  // (tests/emu compiles this file for the host against a SIMT emulator and supplies these few PTX helpers itself)
 __device__ __forceinline__ unsigned long long gtime_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -137,15 +138,18 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+#endif
 // one stored map point {x, y, z, pad}: a single 256-bit load (LDG.E.256, sm_100)
 struct __align__(32) Point4 {
     double x, y, z, w;
 };
+#ifndef KR_EMU
 __device__ __forceinline__ Point4 ld_point(const double *p) {
     Point4 r;
     asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
     return r;
 }
+#endif
 
 // Multi-launch path and the "nothing to do" case (empty map / max_iter <= 0): state in global memory.
 __global__ void k_reg_init(RegState *st, RegArgs a) {
@@ -301,7 +305,11 @@ __device__ __forceinline__ int voxel_of(double x, double vs, double inv_vs, int 
 // ---------------------------------------------------------------------------------------------------------------
 template <bool PERSISTENT>
 __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelArgs a) {
+#ifndef KR_EMU
     extern __shared__ __align__(16) unsigned char s_dyn[];  // KR_WARPS x WarpSm (more than the 48 KB static limit)
+#else
+    __shared__ __align__(16) unsigned char s_dyn[KR_WARPS * sizeof(WarpSm)];
+#endif
     __shared__ PoseState s_ps;
     __shared__ double s_part[KR_WARPS][8];
     __shared__ double s_sum[8];
@@ -1016,6 +1024,7 @@ __global__ void __launch_bounds__(KR_THREADS, KR_MINB) k_register(const KernelAr
 
 
 // ---------------------------------------------------------------------------------------- entry points for the API file
+#ifndef KR_EMU
 // Read bandwidth of an L2-resident buffer on this GPU: the physical ceiling of a path whose working set lives in L2 (bench.py
 // reports the registration kernel's touched bytes against it).  `bytes` (<= 64 MiB) are read `reps` times by one launch of a
 // grid-stride kernel with 128-bit loads; returns GB/s of the best of 3 launches.
@@ -1083,3 +1092,4 @@ cudaError_t kr_launch_l2_read(const void *buf, size_t bytes, int reps, unsigned 
     k_l2_read<<<grid, 256, 0, stream>>>((const uint4 *)buf, bytes / 16, reps, sink);
     return cudaGetLastError();
 }
+#endif  // KR_EMU

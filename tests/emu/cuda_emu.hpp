@@ -223,6 +223,9 @@ inline T __ldg(const T *p) { return *(const volatile T *)p; }
 template <class T>
 inline T __ldcg(const T *p) { return *(const volatile T *)p; }
 inline int4 __ldg(const int4 *p) { int4 v; memcpy(&v, p, sizeof(v)); return v; }
+#ifndef __restrict__
+#define __restrict__ __restrict
+#endif
 inline uint2 __ldcg(const uint2 *p) { uint2 v; memcpy(&v, p, sizeof(v)); return v; }
 template <class T>
 inline void __stcg(T *p, T v) { *(volatile T *)p = v; }
@@ -231,6 +234,7 @@ inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long cmp, unsigned long long v) {
     __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
     return cmp;
@@ -241,6 +245,18 @@ inline void __nanosleep(unsigned) {
 }
 
 // ---- arithmetic intrinsics
+inline float __double2float_rz(double x) {  // round towards zero
+    float f = (float)x;
+    if (std::fabs((double)f) > std::fabs(x)) f = std::nextafterf(f, 0.0f);
+    return f;
+}
+inline float __double2float_ru(double x) {  // round up
+    float f = (float)x;
+    if ((double)f < x) f = std::nextafterf(f, INFINITY);
+    return f;
+}
+inline long long __double_as_longlong(double x) { long long v; memcpy(&v, &x, 8); return v; }
+inline double __longlong_as_double(long long x) { double v; memcpy(&v, &x, 8); return v; }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline double __fma_rn(double a, double b, double c) { return __builtin_fma(a, b, c); }

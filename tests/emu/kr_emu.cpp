@@ -1,0 +1,137 @@
+// Host-side emulation of the registration kernel (kinematic-icp_b200/csrc/kicp_register.cu): the kernel SOURCE is compiled here
+// unchanged against tests/emu/cuda_emu.hpp and run as a small grid of fibers — one grid per "rank" for the sharded path, the
+// peers' mailboxes being plain host memory — on a map laid out exactly as the device holds it (kicp_internal.h).
+// Test infrastructure: tests/test_kernel_emu_cpu.py compares the results with the CPU oracle.  Never part of the product library.
+#include "cuda_emu.hpp"
+
+#define KR_EMU 1
+// the few PTX helpers of the kernel file, host versions
+static inline unsigned long long gtime_ns() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}
+static inline uint32_t ld_acquire_sys_u32(const uint32_t *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline unsigned int ld_acquire_gpu_u32(const unsigned int *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
+static inline unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+struct Point4;
+template <class P = Point4>
+static inline P kr_emu_ld_point(const double *p) {
+    P r;
+    r.x = p[0], r.y = p[1], r.z = p[2], r.w = p[3];
+    return r;
+}
+#define ld_point(p) kr_emu_ld_point(p)
+
+#include "../../kinematic-icp_b200/csrc/kicp_register.cu"
+
+#include <thread>
+#include <vector>
+
+namespace {
+struct HostMap {
+    std::vector<int4> slots;
+    std::vector<double> pts;
+    MapView view;
+};
+// the voxels laid out as the device map holds them: open addressing, linear probing, meta = block << 8 | count; 32-byte points
+void build_map(HostMap &m, const int32_t *keys, const int32_t *counts, const double *pts, int64_t nvox, int32_t cap, double voxel_size) {
+    uint32_t nslots = 1024;
+    while ((int64_t)nslots < 4 * nvox) nslots <<= 1;
+    m.slots.assign(nslots, make_int4(0, 0, 0, (int)KICP_SLOT_EMPTY));
+    m.pts.assign((size_t)std::max<int64_t>(nvox, 1) * cap * KICP_PSTRIDE, 0.0);
+    int64_t off = 0;
+    for (int64_t b = 0; b < nvox; ++b) {
+        uint32_t h = voxel_hash(keys[3 * b], keys[3 * b + 1], keys[3 * b + 2]) & (nslots - 1);
+        while ((uint32_t)m.slots[h].w != KICP_SLOT_EMPTY) h = (h + 1) & (nslots - 1);
+        m.slots[h] = make_int4(keys[3 * b], keys[3 * b + 1], keys[3 * b + 2], (int)(((uint32_t)b << 8) | (uint32_t)counts[b]));
+        for (int j = 0; j < counts[b]; ++j)
+            for (int d = 0; d < 3; ++d) m.pts[((size_t)b * cap + j) * KICP_PSTRIDE + d] = pts[(off + j) * 3 + d];
+        off += counts[b];
+    }
+    m.view = MapView{m.slots.data(), nslots - 1, m.pts.data(), cap, voxel_size};
+}
+struct RankScratch {
+    RegState st;
+    std::vector<double> partials;
+    std::vector<unsigned> nn_g, nn_g2, todo;
+    std::vector<float> nn_l, nn_seed;
+};
+}  // namespace
+
+// One registration of a frame split over `nranks` emulated GPUs (contiguous index ranges, as kb.shard_range does), every rank a
+// grid of `grid` CTAs.  persistent = 1: k_register<true> (nranks > 1: the fused peer-mailbox exchange); persistent = 0 (nranks == 1
+// only): one launch per pass, k_reg_init / k_register<false> / k_solve.  nn_cache = 1: certificates carried between passes.
+// results: one kicp_reg_result per rank.  stats: [3] probes, candidate points, lines of rank 0.  Returns 0, or a negative number
+// when a launch did not leave its counters as the next one needs them.
+extern "C" int kr_emu_register(const int32_t *keys, const int32_t *counts, const double *pts, int64_t nvox, int32_t cap, double voxel_size,
+                               const void *scan, int64_t n, int32_t f32, const double last[7], const double odom[7], double tau,
+                               const kicp_reg_params *params, int32_t grid, int32_t nranks, int32_t persistent, int32_t nn_cache,
+                               int32_t registrations, kicp_reg_result *results, uint64_t *stats) {
+    if (nranks < 1 || nranks > KICP_MAX_RANKS || (nranks > 1 && !persistent)) return -10;
+    HostMap map;
+    build_map(map, keys, counts, pts, nvox, cap, voxel_size);
+    std::vector<RankScratch> rs(nranks);
+    std::vector<P2PMailbox> boxes(nranks);
+    memset(boxes.data(), 0, sizeof(P2PMailbox) * nranks);
+    const int stride = f32 ? 12 : 24;
+    int rc = 0;
+    for (int reg = 0; reg < registrations; ++reg) {  // (several in a row: the counters a launch leaves behind, the mailbox parity and tags)
+        std::vector<std::thread> ranks;
+        for (int r = 0; r < nranks; ++r) {
+            const int64_t lo = n * r / nranks, hi = n * (r + 1) / nranks;
+            RankScratch &s = rs[r];
+            if (reg == 0) {
+                memset(&s.st, 0, sizeof(RegState));
+                s.partials.assign((size_t)2 * grid * 8, 0.0);
+                const size_t m = (size_t)std::max<int64_t>(hi - lo, 1);
+                s.nn_g.assign(m, 0x12345678u), s.nn_g2.assign(m, 0x12345678u), s.todo.assign(m, 0u), s.nn_l.assign(m, 0.f), s.nn_seed.assign(m, 0.f);
+            }
+            KernelArgs a{};
+            a.st = &s.st;
+            a.scan.base = (const unsigned char *)scan + lo * stride, a.scan.n = (int)(hi - lo), a.scan.d_n = nullptr;
+            a.scan.stride = stride, a.scan.ox = 0, a.scan.oy = f32 ? 4 : 8, a.scan.oz = f32 ? 8 : 16, a.scan.f32 = f32;
+            a.map = map.view, a.partials = s.partials.data();
+            a.px.nranks = 1;
+            if (nranks > 1) {
+                for (int q = 0; q < nranks; ++q) a.px.peer[q] = &boxes[q];
+                a.px.nranks = nranks, a.px.rank = r, a.px.parity = reg & 1, a.px.tag_base = (uint32_t)(reg * KICP_MAX_ITERATIONS + 1);
+            }
+            a.up = UploadArgs{nullptr, 0u, 1};
+            a.init.last = Pose{last[0], last[1], last[2], last[3], last[4], last[5], last[6]};
+            a.init.odom = Pose{odom[0], odom[1], odom[2], odom[3], odom[4], odom[5], odom[6]};
+            a.init.tau = tau, a.init.conv = params->convergence_criterion, a.init.fixed_reg = params->fixed_regularization;
+            a.init.adaptive = params->use_adaptive_odometry_regularization ? 1 : 0, a.init.max_iter = params->max_num_iterations,
+            a.init.iters_out = nullptr;
+            int e = 0;
+            a.pow2_voxel = std::frexp(voxel_size, &e) == 0.5 ? 1 : 0;
+            a.collect_stats = 1;
+            if (nn_cache && persistent)
+                a.nn_g = s.nn_g.data(), a.nn_g2 = s.nn_g2.data(), a.nn_l = s.nn_l.data(), a.nn_seed = s.nn_seed.data(), a.todo = s.todo.data();
+            a.result_host = nullptr, a.timeout_ns = 600ull * 1000000000ull;
+            memset(s.st.stats, 0, sizeof(s.st.stats));
+            if (persistent) {
+                // (ranks are concurrent grids: emu::launch keeps one global grid size, identical for all of them)
+                ranks.emplace_back([a, grid]() { emu::launch(grid, KR_THREADS, [a]() { k_register<true>(a); }); });
+            } else {
+                RegState *st = &s.st;
+                emu::launch(1, 32, [st, a]() { k_reg_init(st, a.init); });
+                for (int j = 0; j < a.init.max_iter; ++j) {
+                    emu::launch(grid, KR_THREADS, [a]() { k_register<false>(a); });
+                    emu::launch(1, 32, [st]() { k_solve(st); });
+                }
+            }
+        }
+        for (auto &t : ranks) t.join();
+        for (int r = 0; r < nranks; ++r) {
+            results[r] = rs[r].st.result;
+            const RegState &st = rs[r].st;
+            if (persistent && (st.win_ctr || st.arrive || st.exit_ctr || st.a_arrive || st.abort)) rc = -1;
+            for (int k = 0; k < KICP_MAX_ITERATIONS; ++k)
+                if (persistent && (st.todo_n[k] || st.slow_n[k])) rc = -2;
+        }
+    }
+    if (stats) stats[0] = rs[0].st.stats[0], stats[1] = rs[0].st.stats[1], stats[2] = rs[0].st.stats[2];
+    return rc;
+}
