@@ -359,7 +359,7 @@ class _Pipeline:
     """kinematic_icp::pipeline::KinematicICP behind one of three builds with the same C entry points:
        prefix kref_  oracle/_ref/libkicp_ref.so      the reference's pipeline + the reference's Registration.cpp + CPU map
        prefix kgpu_  oracle/_ref/libkicp_ref_gpu.so  the reference's pipeline source over the product's GPU facade
-       prefix kfac_  kinematic-icp_b200/lib/libkinematic_icp_b200.so   the product's own facade pipeline (GPU)."""
+       prefix kfac_  tests/hooks/_build/libkicp_facade_hooks.so        the product's own facade pipeline (GPU), through the test hooks."""
 
     def __init__(self, L, prefix, max_range=100.0, min_range=0.0, voxel_size=1.0, max_points_per_voxel=20, use_adaptive_threshold=True,
                  fixed_threshold=1.0, max_num_iterations=10, convergence_criterion=1e-3, max_num_threads=1, use_adaptive_reg=True,
@@ -428,6 +428,10 @@ def ref_gpu_available():
     return os.path.exists(os.path.join(_HERE, "_ref", "libkicp_ref_gpu.so"))
 
 
+def facade_hooks_path():
+    """extern "C" hooks over the product's C++ facade (tests/hooks/facade_hooks.cpp, built by kinematic-icp_b200/cpp/Makefile)."""
+    return os.path.normpath(os.path.join(_HERE, "..", "tests", "hooks", "_build", "libkicp_facade_hooks.so"))
+
+
 def facade_pipeline(**kw):
-    root = os.path.normpath(os.path.join(_HERE, "..", "kinematic-icp_b200", "lib"))
-    return _Pipeline(C.CDLL(os.path.join(root, "libkinematic_icp_b200.so")), "kfac_", **kw)
+    return _Pipeline(C.CDLL(facade_hooks_path()), "kfac_", **kw)

@@ -1,4 +1,6 @@
-// extern "C" test hooks over the C++ facade (so tests can drive kinematic_icp::pipeline::KinematicICP from Python).
+// extern "C" test hooks over the C++ facade (so tests can drive kinematic_icp::pipeline::KinematicICP, the PointCloud2 decoder and the TUM
+// writer from Python).  Test infrastructure: built as tests/hooks/_build/libkicp_facade_hooks.so by kinematic-icp_b200/cpp/Makefile, linked
+// AGAINST the product libraries, never into them.
 #include <cstdint>
 #include <vector>
 

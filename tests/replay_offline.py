@@ -58,7 +58,7 @@ if world > 1:
     dist.barrier()
 t0 = time.perf_counter()
 poses, stage_ms = [], []
-KL = C.CDLL(os.path.join(ROOT, "kinematic-icp_b200", "lib", "libkinematic_icp_b200.so"))
+KL = C.CDLL(os.path.join(ROOT, "tests", "hooks", "_build", "libkicp_facade_hooks.so"))
 KL.kfac_debug_frame_timing.argtypes = [ko.c_dp]
 tbuf = np.zeros(8)
 for f, s, o in zip(frames_in, stamps_in, seq["odoms"]):
@@ -75,7 +75,7 @@ if world > 1:
 poses = np.array(poses)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 stamps = 0.1 * np.arange(1, frames + 1)
-L = C.CDLL(os.path.join(ROOT, "kinematic-icp_b200", "lib", "libkinematic_icp_b200.so"))
+L = C.CDLL(os.path.join(ROOT, "tests", "hooks", "_build", "libkicp_facade_hooks.so"))
 L.kfac_write_tum.argtypes = [C.c_char_p, ko.c_dp, ko.c_dp, C.c_int64]
 tum = os.path.join(ROOT, "gpurun_out", "replay_rank%d.tum" % rank)
 assert L.kfac_write_tum(tum.encode(), stamps.ctypes.data_as(ko.c_dp), np.ascontiguousarray(poses).ctypes.data_as(ko.c_dp), frames) == 0

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_tum_writer_format(tmp_path):
     import __graft_entry__ as g
     g.build()
-    L = C.CDLL(os.path.join(ROOT, "kinematic-icp_b200", "lib", "libkinematic_icp_b200.so"))
+    L = C.CDLL(os.path.join(ROOT, "tests", "hooks", "_build", "libkicp_facade_hooks.so"))
     c_dp = C.POINTER(C.c_double)
     L.kfac_write_tum.argtypes = [C.c_char_p, c_dp, c_dp, C.c_int64]
     stamps = np.array([1700000000.123456789, 1700000000.2])
@@ -26,7 +26,7 @@ def test_tum_writer_format(tmp_path):
 def _facade():
     import __graft_entry__ as g
     g.build()
-    return C.CDLL(os.path.join(ROOT, "kinematic-icp_b200", "lib", "libkinematic_icp_b200.so"))
+    return C.CDLL(os.path.join(ROOT, "tests", "hooks", "_build", "libkicp_facade_hooks.so"))
 
 
 def _decode(L, rec, fields, width=None, height=1):
