@@ -44,6 +44,8 @@ def parse_args():
                     help="N > 1 sharded mode: fused peer-memory exchange inside the persistent kernel (default) or NCCL allreduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-replay", action="store_true", help="skip the whole-pipeline replay (kicp_replay) reported under `replay`")
+    ap.add_argument("--sustained", type=int, default=1000,
+                    help="N = 1: registrations of the back-to-back run reported under `sustained` (0 = skip)")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic only: keep L2 warm between steps")
     return ap.parse_args()
 
@@ -503,6 +505,41 @@ def main():
     primary_sharded = world > 1 and args.mode == "sharded"
     main_run = run_mode(primary_sharded)
     replicas_run = run_mode(False) if (world > 1 and primary_sharded) else None
+    # ---- sustained load (N = 1): many registrations back to back in ONE timed region, every one behind an L2 flush; the time of the
+    # same number of flushes alone is measured right after and subtracted.  The 20-step `value` above keeps the GPU busy for a few
+    # milliseconds; this keeps it busy for ~0.4 s (clocks and throttle reasons are sampled through it).
+    sustained = None
+    if world == 1 and args.sustained > 0:
+        try:
+            scan_s = kb.Scan(ctx, w.N)
+            scan_s.upload(w.scan)
+            res_s = kb.pinned_result()
+
+            def back_to_back(k, with_registration):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for i in range(k):
+                    flush_l2(i)
+                    if with_registration:
+                        reg.enqueue(scan_s, gm, w.last_pose, w.rel_odom, w.tau, res_s)
+                e1.record(stream)
+                ctx.synchronize()
+                return e0.elapsed_time(e1)
+
+            back_to_back(10, True)
+            sampler.active = True
+            t_both = back_to_back(args.sustained, True)
+            sampler.active = False
+            t_flush = back_to_back(args.sustained, False)
+            per_ms = (t_both - t_flush) / args.sustained
+            d_s = ko.pose_delta(res_s.pose_np(), main_run["result"].pose_np())
+            sustained = {"registrations": args.sustained, "value": 1e3 / per_ms, "unit": UNIT, "ms_per_step": per_ms,
+                         "region_ms": t_both, "flushes_alone_ms": t_flush, "pose_delta_vs_timed_run": [d_s[0], d_s[1]],
+                         "note": "one CUDA-event pair around %d x (L2 flush + registration) on the library's stream, minus the same number "
+                                 "of flushes alone; frame resident in HBM" % args.sustained}
+            scan_s.close()
+        except Exception as e:  # never let the extra figure take the bench line down
+            sustained = {"unavailable": repr(e)[:200]}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- cross-rank identity of what the sharded run produced (every rank must hold the same pose and the same sums) ----
@@ -646,6 +683,8 @@ def main():
                 "registration kernel": prof.assoc_ms / max(prof.registrations, 1),
                 "launches_after_convergence": prof.idle_ms / max(prof.registrations, 1)},
         }
+        if sustained is not None:
+            line["sustained"] = sustained
         if replay is not None:
             line["replay"] = replay
         if cross_rank_identical is not None:
