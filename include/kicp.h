@@ -87,10 +87,7 @@ int64_t kicp_ctx_launch_count(kicp_ctx *ctx);
  * scans of 49152 points or more (default: smaller scans gain nothing from the extra phase), 2 = always, 0 = never; "overlap_upload" 1 = the
  * host-pointer entry points overlap the frame's upload with the first pass (default); "spin_timeout_ms" = bound of every
  * device-side wait (upload flags, peers of the fused exchange; default 20000); "frame_sync" 1 = kicp_register_frame reads the
- * survivor counts back in the middle of a frame (legacy order; default 0 = ONE host synchronisation per frame, at its end);
- * "upload_threads" = helper threads that stage a PAGEABLE host buffer (std::vector storage, a PointCloud2 byte vector) into the
- * context's page-locked memory while finished pieces go to the copy engine (default 3; 0 = leave pageable copies to the driver;
- * page-locked buffers always go to the copy engine directly).  The environment variable KICP_UPLOAD_THREADS gives the initial value.
+ * survivor counts back in the middle of a frame (legacy order; default 0 = ONE host synchronisation per frame, at its end).
  * Unknown names fail with KICP_ERR_INVALID.
  * Every setting computes the same result up to the summation order. */
 int kicp_ctx_set_option(kicp_ctx *ctx, const char *name, int32_t value);

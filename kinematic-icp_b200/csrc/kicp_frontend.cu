@@ -300,7 +300,7 @@ int enqueue_preprocess(kicp_ctx *c, Scratch &s, int n, const double *stamps, int
                            lidar_to_base[6]};
     for (int k = 0; k < 6; ++k) a.omega[k] = 0.0;
     if (a.deskew) {
-        KICP_TRY(kicp_h2d(c, 1, s.stamps, stamps, (size_t)n * sizeof(double), c->stream));
+        KICP_CUDA(cudaMemcpyAsync(s.stamps, stamps, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         size_t bytes = s.tmp_bytes;
         KICP_CUDA(cub::DeviceReduce::Min(s.tmp, bytes, s.stamps, s.d_mm, n, c->stream));
         bytes = s.tmp_bytes;
@@ -392,7 +392,7 @@ extern "C" int kicp_register_frame(kicp_map *map, const kicp_frame_input *in, co
         KICP_TRY(reserve(c, s, n));
         const bool packed_f64 = in->dtype == KICP_DTYPE_F64 && step == 24 && ox == 0 && oy == 8 && oz == 16;
         if (packed_f64) {
-            KICP_TRY(kicp_h2d(c, 0, s.in, in->data, (size_t)n * sizeof(P3), c->stream));
+            KICP_CUDA(cudaMemcpyAsync(s.in, in->data, (size_t)n * sizeof(P3), cudaMemcpyHostToDevice, c->stream));
         } else {
             const size_t raw_bytes = (size_t)n * step;
             if (raw_bytes > s.raw_cap) {
@@ -402,7 +402,7 @@ extern "C" int kicp_register_frame(kicp_map *map, const kicp_frame_input *in, co
                 KICP_CUDA(cudaMalloc(&s.raw, raw_bytes + raw_bytes / 4));
                 s.raw_cap = raw_bytes + raw_bytes / 4;
             }
-            KICP_TRY(kicp_h2d(c, 0, s.raw, in->data, raw_bytes, c->stream));
+            KICP_CUDA(cudaMemcpyAsync(s.raw, in->data, raw_bytes, cudaMemcpyHostToDevice, c->stream));
             k_ingest<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(s.raw, (int)n, IngestArgs{in->dtype == KICP_DTYPE_F32, step, ox, oy, oz},
                                                                        s.in);
             KICP_CHECK_LAUNCH(c);

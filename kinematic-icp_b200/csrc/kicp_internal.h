@@ -70,10 +70,6 @@ struct kicp_ctx {
     uint32_t *h_chunk_tags = nullptr;    // pinned source of the flag copies
     uint32_t upload_seq = 0;
     int overlap_upload = 1;
-    // staged upload of pageable host buffers (kicp_upload.cu): helper threads, 0 = leave pageable copies to the driver
-    int upload_threads = 3;
-    void *upload = nullptr;
-    void (*upload_free)(kicp_ctx *) = nullptr;
     kicp_reg_result *h_result = nullptr;  // pinned bounce buffer for synchronous calls
     // profiling (kicp_ctx_profile_begin/end): event pairs per registration
     bool profiling = false;
@@ -182,10 +178,3 @@ int kicp_enqueue_registration_device(kicp_map *m, const double *d_xyz, int64_t n
                                      const double odom[7], double tau, const kicp_reg_params *p);
 // defined in kicp_comm.cu
 int kicp_comm_allreduce8(kicp_ctx *ctx, double *d_buf);
-// defined in kicp_upload.cu: host-to-device upload of a caller's buffer; pageable memory is staged in parallel into the context's
-// page-locked area `slot` (0 / 1) while finished pieces go to the copy engine.  kicp_h2d_groups copies [bounds[g], bounds[g+1]) per
-// group g and calls after_group(user, g) right after issuing it.
-int kicp_h2d(kicp_ctx *c, int slot, void *dst, const void *src, size_t bytes, cudaStream_t stream);
-int kicp_h2d_prepare(kicp_ctx *c, int slot, const void *src, size_t total);  // allocations of a staged upload, ahead of time
-int kicp_h2d_groups(kicp_ctx *c, int slot, void *dst, const void *src, const size_t *bounds, int ngroups, cudaStream_t stream,
-                    int (*after_group)(void *, int), void *user);

@@ -67,7 +67,6 @@ extern "C" int kicp_ctx_create(int device, kicp_ctx **out) {
     if (const char *e = getenv("KICP_CTAS_PER_SM")) c->ctas_per_sm_cap = std::min(16, std::max(0, atoi(e)));
     if (const char *e = getenv("KICP_SPIN_TIMEOUT_MS")) c->spin_timeout_ms = std::max(1, atoi(e));
     if (const char *e = getenv("KICP_FRAME_SYNC")) c->frame_sync = atoi(e) ? 1 : 0;
-    if (const char *e = getenv("KICP_UPLOAD_THREADS")) c->upload_threads = std::min(16, std::max(0, atoi(e)));
     *out = c;
     return KICP_OK;
 }
@@ -164,7 +163,6 @@ extern "C" int kicp_ctx_destroy(kicp_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     kicp_comm_destroy(ctx);
     if (ctx->frontend_free) ctx->frontend_free(ctx);
-    if (ctx->upload_free) ctx->upload_free(ctx);
     if (ctx->upload_scan) kicp_scan_destroy(ctx->upload_scan);
     cudaFree(ctx->d_state);
     cudaFree(ctx->d_partials);

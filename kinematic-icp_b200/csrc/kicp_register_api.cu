@@ -15,8 +15,7 @@
 // Per-context options (kicp_ctx_set_option): "persistent" 1 = one cooperative launch per registration (default), 0 = one
 // launch per IRLS iteration; "stats" 1 = count probes / candidate points / lines on the device (kicp_debug_last_stats);
 // "ctas_per_sm" caps the resident CTAs per SM the grid is sized for (0 = occupancy limit); "nn_cache" 0 / 1 / 2 = never / for scans of
-// 49152 points or more (default) / always carry every point's neighbour and its certificate from pass to pass; "spin_timeout_ms" bounds every device-side wait;
-// "upload_threads" = helper threads that stage a pageable host buffer into page-locked memory (kicp_upload.cu), 0 = none.
+// 49152 points or more (default) / always carry every point's neighbour and its certificate from pass to pass; "spin_timeout_ms" bounds every device-side wait.
 extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value) {
     if (!c || !name) return KICP_ERR_INVALID;
     if (!strcmp(name, "persistent")) {
@@ -37,9 +36,6 @@ extern "C" int kicp_ctx_set_option(kicp_ctx *c, const char *name, int32_t value)
     } else if (!strcmp(name, "overlap_upload")) {
         if (value != 0 && value != 1) return KICP_ERR_INVALID;
         c->overlap_upload = value;
-    } else if (!strcmp(name, "upload_threads")) {
-        if (value < 0 || value > 16) return KICP_ERR_INVALID;
-        c->upload_threads = value;
     } else if (!strcmp(name, "frame_sync")) {
         if (value != 0 && value != 1) return KICP_ERR_INVALID;
         c->frame_sync = value;
@@ -84,31 +80,20 @@ struct HostUpload {
     int64_t n, wpc;   // points, windows per chunk
     int64_t stride;   // bytes per point
 };
-static int raise_chunk_flags(void *user, int j);
-struct ChunkFlags {
-    kicp_ctx *c;
-    int copies;
-};
 static int issue_chunks(kicp_ctx *c, const HostUpload &hu) {
     // The kernel always sees KICP_UPLOAD_CHUNKS segments; the host groups them into copies of at least ~384 KB (a small frame is
     // ONE copy and one flag copy: every DMA operation costs microseconds, which a 24 KB scan cannot win back by overlapping).
-    // A pageable source is staged into page-locked memory by helper threads while finished groups go out (kicp_upload.cu).
     const int64_t bytes = hu.n * hu.stride;
     const int copies = (int)std::max<int64_t>(1, std::min<int64_t>(KICP_UPLOAD_CHUNKS, bytes / (384 << 10)));
-    size_t bounds[KICP_UPLOAD_CHUNKS + 1];
-    for (int j = 0; j <= copies; ++j) {
-        const int k = j * KICP_UPLOAD_CHUNKS / copies;  // group j = segments [k(j), k(j+1))
-        bounds[j] = (size_t)(std::min<int64_t>(hu.n, k * hu.wpc * 32) * hu.stride);
+    for (int j = 0; j < copies; ++j) {
+        const int k0 = j * KICP_UPLOAD_CHUNKS / copies, k1 = (j + 1) * KICP_UPLOAD_CHUNKS / copies;  // segments [k0, k1)
+        const int64_t lo = std::min<int64_t>(hu.n, k0 * hu.wpc * 32), hi = std::min<int64_t>(hu.n, k1 * hu.wpc * 32);
+        if (hi > lo)
+            KICP_CUDA(cudaMemcpyAsync(hu.dst + lo * hu.stride, hu.src + lo * hu.stride, (size_t)((hi - lo) * hu.stride),
+                                      cudaMemcpyHostToDevice, c->copy_stream));
+        KICP_CUDA(cudaMemcpyAsync(c->d_chunk_flags + k0, c->h_chunk_tags + k0, (size_t)(k1 - k0) * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                  c->copy_stream));
     }
-    ChunkFlags cf{c, copies};
-    return kicp_h2d_groups(c, 0, hu.dst, hu.src, bounds, copies, c->copy_stream, raise_chunk_flags, &cf);
-}
-static int raise_chunk_flags(void *user, int j) {
-    const ChunkFlags *cf = static_cast<const ChunkFlags *>(user);
-    kicp_ctx *c = cf->c;
-    const int k0 = j * KICP_UPLOAD_CHUNKS / cf->copies, k1 = (j + 1) * KICP_UPLOAD_CHUNKS / cf->copies;  // segments [k0, k1)
-    KICP_CUDA(cudaMemcpyAsync(c->d_chunk_flags + k0, c->h_chunk_tags + k0, (size_t)(k1 - k0) * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                              c->copy_stream));
     return KICP_OK;
 }
 
@@ -221,10 +206,7 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
             if (host_upload && c->overlap_upload) {
                 const uint32_t seq = ++c->upload_seq ? c->upload_seq : ++c->upload_seq;  // never 0
                 for (int k = 0; k < KICP_UPLOAD_CHUNKS; ++k) c->h_chunk_tags[k] = seq;
-                ka.up = UploadArgs{c->d_chunk_flags, seq, (int)host_upload->wpc};
-                // the chunks are issued right AFTER the launch (the kernel waits for their flags): whatever may wait for the device
-                // — the page-locked staging area of a pageable source — is allocated now
-                KICP_TRY(kicp_h2d_prepare(c, 0, host_upload->src, (size_t)(host_upload->n * host_upload->stride)));
+                ka.up = UploadArgs{c->d_chunk_flags, seq, (int)host_upload->wpc};  // (the copies are issued right after the launch)
             }
             if (p2p) {
                 for (int r = 0; r < c->nranks; ++r) ka.px.peer[r] = c->p2p_peer[r];
@@ -245,7 +227,11 @@ static int enqueue_registration(kicp_map *m, const kicp_scan *scan, const double
             KICP_CUDA(kr_launch_register(true, grid, ka, c->stream));
             c->launches++;
             if (pr) KICP_CUDA(cudaEventRecord(e1, c->stream));
-            if (ka.up.flags != nullptr) KICP_TRY(issue_chunks(c, *host_upload));  // (an error here leaves the kernel to its wait timeout)
+            // The frame's chunks go out AFTER the launch: the kernel is already resident and takes every chunk as its flag rises, and the
+            // host-side cost of the copies (for pageable memory the driver stages each of them on this thread) no longer delays the
+            // launch — same box, pageable float32: 2 736 instead of 2 390 scans/s end to end, float64 1 952 instead of 1 771.
+            // (A copy that fails here leaves the kernel to its wait timeout; the call drains both streams and reports the error.)
+            if (ka.up.flags != nullptr) KICP_TRY(issue_chunks(c, *host_upload));
             if (dbg) {
                 cudaError_t e = cudaStreamSynchronize(c->stream);
                 fprintf(stderr, "[kicp] persistent launch (grid %d, n %d): %s\n", grid, n, cudaGetErrorString(e));
@@ -429,7 +415,7 @@ static int register_host(kicp_map *map, const void *data, int64_t n, int32_t dty
         const int64_t windows = (n + 31) / 32;
         hu.wpc = (windows + KICP_UPLOAD_CHUNKS - 1) / KICP_UPLOAD_CHUNKS;
         if (!overlap) {
-            KICP_TRY(kicp_h2d(c, 0, s->d_data, data, (size_t)(n * s->stride), c->stream));
+            KICP_CUDA(cudaMemcpyAsync(s->d_data, data, (size_t)(n * s->stride), cudaMemcpyHostToDevice, c->stream));
         }
     }
     int st = enqueue_registration(map, s, last, odom, tau, params, c->h_result, sharded, overlap ? &hu : nullptr);
