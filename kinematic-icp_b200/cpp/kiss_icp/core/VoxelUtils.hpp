@@ -1,6 +1,8 @@
 // kiss_icp/core/VoxelUtils.hpp surface (KISS-ICP v1.2.0): Voxel, PointToVoxel, VoxelDownsample.
 // VoxelDownsample runs on the device (kicp_voxel_downsample, include/kicp.h): the first point in input order of every
-// voxel, returned in input order.  (The original returns the same set in robin_map iteration order.)
+// voxel, returned in input order.  (The original returns the same set in robin_map iteration order; a caller that down-samples the
+// result again or feeds it to the map's greedy insert — as the pipeline does — therefore sees other points than with the library:
+// DESIGN.md section 2 has the measured size of that gap.)
 #pragma once
 #include <Eigen/Core>
 #include <cmath>

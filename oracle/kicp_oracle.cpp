@@ -270,18 +270,66 @@ size_t VoxelHashMap::NumPoints() const {
     return n;
 }
 
-// VoxelUtils.cpp VoxelDownsample: first point (input order) per voxel.  Output order here is the
-// order of first occurrence (the reference's is robin_map iteration order — a permutation of it).
+// tsl::robin_map<Voxel, T> as VoxelDownsample uses it, restated from memory (tsl/robin_hash.h; UNPINNED, see the header):
+// reserve(n) -> rehash(ceil(float(n) / 0.5f)) -> bucket count = next power of two; insert: start at hash & mask, walk while the
+// walker's distance from its ideal bucket is <= the resident's; place in an empty bucket, else swap with the poorer resident and carry
+// it on (richer stays on equal distance); iteration visits the buckets in index order.  With at most n distinct keys the load never
+// reaches 0.5, so the table does not grow; the probe-length limits of the library (rehash after 4096 / 128 probes) are far away.
+std::vector<size_t> RobinMapIterationOrder(const std::vector<Voxel> &keys, size_t reserve_count, bool mask20) {
+    size_t want = static_cast<size_t>(std::ceil(static_cast<float>(reserve_count) / 0.5f));
+    want = std::max(want, static_cast<size_t>(std::ceil(static_cast<float>(keys.size()) / 0.5f)));
+    size_t nb = 1;
+    while (nb < want) nb <<= 1;
+    const size_t mask = nb - 1;
+    struct Bucket {
+        long dist = -1;  // distance from the ideal bucket, -1 = empty
+        size_t idx = 0;
+    };
+    std::vector<Bucket> b(nb);
+    for (size_t i = 0; i < keys.size(); ++i) {
+        size_t h = VoxelHash()(keys[i]);
+        if (mask20) h &= (static_cast<size_t>(1) << 20) - 1;
+        size_t ib = h & mask;
+        long dist = 0;
+        while (dist <= b[ib].dist) ib = (ib + 1) & mask, ++dist;  // (keys are distinct: no equality test needed)
+        Bucket carry{dist, i};
+        while (b[ib].dist >= 0) {  // robin hood: the walker takes the bucket of a resident that is closer to home, the resident walks on
+            if (carry.dist > b[ib].dist) std::swap(carry, b[ib]);
+            ib = (ib + 1) & mask, ++carry.dist;
+        }
+        b[ib] = carry;
+    }
+    std::vector<size_t> order;
+    order.reserve(keys.size());
+    for (const Bucket &k : b)
+        if (k.dist >= 0) order.push_back(k.idx);
+    return order;
+}
+
+static int g_downsample_order = 0;
+void SetDownsampleOrder(int mode) { g_downsample_order = mode; }
+int GetDownsampleOrder() { return g_downsample_order; }
+
+// VoxelUtils.cpp VoxelDownsample: first point (input order) per voxel.  Output order: the order of first occurrence by default
+// (the reference's is robin_map iteration order — a permutation of it; SetDownsampleOrder(1 | 2) emits that order as recalled).
 std::vector<Vec3> VoxelDownsample(const std::vector<Vec3> &frame, double voxel_size) {
     std::unordered_map<Voxel, size_t, VoxelHash> grid;
     grid.reserve(frame.size());
     std::vector<Vec3> out;
+    std::vector<Voxel> keys;
     for (const Vec3 &p : frame) {
         const Voxel v = PointToVoxel(p, voxel_size);
         if (grid.find(v) == grid.end()) {
             grid.insert({v, out.size()});
             out.push_back(p);
+            keys.push_back(v);
         }
+    }
+    if (g_downsample_order == 1 || g_downsample_order == 2) {
+        const std::vector<size_t> order = RobinMapIterationOrder(keys, frame.size(), g_downsample_order == 2);
+        std::vector<Vec3> permuted(out.size());
+        for (size_t k = 0; k < order.size(); ++k) permuted[k] = out[order[k]];
+        return permuted;
     }
     return out;
 }

@@ -99,6 +99,18 @@ struct VoxelHashMap {
 };
 
 std::vector<Vec3> VoxelDownsample(const std::vector<Vec3> &frame, double voxel_size);
+// Output order of VoxelDownsample (process-wide, test infrastructure):
+//   0 (default)  order of first occurrence — what this restatement and the device code emit;
+//   1            the iteration order of the tsl::robin_map<Voxel, Vector3d> the library fills (`grid.reserve(frame.size())`, then one
+//                insert per new voxel, then begin()..end()), AS RECALLED: power-of-two buckets, max load factor 0.5, robin-hood
+//                displacement with "richer stays on equal distance", iteration in bucket order, hash = the 3-prime XOR;
+//   2            the same with the hash masked to 20 bits (the form KISS-ICP used before v1.0).
+// Modes 1 and 2 are UNPINNED — neither KISS-ICP v1.2.0 nor tsl-robin-map is available offline — and exist to measure how much the
+// known order gap moves a trajectory (tests/test_oracle_kat.py) and to make the diff a one-flag affair the day the library is at hand.
+void SetDownsampleOrder(int mode);
+int GetDownsampleOrder();
+// indices (into `keys`, unique voxels in insertion order) in the iteration order described above
+std::vector<size_t> RobinMapIterationOrder(const std::vector<Voxel> &keys, size_t reserve_count, bool mask20);
 std::vector<Vec3> Preprocess(const std::vector<Vec3> &frame, const std::vector<double> &timestamps,
                              const SE3 &relative_motion, double max_range, double min_range, bool deskew);
 

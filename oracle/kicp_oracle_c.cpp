@@ -130,6 +130,15 @@ void kor_register(void *h, const double *frame, int64_t n, const double *last_po
     }
 }
 
+// iteration order of the (recalled) tsl::robin_map over `n` distinct voxels inserted in the given order after reserve(reserve_count)
+void kor_robin_order(const int32_t *keys, int64_t n, int64_t reserve_count, int mask20, int64_t *out) {
+    std::vector<Voxel> k(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i) k[i] = Voxel{keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]};
+    const auto order = RobinMapIterationOrder(k, static_cast<size_t>(reserve_count), mask20 != 0);
+    for (size_t i = 0; i < order.size(); ++i) out[i] = static_cast<int64_t>(order[i]);
+}
+void kor_set_downsample_order(int mode) { SetDownsampleOrder(mode); }
+int kor_get_downsample_order() { return GetDownsampleOrder(); }
 int64_t kor_voxel_downsample(const double *xyz, int64_t n, double voxel_size, double *out) {
     const auto r = VoxelDownsample(to_vec(xyz, n), voxel_size);
     from_vec(r, out);

@@ -246,6 +246,19 @@ class OracleMap:
         return out, st
 
 
+def set_downsample_order(mode):
+    """Output order of VoxelDownsample in the oracle AND in the reference build (oracle/_ref holds its own copy of the restated
+    KISS-ICP code): 0 = order of first occurrence (default; what the device emits), 1 = tsl::robin_map iteration order as recalled,
+    2 = the same with the pre-v1.0 20-bit hash mask.  Modes 1 / 2 are unpinned (kicp_oracle.hpp)."""
+    L = lib()
+    L.kor_set_downsample_order.argtypes = [C.c_int]
+    L.kor_set_downsample_order(int(mode))
+    if ref_available():
+        R = ref_lib()
+        R.kref_set_downsample_order.argtypes = [C.c_int]
+        R.kref_set_downsample_order(int(mode))
+
+
 def voxel_downsample(pts, voxel_size):
     pts = _pts(pts)
     out = np.empty_like(pts)

@@ -37,6 +37,9 @@ void from_se3(const Sophus::SE3d &T, double *p) {
 
 extern "C" {
 
+// (this library holds its own copy of the restated KISS-ICP code: the down-sample order mode is set per library)
+void kref_set_downsample_order(int mode) { kicp_oracle::SetDownsampleOrder(mode); }
+
 void *kref_map_create(double voxel_size, double max_distance, unsigned max_points_per_voxel) {
     return new kiss_icp::VoxelHashMap(voxel_size, max_distance, max_points_per_voxel);
 }
