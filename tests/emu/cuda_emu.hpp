@@ -13,6 +13,8 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
+#include <memory>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -22,7 +24,8 @@
 #include <string>
 #include <thread>
 #include <vector>
-// (after the standard headers: cuda's host_defines.h turns __noinline__ into a macro, which libstdc++ uses as an attribute name)
+// (after EVERY standard header a harness needs — include them above, not in the harness: cuda's host_defines.h turns __noinline__
+// into a macro, which libstdc++ uses as an attribute name)
 #include <cuda_runtime.h>
 
 #undef __shared__

@@ -26,8 +26,6 @@ static inline P kr_emu_ld_point(const double *p) {
 
 #include "../../kinematic-icp_b200/csrc/kicp_register.cu"
 
-#include <thread>
-#include <vector>
 
 namespace {
 struct HostMap {
@@ -65,10 +63,13 @@ struct RankScratch {
 // only): one launch per pass, k_reg_init / k_register<false> / k_solve.  nn_cache = 1: certificates carried between passes.
 // results: one kicp_reg_result per rank.  stats: [3] probes, candidate points, lines of rank 0.  Returns 0, or a negative number
 // when a launch did not leave its counters as the next one needs them.
+// late_upload = 1 (persistent, one rank): the kernel is started on a frame buffer full of NaN; an "uploader" thread then copies the
+// frame in, segment by segment with pauses, raising each segment's flag after its bytes — the protocol of the host-pointer entry
+// points (kicp_register_api.cu: the chunks are issued right after the launch).  A window that read its segment early would see NaN.
 extern "C" int kr_emu_register(const int32_t *keys, const int32_t *counts, const double *pts, int64_t nvox, int32_t cap, double voxel_size,
                                const void *scan, int64_t n, int32_t f32, const double last[7], const double odom[7], double tau,
                                const kicp_reg_params *params, int32_t grid, int32_t nranks, int32_t persistent, int32_t nn_cache,
-                               int32_t registrations, kicp_reg_result *results, uint64_t *stats) {
+                               int32_t registrations, kicp_reg_result *results, uint64_t *stats, int32_t late_upload) {
     if (nranks < 1 || nranks > KICP_MAX_RANKS || (nranks > 1 && !persistent)) return -10;
     HostMap map;
     build_map(map, keys, counts, pts, nvox, cap, voxel_size);
@@ -79,6 +80,8 @@ extern "C" int kr_emu_register(const int32_t *keys, const int32_t *counts, const
     int rc = 0;
     for (int reg = 0; reg < registrations; ++reg) {  // (several in a row: the counters a launch leaves behind, the mailbox parity and tags)
         std::vector<std::thread> ranks;
+        std::vector<std::unique_ptr<std::vector<unsigned char>>> late_bufs;  // (kept alive until the threads have joined)
+        std::vector<std::unique_ptr<std::vector<uint32_t>>> late_flags;
         for (int r = 0; r < nranks; ++r) {
             const int64_t lo = n * r / nranks, hi = n * (r + 1) / nranks;
             RankScratch &s = rs[r];
@@ -99,6 +102,18 @@ extern "C" int kr_emu_register(const int32_t *keys, const int32_t *counts, const
                 a.px.nranks = nranks, a.px.rank = r, a.px.parity = reg & 1, a.px.tag_base = (uint32_t)(reg * KICP_MAX_ITERATIONS + 1);
             }
             a.up = UploadArgs{nullptr, 0u, 1};
+            std::vector<unsigned char> *late = nullptr;
+            std::vector<uint32_t> *flags = nullptr;
+            int64_t wpc = 1;
+            if (late_upload && persistent && nranks == 1 && hi > lo) {
+                const int64_t windows = (hi - lo + 31) / 32;
+                wpc = (windows + KICP_UPLOAD_CHUNKS - 1) / KICP_UPLOAD_CHUNKS;  // as register_host computes it
+                late_bufs.emplace_back(new std::vector<unsigned char>((size_t)(hi - lo) * stride, 0xFF));  // all-ones bytes: NaN in float32 and float64
+                late_flags.emplace_back(new std::vector<uint32_t>(KICP_UPLOAD_CHUNKS, 0u));
+                late = late_bufs.back().get(), flags = late_flags.back().get();
+                a.scan.base = late->data();
+                a.up = UploadArgs{flags->data(), (uint32_t)(reg + 1), (int)wpc};
+            }
             a.init.last = Pose{last[0], last[1], last[2], last[3], last[4], last[5], last[6]};
             a.init.odom = Pose{odom[0], odom[1], odom[2], odom[3], odom[4], odom[5], odom[6]};
             a.init.tau = tau, a.init.conv = params->convergence_criterion, a.init.fixed_reg = params->fixed_regularization;
@@ -114,6 +129,19 @@ extern "C" int kr_emu_register(const int32_t *keys, const int32_t *counts, const
             if (persistent) {
                 // (ranks are concurrent grids: emu::launch keeps one global grid size, identical for all of them)
                 ranks.emplace_back([a, grid]() { emu::launch(grid, KR_THREADS, [a]() { k_register<true>(a); }); });
+                if (late) {  // the uploader: starts AFTER the launch, like the host-pointer entry points
+                    const unsigned char *src = (const unsigned char *)scan + lo * stride;
+                    const int64_t npts = hi - lo;
+                    const uint32_t seq = (uint32_t)(reg + 1);
+                    ranks.emplace_back([late, flags, src, npts, wpc, stride, seq]() {
+                        for (int k = 0; k < KICP_UPLOAD_CHUNKS; ++k) {
+                            std::this_thread::sleep_for(std::chrono::milliseconds(3));
+                            const int64_t p0 = std::min<int64_t>(npts, (int64_t)k * wpc * 32), p1 = std::min<int64_t>(npts, (int64_t)(k + 1) * wpc * 32);
+                            if (p1 > p0) memcpy(late->data() + p0 * stride, src + p0 * stride, (size_t)(p1 - p0) * stride);
+                            __atomic_store_n(&(*flags)[k], seq, __ATOMIC_RELEASE);
+                        }
+                    });
+                }
             } else {
                 RegState *st = &s.st;
                 emu::launch(1, 32, [st, a]() { k_reg_init(st, a.init); });

@@ -36,7 +36,7 @@ def emu():
 
 
 def run_emu(lib, om, scan, last, odom, tau, grid=3, nranks=1, persistent=1, nn_cache=1, registrations=1, max_iter=10, conv=1e-3,
-            adaptive=True, fixed_reg=0.0):
+            adaptive=True, fixed_reg=0.0, late_upload=0):
     from kinematic_icp_b200 import _capi
     keys, counts, pts = om.export_voxels()
     keys = np.ascontiguousarray(keys, dtype=np.int32)
@@ -51,7 +51,8 @@ def run_emu(lib, om, scan, last, odom, tau, grid=3, nranks=1, persistent=1, nn_c
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
     rc = lib.kr_emu_register(vp(keys), vp(counts), vp(pts), C.c_int64(len(counts)), C.c_int32(om.max_points_per_voxel), C.c_double(om.voxel_size),
                              vp(scan), C.c_int64(len(scan)), C.c_int32(1 if f32 else 0), vp(last), vp(odom), C.c_double(tau), C.byref(p),
-                             C.c_int32(grid), C.c_int32(nranks), C.c_int32(persistent), C.c_int32(nn_cache), C.c_int32(registrations), res, stats)
+                             C.c_int32(grid), C.c_int32(nranks), C.c_int32(persistent), C.c_int32(nn_cache), C.c_int32(registrations), res, stats,
+                             C.c_int32(late_upload))
     assert rc == 0, "a launch must leave its counters zero for the next one: rc %d" % rc
     return list(res), list(stats)
 
@@ -93,6 +94,18 @@ def test_sharded_ranks_agree_bit_for_bit(emu, oracle, workload, cfg, grid, nrank
     ko = oracle
     w = workload(cfg)
     check(emu, ko, w.map, w.scan, w.last_pose, w.rel_odom, w.tau, grid=grid, nranks=nranks, nn_cache=nn_cache, registrations=3)
+
+
+@pytest.mark.parametrize("cfg,n,grid", [(1, None, 2), (2, None, 3), (1, 100, 2)])
+def test_frame_uploaded_while_the_kernel_runs(emu, oracle, workload, cfg, n, grid):
+    """The host-pointer entry points launch the persistent kernel first and issue the frame's chunks right after; the first pass
+    takes every chunk as its flag rises.  Here the kernel starts on a buffer full of NaN and an uploader thread fills it in segment by
+    segment, raising each flag after its bytes: any window that read its segment before the flag would poison the sums."""
+    ko = oracle
+    w = workload(cfg)
+    scan = w.scan if n is None else w.scan[:n]
+    check(emu, ko, w.map, scan, w.last_pose, w.rel_odom, w.tau, grid=grid, late_upload=1, registrations=2)
+    check(emu, ko, w.map, scan.astype(np.float32), w.last_pose, w.rel_odom, w.tau, grid=grid, late_upload=1)
 
 
 def test_kernel_edge_cases(emu, oracle, workload):
