@@ -12,6 +12,7 @@
 #include <ucontext.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <chrono>
 #include <memory>
@@ -116,7 +117,48 @@ inline T from_bits(uint64_t b) {
     return v;
 }
 
-// run `kernel(args)` as a grid of `grid` CTAs x `threads` threads (threads a multiple of 32); one OS thread per CTA
+// one CTA of `threads` threads on the calling OS thread (fibers and their stacks are reused from CTA to CTA)
+template <class F>
+inline void run_cta(int b, int threads, F &body, std::vector<Fiber> &fibers) {
+    Cta c;
+    memset(&c, 0, sizeof(c));
+    c.nthreads = threads;
+    cta = &c;
+    block_idx = {(unsigned)b, 0, 0};
+    struct Tramp {
+        static void run(unsigned lo, unsigned hi) {
+            F *fn = reinterpret_cast<F *>(((uintptr_t)hi << 32) | lo);
+            (*fn)();
+            cur->done = true;
+            swapcontext(&cur->ctx, &sched_ctx);
+        }
+    };
+    if ((int)fibers.size() != threads) fibers.resize(threads);
+    for (int t = 0; t < threads; ++t) {
+        Fiber &f = fibers[t];
+        f.tid = {(unsigned)t, 0, 0}, f.lane = t & 31, f.wid = t >> 5;
+        f.wcoll[0] = f.wcoll[1] = 0, f.wphase = 0, f.bars = 0, f.done = false;
+        if (f.stack.empty()) f.stack.resize(256 << 10);
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack.data(), f.ctx.uc_stack.ss_size = f.stack.size(), f.ctx.uc_link = nullptr;
+        const uintptr_t pf = (uintptr_t)&body;
+        makecontext(&f.ctx, (void (*)())Tramp::run, 2, (unsigned)(pf & 0xFFFFFFFFu), (unsigned)(pf >> 32));
+    }
+    int alive = threads;
+    while (alive > 0) {
+        alive = 0;
+        for (int t = 0; t < threads; ++t) {
+            if (fibers[t].done) continue;
+            cur = &fibers[t];
+            swapcontext(&sched_ctx, &fibers[t].ctx);
+            if (!fibers[t].done) alive++;
+        }
+    }
+    cta = nullptr;
+}
+
+// run `kernel_body` as a grid of `grid` CTAs x `threads` threads (threads a multiple of 32), ALL CTAs resident at once — one OS
+// thread each — which is what a cooperative launch guarantees and what a kernel with grid-wide barriers needs
 template <class F>
 inline void launch(int grid, int threads, F kernel_body) {
     grid_dim = {(unsigned)grid, 1, 1};
@@ -124,41 +166,27 @@ inline void launch(int grid, int threads, F kernel_body) {
     std::vector<std::thread> pool;
     for (int b = 0; b < grid; ++b) {
         pool.emplace_back([=]() {
-            Cta c;
-            memset(&c, 0, sizeof(c));
-            c.nthreads = threads;
-            cta = &c;
-            block_idx = {(unsigned)b, 0, 0};
-            std::vector<Fiber> fibers(threads);
-            struct Tramp {
-                static void run(unsigned lo, unsigned hi) {
-                    F *fn = reinterpret_cast<F *>(((uintptr_t)hi << 32) | lo);
-                    (*fn)();
-                    cur->done = true;
-                    swapcontext(&cur->ctx, &sched_ctx);
-                }
-            };
             F body = kernel_body;
-            for (int t = 0; t < threads; ++t) {
-                Fiber &f = fibers[t];
-                f.tid = {(unsigned)t, 0, 0}, f.lane = t & 31, f.wid = t >> 5;
-                f.wcoll[0] = f.wcoll[1] = 0, f.wphase = 0, f.bars = 0, f.done = false;
-                f.stack.resize(256 << 10);
-                getcontext(&f.ctx);
-                f.ctx.uc_stack.ss_sp = f.stack.data(), f.ctx.uc_stack.ss_size = f.stack.size(), f.ctx.uc_link = nullptr;
-                const uintptr_t pf = (uintptr_t)&body;
-                makecontext(&f.ctx, (void (*)())Tramp::run, 2, (unsigned)(pf & 0xFFFFFFFFu), (unsigned)(pf >> 32));
-            }
-            int alive = threads;
-            while (alive > 0) {
-                alive = 0;
-                for (int t = 0; t < threads; ++t) {
-                    if (fibers[t].done) continue;
-                    cur = &fibers[t];
-                    swapcontext(&sched_ctx, &fibers[t].ctx);
-                    if (!fibers[t].done) alive++;
-                }
-            }
+            std::vector<Fiber> fibers;
+            run_cta(b, threads, body, fibers);
+        });
+    }
+    for (auto &t : pool) t.join();
+}
+
+// an ordinary launch: CTAs are handed to `workers` OS threads in index order, so only some are resident at a time — fine for
+// kernels whose CTAs meet through atomics and short critical sections only (no grid-wide barrier)
+template <class F>
+inline void launch_waves(int grid, int threads, F kernel_body, int workers = 6) {
+    grid_dim = {(unsigned)grid, 1, 1};
+    block_dim = {(unsigned)threads, 1, 1};
+    std::atomic<int> next{0};
+    std::vector<std::thread> pool;
+    for (int w = 0; w < std::min(workers, grid); ++w) {
+        pool.emplace_back([&next, grid, threads, kernel_body]() {
+            F body = kernel_body;
+            std::vector<Fiber> fibers;
+            for (int b = next.fetch_add(1); b < grid; b = next.fetch_add(1)) run_cta(b, threads, body, fibers);
         });
     }
     for (auto &t : pool) t.join();
@@ -238,6 +266,11 @@ inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned v) {
+    __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return cmp;
+}
+inline int atomicExch(volatile int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long cmp, unsigned long long v) {
     __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
     return cmp;
