@@ -1,0 +1,74 @@
+// Host-side emulation of the front-end kernels (kinematic-icp_b200/csrc/kicp_frontend_kernels.cuh): the kernel SOURCE is compiled
+// here unchanged against tests/emu/cuda_emu.hpp; the launch sequences of kicp_frontend.cu (enqueue_downsample, enqueue_preprocess,
+// the ingest of kicp_register_frame) are restated with host memory, a host min/max in place of cub::DeviceReduce and a host stable
+// select in place of cub::DeviceSelect::Flagged.  Test infrastructure (tests/test_frontend_kernels_emu_cpu.py); build with
+// -ffp-contract=off (the product compiles these kernels with -fmad=false).  Never part of the product library.
+#include "cuda_emu.hpp"
+
+#include "../../kinematic-icp_b200/csrc/kicp_frontend_kernels.cuh"
+
+namespace {
+int64_t select_flagged(const P3 *src, const unsigned char *flags, int64_t n, double *out) {
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; ++i)
+        if (flags[i]) out[3 * m] = src[i].x, out[3 * m + 1] = src[i].y, out[3 * m + 2] = src[i].z, ++m;
+    return m;
+}
+}  // namespace
+
+extern "C" {
+// kiss_icp::VoxelDownsample: enqueue_downsample (scratch hash, atomicMin of the input index per voxel, flag, stable select)
+int64_t kf_emu_voxel_downsample(const double *xyz, int64_t n, double voxel_size, double *out) {
+    if (n == 0) return 0;
+    uint32_t nslots = 1024;
+    while ((int64_t)nslots < 2 * n) nslots <<= 1;
+    std::vector<int4> slots(nslots, make_int4(-1, -1, -1, (int)KICP_SLOT_EMPTY));
+    std::vector<int> first_idx(nslots), slot_of((size_t)n);
+    std::vector<unsigned char> flags((size_t)n);
+    const P3 *src = reinterpret_cast<const P3 *>(xyz);
+    int4 *sl = slots.data();
+    int *fi = first_idx.data(), *so = slot_of.data();
+    unsigned char *fl = flags.data();
+    const int nn = (int)n, grid = (int)((n + 255) / 256);
+    emu::launch_waves((int)((nslots + 255) / 256), 256, [=]() { k_fill_int(fi, 0x7FFFFFFF, (int)nslots); });
+    emu::launch_waves(grid, 256, [=]() { k_ds_insert(src, nn, nullptr, voxel_size, sl, nslots - 1, fi, so); });
+    emu::launch_waves(grid, 256, [=]() { k_ds_flag(nn, nullptr, fi, so, fl); });
+    return select_flagged(src, fl, n, out);
+}
+
+// kiss_icp::Preprocessor::Preprocess + the transform to the base frame: enqueue_preprocess.  omega = log(relative_motion) as
+// (upsilon, omega), which the product computes on the host once per frame.
+int64_t kf_emu_preprocess(const double *xyz, int64_t n, const double *stamps, int64_t n_stamps, const double omega[6],
+                          const double lidar_to_base[7], double max_range, double min_range, int32_t deskew, double *out) {
+    if (n == 0) return 0;
+    PreArgs a;
+    a.deskew = (deskew && n_stamps > 0) ? 1 : 0;
+    a.max_range = max_range, a.min_range = min_range;
+    a.lidar_to_base = Pose{lidar_to_base[0], lidar_to_base[1], lidar_to_base[2], lidar_to_base[3], lidar_to_base[4], lidar_to_base[5],
+                           lidar_to_base[6]};
+    for (int k = 0; k < 6; ++k) a.omega[k] = a.deskew ? omega[k] : 0.0;
+    double mm[2] = {0.0, 0.0};
+    if (a.deskew) {
+        mm[0] = mm[1] = stamps[0];
+        for (int64_t i = 1; i < n; ++i) mm[0] = std::min(mm[0], stamps[i]), mm[1] = std::max(mm[1], stamps[i]);
+    }
+    std::vector<P3> mid((size_t)n);
+    std::vector<unsigned char> flags((size_t)n);
+    const P3 *src = reinterpret_cast<const P3 *>(xyz);
+    P3 *md = mid.data();
+    unsigned char *fl = flags.data();
+    const double *dmm = mm;
+    const int nn = (int)n;
+    emu::launch_waves((int)((n + 255) / 256), 256, [=]() { k_preprocess(src, stamps, dmm, nn, a, md, fl); });
+    return select_flagged(md, fl, n, out);
+}
+
+// PointCloud2-shaped ingest: float32 or float64 fields at a byte stride widened to packed doubles
+void kf_emu_ingest(const unsigned char *raw, int64_t n, int32_t is_f32, int32_t step, int32_t ox, int32_t oy, int32_t oz, double *out) {
+    if (n == 0) return;
+    P3 *o = reinterpret_cast<P3 *>(out);
+    const IngestArgs a{is_f32, step, ox, oy, oz};
+    const int nn = (int)n;
+    emu::launch_waves((int)((n + 255) / 256), 256, [=]() { k_ingest(raw, nn, a, o); });
+}
+}

@@ -1,0 +1,107 @@
+"""The front-end kernels' LOGIC, checked without a GPU: kinematic-icp_b200/csrc/kicp_frontend_kernels.cuh (VoxelDownsample's
+min-index-per-voxel insert with slot locking, Preprocess with de-skew / range filter / base transform, the PointCloud2 ingest) compiled
+unchanged by g++ against the SIMT emulator and driven by the launch sequences of kicp_frontend.cu restated on host memory
+(tests/emu/kf_emu.cpp).  Same assertions as tests/test_gpu_frontend.py makes on the device.  Test infrastructure."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    out = os.path.join(EMU, "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libkf_emu.so")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-I" + cuda_inc, "-I" + os.path.join(ROOT, "include"),
+                    "-I" + os.path.join(ROOT, "kinematic-icp_b200", "csrc"), "-o", so, os.path.join(EMU, "kf_emu.cpp"), "-lpthread"], check=True)
+    L = C.CDLL(so)
+    L.kf_emu_voxel_downsample.restype = C.c_int64
+    L.kf_emu_voxel_downsample.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p]
+    L.kf_emu_preprocess.restype = C.c_int64
+    L.kf_emu_preprocess.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int32,
+                                    C.c_void_p]
+    L.kf_emu_ingest.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    return L
+
+
+def downsample(L, pts, vs):
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    out = np.zeros((max(len(pts), 1), 3))
+    m = L.kf_emu_voxel_downsample(pts.ctypes.data, len(pts), vs, out.ctypes.data)
+    return out[:m]
+
+
+def preprocess(L, ko, pts, stamps, motion, max_range, min_range, deskew, lidar_to_base=None):
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    stamps = np.ascontiguousarray(stamps, dtype=np.float64)
+    omega = np.ascontiguousarray(ko.se3_log(motion), dtype=np.float64)
+    l2b = np.ascontiguousarray(ko.IDENTITY if lidar_to_base is None else lidar_to_base, dtype=np.float64)
+    out = np.zeros((max(len(pts), 1), 3))
+    m = L.kf_emu_preprocess(pts.ctypes.data, len(pts), stamps.ctypes.data if len(stamps) else None, len(stamps), omega.ctypes.data,
+                            l2b.ctypes.data, max_range, min_range, 1 if deskew else 0, out.ctypes.data)
+    return out[:m]
+
+
+def test_voxel_downsample_bit_exact(emu, oracle, workload):
+    """First point (input order) per voxel, survivors in input order — identical arrays; then the pipeline's double down-sample."""
+    ko = oracle
+    rng = np.random.default_rng(21)
+    clouds = [rng.normal(size=(12000, 3)) * [8.0, 8.0, 1.0] - [3.0, 0.0, 0.5], workload(2).scan, np.zeros((0, 3)),
+              np.array([[0.25, -0.25, 7.0]])]
+    for pts in clouds:
+        for vs in (0.5, 1.5, 0.37):
+            out = downsample(emu, pts, vs)
+            ref = ko.voxel_downsample(pts, vs) if len(pts) else np.zeros((0, 3))
+            assert out.shape == ref.shape and np.array_equal(out, ref)
+    w = workload(2)
+    src = downsample(emu, downsample(emu, w.scan, 0.5), 1.5)
+    assert np.array_equal(src, ko.voxel_downsample(ko.voxel_downsample(w.scan, 0.5), 1.5))
+
+
+def test_preprocess_bit_exact_and_deskew(emu, oracle, workload):
+    ko = oracle
+    w = workload(2)
+    pts = np.concatenate([w.scan, w.scan * 3.0, w.scan * 0.01])  # ranges from centimetres to beyond max_range
+    out = preprocess(emu, ko, pts, np.zeros(0), ko.IDENTITY, 100.0, 0.5, False)
+    ref = ko.preprocess(pts, np.zeros(0), ko.IDENTITY, 100.0, 0.5, False)
+    assert np.array_equal(out, ref) and 0 < len(ref) < len(pts)
+    # deskew requested but no stamps: the frame is used as is (Preprocessing.cpp)
+    assert np.array_equal(preprocess(emu, ko, pts, np.zeros(0), w.rel_odom, 100.0, 0.5, True), ref)
+    # with the transform to the base frame fused in
+    l2b = ko.se3_exp([0.2, -0.1, 0.3, 0.01, -0.02, 0.05])
+    out = preprocess(emu, ko, pts, np.zeros(0), ko.IDENTITY, 100.0, 0.5, False, lidar_to_base=l2b)
+    assert np.array_equal(out, ko.se3_transform(l2b, ref))
+    # de-skew: same kept set, points to 1e-12 m (the tolerance of the GPU test, where sin / cos differ from glibc's in the last bits)
+    rng = np.random.default_rng(5)
+    stamps = rng.uniform(10.0, 10.1, size=len(w.scan))
+    motion = ko.se3_exp([0.6, 0.02, 0.0, 0.001, -0.002, 0.03])
+    out = preprocess(emu, ko, w.scan, stamps, motion, 100.0, 0.0, True)
+    ref = ko.preprocess(w.scan, stamps, motion, 100.0, 0.0, True)
+    assert out.shape == ref.shape and np.abs(out - ref).max() < 1e-12
+
+
+def test_ingest_widens_pointcloud2_fields(emu):
+    """float32 x, y, z at unaligned offsets inside a 22-byte record, and float64 fields at a stride: widened exactly."""
+    rng = np.random.default_rng(9)
+    n = 3000
+    xyz32 = rng.normal(size=(n, 3)).astype(np.float32) * 30
+    rec = np.zeros(n, dtype=np.dtype({"names": ["pad", "x", "y", "z", "i"], "formats": ["u1", "<f4", "<f4", "<f4", "<f4"], "offsets": [0, 1, 5, 9, 13],
+                                     "itemsize": 22}))
+    rec["x"], rec["y"], rec["z"] = xyz32[:, 0], xyz32[:, 1], xyz32[:, 2]
+    raw = np.frombuffer(rec.tobytes(), dtype=np.uint8).copy()
+    out = np.zeros((n, 3))
+    emu.kf_emu_ingest(raw.ctypes.data, n, 1, 22, 1, 5, 9, out.ctypes.data)
+    assert np.array_equal(out, xyz32.astype(np.float64))
+    xyz64 = rng.normal(size=(n, 3)) * 30
+    rec = np.zeros(n, dtype=np.dtype({"names": ["x", "y", "z", "t"], "formats": ["<f8", "<f8", "<f8", "<f8"], "offsets": [0, 8, 16, 24], "itemsize": 40}))
+    rec["x"], rec["y"], rec["z"] = xyz64[:, 0], xyz64[:, 1], xyz64[:, 2]
+    raw = np.frombuffer(rec.tobytes(), dtype=np.uint8).copy()
+    emu.kf_emu_ingest(raw.ctypes.data, n, 0, 40, 0, 8, 16, out.ctypes.data)
+    assert np.array_equal(out, xyz64)
