@@ -110,6 +110,63 @@ int km_emu_remove_far(void *h, const double origin[3]) {
     return 0;
 }
 
+// VoxelHashMap::Update(points, pose) as kicp_register_frame issues it (kicp_map_update_pose_async): the point count and the pose are
+// READ BY THE KERNELS from device-resident words (`d_n`, the registration's result block), nothing comes back to the host in between;
+// the eviction always compacts into the spare arrays, over an upper bound of the block count.  status != KICP_OK in the result block
+// (a NaN pose) must leave the map untouched.
+int km_emu_update_pose_async(void *h, const double *xyz, int64_t n_max, int32_t n_actual, const double pose7[7], int32_t status) {
+    EmuMap &m = *static_cast<EmuMap *>(h);
+    if (n_max <= 0) return -3;
+    if ((uint64_t)m.num_blocks + (uint64_t)n_max > m.blocks_cap) return -1;
+    std::vector<double> xyz_t((size_t)n_max * 3);
+    std::vector<int32_t> next((size_t)n_max), touched((size_t)n_max);
+    uint32_t counters[8] = {m.num_blocks, 0, 0, 0, 0, 0, 0, 0};
+    const int d_n_word = n_actual;
+    kicp_reg_result res;
+    memset(&res, 0, sizeof(res));
+    for (int k = 0; k < 7; ++k) res.pose[k] = pose7[k];
+    res.status = status;
+    MapRW rw = m.rw();
+    double *xt = xyz_t.data();
+    int32_t *nx = next.data(), *tc = touched.data();
+    uint32_t *ctr = counters;
+    const int *d_n = &d_n_word;
+    const kicp_reg_result *d_res = &res;
+    const int pgrid = (int)((n_max + 255) / 256);
+    emu::launch_waves(pgrid, 256, [=]() { k_add_find_or_create(rw, xyz, n_max, 1, Pose{0, 0, 0, 1, 0, 0, 0}, xt, nx, ctr, tc, d_n, d_res); });
+    const double map_resolution = std::sqrt(m.voxel_size * m.voxel_size / (double)m.cap);
+    emu::launch_waves(pgrid, 256, [=]() { k_add_commit(rw, xt, nx, ctr, tc, map_resolution); });
+    const uint32_t ub = (uint32_t)std::min<uint64_t>((uint64_t)m.num_blocks + (uint64_t)n_max, m.blocks_cap);
+    std::vector<uint32_t> keep(ub), new_id(ub);
+    {
+        const int4 *blk = m.blk.data();
+        const double *pts = m.pts.data();
+        uint32_t *kp = keep.data();
+        const int cap = m.cap;
+        const double md2 = m.max_distance * m.max_distance;
+        emu::launch_waves((int)((ub + 255) / 256), 256, [=]() { k_mark_far(blk, pts, cap, ub, 0.0, 0.0, 0.0, md2, kp, ctr, d_res); });
+        uint32_t run = 0;
+        for (uint32_t b = 0; b < ub; ++b) new_id[b] = run, run += keep[b];
+        const uint32_t *ni = new_id.data();
+        int4 *bo = m.blk_spare.data();
+        double *po = m.pts_spare.data();
+        emu::launch_waves((int)(((uint64_t)ub * 32 + 255) / 256), 256, [=]() { k_compact_blocks(blk, pts, cap, ub, kp, ni, bo, po); });
+    }
+    std::swap(m.blk, m.blk_spare);
+    std::swap(m.pts, m.pts_spare);
+    std::fill(m.slots.begin(), m.slots.end(), make_int4(-1, -1, -1, (int)KICP_SLOT_EMPTY));
+    {
+        int4 *slots = m.slots.data();
+        const int4 *blk = m.blk.data();
+        const uint32_t mask = m.nslots - 1;
+        emu::launch_waves((int)((ub + 255) / 256), 256, [=]() { k_table_rebuild(slots, mask, blk, ub, ctr); });
+    }
+    // kicp_map_finish_update
+    m.num_blocks = counters[0] - counters[4];
+    m.num_points += (int64_t)counters[3] - (int64_t)counters[5];
+    return counters[2] ? -2 : 0;
+}
+
 // kicp_map_load_voxels: voxel v becomes block v, then the table is rebuilt
 int km_emu_load_voxels(void *h, const int32_t *keys, const int32_t *counts, const double *points, int64_t nvox) {
     EmuMap &m = *static_cast<EmuMap *>(h);

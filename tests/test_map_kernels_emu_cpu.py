@@ -33,6 +33,7 @@ def emu():
         f.restype, f.argtypes = C.c_int64, [C.c_void_p]
     L.km_emu_add_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.km_emu_remove_far.argtypes = [C.c_void_p, C.c_void_p]
+    L.km_emu_update_pose_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32]
     L.km_emu_load_voxels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     L.km_emu_export.restype = C.c_int64
     L.km_emu_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -48,6 +49,11 @@ class EmuMap:
         pts = np.ascontiguousarray(pts, dtype=np.float64)
         p = None if pose is None else np.ascontiguousarray(pose, dtype=np.float64)
         assert self.L.km_emu_add_points(self.h, pts.ctypes.data, len(pts), None if p is None else p.ctypes.data) == 0
+
+    def update_pose_async(self, pts, n_actual, pose, status=0):
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        assert self.L.km_emu_update_pose_async(self.h, pts.ctypes.data, len(pts), n_actual, p.ctypes.data, status) == 0
 
     def remove_far(self, origin):
         o = np.ascontiguousarray(origin, dtype=np.float64)
@@ -143,6 +149,30 @@ def test_update_pose_bit_exact(emu, oracle, workload):
         em.remove_far(pose[4:])
         pose = ko.se3_compose(pose, ko.se3_exp([0.8, 0.05, 0, 0, 0, 0.03]))
     same_map(em, om)
+    em.close()
+
+
+def test_frame_path_update_with_count_and_pose_on_the_device(emu, oracle, workload):
+    """The map update of kicp_register_frame: buffer sized for the worst case, the actual survivor count and the pose read by the
+    kernels themselves, eviction over an upper bound of the block count; a registration that failed (NaN pose) leaves the map alone."""
+    ko = oracle
+    w = workload(1)
+    om = ko.OracleMap(1.0, 40.0, 20)
+    em = EmuMap(emu, 1.0, 40.0, 20)
+    pose = ko.planar_pose(50.0, 0.0, 1.2)
+    rng = np.random.default_rng(8)
+    for k in range(4):
+        n_actual = int(rng.integers(len(w.scan) // 2, len(w.scan)))
+        buf = np.concatenate([w.scan[:n_actual], np.full((len(w.scan) - n_actual, 3), 1e9)])  # the tail must never be read
+        om.update_pose(w.scan[:n_actual], pose)
+        em.update_pose_async(buf, n_actual, pose)
+        assert em.num_points() == om.num_points() and em.num_voxels() == om.num_voxels()
+        pose = ko.se3_compose(pose, ko.se3_exp([6.0, 0.3, 0, 0, 0, 0.05]))  # far enough for voxels to die (max_distance 40)
+    same_map(em, om)
+    before = em.export_voxels()
+    em.update_pose_async(w.scan, len(w.scan), np.full(7, np.nan), status=16)  # KICP_WARN_NO_CORRESPONDENCES
+    after = em.export_voxels()
+    assert all(np.array_equal(a, b) for a, b in zip(before, after))
     em.close()
 
 
