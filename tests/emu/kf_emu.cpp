@@ -18,8 +18,12 @@ int64_t select_flagged(const P3 *src, const unsigned char *flags, int64_t n, dou
 
 extern "C" {
 // kiss_icp::VoxelDownsample: enqueue_downsample (scratch hash, atomicMin of the input index per voxel, flag, stable select)
-int64_t kf_emu_voxel_downsample(const double *xyz, int64_t n, double voxel_size, double *out) {
+// n_actual >= 0: the stage runs as in a frame whose survivor count lives on the device — grid sized for the upper bound n, the
+// kernels read the count from a device word (`d_n`) and the tail threads retire; -1: the count is the host's n.
+int64_t kf_emu_voxel_downsample(const double *xyz, int64_t n, double voxel_size, double *out, int32_t n_actual) {
     if (n == 0) return 0;
+    const int d_n_word = n_actual;
+    const int *d_n = n_actual >= 0 ? &d_n_word : nullptr;
     uint32_t nslots = 1024;
     while ((int64_t)nslots < 2 * n) nslots <<= 1;
     std::vector<int4> slots(nslots, make_int4(-1, -1, -1, (int)KICP_SLOT_EMPTY));
@@ -31,8 +35,8 @@ int64_t kf_emu_voxel_downsample(const double *xyz, int64_t n, double voxel_size,
     unsigned char *fl = flags.data();
     const int nn = (int)n, grid = (int)((n + 255) / 256);
     emu::launch_waves((int)((nslots + 255) / 256), 256, [=]() { k_fill_int(fi, 0x7FFFFFFF, (int)nslots); });
-    emu::launch_waves(grid, 256, [=]() { k_ds_insert(src, nn, nullptr, voxel_size, sl, nslots - 1, fi, so); });
-    emu::launch_waves(grid, 256, [=]() { k_ds_flag(nn, nullptr, fi, so, fl); });
+    emu::launch_waves(grid, 256, [=]() { k_ds_insert(src, nn, d_n, voxel_size, sl, nslots - 1, fi, so); });
+    emu::launch_waves(grid, 256, [=]() { k_ds_flag(nn, d_n, fi, so, fl); });
     return select_flagged(src, fl, n, out);
 }
 

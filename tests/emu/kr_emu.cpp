@@ -69,7 +69,9 @@ struct RankScratch {
 extern "C" int kr_emu_register(const int32_t *keys, const int32_t *counts, const double *pts, int64_t nvox, int32_t cap, double voxel_size,
                                const void *scan, int64_t n, int32_t f32, const double last[7], const double odom[7], double tau,
                                const kicp_reg_params *params, int32_t grid, int32_t nranks, int32_t persistent, int32_t nn_cache,
-                               int32_t registrations, kicp_reg_result *results, uint64_t *stats, int32_t late_upload) {
+                               int32_t registrations, kicp_reg_result *results, uint64_t *stats, int32_t late_upload, int32_t device_count) {
+    static int device_count_word;  // (read by the kernels through a pointer, like the survivor count a frame leaves in device memory)
+    device_count_word = device_count;
     if (nranks < 1 || nranks > KICP_MAX_RANKS || (nranks > 1 && !persistent)) return -10;
     HostMap map;
     build_map(map, keys, counts, pts, nvox, cap, voxel_size);
@@ -94,6 +96,7 @@ extern "C" int kr_emu_register(const int32_t *keys, const int32_t *counts, const
             KernelArgs a{};
             a.st = &s.st;
             a.scan.base = (const unsigned char *)scan + lo * stride, a.scan.n = (int)(hi - lo), a.scan.d_n = nullptr;
+            if (device_count >= 0 && nranks == 1) a.scan.d_n = &device_count_word;  // the frame path: n is only an upper bound
             a.scan.stride = stride, a.scan.ox = 0, a.scan.oy = f32 ? 4 : 8, a.scan.oz = f32 ? 8 : 16, a.scan.f32 = f32;
             a.map = map.view, a.partials = s.partials.data();
             a.px.nranks = 1;

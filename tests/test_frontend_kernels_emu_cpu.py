@@ -23,7 +23,7 @@ def emu():
                     "-I" + os.path.join(ROOT, "kinematic-icp_b200", "csrc"), "-o", so, os.path.join(EMU, "kf_emu.cpp"), "-lpthread"], check=True)
     L = C.CDLL(so)
     L.kf_emu_voxel_downsample.restype = C.c_int64
-    L.kf_emu_voxel_downsample.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p]
+    L.kf_emu_voxel_downsample.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_int32]
     L.kf_emu_preprocess.restype = C.c_int64
     L.kf_emu_preprocess.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int32,
                                     C.c_void_p]
@@ -31,10 +31,10 @@ def emu():
     return L
 
 
-def downsample(L, pts, vs):
+def downsample(L, pts, vs, n_actual=-1):
     pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
     out = np.zeros((max(len(pts), 1), 3))
-    m = L.kf_emu_voxel_downsample(pts.ctypes.data, len(pts), vs, out.ctypes.data)
+    m = L.kf_emu_voxel_downsample(pts.ctypes.data, len(pts), vs, out.ctypes.data, n_actual)
     return out[:m]
 
 
@@ -63,6 +63,13 @@ def test_voxel_downsample_bit_exact(emu, oracle, workload):
     w = workload(2)
     src = downsample(emu, downsample(emu, w.scan, 0.5), 1.5)
     assert np.array_equal(src, ko.voxel_downsample(ko.voxel_downsample(w.scan, 0.5), 1.5))
+    # a stage of a frame: the buffer is sized for the worst case, the survivor count of the stage before sits in a device word,
+    # the tail of the buffer (here: points that would open voxels of their own) must not be seen
+    for n_actual in (0, 1, 5000, len(w.scan)):
+        buf = np.concatenate([w.scan[:n_actual], w.scan[n_actual:] + 1000.0])
+        out = downsample(emu, buf, 0.5, n_actual=n_actual)
+        ref = ko.voxel_downsample(w.scan[:n_actual], 0.5) if n_actual else np.zeros((0, 3))
+        assert out.shape == ref.shape and np.array_equal(out, ref)
 
 
 def test_preprocess_bit_exact_and_deskew(emu, oracle, workload):

@@ -36,7 +36,7 @@ def emu():
 
 
 def run_emu(lib, om, scan, last, odom, tau, grid=3, nranks=1, persistent=1, nn_cache=1, registrations=1, max_iter=10, conv=1e-3,
-            adaptive=True, fixed_reg=0.0, late_upload=0):
+            adaptive=True, fixed_reg=0.0, late_upload=0, device_count=-1):
     from kinematic_icp_b200 import _capi
     keys, counts, pts = om.export_voxels()
     keys = np.ascontiguousarray(keys, dtype=np.int32)
@@ -52,7 +52,7 @@ def run_emu(lib, om, scan, last, odom, tau, grid=3, nranks=1, persistent=1, nn_c
     rc = lib.kr_emu_register(vp(keys), vp(counts), vp(pts), C.c_int64(len(counts)), C.c_int32(om.max_points_per_voxel), C.c_double(om.voxel_size),
                              vp(scan), C.c_int64(len(scan)), C.c_int32(1 if f32 else 0), vp(last), vp(odom), C.c_double(tau), C.byref(p),
                              C.c_int32(grid), C.c_int32(nranks), C.c_int32(persistent), C.c_int32(nn_cache), C.c_int32(registrations), res, stats,
-                             C.c_int32(late_upload))
+                             C.c_int32(late_upload), C.c_int32(device_count))
     assert rc == 0, "a launch must leave its counters zero for the next one: rc %d" % rc
     return list(res), list(stats)
 
@@ -106,6 +106,26 @@ def test_frame_uploaded_while_the_kernel_runs(emu, oracle, workload, cfg, n, gri
     scan = w.scan if n is None else w.scan[:n]
     check(emu, ko, w.map, scan, w.last_pose, w.rel_odom, w.tau, grid=grid, late_upload=1, registrations=2)
     check(emu, ko, w.map, scan.astype(np.float32), w.last_pose, w.rel_odom, w.tau, grid=grid, late_upload=1)
+
+
+@pytest.mark.parametrize("count", [0, 1, 700, 1992])
+def test_point_count_read_from_device_memory(emu, oracle, workload, count):
+    """kicp_register_frame registers a frame whose survivor count only exists on the device: the grid is planned for an upper bound,
+    the kernel reads the count itself.  The points beyond the count (here far away, they would all be rejected — or poison N) are not
+    part of the frame."""
+    from kinematic_icp_b200 import _capi
+    ko = oracle
+    w = workload(1)
+    count = min(count, w.N)
+    buf = np.concatenate([w.scan[:count], np.full((w.N - count, 3), np.nan)])
+    res, _ = run_emu(emu, w.map, buf, w.last_pose, w.rel_odom, w.tau, grid=3, device_count=count)
+    if count == 0:
+        assert np.all(np.isnan(res[0].pose_np())) and res[0].status == _capi.KICP_WARN_NO_CORRESPONDENCES
+        return
+    po, st = w.map.register(w.scan[:count], w.last_pose, w.rel_odom, w.tau)
+    dt, ang = ko.pose_delta(res[0].pose_np(), po)
+    assert dt <= TOL_T and ang <= TOL_R and res[0].iterations == st.iterations
+    assert np.array_equal(res[0].sums_np()[:, 5], st.sums_np()[:, 5])
 
 
 def test_kernel_edge_cases(emu, oracle, workload):
