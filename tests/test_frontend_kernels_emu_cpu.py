@@ -2,51 +2,28 @@
 min-index-per-voxel insert with slot locking, Preprocess with de-skew / range filter / base transform, the PointCloud2 ingest) compiled
 unchanged by g++ against the SIMT emulator and driven by the launch sequences of kicp_frontend.cu restated on host memory
 (tests/emu/kf_emu.cpp).  Same assertions as tests/test_gpu_frontend.py makes on the device.  Test infrastructure."""
-import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EMU = os.path.join(ROOT, "tests", "emu")
+
+
+from emu import harness as H
 
 
 @pytest.fixture(scope="module")
 def emu():
-    out = os.path.join(EMU, "_build")
-    os.makedirs(out, exist_ok=True)
-    so = os.path.join(out, "libkf_emu.so")
-    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-I" + cuda_inc, "-I" + os.path.join(ROOT, "include"),
-                    "-I" + os.path.join(ROOT, "kinematic-icp_b200", "csrc"), "-o", so, os.path.join(EMU, "kf_emu.cpp"), "-lpthread"], check=True)
-    L = C.CDLL(so)
-    L.kf_emu_voxel_downsample.restype = C.c_int64
-    L.kf_emu_voxel_downsample.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_int32]
-    L.kf_emu_preprocess.restype = C.c_int64
-    L.kf_emu_preprocess.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int32,
-                                    C.c_void_p]
-    L.kf_emu_ingest.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
-    return L
+    return H.kf_lib()
 
 
-def downsample(L, pts, vs, n_actual=-1):
-    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
-    out = np.zeros((max(len(pts), 1), 3))
-    m = L.kf_emu_voxel_downsample(pts.ctypes.data, len(pts), vs, out.ctypes.data, n_actual)
-    return out[:m]
+def downsample(_lib, pts, vs, n_actual=-1):
+    return H.downsample(pts, vs, n_actual)
 
 
-def preprocess(L, ko, pts, stamps, motion, max_range, min_range, deskew, lidar_to_base=None):
-    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
-    stamps = np.ascontiguousarray(stamps, dtype=np.float64)
-    omega = np.ascontiguousarray(ko.se3_log(motion), dtype=np.float64)
-    l2b = np.ascontiguousarray(ko.IDENTITY if lidar_to_base is None else lidar_to_base, dtype=np.float64)
-    out = np.zeros((max(len(pts), 1), 3))
-    m = L.kf_emu_preprocess(pts.ctypes.data, len(pts), stamps.ctypes.data if len(stamps) else None, len(stamps), omega.ctypes.data,
-                            l2b.ctypes.data, max_range, min_range, 1 if deskew else 0, out.ctypes.data)
-    return out[:m]
+def preprocess(_lib, ko, pts, stamps, motion, max_range, min_range, deskew, lidar_to_base=None):
+    return H.preprocess(ko, pts, stamps, motion, max_range, min_range, deskew, lidar_to_base)
 
 
 def test_voxel_downsample_bit_exact(emu, oracle, workload):

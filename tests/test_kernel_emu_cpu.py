@@ -11,50 +11,26 @@ correspondence count in every pass (any neighbour or gate flip would show there)
 
 This is test infrastructure: nothing here is linked into the product, and the GPU parity tests remain the proof for the device
 build — the emulator cannot see the GPU memory model, launch limits or register-level hazards."""
-import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EMU = os.path.join(ROOT, "tests", "emu")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 TOL_T, TOL_R = 1e-6, 1e-7
 
 
+from emu import harness as H
+
+
 @pytest.fixture(scope="module")
 def emu():
-    out = os.path.join(EMU, "_build")
-    os.makedirs(out, exist_ok=True)
-    so = os.path.join(out, "libkr_emu.so")
-    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-I" + cuda_inc, "-I" + os.path.join(ROOT, "include"),
-                    "-I" + os.path.join(ROOT, "kinematic-icp_b200", "csrc"), "-o", so, os.path.join(EMU, "kr_emu.cpp"), "-lpthread"], check=True)
-    return C.CDLL(so)
+    return H.kr_lib()
 
 
-def run_emu(lib, om, scan, last, odom, tau, grid=3, nranks=1, persistent=1, nn_cache=1, registrations=1, max_iter=10, conv=1e-3,
-            adaptive=True, fixed_reg=0.0, late_upload=0, device_count=-1):
-    from kinematic_icp_b200 import _capi
-    keys, counts, pts = om.export_voxels()
-    keys = np.ascontiguousarray(keys, dtype=np.int32)
-    counts = np.ascontiguousarray(counts, dtype=np.int32)
-    pts = np.ascontiguousarray(pts, dtype=np.float64)
-    f32 = scan.dtype == np.float32
-    scan = np.ascontiguousarray(scan)
-    last, odom = np.ascontiguousarray(last, dtype=np.float64), np.ascontiguousarray(odom, dtype=np.float64)
-    p = _capi.RegParams(max_iter, 1 if adaptive else 0, conv, fixed_reg)
-    res = (_capi.RegResult * nranks)()
-    stats = (C.c_uint64 * 3)()
-    vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = lib.kr_emu_register(vp(keys), vp(counts), vp(pts), C.c_int64(len(counts)), C.c_int32(om.max_points_per_voxel), C.c_double(om.voxel_size),
-                             vp(scan), C.c_int64(len(scan)), C.c_int32(1 if f32 else 0), vp(last), vp(odom), C.c_double(tau), C.byref(p),
-                             C.c_int32(grid), C.c_int32(nranks), C.c_int32(persistent), C.c_int32(nn_cache), C.c_int32(registrations), res, stats,
-                             C.c_int32(late_upload), C.c_int32(device_count))
-    assert rc == 0, "a launch must leave its counters zero for the next one: rc %d" % rc
-    return list(res), list(stats)
+def run_emu(lib, om, scan, last, odom, tau, **kw):
+    return H.register(om, scan, last, odom, tau, **kw)
 
 
 def check(lib, ko, om, scan, last, odom, tau, **kw):

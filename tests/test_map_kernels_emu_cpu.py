@@ -5,87 +5,25 @@ to a few OS threads, fibers inside) and driven by the launch sequences of kicp_m
 The map must equal the CPU oracle's bit for bit — the same assertions as tests/test_gpu_parity.py makes on the device.
 
 Test infrastructure; the GPU suite remains the proof for the device build."""
-import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EMU = os.path.join(ROOT, "tests", "emu")
 DBL_MAX = np.finfo(np.float64).max
+
+
+from emu import harness as H
 
 
 @pytest.fixture(scope="module")
 def emu():
-    out = os.path.join(EMU, "_build")
-    os.makedirs(out, exist_ok=True)
-    so = os.path.join(out, "libkm_emu.so")
-    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-I" + cuda_inc, "-I" + os.path.join(ROOT, "include"),
-                    "-I" + os.path.join(ROOT, "kinematic-icp_b200", "csrc"), "-o", so, os.path.join(EMU, "km_emu.cpp"), "-lpthread"], check=True)
-    L = C.CDLL(so)
-    L.km_emu_create.restype = C.c_void_p
-    L.km_emu_create.argtypes = [C.c_double, C.c_double, C.c_int32, C.c_uint32]
-    L.km_emu_destroy.argtypes = [C.c_void_p]
-    for f in (L.km_emu_num_points, L.km_emu_num_voxels):
-        f.restype, f.argtypes = C.c_int64, [C.c_void_p]
-    L.km_emu_add_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
-    L.km_emu_remove_far.argtypes = [C.c_void_p, C.c_void_p]
-    L.km_emu_update_pose_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32]
-    L.km_emu_load_voxels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
-    L.km_emu_export.restype = C.c_int64
-    L.km_emu_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    L.km_emu_nearest.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
-    return L
+    return H.km_lib()
 
 
-class EmuMap:
-    def __init__(self, L, voxel_size, max_distance, cap, blocks_cap=60000):
-        self.L, self.h = L, C.c_void_p(L.km_emu_create(voxel_size, max_distance, cap, blocks_cap))
-
-    def add_points(self, pts, pose=None):
-        pts = np.ascontiguousarray(pts, dtype=np.float64)
-        p = None if pose is None else np.ascontiguousarray(pose, dtype=np.float64)
-        assert self.L.km_emu_add_points(self.h, pts.ctypes.data, len(pts), None if p is None else p.ctypes.data) == 0
-
-    def update_pose_async(self, pts, n_actual, pose, status=0):
-        pts = np.ascontiguousarray(pts, dtype=np.float64)
-        p = np.ascontiguousarray(pose, dtype=np.float64)
-        assert self.L.km_emu_update_pose_async(self.h, pts.ctypes.data, len(pts), n_actual, p.ctypes.data, status) == 0
-
-    def remove_far(self, origin):
-        o = np.ascontiguousarray(origin, dtype=np.float64)
-        assert self.L.km_emu_remove_far(self.h, o.ctypes.data) == 0
-
-    def load_voxels(self, keys, counts, pts):
-        keys = np.ascontiguousarray(keys, dtype=np.int32)
-        counts = np.ascontiguousarray(counts, dtype=np.int32)
-        pts = np.ascontiguousarray(pts, dtype=np.float64)
-        assert self.L.km_emu_load_voxels(self.h, keys.ctypes.data, counts.ctypes.data, pts.ctypes.data, len(counts)) == 0
-
-    def num_points(self):
-        return int(self.L.km_emu_num_points(self.h))
-
-    def num_voxels(self):
-        return int(self.L.km_emu_num_voxels(self.h))
-
-    def export_voxels(self):
-        nv, npts = self.num_voxels(), self.num_points()
-        keys, counts, pts = np.zeros((nv, 3), np.int32), np.zeros(nv, np.int32), np.zeros((npts, 3))
-        assert self.L.km_emu_export(self.h, keys.ctypes.data, counts.ctypes.data, pts.ctypes.data) == nv
-        assert int(counts.sum()) == npts
-        return keys, counts, pts
-
-    def nearest(self, q):
-        q = np.ascontiguousarray(q, dtype=np.float64)
-        out_p, out_d = np.zeros((len(q), 3)), np.zeros(len(q))
-        assert self.L.km_emu_nearest(self.h, q.ctypes.data, len(q), out_p.ctypes.data, out_d.ctypes.data) == 0
-        return out_p, out_d
-
-    def close(self):
-        self.L.km_emu_destroy(self.h)
+def EmuMap(_lib, voxel_size, max_distance, cap):
+    return H.EmuMap(voxel_size, max_distance, cap)
 
 
 def sorted_voxels(keys, counts, pts):
