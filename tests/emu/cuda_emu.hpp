@@ -82,6 +82,30 @@ inline Idx3 block_dim = {1, 1, 1};
 
 inline void yield() { swapcontext(&cur->ctx, &sched_ctx); }
 
+// Interleaving stress (environment KICP_EMU_CHAOS = seed, 0 / unset = off): every global-memory access that can order threads — the
+// atomics, __ldcg / __stcg, the fences — additionally gives the fiber's turn away with probability 1/4, so that the lanes of a warp and
+// the warps of a CTA run in many more orders than the plain round robin produces.  Collectives keep their meaning (all 32 lanes meet).
+// A harness opts in with `#define EMU_CHAOS 1` before this header — and must not, if its kernels hold spin locks: the fibers of a CTA share
+// one OS thread, so a lock holder that gives its turn away inside the critical section starves the spinners for ever (on the device the
+// holder simply keeps running).  The registration kernel has no such locks: all of its waits are collectives or sleep.
+inline unsigned chaos_seed() {
+    static const unsigned seed = []() {
+        const char *e = getenv("KICP_EMU_CHAOS");
+        return e ? (unsigned)strtoul(e, nullptr, 10) : 0u;
+    }();
+    return seed;
+}
+inline thread_local uint64_t chaos_state = 0;
+inline void chaos_point() {
+#ifndef EMU_CHAOS
+    return;
+#endif
+    if (!chaos_seed() || !cur) return;
+    if (!chaos_state) chaos_state = 0x9E3779B97F4A7C15ull * (chaos_seed() + 1) + (uint64_t)(uintptr_t)cta;
+    chaos_state ^= chaos_state << 13, chaos_state ^= chaos_state >> 7, chaos_state ^= chaos_state << 17;
+    if ((chaos_state & 3u) == 0u) yield();
+}
+
 // all 32 lanes of the calling fiber's warp deposit a value and leave together; returns the buffer holding the 32 values
 inline const uint64_t *exchange(uint64_t v) {
     Fiber *f = cur;
@@ -252,27 +276,46 @@ inline void __syncthreads() { emu::syncthreads(); }
 template <class T>
 inline T __ldg(const T *p) { return *(const volatile T *)p; }
 template <class T>
-inline T __ldcg(const T *p) { return *(const volatile T *)p; }
+inline T __ldcg(const T *p) {
+    emu::chaos_point();
+    return *(const volatile T *)p;
+}
 inline int4 __ldg(const int4 *p) { int4 v; memcpy(&v, p, sizeof(v)); return v; }
 #ifndef __restrict__
 #define __restrict__ __restrict
 #endif
 inline uint2 __ldcg(const uint2 *p) { uint2 v; memcpy(&v, p, sizeof(v)); return v; }
 template <class T>
-inline void __stcg(T *p, T v) { *(volatile T *)p = v; }
-inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __stcg(T *p, T v) {
+    emu::chaos_point();
+    *(volatile T *)p = v;
+}
+inline void __threadfence() {
+    emu::chaos_point();
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+}
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicAdd(unsigned *p, unsigned v) {
+    emu::chaos_point();
+    return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST);
+}
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
-inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicExch(int *p, int v) {
+    emu::chaos_point();
+    return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST);
+}
 inline int atomicMin(int *p, int v) {
     int old = __atomic_load_n(p, __ATOMIC_RELAXED);
     while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_RELAXED)) {
     }
     return old;
 }
-inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicExch(unsigned *p, unsigned v) {
+    emu::chaos_point();
+    return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST);
+}
 inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned v) {
+    emu::chaos_point();
     __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
     return cmp;
 }

@@ -2,6 +2,7 @@
 // unchanged against tests/emu/cuda_emu.hpp and run as a small grid of fibers — one grid per "rank" for the sharded path, the
 // peers' mailboxes being plain host memory — on a map laid out exactly as the device holds it (kicp_internal.h).
 // Test infrastructure: tests/test_kernel_emu_cpu.py compares the results with the CPU oracle.  Never part of the product library.
+#define EMU_CHAOS 1  // interleaving stress on request (KICP_EMU_CHAOS = seed): this kernel waits through collectives and sleeps only
 #include "cuda_emu.hpp"
 
 #define KR_EMU 1

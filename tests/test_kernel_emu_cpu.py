@@ -84,6 +84,20 @@ def test_frame_uploaded_while_the_kernel_runs(emu, oracle, workload, cfg, n, gri
     check(emu, ko, w.map, scan.astype(np.float32), w.last_pose, w.rel_odom, w.tau, grid=grid, late_upload=1)
 
 
+@pytest.mark.parametrize("seed", [1])
+def test_interleaving_stress(oracle, workload, seed):
+    """The same checks in a fresh process with KICP_EMU_CHAOS = seed: every atomic, fence and L2 load / store of the kernel
+    additionally gives the fiber's turn away with probability 1/4, so lanes, warps and ranks interleave in many more orders than the
+    round robin produces — certificates, the sharded exchange and the upload flags included."""
+    import subprocess
+    import sys
+    env = dict(os.environ, KICP_EMU_CHAOS=str(seed))
+    sel = "(sharded and 1-2-2-1) or (sharded and 2-2-2-1) or (uploaded and 1-) or (matches_oracle and 1-)"  # (other seeds, other cases: by hand)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", sel, "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("count", [0, 1, 700, 1992])
 def test_point_count_read_from_device_memory(emu, oracle, workload, count):
     """kicp_register_frame registers a frame whose survivor count only exists on the device: the grid is planned for an upper bound,
