@@ -62,7 +62,7 @@ def test_kernel_matches_oracle(emu, oracle, workload, cfg, grid, persistent, nn_
     assert dt <= 1e-12 and ang <= 1e-12
 
 
-@pytest.mark.parametrize("cfg,grid,nranks,nn_cache", [(1, 2, 2, 1), (2, 2, 2, 1), (2, 2, 3, 0)])
+@pytest.mark.parametrize("cfg,grid,nranks,nn_cache", [(1, 2, 2, 1), (2, 2, 2, 1), (2, 2, 3, 0), (2, 1, 8, 1), (1, 1, 4, 0)])
 def test_sharded_ranks_agree_bit_for_bit(emu, oracle, workload, cfg, grid, nranks, nn_cache):
     """kicp_register_sharded's fused exchange: every rank writes its 8 sums into every rank's mailbox as tagged 8-byte words, every
     CTA adds them in rank order — identical inputs, identical order, identical pose on all ranks; three registrations in a row
