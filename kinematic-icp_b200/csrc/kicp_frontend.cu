@@ -3,14 +3,13 @@
 //   kiss_icp::VoxelDownsample(frame, voxel_size)          first point (input order) of every voxel
 //   kiss_icp::Preprocessor::Preprocess(frame, stamps, T)  de-skew p <- exp((s-1) log T) p, then keep min < |p| < max
 // followed by the transform to the robot base frame.  Output order is the input order of the survivors (stable stream
-// compaction), which is what the CPU restatement produces.  Compiled with -fmad=false like kicp_map.cu: voxel floors and
+// compaction — the library's own single-pass scan, kicp_scan.cuh, fused into the kernels that decide what survives), which is what
+// the CPU restatement produces.  Compiled with -fmad=false like kicp_map.cu: voxel floors and
 // range tests are evaluated in plain IEEE order.
 #include <cfloat>
 #include <chrono>
 #include <cmath>
 #include <cstring>
-#include <cub/device/device_reduce.cuh>
-#include <cub/device/device_select.cuh>
 
 #include "kicp_device.cuh"
 
@@ -21,8 +20,9 @@ using namespace kicp_dev;
 // ------------------------------------------------------------------------------------------------------------ host
 namespace {
 struct Scratch {
-    P3 *in = nullptr, *mid = nullptr, *out = nullptr, *out2 = nullptr, *out3 = nullptr;
-    double *stamps = nullptr, *d_mm = nullptr;
+    P3 *in = nullptr, *out = nullptr, *out2 = nullptr, *out3 = nullptr;
+    double *stamps = nullptr, *d_mm = nullptr;  // d_mm: {min, max} of the stamps, then the per-CTA partials of their reduction
+    unsigned int *d_mm_ticket = nullptr;
     unsigned char *raw = nullptr;
     size_t raw_cap = 0;
     int *h_count = nullptr;  // pinned, 4 ints
@@ -32,17 +32,14 @@ struct Scratch {
     P3 *h_frame = nullptr, *h_source = nullptr;  // pinned staging of the two clouds RegisterFrame returns (cap points each)
     int64_t staged_frame = 0, staged_source = 0;
     double timing[8] = {0};  // host-side stage times of the last kicp_register_frame, milliseconds (debug export)
-    unsigned char *flags = nullptr;
     int *first_idx = nullptr, *slot_of = nullptr, *d_count = nullptr;
     int4 *slots = nullptr;
-    void *tmp = nullptr;
-    size_t tmp_bytes = 0;
     int64_t cap = 0;
     uint32_t nslots = 0;
 };
 void release(Scratch &s) {
-    cudaFree(s.in), cudaFree(s.mid), cudaFree(s.out), cudaFree(s.out2), cudaFree(s.out3), cudaFree(s.stamps), cudaFree(s.flags);
-    cudaFree(s.first_idx), cudaFree(s.slot_of), cudaFree(s.slots), cudaFree(s.tmp), cudaFree(s.d_count), cudaFree(s.d_mm);
+    cudaFree(s.in), cudaFree(s.out), cudaFree(s.out2), cudaFree(s.out3), cudaFree(s.stamps), cudaFree(s.d_mm_ticket);
+    cudaFree(s.first_idx), cudaFree(s.slot_of), cudaFree(s.slots), cudaFree(s.d_count), cudaFree(s.d_mm);
     cudaFree(s.raw), cudaFreeHost(s.h_count), cudaFreeHost(s.h_frame), cudaFreeHost(s.h_source), cudaFreeHost(s.h_mapctr);
     if (s.ev_front) cudaEventDestroy(s.ev_front);
     s = Scratch();
@@ -72,28 +69,22 @@ int reserve(kicp_ctx *c, Scratch &s, int64_t n) {
     uint32_t nslots = 1;
     while (nslots < (uint64_t)cap * 2) nslots <<= 1;
     KICP_CUDA(cudaMalloc(&s.in, cap * sizeof(P3)));
-    KICP_CUDA(cudaMalloc(&s.mid, cap * sizeof(P3)));
     KICP_CUDA(cudaMalloc(&s.out, cap * sizeof(P3)));
     KICP_CUDA(cudaMalloc(&s.out2, cap * sizeof(P3)));
     KICP_CUDA(cudaMalloc(&s.out3, cap * sizeof(P3)));
-    KICP_CUDA(cudaMalloc(&s.d_mm, 2 * sizeof(double)));
+    KICP_CUDA(cudaMalloc(&s.d_mm, (2 + 2 * kMinMaxMaxGrid) * sizeof(double)));
+    KICP_CUDA(cudaMalloc(&s.d_mm_ticket, sizeof(unsigned int)));
+    KICP_CUDA(cudaMemsetAsync(s.d_mm_ticket, 0, sizeof(unsigned int), c->stream));
     KICP_CUDA(cudaMallocHost(&s.h_count, 4 * sizeof(int)));
     KICP_CUDA(cudaMallocHost(&s.h_mapctr, 8 * sizeof(uint32_t)));
     KICP_CUDA(cudaEventCreateWithFlags(&s.ev_front, cudaEventDisableTiming));
     KICP_CUDA(cudaMallocHost(&s.h_frame, cap * sizeof(P3)));
     KICP_CUDA(cudaMallocHost(&s.h_source, cap * sizeof(P3)));
     KICP_CUDA(cudaMalloc(&s.stamps, cap * sizeof(double)));
-    KICP_CUDA(cudaMalloc(&s.flags, cap));
     KICP_CUDA(cudaMalloc(&s.first_idx, (size_t)nslots * sizeof(int)));
     KICP_CUDA(cudaMalloc(&s.slot_of, cap * sizeof(int)));
     KICP_CUDA(cudaMalloc(&s.slots, (size_t)nslots * sizeof(int4)));
     KICP_CUDA(cudaMalloc(&s.d_count, 4 * sizeof(int)));
-    size_t b1 = 0, b2 = 0, b3 = 0;
-    KICP_CUDA(cub::DeviceSelect::Flagged(nullptr, b1, s.in, s.flags, s.out, s.d_count, (int)cap, c->stream));
-    KICP_CUDA(cub::DeviceReduce::Min(nullptr, b2, s.stamps, s.stamps, (int)cap, c->stream));
-    KICP_CUDA(cub::DeviceReduce::Max(nullptr, b3, s.stamps, s.stamps, (int)cap, c->stream));
-    s.tmp_bytes = std::max(b1, std::max(b2, b3));
-    KICP_CUDA(cudaMalloc(&s.tmp, s.tmp_bytes));
     s.cap = cap, s.nslots = nslots;
     return KICP_OK;
 }
@@ -131,19 +122,19 @@ void se3_log_host(const double p[7], double out[6]) {
     out[3] = w[0], out[4] = w[1], out[5] = w[2];
 }
 
-// VoxelDownsample of src[0, n) (n = *d_n when given, else n_max) into dst, survivor count to d_count_out; all on the stream
+// VoxelDownsample of src[0, n) (n = *d_n when given, else n_max) into dst, survivor count to d_count_out; all on the stream:
+// clear the scratch hash, claim a slot per voxel with the smallest input index, select the points that hold their voxel's index
 int enqueue_downsample(kicp_ctx *c, Scratch &s, const P3 *src, int n_max, const int *d_n, double voxel_size, P3 *dst, int *d_count_out) {
-    KICP_CUDA(cudaMemsetAsync(s.slots, 0xFF, (size_t)s.nslots * sizeof(int4), c->stream));
     const int threads = 256, blocks = (n_max + threads - 1) / threads;
-    k_fill_int<<<(s.nslots + 255) / 256, 256, 0, c->stream>>>(s.first_idx, 0x7FFFFFFF, (int)s.nslots);
+    k_ds_clear<<<(s.nslots + 255) / 256, 256, 0, c->stream>>>(s.slots, s.first_idx, (int)s.nslots);
     KICP_CHECK_LAUNCH(c);
     k_ds_insert<<<blocks, threads, 0, c->stream>>>(src, n_max, d_n, voxel_size, s.slots, s.nslots - 1, s.first_idx, s.slot_of);
     KICP_CHECK_LAUNCH(c);
-    k_ds_flag<<<blocks, threads, 0, c->stream>>>(n_max, d_n, s.first_idx, s.slot_of, s.flags);
+    kicp_scan_args sa;
+    KICP_TRY(kicp_scan_next(c, n_max, &sa));
+    k_ds_select<<<(n_max + kScanTile - 1) / kScanTile, kScanThreads, 0, c->stream>>>(src, n_max, d_n, s.first_idx, s.slot_of, dst, d_count_out,
+                                                                                    sa);
     KICP_CHECK_LAUNCH(c);
-    size_t bytes = s.tmp_bytes;
-    KICP_CUDA(cub::DeviceSelect::Flagged(s.tmp, bytes, src, s.flags, dst, d_count_out, n_max, c->stream));
-    c->launches += 2;  // CUB's select passes (library kernels)
     return KICP_OK;
 }
 
@@ -158,19 +149,15 @@ int enqueue_preprocess(kicp_ctx *c, Scratch &s, int n, const double *stamps, int
     for (int k = 0; k < 6; ++k) a.omega[k] = 0.0;
     if (a.deskew) {
         KICP_CUDA(cudaMemcpyAsync(s.stamps, stamps, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        size_t bytes = s.tmp_bytes;
-        KICP_CUDA(cub::DeviceReduce::Min(s.tmp, bytes, s.stamps, s.d_mm, n, c->stream));
-        bytes = s.tmp_bytes;
-        KICP_CUDA(cub::DeviceReduce::Max(s.tmp, bytes, s.stamps, s.d_mm + 1, n, c->stream));
-        c->launches += 2;
+        const int grid = std::min(kMinMaxMaxGrid, (n + 2047) / 2048);
+        k_stamp_minmax<<<grid, 256, 0, c->stream>>>(s.stamps, n, s.d_mm + 2, s.d_mm_ticket, s.d_mm);
+        KICP_CHECK_LAUNCH(c);
         se3_log_host(relative_motion, a.omega);
     }
-    const int threads = 256, blocks = (n + threads - 1) / threads;
-    k_preprocess<<<blocks, threads, 0, c->stream>>>(s.in, s.stamps, s.d_mm, n, a, s.mid, s.flags);
+    kicp_scan_args sa;
+    KICP_TRY(kicp_scan_next(c, n, &sa));
+    k_preprocess_select<<<(n + kScanTile - 1) / kScanTile, kScanThreads, 0, c->stream>>>(s.in, s.stamps, s.d_mm, n, a, dst, d_count_out, sa);
     KICP_CHECK_LAUNCH(c);
-    size_t bytes = s.tmp_bytes;
-    KICP_CUDA(cub::DeviceSelect::Flagged(s.tmp, bytes, s.mid, s.flags, dst, d_count_out, n, c->stream));
-    c->launches += 2;
     return KICP_OK;
 }
 }  // namespace

@@ -1,13 +1,15 @@
 // Kernels of the device-side front end (included by kicp_frontend.cu, which is compiled with -fmad=false): VoxelDownsample's
-// min-index-per-voxel insert and flag pass, the PointCloud2 ingest, Preprocess (de-skew, range filter, base transform).  A header of
-// its own so that tests/emu can compile the kernels for the host against the SIMT emulator without the CUB / CUDA-runtime
-// orchestration of kicp_frontend.cu.
+// min-index-per-voxel insert and its order-preserving select, the PointCloud2 ingest, the stamps' min / max, Preprocess (de-skew,
+// range filter, base transform) compacting its survivors as it goes.  The selects are the library's own single-pass scans
+// (kicp_scan.cuh) fused into the kernels that decide what survives: no flag arrays, no library kernels.  A header of its own so that
+// tests/emu can compile the kernels for the host against the SIMT emulator without the CUDA-runtime orchestration of kicp_frontend.cu.
 #pragma once
 #include <cfloat>
 #include <cmath>
 #include <cstring>
 
 #include "kicp_device.cuh"
+#include "kicp_scan.cuh"
 
 using namespace kicp_dev;
 
@@ -50,17 +52,37 @@ __global__ void k_ds_insert(const P3 *__restrict__ pts, int n_max, const int *__
     slot_of[i] = (int)h;
 }
 
-__global__ void k_ds_flag(int n_max, const int *__restrict__ d_n, const int *__restrict__ first_idx, const int *__restrict__ slot_of,
-                          unsigned char *flags) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_max) return;
+// The survivors of the down-sample — the points whose index is the smallest of their voxel — copied to `dst` in input order; their
+// number goes to *d_count_out.  Grid = ceil(n_max / kScanTile) CTAs of kScanThreads threads (kicp_scan.cuh).
+__global__ void __launch_bounds__(kScanThreads) k_ds_select(const P3 *__restrict__ src, int n_max, const int *__restrict__ d_n,
+                                                            const int *__restrict__ first_idx, const int *__restrict__ slot_of, P3 *dst,
+                                                            int *d_count_out, kicp_scan_args sa) {
+    __shared__ uint32_t s_warp[kScanWarps + 1];
+    const uint32_t tile = scan_take_tile(sa, &s_warp[kScanWarps]);
     const int n = d_n ? min(*d_n, n_max) : n_max;
-    flags[i] = (i < n && first_idx[slot_of[i]] == i) ? 1 : 0;
+    const int64_t i0 = scan_first_item(tile);
+    bool keep[kScanItems];
+    uint32_t rank[kScanItems];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int64_t i = i0 + 32 * k;
+        keep[k] = i < n && first_idx[slot_of[i]] == (int)i;
+    }
+    const uint32_t warp_total = scan_warp_ranks(keep, rank);
+    uint32_t inclusive;
+    const uint32_t base = scan_offset(sa, tile, warp_total, s_warp, inclusive);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+        if (keep[k]) dst[base + rank[k]] = src[i0 + 32 * k];
+    if (tile == gridDim.x - 1 && threadIdx.x == 0) *d_count_out = (int)inclusive;
 }
 
-__global__ void k_fill_int(int *p, int v, int n) {
+// empties the scratch hash of the down-sample: every slot free, no first index yet
+__global__ void k_ds_clear(int4 *slots, int *first_idx, int nslots) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
+    if (i >= nslots) return;
+    slots[i] = make_int4(-1, -1, -1, -1);  // w = KICP_SLOT_EMPTY
+    first_idx[i] = 0x7FFFFFFF;
 }
 
 // ---------------------------------------------------------------------------------------------------------- ingest
@@ -134,12 +156,56 @@ __device__ void se3_exp_apply(const double a[6], double px, double py, double pz
     ox = rx + tx, oy = ry + ty, oz = rz + tz;
 }
 
-// `d_mm` = {min, max} of the stamps, reduced on the device just before (no host round trip)
-__global__ void k_preprocess(const P3 *__restrict__ pts, const double *__restrict__ stamps, const double *__restrict__ d_mm, int n,
-                             PreArgs a, P3 *out, unsigned char *flags) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    P3 p = pts[i];
+// {min, max} of the stamps (Preprocessing.cpp normalises them with std::minmax_element): every CTA reduces a grid-stride share into
+// `partial[2 * blockIdx.x]`, the CTA that finishes last (ticket) reduces the partials into d_mm and puts the ticket back to zero.
+// Grid <= kMinMaxMaxGrid CTAs of 256 threads.
+constexpr int kMinMaxMaxGrid = 128;
+__global__ void __launch_bounds__(256) k_stamp_minmax(const double *__restrict__ v, int n, double *partial, unsigned int *ticket, double *d_mm) {
+    __shared__ double s_lo[8], s_hi[8];
+    __shared__ uint32_t s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double lo = DBL_MAX, hi = -DBL_MAX;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = v[i];
+        lo = x < lo ? x : lo, hi = x > hi ? x : hi;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        const double l2 = __shfl_xor_sync(0xFFFFFFFFu, lo, d), h2 = __shfl_xor_sync(0xFFFFFFFFu, hi, d);
+        lo = l2 < lo ? l2 : lo, hi = h2 > hi ? h2 : hi;
+    }
+    if (lane == 0) s_lo[warp] = lo, s_hi[warp] = hi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) lo = s_lo[w] < lo ? s_lo[w] : lo, hi = s_hi[w] > hi ? s_hi[w] : hi;
+        __stcg(&partial[2 * blockIdx.x], lo), __stcg(&partial[2 * blockIdx.x + 1], hi);
+        __threadfence();
+        const uint32_t t = atomicAdd(ticket, 1u);
+        s_last = t == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!*(volatile uint32_t *)&s_last) return;  // the whole CTA leaves or stays
+    __threadfence();
+    lo = DBL_MAX, hi = -DBL_MAX;
+    if (threadIdx.x < gridDim.x) lo = __ldcg(&partial[2 * threadIdx.x]), hi = __ldcg(&partial[2 * threadIdx.x + 1]);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        const double l2 = __shfl_xor_sync(0xFFFFFFFFu, lo, d), h2 = __shfl_xor_sync(0xFFFFFFFFu, hi, d);
+        lo = l2 < lo ? l2 : lo, hi = h2 > hi ? h2 : hi;
+    }
+    __syncthreads();
+    if (lane == 0) s_lo[warp] = lo, s_hi[warp] = hi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) lo = s_lo[w] < lo ? s_lo[w] : lo, hi = s_hi[w] > hi ? s_hi[w] : hi;
+        d_mm[0] = lo, d_mm[1] = hi;
+        atomicExch(ticket, 0u);
+    }
+}
+
+// One point through Preprocess: de-skew, range test, transform to the base frame.  Returns whether the point is kept.
+__device__ __forceinline__ bool preprocess_point(P3 p, const double *__restrict__ stamps, const double *__restrict__ d_mm, int64_t i,
+                                                 const PreArgs &a, P3 &out) {
     if (a.deskew) {
         const double t_min = d_mm[0], t_span = d_mm[1] - d_mm[0];
         const double stamp = (stamps[i] - t_min) / t_span;
@@ -150,8 +216,34 @@ __global__ void k_preprocess(const P3 *__restrict__ pts, const double *__restric
         p.x = ox, p.y = oy, p.z = oz;
     }
     const double r = sqrt(p.x * p.x + p.y * p.y + p.z * p.z);
-    flags[i] = (r < a.max_range && r > a.min_range) ? 1 : 0;
     double bx, by, bz;
     pose_apply(a.lidar_to_base, p.x, p.y, p.z, bx, by, bz);  // preprocessed_frame_in_base (KinematicICP.cpp:59)
-    out[i] = P3{bx, by, bz};
+    out = P3{bx, by, bz};
+    return r < a.max_range && r > a.min_range;
+}
+
+// Preprocess of pts[0, n): the kept points, in the base frame, to `out` in input order and their number to *d_count_out.
+// `d_mm` = {min, max} of the stamps, reduced on the device just before (no host round trip).  Grid as k_ds_select.
+__global__ void __launch_bounds__(kScanThreads) k_preprocess_select(const P3 *__restrict__ pts, const double *__restrict__ stamps,
+                                                                    const double *__restrict__ d_mm, int n, PreArgs a, P3 *out,
+                                                                    int *d_count_out, kicp_scan_args sa) {
+    __shared__ uint32_t s_warp[kScanWarps + 1];
+    const uint32_t tile = scan_take_tile(sa, &s_warp[kScanWarps]);
+    const int64_t i0 = scan_first_item(tile);
+    bool keep[kScanItems];
+    uint32_t rank[kScanItems];
+    P3 q[kScanItems];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int64_t i = i0 + 32 * k;
+        keep[k] = false;
+        if (i < n) keep[k] = preprocess_point(pts[i], stamps, d_mm, i, a, q[k]);
+    }
+    const uint32_t warp_total = scan_warp_ranks(keep, rank);
+    uint32_t inclusive;
+    const uint32_t base = scan_offset(sa, tile, warp_total, s_warp, inclusive);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+        if (keep[k]) out[base + rank[k]] = q[k];
+    if (tile == gridDim.x - 1 && threadIdx.x == 0) *d_count_out = (int)inclusive;
 }

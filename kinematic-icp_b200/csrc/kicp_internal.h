@@ -42,6 +42,14 @@ struct P2PMailbox {
     unsigned long long ll[2][KICP_MAX_ITERATIONS][KICP_MAX_RANKS][16];
 };
 
+// Per-launch arguments of the single-pass scans (kicp_scan.cuh): one status word per tile, the ticket counter that hands the tiles
+// out, and the number of the launch (never 0) that tells this launch's status words from those of earlier ones.
+struct kicp_scan_args {
+    unsigned long long *status;
+    unsigned int *ticket;
+    uint32_t launch;
+};
+
 struct kicp_ctx {
     int device = 0;
     int sm_count = 148;
@@ -82,6 +90,10 @@ struct kicp_ctx {
     std::vector<ProfReg> prof;
     int32_t *d_prof_iters = nullptr;
     int64_t prof_cap = 0;
+    // state of the single-pass scans (kicp_scan.cuh; stream-ordered, shared by the front end and the maps of this context)
+    unsigned long long *d_scan_status = nullptr;
+    unsigned int *d_scan_ticket = nullptr;
+    uint32_t scan_tiles_cap = 0, scan_launch = 0;
     // front-end scratch (kicp_frontend.cu owns the type): frame buffers, down-sample hash, pinned staging of the clouds
     void *frontend = nullptr;
     void (*frontend_free)(kicp_ctx *) = nullptr;
@@ -118,8 +130,6 @@ struct kicp_map {
     // scratch of RemovePointsFarFromLocation: survivor flags / new ids, and the spare header+point arrays the
     // survivors are compacted into (swapped with blk/pts afterwards)
     uint32_t *d_keep = nullptr, *d_new_id = nullptr;
-    void *d_scan_tmp = nullptr;  // cub::DeviceScan workspace
-    size_t scan_tmp_bytes = 0;
     int4 *blk_spare = nullptr;
     double *pts_spare = nullptr;
     MapView view() const { return MapView{slots, nslots - 1, pts, (int)cap, voxel_size}; }
@@ -159,6 +169,9 @@ int kicp_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
         if (s__ != KICP_OK) return s__; \
     } while (0)
 
+// defined in kicp_map.cu: arguments of the next scan launch over `items` items on the context stream (grows the status array when
+// it has to — synchronising — and numbers the launch)
+int kicp_scan_next(kicp_ctx *c, int64_t items, kicp_scan_args *out);
 // defined in kicp_map.cu, used by the registration entry points
 int kicp_scan_reserve_bytes(kicp_scan *scan, int64_t bytes);
 // dtype / point_step / field offsets as in kicp_frame_input (point_step 0 = tightly packed x,y,z); fields must be aligned

@@ -11,7 +11,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
-#include <cub/device/device_scan.cuh>
 
 #include "kicp_device.cuh"
 
@@ -172,6 +171,8 @@ extern "C" int kicp_ctx_destroy(kicp_ctx *ctx) {
     cudaFree(ctx->d_nn_seed);
     cudaFree(ctx->d_todo);
     cudaFree(ctx->d_prof_iters);
+    cudaFree(ctx->d_scan_status);
+    cudaFree(ctx->d_scan_ticket);
     cudaFreeHost(ctx->h_result);
     cudaFreeHost(ctx->h_chunk_tags);
     cudaFree(ctx->d_chunk_flags);
@@ -182,6 +183,43 @@ extern "C" int kicp_ctx_destroy(kicp_ctx *ctx) {
 }
 
 #include "kicp_map_kernels.cuh"  // struct MapRW and every kernel of this file
+
+// Arguments of the next scan launch over `items` items on the context stream.  The status array grows with the largest launch seen
+// (rarely, synchronising); launches are numbered from 1, and should the 32-bit number ever wrap the array is cleared first, so that
+// a word of an earlier launch can never pass for one of this launch.
+int kicp_scan_next(kicp_ctx *c, int64_t items, kicp_scan_args *out) {
+    if (!c || !out || items < 0 || items >= (1ll << 30)) return KICP_ERR_INVALID;
+    const uint32_t tiles = (uint32_t)((items + kicp_dev::kScanTile - 1) / kicp_dev::kScanTile) + 1;
+    if (tiles > c->scan_tiles_cap) {
+        KICP_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_scan_status);
+        c->d_scan_status = nullptr, c->scan_tiles_cap = 0;
+        const uint32_t cap = std::max<uint32_t>(tiles + tiles / 2, 1024u);
+        KICP_CUDA(cudaMalloc(&c->d_scan_status, (size_t)cap * sizeof(unsigned long long)));
+        KICP_CUDA(cudaMemsetAsync(c->d_scan_status, 0, (size_t)cap * sizeof(unsigned long long), c->stream));
+        c->scan_tiles_cap = cap, c->scan_launch = 0;
+    }
+    if (!c->d_scan_ticket) {
+        KICP_CUDA(cudaMalloc(&c->d_scan_ticket, sizeof(unsigned int)));
+        KICP_CUDA(cudaMemsetAsync(c->d_scan_ticket, 0, sizeof(unsigned int), c->stream));
+    }
+    if (++c->scan_launch == 0) {
+        KICP_CUDA(cudaMemsetAsync(c->d_scan_status, 0, (size_t)c->scan_tiles_cap * sizeof(unsigned long long), c->stream));
+        c->scan_launch = 1;
+    }
+    out->status = c->d_scan_status, out->ticket = c->d_scan_ticket, out->launch = c->scan_launch;
+    return KICP_OK;
+}
+
+// out[i] = in[0] + ... + in[i-1], i < n, on the context stream (renumbering of the surviving blocks, first point of every block)
+static int enqueue_exclusive_sum(kicp_ctx *c, const uint32_t *in, uint32_t *out, uint32_t n) {
+    if (n == 0) return KICP_OK;
+    kicp_scan_args sa;
+    KICP_TRY(kicp_scan_next(c, n, &sa));
+    k_exclusive_sum<<<(n + kicp_dev::kScanTile - 1) / kicp_dev::kScanTile, kicp_dev::kScanThreads, 0, c->stream>>>(in, out, n, sa);
+    KICP_CHECK_LAUNCH(c);
+    return KICP_OK;
+}
 
 // -------------------------------------------------------------------------------------------- host-side storage
 static uint32_t next_pow2(uint64_t v) {
@@ -212,8 +250,6 @@ static int map_rebuild_table(kicp_map *m, uint32_t nslots) {
 static int map_alloc_storage(kicp_map *m, uint32_t ncap) {
     kicp_ctx *c = m->ctx;
     const uint32_t slots_cap = std::max<uint32_t>(next_pow2((uint64_t)ncap * 4), 1024u);
-    size_t scan_bytes = 0;
-    KICP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)ncap, c->stream));
     const size_t pts_bytes = (size_t)ncap * m->cap * KICP_PSTRIDE * sizeof(double);
     size_t off = 0;
     auto carve = [&off](size_t bytes) {
@@ -224,7 +260,7 @@ static int map_alloc_storage(kicp_map *m, uint32_t ncap) {
     const size_t o_blk = carve((size_t)ncap * sizeof(int4)), o_pts = carve(pts_bytes), o_head = carve((size_t)ncap * sizeof(int32_t));
     const size_t o_blk2 = carve((size_t)ncap * sizeof(int4)), o_pts2 = carve(pts_bytes);
     const size_t o_keep = carve((size_t)ncap * sizeof(uint32_t)), o_id = carve((size_t)ncap * sizeof(uint32_t));
-    const size_t o_slots = carve((size_t)slots_cap * sizeof(int4)), o_scan = carve(scan_bytes);
+    const size_t o_slots = carve((size_t)slots_cap * sizeof(int4));
     char *slab = nullptr;
     KICP_CUDA(cudaMalloc(&slab, off));
     int4 *nblk = reinterpret_cast<int4 *>(slab + o_blk);
@@ -244,7 +280,6 @@ static int map_alloc_storage(kicp_map *m, uint32_t ncap) {
     m->blk_spare = reinterpret_cast<int4 *>(slab + o_blk2), m->pts_spare = reinterpret_cast<double *>(slab + o_pts2);
     m->d_keep = reinterpret_cast<uint32_t *>(slab + o_keep), m->d_new_id = reinterpret_cast<uint32_t *>(slab + o_id);
     m->slots = reinterpret_cast<int4 *>(slab + o_slots), m->slots_cap = slots_cap;
-    m->d_scan_tmp = slab + o_scan, m->scan_tmp_bytes = scan_bytes;
     // the table moved with the slab: rebuild it at its previous size (or the minimum for a new map)
     return map_rebuild_table(m, std::max<uint32_t>(std::min(m->nslots, slots_cap), 1024u));
 }
@@ -412,9 +447,7 @@ extern "C" int kicp_map_remove_far(kicp_map *m, const double origin[3]) {
     if (res[4] > 0) {
         // compact surviving blocks (order preserved) into the spare arrays, swap, and rebuild the table
         const uint32_t survivors = m->num_blocks - res[4];
-        size_t scan_bytes = m->scan_tmp_bytes;
-        KICP_CUDA(cub::DeviceScan::ExclusiveSum(m->d_scan_tmp, scan_bytes, keep, new_id, (int)m->num_blocks, c->stream));
-        c->launches += 2;  // CUB's scan passes (library kernels)
+        KICP_TRY(enqueue_exclusive_sum(c, keep, new_id, m->num_blocks));
         k_compact_blocks<<<(unsigned)(((uint64_t)m->num_blocks * 32 + 255) / 256), 256, 0, c->stream>>>(
             m->blk, m->pts, (int)m->cap, m->num_blocks, keep, new_id, m->blk_spare, m->pts_spare);
         KICP_CHECK_LAUNCH(c);
@@ -470,9 +503,7 @@ int kicp_map_update_pose_async(kicp_map *m, const double *d_xyz, int64_t n_max, 
     k_mark_far<<<(ub + 255) / 256, 256, 0, c->stream>>>(m->blk, m->pts, (int)m->cap, ub, 0.0, 0.0, 0.0, m->max_distance * m->max_distance,
                                                      m->d_keep, m->d_counters, d_res);
     KICP_CHECK_LAUNCH(c);
-    size_t scan_bytes = m->scan_tmp_bytes;
-    KICP_CUDA(cub::DeviceScan::ExclusiveSum(m->d_scan_tmp, scan_bytes, m->d_keep, m->d_new_id, (int)ub, c->stream));
-    c->launches += 2;  // CUB's scan passes (library kernels)
+    KICP_TRY(enqueue_exclusive_sum(c, m->d_keep, m->d_new_id, ub));
     k_compact_blocks<<<(unsigned)(((uint64_t)ub * 32 + 255) / 256), 256, 0, c->stream>>>(m->blk, m->pts, (int)m->cap, ub, m->d_keep,
                                                                                        m->d_new_id, m->blk_spare, m->pts_spare);
     KICP_CHECK_LAUNCH(c);
@@ -519,9 +550,11 @@ static int map_download_packed(kicp_map *m, double *out_xyz, std::vector<int4> *
     if (m->num_blocks == 0) return KICP_OK;
     k_block_counts<<<(m->num_blocks + 255) / 256, 256, 0, c->stream>>>(m->blk, m->num_blocks, m->d_keep);
     KICP_CHECK_LAUNCH(c);
-    size_t scan_bytes = m->scan_tmp_bytes;
-    KICP_CUDA(cub::DeviceScan::ExclusiveSum(m->d_scan_tmp, scan_bytes, m->d_keep, m->d_new_id, (int)m->num_blocks, c->stream));
-    c->launches += 2;  // CUB's scan passes (library kernels)
+    if (m->num_points >= (1ll << 30)) {
+        kicp_set_error("voxel map: export of 2^30 points or more is not supported");
+        return KICP_ERR_CAPACITY;
+    }
+    KICP_TRY(enqueue_exclusive_sum(c, m->d_keep, m->d_new_id, m->num_blocks));
     k_pack_points<<<(unsigned)(((uint64_t)m->num_blocks * 32 + 255) / 256), 256, 0, c->stream>>>(m->blk, m->pts, (int)m->cap, m->num_blocks,
                                                                                                 m->d_new_id, m->pts_spare);
     KICP_CHECK_LAUNCH(c);

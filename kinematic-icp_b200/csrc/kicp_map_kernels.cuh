@@ -1,15 +1,38 @@
 // Kernels of the device-resident kiss_icp::VoxelHashMap (included by kicp_map.cu, which is compiled with -fmad=false: every decision
 // — voxel floor, the < map_resolution spacing test, the >= max_distance^2 eviction test, the nearest-neighbour argmin — is evaluated
 // in plain IEEE double arithmetic in the reference's operation order).  A header of its own so that tests/emu can compile the kernels
-// for the host against the SIMT emulator without the CUB / CUDA-runtime orchestration of kicp_map.cu.
+// for the host against the SIMT emulator without the CUDA-runtime orchestration of kicp_map.cu.
 #pragma once
 #include <cfloat>
 
 #include "kicp_device.cuh"
+#include "kicp_scan.cuh"
 
 using namespace kicp_dev;
 
 // -------------------------------------------------------------------------------------------------- map kernels
+// out[i] = in[0] + ... + in[i-1] for i < n (uint32, total < 2^30); grid = ceil(n / kScanTile) CTAs of kScanThreads threads
+__global__ void __launch_bounds__(kScanThreads) k_exclusive_sum(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t n,
+                                                                kicp_scan_args a) {
+    __shared__ uint32_t s_warp[kScanWarps + 1];
+    const uint32_t tile = scan_take_tile(a, &s_warp[kScanWarps]);
+    const int64_t i0 = scan_first_item(tile);
+    uint32_t v[kScanItems], excl[kScanItems];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int64_t i = i0 + 32 * k;
+        v[k] = i < (int64_t)n ? in[i] : 0u;
+    }
+    const uint32_t warp_total = scan_warp_values(v, excl);
+    uint32_t inclusive;
+    const uint32_t base = scan_offset(a, tile, warp_total, s_warp, inclusive);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int64_t i = i0 + 32 * k;
+        if (i < (int64_t)n) out[i] = base + excl[k];
+    }
+}
+
 struct MapRW {
     int4 *slots;
     uint32_t mask;

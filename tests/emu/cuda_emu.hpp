@@ -324,6 +324,10 @@ inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long cm
     __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
     return cmp;
 }
+inline void __trap() {
+    fprintf(stderr, "emu: __trap()\n");
+    abort();
+}
 inline void __nanosleep(unsigned) {
     emu::yield();
     sched_yield();

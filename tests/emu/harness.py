@@ -73,6 +73,8 @@ def km_lib():
             f.restype, f.argtypes = C.c_int64, [C.c_void_p]
         L.km_emu_add_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.km_emu_remove_far.argtypes = [C.c_void_p, C.c_void_p]
+        L.km_emu_exclusive_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.km_emu_exclusive_sum.restype = None
         L.km_emu_update_pose_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32]
         L.km_emu_load_voxels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         L.km_emu_export.restype = C.c_int64

@@ -1,11 +1,12 @@
 // Host-side emulation of the voxel-map kernels (kinematic-icp_b200/csrc/kicp_map_kernels.cuh): the kernel SOURCE is compiled here
 // unchanged against tests/emu/cuda_emu.hpp; the launch sequences of kicp_map.cu (map_add_points_impl, kicp_map_remove_far,
-// kicp_map_load_voxels, kicp_map_nearest) are restated with host memory in place of the slab and a host prefix sum in place of
-// cub::DeviceScan.  Test infrastructure: tests/test_map_kernels_emu_cpu.py compares the map with the CPU oracle bit for bit.
+// kicp_map_load_voxels, kicp_map_nearest) are restated with host memory in place of the slab; the renumbering of the surviving blocks
+// runs the product's own single-pass scan (k_exclusive_sum, kicp_scan.cuh) with its state kept across launches.  Test infrastructure: tests/test_map_kernels_emu_cpu.py compares the map with the CPU oracle bit for bit.
 // Build with -ffp-contract=off (the product compiles these kernels with -fmad=false).  Never part of the product library.
 #include "cuda_emu.hpp"
 
 #include "../../kinematic-icp_b200/csrc/kicp_map_kernels.cuh"
+#include "scan_state.hpp"
 
 namespace {
 struct EmuMap {
@@ -33,9 +34,18 @@ void rebuild_table(EmuMap &m) {  // map_rebuild_table: clear, then one thread pe
         emu::launch_waves((int)((nb + 255) / 256), 256, [=]() { k_table_rebuild(slots, mask, blk, nb); });
     }
 }
+// enqueue_exclusive_sum of kicp_map.cu
+void exclusive_sum(const uint32_t *in, uint32_t *out, uint32_t n) {
+    if (n == 0) return;
+    const kicp_scan_args sa = emu::scan_state().next(n, kScanTile);
+    emu::launch_waves((int)((n + kScanTile - 1) / kScanTile), kScanThreads, [=]() { k_exclusive_sum(in, out, n, sa); });
+}
 }  // namespace
 
 extern "C" {
+// the scan alone (tests/test_map_kernels_emu_cpu.py: sizes around the tile and look-back boundaries, many launches on one state)
+void km_emu_exclusive_sum(const uint32_t *in, uint32_t *out, uint32_t n) { exclusive_sum(in, out, n); }
+
 void *km_emu_create(double voxel_size, double max_distance, int32_t cap, uint32_t blocks_cap) {
     EmuMap *m = new EmuMap();
     m->voxel_size = voxel_size, m->max_distance = max_distance, m->cap = cap, m->blocks_cap = blocks_cap;
@@ -91,8 +101,7 @@ int km_emu_remove_far(void *h, const double origin[3]) {
         emu::launch_waves((int)((nb + 255) / 256), 256, [=]() { k_mark_far(blk, pts, cap, nb, ox, oy, oz, md2, kp, ctr); });
     }
     if (counters[4] > 0) {
-        uint32_t run = 0;  // (cub::DeviceScan::ExclusiveSum in the product)
-        for (uint32_t b = 0; b < m.num_blocks; ++b) new_id[b] = run, run += keep[b];
+        exclusive_sum(keep.data(), new_id.data(), m.num_blocks);
         const int4 *blk = m.blk.data();
         const double *pts = m.pts.data();
         const uint32_t *kp = keep.data(), *ni = new_id.data();
@@ -145,8 +154,7 @@ int km_emu_update_pose_async(void *h, const double *xyz, int64_t n_max, int32_t 
         const int cap = m.cap;
         const double md2 = m.max_distance * m.max_distance;
         emu::launch_waves((int)((ub + 255) / 256), 256, [=]() { k_mark_far(blk, pts, cap, ub, 0.0, 0.0, 0.0, md2, kp, ctr, d_res); });
-        uint32_t run = 0;
-        for (uint32_t b = 0; b < ub; ++b) new_id[b] = run, run += keep[b];
+        exclusive_sum(keep.data(), new_id.data(), ub);
         const uint32_t *ni = new_id.data();
         int4 *bo = m.blk_spare.data();
         double *po = m.pts_spare.data();

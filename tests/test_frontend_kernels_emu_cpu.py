@@ -89,3 +89,37 @@ def test_ingest_widens_pointcloud2_fields(emu):
     raw = np.frombuffer(rec.tobytes(), dtype=np.uint8).copy()
     emu.kf_emu_ingest(raw.ctypes.data, n, 0, 40, 0, 8, 16, out.ctypes.data)
     assert np.array_equal(out, xyz64)
+
+
+def test_fused_selects_over_many_tiles(emu, oracle):
+    """The order-preserving selects fused into k_ds_select / k_preprocess_select (kicp_scan.cuh) on frames of a few hundred tiles:
+    look-back over more than one window of 32 tiles, tiles with no survivor at all, everything kept, a device-resident count that ends
+    in the middle of a tile — survivors in input order, bit for bit, and the count the last tile writes."""
+    ko = oracle
+    rng = np.random.default_rng(404)
+    n = 150_000
+    pts = rng.normal(size=(n, 3)) * [30.0, 30.0, 2.0]
+    pts[40_000:90_000] = pts[:50_000] * 1e-3 + 5.0  # 49 consecutive tiles whose points all fall into a handful of voxels already taken
+    for vs in (0.5, 1.5):
+        out = downsample(emu, pts, vs)
+        assert np.array_equal(out, ko.voxel_downsample(pts, vs))
+    for n_actual in (1023, 1024, 1025, 40_000, 100_001):
+        buf = np.concatenate([pts[:n_actual], pts[n_actual:] + 1000.0])
+        assert np.array_equal(downsample(emu, buf, 0.5, n_actual=n_actual), ko.voxel_downsample(pts[:n_actual], 0.5))
+    # Preprocess: nothing kept, everything kept, a long gap in the middle
+    far = pts * 100.0
+    assert len(preprocess(emu, ko, far, np.zeros(0), ko.IDENTITY, 100.0, 0.5, False)) == len(ko.preprocess(far, np.zeros(0), ko.IDENTITY, 100.0, 0.5, False))
+    keep_all = preprocess(emu, ko, pts, np.zeros(0), ko.IDENTITY, 1e9, 0.0, False)
+    assert np.array_equal(keep_all, ko.preprocess(pts, np.zeros(0), ko.IDENTITY, 1e9, 0.0, False)) and len(keep_all) == n
+    gap = pts.copy()
+    gap[10_000:120_000] *= 1e-4  # inside min_range
+    out = preprocess(emu, ko, gap, np.zeros(0), ko.IDENTITY, 100.0, 0.5, False)
+    ref = ko.preprocess(gap, np.zeros(0), ko.IDENTITY, 100.0, 0.5, False)
+    assert np.array_equal(out, ref) and 0 < len(ref) < n
+    # de-skew on a frame of many tiles: the stamps' min / max come from k_stamp_minmax (several CTAs + the last one's final pass)
+    stamps = rng.uniform(3.0, 3.1, size=n)
+    stamps[77_777], stamps[3] = 2.95, 3.15  # the extremes sit in different CTAs' shares
+    motion = ko.se3_exp([0.6, 0.02, 0.0, 0.001, -0.002, 0.03])
+    out = preprocess(emu, ko, pts, stamps, motion, 100.0, 0.5, True)
+    ref = ko.preprocess(pts, stamps, motion, 100.0, 0.5, True)
+    assert out.shape == ref.shape and np.abs(out - ref).max() < 1e-12

@@ -129,3 +129,17 @@ def test_nearest_neighbour_bit_exact(emu, oracle, workload):
     assert np.array_equal(dg, do) and np.array_equal(pg, po)
     assert (do == DBL_MAX).sum() > 0
     em.close()
+
+
+def test_single_pass_exclusive_sum(emu):
+    """kicp_scan.cuh alone: the chained scan with decoupled look-back that renumbers the surviving blocks (and, fused into the front
+    end's kernels, compacts the frame).  Sizes around the warp, tile (1 024 items) and look-back window (32 tiles) boundaries, all
+    launches on ONE state: the status words of earlier launches are still there and must read as 'not written yet'."""
+    rng = np.random.default_rng(77)
+    sizes = [1, 2, 31, 32, 33, 127, 128, 129, 1023, 1024, 1025, 2048, 3000, 32 * 1024, 33 * 1024 - 1, 33 * 1024 + 5, 70001, 300000, 7, 1024]
+    for rep, n in enumerate(sizes * 2):
+        v = rng.integers(0, 21, size=n, dtype=np.uint32) if rep % 3 else np.ones(n, dtype=np.uint32)
+        out = np.full(n, 0xFFFFFFFF, dtype=np.uint32)
+        emu.km_emu_exclusive_sum(v.ctypes.data, out.ctypes.data, n)
+        ref = np.concatenate([[0], np.cumsum(v[:-1], dtype=np.uint64)]).astype(np.uint32)
+        assert np.array_equal(out, ref), n
