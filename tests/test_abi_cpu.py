@@ -27,6 +27,26 @@ def test_library_exports_every_declared_symbol():
     assert declared == {s[0] for s in _capi.SYMBOLS}, "python binding and header disagree"
 
 
+def test_every_device_kernel_is_the_librarys_own():
+    """No library kernels on any path of the product: the only device functions in libkicp_b200.so are this repo's own `k_*` kernels —
+    no cub:: / thrust:: instantiations (the selects, reductions and scans of the frame path are kicp_scan.cuh fused into the kernels
+    that decide) — and the library links neither cuBLAS nor any other device library beside the CUDA runtime."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    _build()
+    from kinematic_icp_b200 import _capi
+    listing = subprocess.run(["cuobjdump", "-sass", _capi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    kernels = re.findall(r"Function : (\S+)", listing)
+    assert len(kernels) >= 20
+    foreign = [k for k in kernels if not re.match(r"_Z\d+k_[a-z0-9_]+", k)]
+    assert not foreign, foreign
+    needed = subprocess.run(["readelf", "-d", _capi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    libs = re.findall(r"\(NEEDED\)\s+Shared library: \[(.*?)\]", needed)
+    assert not [l for l in libs if re.search(r"cublas|cusolver|cusparse|cufft|curand|nvrtc|cudnn", l)], libs
+
+
 def test_struct_layout_matches_header(tmp_path):
     """sizeof / offsetof of every struct of include/kicp.h as gcc lays it out == the ctypes mirror (and the header is plain C)."""
     import subprocess
