@@ -200,8 +200,17 @@ inline void launch(int grid, int threads, F kernel_body) {
 
 // an ordinary launch: CTAs are handed to `workers` OS threads in index order, so only some are resident at a time — fine for
 // kernels whose CTAs meet through atomics and short critical sections only (no grid-wide barrier)
+// (environment KICP_EMU_WORKERS overrides the number of OS threads: 1 = CTAs strictly one after the other, 16+ = many CTAs in flight)
+inline int wave_workers(int dflt) {
+    static const int env = []() {
+        const char *e = getenv("KICP_EMU_WORKERS");
+        return e ? atoi(e) : 0;
+    }();
+    return env > 0 ? env : dflt;
+}
 template <class F>
 inline void launch_waves(int grid, int threads, F kernel_body, int workers = 6) {
+    workers = wave_workers(workers);
     grid_dim = {(unsigned)grid, 1, 1};
     block_dim = {(unsigned)threads, 1, 1};
     std::atomic<int> next{0};

@@ -143,3 +143,18 @@ def test_single_pass_exclusive_sum(emu):
         emu.km_emu_exclusive_sum(v.ctypes.data, out.ctypes.data, n)
         ref = np.concatenate([[0], np.cumsum(v[:-1], dtype=np.uint64)]).astype(np.uint32)
         assert np.array_equal(out, ref), n
+
+
+@pytest.mark.parametrize("workers", [1, 2, 24])
+def test_single_pass_scans_with_other_amounts_of_concurrency(workers):
+    """The look-back protocol must not care how many tiles are in flight: the scan and fused-select tests again in a fresh process
+    with the CTAs of every launch handed to 1 OS thread (every predecessor has finished: the nearest status word is always a PREFIX),
+    2 (the predecessor is usually still running) and 24 (many AGGREGATE words in the look-back window)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, KICP_EMU_WORKERS=str(workers))
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_map_kernels_emu_cpu.py"),
+                        os.path.join(here, "test_frontend_kernels_emu_cpu.py"), "-x", "-q", "-k", "single_pass_exclusive_sum or fused_selects",
+                        "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
